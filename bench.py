@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""Benchmark of the DRSA/LRP hot path on B200 (contract: see the task statement / DESIGN.md).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm
+
+Workload (config.workload = "cfg2"): BASELINE.json configs[1] -- DRSA at the last conv of the
+widened genre CNN: N = 10 000 samples x P = 64 positions -> M = 640 000 (activation, context)
+rows per GPU, d = 256, K = 4 concepts of d_k = 64.  A "step" is one DRSA optimisation step
+(row pass + d*m all-reduce + ascent + polar retraction).  Rows shard across ranks with the
+per-GPU row count fixed (weak scaling); `value` is whole-job throughput in cfg2-sized steps per
+second, i.e. (rows processed per step by all ranks / 640 000) * steps/s, which equals plain
+steps/s at N = 1.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG2 = dict(samples=10_000, positions=64, d=256, K=4)
+METRIC = "DRSA steps/s (cfg2: M=640k rows x d=256, K=4; LRP context vecs/s reported in 'lrp')"
+UNIT = "steps/s"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def synth_rows_cuda(M: int, d: int, seed: int, device):
+    """SURVEY 8(d) synthetic pairs, generated on the device: A = relu(randn)*mask, C = randn*(A>0),
+    each normalised like normalize_vectors."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    A = torch.relu(torch.randn(M, d, generator=g, device=device)) * (torch.rand(M, d, generator=g, device=device) < 0.7)
+    C = torch.randn(M, d, generator=g, device=device) * (A > 0)
+    nv = lambda v: v / torch.sqrt(torch.mean(v * v)) / d ** 0.25
+    return nv(A).contiguous(), nv(C).contiguous()
+
+
+# =========================================================================== this repo's arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from cxai.xai.drsa.drsa import SubspaceOptimizer
+    from oracle import drsa_ref                      # cpu_baseline leg only
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    M, d, K = CFG2["samples"] * CFG2["positions"], CFG2["d"], CFG2["K"]
+    if args.rows:
+        M = args.rows
+    m = d
+    A, C = synth_rows_cuda(M, d, 20262 + rank, dev)
+    U0 = drsa_ref.synth_U0(d, seed=5)
+    peaks = _peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    opt = SubspaceOptimizer(U0, A, C, None, num_concepts=K, device=dev, precision=args.precision)
+    opt._rows.split_u(opt.U)
+    opt.reset_log(args.warmup + args.steps + 8)
+    opt.enqueue_steps(max(args.warmup, 3))          # warm-up (also captures the CUDA graph)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    opt.enqueue_steps(args.steps)                   # EXACTLY K steps
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    # ---- dominant kernel alone (row pass = tcgen05 kernel + partial reduce), CUDA events on its stream
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        opt._rows.step(opt.U)
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(args.steps):
+        opt._rows.step(opt.U)
+    k1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_kernel = k0.elapsed_time(k1) / args.steps
+    status = opt._rows.status.cpu().numpy().tolist()
+
+    # ---- end to end through the public API with HOST buffers: construct (H2D + pack) + run + D2H
+    e2e_steps = args.e2e_steps
+    Ah, Ch = A.cpu().pin_memory(), C.cpu().pin_memory()
+    del opt
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    opt2 = SubspaceOptimizer(U0, Ah, Ch, None, num_concepts=K, device=dev, precision=args.precision)
+    opt2.run(steps=e2e_steps, save=False)
+    U_host = opt2.U.cpu()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e2e = float(te.item())
+    objs = opt2.obj_history
+    h2d = (Ah.numel() + Ch.numel() + U0.numel()) * 4
+    d2h = U_host.numel() * 4 + (e2e_steps + 1) * 4
+
+    if rank == 0:
+        ms_per_step = ms_total / args.steps
+        scale = (M * world) / float(CFG2["samples"] * CFG2["positions"])
+        value = scale * 1000.0 / ms_per_step
+        flops = 8.0 * M * d * m
+        achieved = flops / (ms_kernel * 1e-3) / 1e12
+        elem = 2 if opt2.precision == "tc" else 4
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 operands (U split hi+lo) / f32 accumulate" if opt2.precision == "tc" else "f32",
+            "data": "synthetic",
+            "config": {"workload": "cfg2" if not args.rows else f"custom rows={M}", "rows_per_gpu": M, "d": d, "m": m, "K": K,
+                       "d_k": m // K, "precision": opt2.precision, "cuda_graph": bool(opt2.use_cuda_graph),
+                       "l2_policy": f"inputs larger than L2 ({2 * M * d * elem / 1e6:.0f} MB of rows per step vs 126 MB L2)",
+                       "retraction_sweeps_last_step": status[0], "retraction_not_converged": status[1]},
+            "rows_per_s": M * world * 1000.0 / ms_per_step,
+            "gpu_launches": int(args.steps * launches_per_step(opt2)),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["tf_sustained"], "traffic": TRAFFIC_BYTES_PER_LAUNCH,
+                         "kernel": "drsa_tc_step_kernel (+ tc_reduce_kernel)" if opt2.precision == "tc" else "sgemm_kernel chain",
+                         "kernel_ms": ms_kernel, "algorithmic_flop_per_launch": flops,
+                         "algorithmic_bytes_per_launch": 2.0 * M * d * elem,
+                         "executed_mma_flop_per_launch": flops * 1.5 if opt2.precision == "tc" else flops,
+                         "hbm_frac": (2.0 * M * d * elem / (ms_kernel * 1e-3) / 1e9) / peaks["hbm"],
+                         "peak_source": peaks["source"] + "; sustained bf16 figure (kernel timed in a loop)",
+                         "share_of_step": ms_kernel / ms_per_step},
+            "e2e": {"value": scale * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_steps,
+                    "d2h_bytes_per_step": d2h / e2e_steps, "steps": e2e_steps,
+                    "what": "SubspaceOptimizer(U0, A_host_pinned, C_host_pinned).run(steps) + U.cpu(): H2D of all rows, "
+                            "fp16 pack, steps, final objective, D2H of U and the objective history, wall clock"},
+            "clocks": clocks,
+            "objective_first_last": [float(objs[0]), float(objs[-1])],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(M, d, K, budget_s=args.cpu_budget)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one drsa_tc_step_kernel launch at cfg2 from the committed
+# ncu --set full capture (profiles/); None until a capture exists.
+TRAFFIC_BYTES_PER_LAUNCH = None
+
+
+def launches_per_step(opt) -> int:
+    """Kernels of libdrsa_b200.so launched per DRSA step (counted from the host code in csrc/)."""
+    it = opt.retraction_iters
+    row = 2 if opt.precision == "tc" else 8 * max(1, -(-opt.act_vecs.size(0) // (1 << 18)))
+    return row + 1 + 3 + 3 * it + 1     # ascent, gram+norm+scale, (gram, residual, multiply) x sweeps, select
+
+
+# =========================================================================== CPU baseline / reference arm
+def cpu_step_time(M_sample: int, d: int, K: int, budget_s: float, threads: int):
+    """Times the reference's algorithm (torch CPU ops in the reference's order: obj_val, autograd
+    backward, orthogonalize with the fp64 eigh -- oracle/drsa_ref.step_autograd restates drsa.py:84-104)."""
+    import torch
+    from oracle import drsa_ref
+    torch.set_num_threads(threads)
+    A, C = drsa_ref.synth_pairs(M_sample, d, 20262, structured=False)
+    U = drsa_ref.synth_U0(d, seed=5)
+    _, _, U = drsa_ref.step_autograd(A, C, U, K)          # warm-up
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 50):
+        t0 = time.perf_counter()
+        _, _, U = drsa_ref.step_autograd(A, C, U, K)
+        times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), len(times)
+
+
+def cpu_baseline(M: int, d: int, K: int, budget_s: float = 15.0):
+    import torch
+    threads = os.cpu_count() or 1
+    M_sample = min(M, 64_000)
+    t, n = cpu_step_time(M_sample, d, K, budget_s, threads)
+    return {"value": (M_sample / M) / t, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} steps of the reference algorithm (oracle/drsa_ref.step_autograd, torch {torch.__version__} CPU, "
+                      f"{threads} threads) on {M_sample} of the {M} rows; steps/s scaled linearly in rows",
+            "sample_ms_per_step": t * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    M, d, K = CFG2["samples"] * CFG2["positions"], CFG2["d"], CFG2["K"]
+    if args.rows:
+        M = args.rows
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    threads = os.cpu_count() or 1
+    M_sample = min(M, 64_000)
+    from oracle import drsa_ref
+    torch.set_num_threads(threads)
+    A, C = drsa_ref.synth_pairs(M_sample, d, 20262, structured=False)
+    U = drsa_ref.synth_U0(d, seed=5)
+    for _ in range(max(1, min(args.warmup, 3))):
+        _, _, U = drsa_ref.step_autograd(A, C, U, K)
+    steps = min(args.steps, 40)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, _, U = drsa_ref.step_autograd(A, C, U, K)
+    t = (time.perf_counter() - t0) / steps
+    value = (M_sample / M) / t
+    sample = (f"{steps} steps of the reference algorithm (drsa.py:84-104 restated in oracle/drsa_ref.step_autograd; "
+              f"/root/reference is a Python repo that cannot travel to the GPU box) on {M_sample} of {M} rows, torch CPU, "
+              f"{threads} threads; steps/s scaled linearly in rows")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": max(1, min(args.warmup, 3)), "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2" if not args.rows else f"custom rows={M}", "rows_per_gpu": M, "d": d, "m": d, "K": K,
+                   "d_k": d // K},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="tc", choices=["tc", "fp32", "auto"])
+    ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (default: cfg2 = 640000)")
+    ap.add_argument("--e2e-steps", type=int, default=500)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,343 @@
+"""DRSA subspace optimisation on B200 -- drop-in for the reference's ``cxai.xai.drsa.drsa``.
+
+Same names, arguments and on-disk outputs as the reference module
+(``cxai/xai/drsa/drsa.py`` in sharckhai/drsa-audio: ``SubspaceOptimizer`` :15-168,
+``generalized_fmean`` :171, ``project_grad`` :186, ``orthogonalize`` :202,
+``objective_fn`` :224, ``main`` :241), but every device operation on the path is a call
+into ``libdrsa_b200.so`` (hand-written sm_100a CUDA, see ``include/drsa_b200.h``):
+
+* one fused row pass per step (projection, per-concept ReLU'd relevance, pooling sums and the
+  un-normalised gradient) instead of 4 GEMMs + ~10 elementwise kernels + autograd,
+* the ascent step and the polar retraction on the device (the reference round-trips through
+  a host fp64 ``eigh`` each step, drsa.py:216),
+* the objective history kept in a device buffer and copied once at the end (the reference
+  synchronises twice per step, drsa.py:104 and :216).
+
+Rows shard across ranks: with ``torch.distributed`` initialised (NCCL), each rank holds a
+slice of the rows, U is replicated, and one all-reduce of ``d*m + K`` floats per step joins
+the row sums.  There is no CPU / PyTorch fallback: without the CUDA library the calls raise.
+"""
+from __future__ import annotations
+
+import math
+import os
+import pickle
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from drsa_audio_b200 import _lib as _L
+
+__all__ = ["SubspaceOptimizer", "generalized_fmean", "project_grad", "orthogonalize", "objective_fn", "main"]
+
+_DEFAULT_DEVICE = torch.device("cuda")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _as_device(device) -> torch.device:
+    dev = device if isinstance(device, torch.device) else torch.device(device)
+    if dev.type != "cuda":
+        raise _L.DRSAError(f"this build of cxai.xai.drsa runs on CUDA (sm_100a) only, got device '{dev}'")
+    if not torch.cuda.is_available():
+        raise _L.DRSAError("no CUDA device available and no fallback path exists")
+    return dev
+
+
+def _f32c(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _pow2_scale(absmax: float) -> float:
+    """Power of two s with absmax*s in [128, 256): keeps fp16 far from overflow and lifts small
+    values out of the subnormal range; exact to undo."""
+    if not math.isfinite(absmax) or absmax <= 0.0:
+        return 1.0
+    return float(2.0 ** (7 - math.floor(math.log2(absmax))))
+
+
+class _RowPass:
+    """Device state of one row shard: the (packed) rows, workspaces and the step/finish calls."""
+
+    def __init__(self, act: torch.Tensor, ctx: torch.Tensor, d: int, m: int, K: int, precision: str):
+        lib = _L.lib()
+        self.lib = lib
+        self.M, self.d, self.m, self.K = int(act.shape[0]), d, m, K
+        dev = act.device
+        tc_ok = lib.drsa_step_workspace_bytes(max(self.M, 1), d, m, K, _L.PREC_TC_F16X2) >= 0
+        if precision == "auto":
+            precision = "tc" if (tc_ok and self.M >= 8192) else "fp32"
+        if precision == "tc" and not tc_ok:
+            raise _L.DRSAError(f"precision='tc' does not support d={d}, m={m}, K={K}")
+        if precision not in ("tc", "fp32"):
+            raise ValueError("precision must be 'auto', 'tc' or 'fp32'")
+        self.precision = precision
+        self.prec_code = _L.PREC_TC_F16X2 if precision == "tc" else _L.PREC_FP32
+        self.sums = torch.zeros(d * m + K, dtype=torch.float32, device=dev)
+        self.status = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.scaleA = self.scaleC = 1.0
+        self.Ut_hi = self.Ut_lo = None
+        if self.M > 0:
+            ws = _L.check(lib.drsa_step_workspace_bytes(self.M, d, m, K, self.prec_code), "drsa_step_workspace_bytes")
+            self.ws_step = torch.empty(max(int(ws), 256), dtype=torch.uint8, device=dev)
+        if precision == "tc":
+            self.Ut_hi = torch.empty(m, d, dtype=torch.float16, device=dev)
+            self.Ut_lo = torch.empty(m, d, dtype=torch.float16, device=dev)
+            self.A, self.scaleA = self._pack(act)
+            self.C, self.scaleC = self._pack(ctx)
+        else:
+            self.A, self.C = act, ctx
+        wf = _L.check(lib.drsa_finish_workspace_bytes(d, m), "drsa_finish_workspace_bytes")
+        self.ws_fin = torch.empty(int(wf), dtype=torch.uint8, device=dev)
+
+    def _pack(self, x: torch.Tensor):
+        if x.numel() == 0:
+            return torch.empty_like(x, dtype=torch.float16), 1.0
+        mx = torch.zeros(1, dtype=torch.float32, device=x.device)
+        _L.check(self.lib.drsa_absmax(_ptr(x), x.numel(), _ptr(mx), _stream()), "drsa_absmax")
+        scale = _pow2_scale(float(mx.item()))          # one host sync, once per optimiser
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            t = torch.tensor([scale], dtype=torch.float64, device=x.device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)   # same scale on every rank
+            scale = float(t.item())
+        out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+        _L.check(self.lib.drsa_pack_f16(_ptr(x), x.numel(), scale, _ptr(out), _stream()), "drsa_pack_f16")
+        return out, scale
+
+    def split_u(self, U: torch.Tensor):
+        if self.precision == "tc":
+            _L.check(self.lib.drsa_split_u(_ptr(U), self.d, self.m, _ptr(self.Ut_hi), _ptr(self.Ut_lo), _stream()),
+                     "drsa_split_u")
+
+    def step(self, U: torch.Tensor):
+        """Row sums of this shard into self.sums (drsa.py:148-155 + backward of :100)."""
+        if self.M == 0:
+            self.sums.zero_()
+            return
+        _L.check(self.lib.drsa_step(_ptr(self.A), _ptr(self.C), _ptr(U), _ptr(self.Ut_hi), _ptr(self.Ut_lo), self.M,
+                                    self.d, self.m, self.K, self.prec_code, self.scaleA, self.scaleC,
+                                    _ptr(self.sums), _ptr(self.ws_step), self.ws_step.numel(), _stream()),
+                 "drsa_step")
+
+    def finish(self, U: torch.Tensor, M_global: int, obj_log: Optional[torch.Tensor], log_index: int, update: bool,
+               max_iters: int, tol: float):
+        _L.check(self.lib.drsa_finish_step(_ptr(self.sums), M_global, _ptr(U), self.d, self.m, self.K,
+                                           _ptr(U) if update else None,
+                                           _ptr(self.Ut_hi) if update else None, _ptr(self.Ut_lo) if update else None,
+                                           _ptr(obj_log), log_index, max_iters, tol, _ptr(self.status),
+                                           _ptr(self.ws_fin), self.ws_fin.numel(), _stream()),
+                 "drsa_finish_step")
+
+
+class SubspaceOptimizer:
+    """Gradient ascent on the DRSA objective with a polar retraction after every step.
+
+    Mirrors the reference class (drsa.py:15-168): same constructor arguments and attributes
+    (``U, act_vecs, ctx_vecs, num_concepts, d_k, obj_fn, device, path_to_model``), ``run``,
+    ``obj_val``, ``save_model`` and ``save_train_stats``.
+
+    Extra keyword arguments (all optional, defaults keep the reference behaviour):
+        precision: 'auto' | 'tc' | 'fp32' -- arithmetic of the row pass (see include/drsa_b200.h).
+        process_group: torch.distributed group over which the rows are sharded; ``activation_vecs``
+            / ``context_vecs`` are then this rank's slice.  Defaults to the world group if
+            torch.distributed is initialised.
+        retraction_iters / retraction_tol: bounds of the on-device Newton-Schulz polar iteration.
+        use_cuda_graph: capture one step and replay it (single process only).
+    """
+
+    def __init__(self, U: torch.Tensor, activation_vecs: torch.Tensor, context_vecs: torch.Tensor,
+                 path_to_model: Optional[str], num_concepts: int = 4, device=_DEFAULT_DEVICE, *,
+                 precision: str = "auto", process_group=None, retraction_iters: int = 8,
+                 retraction_tol: float = 1e-6, use_cuda_graph: bool = True) -> None:
+        assert num_concepts > 0, "num_concepts must be a positive number"
+        assert U.size(1) % num_concepts == 0, "num_concepts must be a divisor of the number of columns of U"
+        assert activation_vecs.shape == context_vecs.shape and activation_vecs.dim() == 2
+        assert activation_vecs.size(1) == U.size(0), "vector dimension must equal the number of rows of U"
+        self.device = _as_device(device)
+        self.path_to_model = path_to_model
+        self.num_concepts = num_concepts
+        self.d_k = U.size(1) // num_concepts          # drsa.py:68 (U square there)
+        self.obj_fn = objective_fn
+        with torch.cuda.device(self.device):
+            self.U = _f32c(U, self.device).clone()
+            self.act_vecs = _f32c(activation_vecs, self.device)
+            self.ctx_vecs = _f32c(context_vecs, self.device)
+            self._dist = torch.distributed.is_available() and torch.distributed.is_initialized()
+            self._group = process_group
+            self._rows = _RowPass(self.act_vecs, self.ctx_vecs, U.size(0), U.size(1), num_concepts, precision)
+        self.precision = self._rows.precision
+        self.retraction_iters, self.retraction_tol = retraction_iters, retraction_tol
+        self.use_cuda_graph = use_cuda_graph and not self._dist
+        M_local = torch.tensor([self.act_vecs.size(0)], dtype=torch.int64, device=self.device)
+        if self._dist:
+            torch.distributed.all_reduce(M_local, group=self._group)
+        self.M_global = int(M_local.item())
+        self.obj_history: Optional[np.ndarray] = None
+        self.last_status: Optional[np.ndarray] = None
+
+    # ------------------------------------------------------------------ one step
+    def _step(self, obj_log: torch.Tensor, log_index: int, update: bool) -> None:
+        self._rows.step(self.U)
+        if self._dist:
+            torch.distributed.all_reduce(self._rows.sums, group=self._group)   # d*m + K floats over NVLink
+        self._rows.finish(self.U, self.M_global, obj_log, log_index, update, self.retraction_iters,
+                          self.retraction_tol)
+
+    def run(self, steps: int = 2000, save: bool = True) -> None:
+        """``steps`` ascent steps; the objective is logged before every update plus once at the end
+        (drsa.py:84-117), then U and the statistics are written (drsa.py:119-120)."""
+        with torch.cuda.device(self.device):
+            self._rows.split_u(self.U)
+            self.reset_log(steps + 1)
+            self.enqueue_steps(steps)
+            self._step(self._obj_log, -1, False)          # final evaluation, no update (drsa.py:109-117)
+            hist = self._obj_log[: steps + 1].cpu().numpy()   # the only device->host copy of the loop
+            self.last_status = self._rows.status.cpu().numpy()
+        self.obj_history = hist
+        if save and self.path_to_model is not None:
+            self.save_model()
+            self.save_train_stats([np.asarray(v) for v in hist])
+
+    def reset_log(self, capacity: int) -> None:
+        """(Re)allocate the device-side objective log and rewind its cursor."""
+        log = getattr(self, "_obj_log", None)
+        if log is None or log.numel() < capacity:
+            self._obj_log = torch.zeros(max(capacity, 4096), dtype=torch.float32, device=self.device)
+            self._graph = None                            # the log pointer is baked into the graph
+        self._rows.status.zero_()
+
+    def enqueue_steps(self, n: int) -> None:
+        """Enqueue ``n`` ascent steps on the current stream without any host synchronisation.  Each
+        step appends its objective to the device log.  Single process: one step is captured in a CUDA
+        graph once and replayed."""
+        if n <= 0:
+            return
+        if not (self.use_cuda_graph and n >= 4):
+            for _ in range(n):
+                self._step(self._obj_log, -1, True)
+            return
+        if getattr(self, "_graph", None) is None:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._step(self._obj_log, -1, True)       # warm-up outside the graph (lazy module init)
+            torch.cuda.current_stream().wait_stream(side)
+            n -= 1
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._step(self._obj_log, -1, True)       # capture does not execute
+            self._graph = graph
+        for _ in range(n):
+            self._graph.replay()
+
+    # ------------------------------------------------------------------ objective (static, differentiable)
+    @staticmethod
+    def obj_val(act_vecs: torch.Tensor, context_vecs: torch.Tensor, U: torch.Tensor, obj_fn=None,
+                num_concepts: int = 4, d_k: Optional[int] = None) -> torch.Tensor:
+        """DRSA objective of drsa.py:123-155 as a 0-dim tensor on U's device, differentiable w.r.t. U
+        (the backward is the fused gradient of the same row pass).  ``obj_fn`` is accepted for
+        signature compatibility; the pooling of drsa.py:224-238 is what the kernel implements."""
+        if obj_fn is not None and obj_fn is not objective_fn:
+            raise _L.DRSAError("obj_val implements the reference's objective_fn only")
+        if d_k is not None and d_k * num_concepts != U.size(1):
+            raise ValueError("num_concepts * d_k must equal the number of columns of U")
+        return _ObjVal.apply(act_vecs, context_vecs, U, num_concepts)
+
+    # ------------------------------------------------------------------ outputs (formats of drsa.py:157-168)
+    def save_train_stats(self, obj_arr: List[np.ndarray]) -> None:
+        import pandas as pd
+        pd.DataFrame({"loss": obj_arr}).to_csv(os.path.join(self.path_to_model, "train_stats.csv"))
+
+    def save_model(self) -> None:
+        with open(os.path.join(self.path_to_model, "projection_matrix.pkl"), "wb") as file:
+            pickle.dump(self.U.detach().cpu().numpy(), file)
+
+
+class _ObjVal(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, act, cvec, U, K):
+        dev = _as_device(U.device if U.is_cuda else _DEFAULT_DEVICE)
+        with torch.cuda.device(dev):
+            A, Cv, Uc = _f32c(act, dev), _f32c(cvec, dev), _f32c(U, dev)
+            rows = _RowPass(A, Cv, Uc.size(0), Uc.size(1), K, "fp32")
+            rows.step(Uc)
+            obj = torch.zeros(1, dtype=torch.float32, device=dev)
+            rows.finish(Uc, A.size(0), obj, 0, False, 1, 1e-6)
+        ctx.save_for_backward(rows.sums, obj)
+        ctx.shape = (Uc.size(0), Uc.size(1), K, A.size(0))
+        return obj[0].to(device=U.device, dtype=U.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        sums, obj = ctx.saved_tensors
+        d, m, K, M = ctx.shape
+        X = sums[: d * m].view(d, m)
+        q = torch.sqrt(sums[d * m:] / M)
+        coef = torch.sqrt(obj) / (K * M * q ** 1.5)
+        grad = X * coef.repeat_interleave(m // K)[None, :]
+        return None, None, (grad * grad_out.to(grad.device)).to(device=grad_out.device, dtype=grad_out.dtype), None
+
+
+# ---------------------------------------------------------------------- module-level functions
+def generalized_fmean(x: torch.Tensor, p: float = 0.5) -> torch.Tensor:
+    """F-mean with F(t) = t^p over dim 0 (drsa.py:171-182)."""
+    return torch.pow(torch.mean(torch.pow(x, p), dim=0), 1 / p)
+
+
+@torch.no_grad()
+def project_grad(gradient: torch.Tensor, U: torch.Tensor) -> torch.Tensor:
+    """Unused in the reference as well (drsa.py:186-198); kept for API completeness."""
+    return gradient - torch.matmul(torch.matmul(U.T, gradient), U.T)
+
+
+@torch.no_grad()
+def orthogonalize(U: torch.Tensor, max_iters: int = 24, tol: float = 1e-6) -> torch.Tensor:
+    """U (U^T U)^(-1/2) -- the reference's retraction (drsa.py:201-221), computed on the device."""
+    dev = _as_device(U.device if U.is_cuda else _DEFAULT_DEVICE)
+    lib = _L.lib()
+    with torch.cuda.device(dev):
+        Y = _f32c(U, dev)
+        d, m = Y.shape
+        out = torch.empty_like(Y)
+        ws = torch.empty(int(_L.check(lib.drsa_finish_workspace_bytes(d, m))), dtype=torch.uint8, device=dev)
+        status = torch.zeros(4, dtype=torch.int32, device=dev)
+        _L.check(lib.drsa_polar_retract(_ptr(Y), d, m, _ptr(out), max_iters, tol, _ptr(status), _ptr(ws), ws.numel(),
+                                        _stream()), "drsa_polar_retract")
+    return out.to(U.dtype)
+
+
+def objective_fn(input: torch.Tensor) -> torch.Tensor:
+    """Soft-max pooling over rows (p = 2), soft-min pooling over concepts (p = 0.5) -- drsa.py:224-238."""
+    return generalized_fmean(generalized_fmean(input, 2), 0.5)
+
+
+def main(activation_vecs: torch.Tensor, context_vecs: torch.Tensor, model_root: str, num_concepts: int = 4,
+         steps: int = 2000, runs: int = 3, seed: int = 42, device=_DEFAULT_DEVICE, **optimizer_kwargs) -> None:
+    """Several runs from differently permuted random orthogonal starts (drsa.py:241-300): numpy is
+    seeded once, ``ortho_group.rvs(d)`` draws U, each run permutes the columns of the *previous*
+    run's start (the permutations compound) and writes into ``model_root/run{r}``."""
+    from scipy.stats import ortho_group
+
+    np.random.seed(seed)
+    device = _as_device(device)
+    print(f"Starting DRSA training on device {device} ...")
+    d = activation_vecs.size(-1)
+    U = ortho_group.rvs(d)
+    print("Orthogonal projection matrix U of size (%2d x %2d)" % (d, d))
+    for run in range(1, runs + 1):
+        model_path = os.path.join(model_root, f"run{run}")
+        os.makedirs(model_path, exist_ok=True)
+        mask = np.random.permutation(d)
+        U = U[:, mask]
+        print("-" * 20, f"\nStarting RUN {run}")
+        opt = SubspaceOptimizer(torch.tensor(U, dtype=activation_vecs.dtype), activation_vecs, context_vecs,
+                                model_path, num_concepts=num_concepts, device=device, **optimizer_kwargs)
+        opt.run(steps=steps)
+    print("Done!")

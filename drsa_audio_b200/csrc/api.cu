@@ -1,0 +1,212 @@
+// extern "C" surface of libdrsa_b200.so (see include/drsa_b200.h).  Argument checking lives
+// here; the kernels live in the other translation units.
+#include "common.cuh"
+
+namespace drsa {
+thread_local int g_last_cuda_error = 0;
+
+int require_sm100() {
+  static int cached = 1;   // 1 = unknown
+  if (cached == 1) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+      cudaGetLastError();
+      return DRSA_ERR_ARCH;
+    }
+    cached = (prop.major == 10) ? DRSA_OK : DRSA_ERR_ARCH;
+  }
+  return cached;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      n = v;
+    else { cudaGetLastError(); return 148; }
+  }
+  return n;
+}
+
+// defined in the other translation units
+int64_t step_fp32_workspace_bytes(int64_t M, int d, int m, int K);
+int step_fp32(const float* A, const float* C, const float* U, int64_t M, int d, int m, int K, float* sums,
+              void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+bool tc_shape_supported(int d, int m, int K);
+int64_t step_tc_workspace_bytes(int64_t M, int d, int m, int K);
+int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_lo, int64_t M, int d, int m, int K,
+            float scaleA, float scaleC, float* sums, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+int pack_f16(const float* in, int64_t count, float scale, void* out, cudaStream_t stream);
+int absmax(const float* in, int64_t count, float* out, cudaStream_t stream);
+int64_t finish_workspace_bytes(int d, int m);
+int finish_step(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out, void* Ut_hi,
+                void* Ut_lo, float* obj_log, int64_t log_index, int max_iters, float tol, int* status,
+                void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+int polar_retract(const float* Y, int d, int m, float* U_out, int max_iters, float tol, int* status, void* workspace,
+                  int64_t workspace_bytes, cudaStream_t stream);
+int split_u(const float* U, int d, int m, void* Ut_hi, void* Ut_lo, cudaStream_t stream);
+int selftest_umma(int variant, float* max_err_host);
+int64_t subspace_relevances_workspace_bytes(int64_t B, int64_t P, int d, int m);
+int subspace_relevances(const float* act, const float* ctx, const float* U, int64_t B, int64_t P, int d, int m, int K,
+                        float* out, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+int context_gather(const float* a_map, const float* R_map, int64_t N, int d, int HW, const int64_t* idx, int L,
+                   float* act_out, float* ctx_out, double* sumsq, cudaStream_t stream);
+int context_vectors(const float* a, const float* R, int64_t count, float* out, cudaStream_t stream);
+int sumsq(const float* v, int64_t count, double* out, cudaStream_t stream);
+int normalize(float* v, int64_t rows, int d, const double* sumsq, int64_t count_global, cudaStream_t stream);
+
+static bool shape_ok(int64_t M, int d, int m, int K) {
+  return M > 0 && d > 0 && m > 0 && K > 0 && m <= d && m % K == 0;
+}
+}  // namespace drsa
+
+using namespace drsa;
+
+extern "C" {
+
+const char* drsa_status_string(int status) {
+  switch (status) {
+    case DRSA_OK: return "ok";
+    case DRSA_ERR_ARG: return "invalid argument";
+    case DRSA_ERR_SHAPE: return "shape not supported by this precision mode";
+    case DRSA_ERR_ARCH: return "device is not sm_100 (no fallback path exists)";
+    case DRSA_ERR_ALIGN: return "pointer or leading dimension not 16-byte aligned";
+    case DRSA_ERR_WORKSPACE: return "workspace too small";
+    case DRSA_ERR_CUDA: return "CUDA call failed (see drsa_last_cuda_error)";
+    case DRSA_ERR_RANGE: return "value out of range for this precision mode";
+    default: return "unknown status";
+  }
+}
+
+int drsa_version(void) { return DRSA_B200_VERSION; }
+int drsa_last_cuda_error(void) { return g_last_cuda_error; }
+
+int drsa_check_device(int device) {
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); return DRSA_ERR_ARCH; }
+  return prop.major == 10 ? DRSA_OK : DRSA_ERR_ARCH;
+}
+
+int drsa_pack_f16(const float* in, int64_t count, float scale, void* out_f16, void* stream) {
+  if (in == nullptr || out_f16 == nullptr || count <= 0 || !(scale > 0.f)) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return pack_f16(in, count, scale, out_f16, static_cast<cudaStream_t>(stream));
+}
+
+int drsa_absmax(const float* in, int64_t count, float* out, void* stream) {
+  if (in == nullptr || out == nullptr || count <= 0) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return absmax(in, count, out, static_cast<cudaStream_t>(stream));
+}
+
+int64_t drsa_step_workspace_bytes(int64_t M, int d, int m, int K, int precision) {
+  if (!shape_ok(M, d, m, K)) return DRSA_ERR_ARG;
+  if (precision == DRSA_PREC_FP32) return step_fp32_workspace_bytes(M, d, m, K);
+  if (precision == DRSA_PREC_TC_F16X2) {
+    if (!tc_shape_supported(d, m, K)) return DRSA_ERR_SHAPE;
+    return step_tc_workspace_bytes(M, d, m, K);
+  }
+  return DRSA_ERR_ARG;
+}
+
+int drsa_step(const void* A, const void* C, const float* U, const void* Ut_hi, const void* Ut_lo, int64_t M, int d,
+              int m, int K, int precision, float scaleA, float scaleC, float* sums, void* workspace,
+              int64_t workspace_bytes, void* stream) {
+  if (A == nullptr || C == nullptr || sums == nullptr || workspace == nullptr || !shape_ok(M, d, m, K))
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (precision == DRSA_PREC_FP32) {
+    if (U == nullptr) return DRSA_ERR_ARG;
+    return step_fp32(static_cast<const float*>(A), static_cast<const float*>(C), U, M, d, m, K, sums, workspace,
+                     workspace_bytes, s);
+  }
+  if (precision == DRSA_PREC_TC_F16X2) {
+    if (Ut_hi == nullptr || Ut_lo == nullptr || !(scaleA > 0.f) || !(scaleC > 0.f)) return DRSA_ERR_ARG;
+    return step_tc(A, C, Ut_hi, Ut_lo, M, d, m, K, scaleA, scaleC, sums, workspace, workspace_bytes, s);
+  }
+  return DRSA_ERR_ARG;
+}
+
+int drsa_split_u(const float* U, int d, int m, void* Ut_hi, void* Ut_lo, void* stream) {
+  if (U == nullptr || Ut_hi == nullptr || Ut_lo == nullptr || d <= 0 || m <= 0) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return split_u(U, d, m, Ut_hi, Ut_lo, static_cast<cudaStream_t>(stream));
+}
+
+int64_t drsa_finish_workspace_bytes(int d, int m) {
+  if (d <= 0 || m <= 0 || m > d) return DRSA_ERR_ARG;
+  return finish_workspace_bytes(d, m);
+}
+
+int drsa_finish_step(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out,
+                     void* Ut_hi, void* Ut_lo, float* obj_log, int64_t log_index, int max_iters, float tol,
+                     int* status, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (sums == nullptr || !shape_ok(M_global, d, m, K) || workspace == nullptr) return DRSA_ERR_ARG;
+  if (U_out != nullptr && (U == nullptr || max_iters < 1 || !(tol > 0.f))) return DRSA_ERR_ARG;
+  if ((Ut_hi == nullptr) != (Ut_lo == nullptr)) return DRSA_ERR_ARG;
+  if (K > 1024) return DRSA_ERR_SHAPE;
+  if (obj_log != nullptr && log_index < 0 && status == nullptr) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return finish_step(sums, M_global, U, d, m, K, U_out, Ut_hi, Ut_lo, obj_log, log_index, max_iters, tol, status,
+                     workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int drsa_polar_retract(const float* Y, int d, int m, float* U_out, int max_iters, float tol, int* status,
+                       void* workspace, int64_t workspace_bytes, void* stream) {
+  if (Y == nullptr || U_out == nullptr || workspace == nullptr || d <= 0 || m <= 0 || m > d || max_iters < 1 ||
+      !(tol > 0.f))
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return polar_retract(Y, d, m, U_out, max_iters, tol, status, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int64_t drsa_subspace_relevances_workspace_bytes(int64_t B, int64_t P, int d, int m) {
+  if (B <= 0 || P <= 0 || d <= 0 || m <= 0) return DRSA_ERR_ARG;
+  return subspace_relevances_workspace_bytes(B, P, d, m);
+}
+
+int drsa_subspace_relevances(const float* act, const float* ctx, const float* U, int64_t B, int64_t P, int d, int m,
+                             int K, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (act == nullptr || ctx == nullptr || U == nullptr || out == nullptr || workspace == nullptr ||
+      !shape_ok(B * P, d, m, K) || B <= 0 || P <= 0)
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return subspace_relevances(act, ctx, U, B, P, d, m, K, out, workspace, workspace_bytes,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int drsa_context_gather(const float* a_map, const float* R_map, int64_t N, int d, int HW, const int64_t* idx, int L,
+                        float* act_out, float* ctx_out, double* sumsq, void* stream) {
+  if (a_map == nullptr || R_map == nullptr || act_out == nullptr || ctx_out == nullptr || N <= 0 || d <= 0 ||
+      HW <= 0 || L <= 0 || (idx == nullptr && L != HW))
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return context_gather(a_map, R_map, N, d, HW, idx, L, act_out, ctx_out, sumsq, static_cast<cudaStream_t>(stream));
+}
+
+int drsa_context_vectors(const float* a, const float* R, int64_t count, float* out, void* stream) {
+  if (a == nullptr || R == nullptr || out == nullptr || count <= 0) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return context_vectors(a, R, count, out, static_cast<cudaStream_t>(stream));
+}
+
+int drsa_sumsq(const float* v, int64_t count, double* out, void* stream) {
+  if (v == nullptr || out == nullptr || count <= 0) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return sumsq(v, count, out, static_cast<cudaStream_t>(stream));
+}
+
+int drsa_normalize(float* v, int64_t rows, int d, const double* sumsq, int64_t count_global, void* stream) {
+  if (v == nullptr || sumsq == nullptr || rows <= 0 || d <= 0 || count_global <= 0) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return normalize(v, rows, d, sumsq, count_global, static_cast<cudaStream_t>(stream));
+}
+
+int drsa_selftest_umma(int variant, float* max_err_host) { return selftest_umma(variant, max_err_host); }
+
+}  // extern "C"

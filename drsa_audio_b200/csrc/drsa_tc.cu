@@ -1,0 +1,608 @@
+// DRSA row pass on the 5th-generation tensor cores (DRSA_PREC_TC_F16X2).
+//
+// One kernel does, per tile of 128 (activation, context) rows and per group of 128 projected
+// columns (= 128/d_k whole concepts), everything drsa.py:148-155 and the backward of drsa.py:100
+// do, without the projected activations ever leaving the SM:
+//
+//   GEMM1 (tcgen05.mma SS, fp16 x fp16 -> fp32 in TMEM), transposed so that a TMEM lane is a
+//          projected column j and a TMEM column is a row r of the tile:
+//              HA^T[j][r] = sum_i U^T[j][i] A[r][i]        (U^T = hi + lo, two MMAs)
+//              HC^T[j][r] = sum_i U^T[j][i] C[r][i]
+//   epilogue (4 warps, tcgen05.ld): s_rk = sum_{j in k} HA^T[j][r] HC^T[j][r] is a reduction across
+//          TMEM lanes -> warp transpose-reduce (31 shuffles per 32 rows) + a 2 KB smem exchange;
+//          g = relu(s) ; sumsq_k += g^2 ; P^T = g * HC^T and Q^T = g * HA^T are written back over
+//          HA^T / HC^T in TMEM as packed fp16 (tcgen05.st) -- the A operand of GEMM2.
+//   GEMM2 (tcgen05.mma TS, A operand from TMEM, B operand = the same row tile read MN-major):
+//              X^T[j][i] += sum_r P^T[j][r] A[r][i] + Q^T[j][r] C[r][i]
+//          accumulated in TMEM over ALL row tiles of the CTA and written out once.
+//
+// A and C are stored once as scaled fp16 (drsa_pack_f16), U^T is split into fp16 hi + lo every
+// step (its rounding is systematic, that of the rows averages out over M).
+// Operand staging: TMA (cp.async.bulk.tensor, 128-byte swizzle) into an mbarrier ring;
+// U^T of the CTA's column group stays resident in shared memory.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) + TMEM owner,
+// warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
+#include <cuda.h>
+#include <vector>
+#include <cmath>
+#include <cstdlib>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace drsa {
+
+// ----------------------------------------------------------------------------- tensor maps
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+}  // namespace
+
+int make_tmap_f16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return DRSA_ERR_CUDA;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return DRSA_ERR_CUDA; }
+  return DRSA_OK;
+}
+
+namespace {
+using namespace tc;
+
+constexpr int kRows = 128;             // rows of A / C per tile (MMA N of GEMM1, K of GEMM2)
+constexpr int kNG = 128;               // projected columns per CTA (MMA M)
+constexpr int kPanelBytes = 128 * 128; // one [128 x 64] fp16 box, 128-byte rows
+constexpr int kThreads = 192;
+constexpr int kRedBytes = 4 * kRows * 4;
+constexpr int kBarBytes = 256;
+
+template <int D>
+struct Cfg {
+  static constexpr int kPanels = D / 64;
+  static constexpr int kUBytes = 2 * kPanels * kPanelBytes;   // U^T hi + lo of this column group
+  static constexpr int kStageBytes = 2 * kPanelBytes;         // A panel + C panel
+  static constexpr int kStages = (D >= 256) ? 3 : 4;
+  static constexpr int kDataBytes = kUBytes + kStages * kStageBytes;
+  static constexpr int kSmemBytes = kDataBytes + kRedBytes + kBarBytes;
+};
+
+__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("{\n\t.reg .b16 l, h;\n\t"
+      "cvt.rn.satfinite.f16.f32 l, %1;\n\t"
+      "cvt.rn.satfinite.f16.f32 h, %2;\n\t"
+      "mov.b32 %0, {l, h};\n\t}"
+      : "=r"(r)
+      : "f"(lo), "f"(hi));
+  return r;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 1)
+drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC,
+                    const __grid_constant__ CUtensorMap tmUh, const __grid_constant__ CUtensorMap tmUl,
+                    int num_tiles, int G, int nRB, int d_k, float inv_scale, float* __restrict__ part,
+                    float* __restrict__ ss_part, int* __restrict__ err_flag) {
+  using C = Cfg<D>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sU_hi = smem;
+  uint8_t* sU_lo = smem + C::kPanels * kPanelBytes;
+  uint8_t* sStage = smem + C::kUBytes;
+  float* red = reinterpret_cast<float*>(smem + C::kDataBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kDataBytes + kRedBytes);
+  uint64_t* full = bars;            // [kStages]
+  uint64_t* empty = bars + 8;       // [kStages]
+  uint64_t* u_full = bars + 16;
+  uint64_t* h_full = bars + 17;
+  uint64_t* p_full = bars + 18;
+  uint64_t* x_full = bars + 19;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x % G, rb = blockIdx.x / G;
+
+  if ((smem_u32(smem) & 1023u) != 0) {   // 128-byte swizzle needs 1024-byte aligned panels
+    if (threadIdx.x == 0) atomicExch(err_flag, 1);
+    return;
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(u_full, 1); mbar_init(h_full, 1); mbar_init(p_full, 128); mbar_init(x_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmC); tma_prefetch_desc(&tmUh); tma_prefetch_desc(&tmUl);
+      mbar_expect_tx(u_full, C::kUBytes);
+      for (int p = 0; p < C::kPanels; ++p) {
+        tma_load_2d(sU_hi + p * kPanelBytes, &tmUh, u_full, 64 * p, g * kNG);
+        tma_load_2d(sU_lo + p * kPanelBytes, &tmUl, u_full, 64 * p, g * kNG);
+      }
+      int stage = 0; uint32_t phase = 0;
+      for (int t = rb; t < num_tiles; t += nRB) {
+        for (int pass = 0; pass < 2; ++pass) {          // the row tile is streamed once per GEMM
+          for (int p = 0; p < C::kPanels; ++p) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], C::kStageBytes);
+            uint8_t* dst = sStage + stage * C::kStageBytes;
+            tma_load_2d(dst, &tmA, &full[stage], 64 * p, t * kRows);
+            tma_load_2d(dst + kPanelBytes, &tmC, &full[stage], 64 * p, t * kRows);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_idesc_f16(kNG, kRows, 0, 0);   // U^T (K-major) x tile (K-major)
+      constexpr uint32_t idesc2 = make_idesc_f16(kNG, 64, 0, 1);      // P^T (TMEM)   x tile (MN-major)
+      const uint32_t tX = tmem_base, tHA = tmem_base + 256, tHC = tmem_base + 384;
+      mbar_wait(u_full, 0);
+      tc_fence_after();
+      int stage = 0; uint32_t phase = 0, tile_parity = 0; bool first = true;
+      for (int t = rb; t < num_tiles; t += nRB) {
+        // ---- GEMM1: HA^T, HC^T [128 cols of U x 128 rows], K = D
+        for (int p = 0; p < C::kPanels; ++p) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t uh = smem_u32(sU_hi + p * kPanelBytes), ul = smem_u32(sU_lo + p * kPanelBytes);
+          const uint32_t bA = smem_u32(sStage + stage * C::kStageBytes), bC = bA + kPanelBytes;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t acc = (p | kk) ? 1u : 0u;
+            const uint64_t d_uh = make_smem_desc_sw128(uh + kk * 32, 16, 1024);
+            const uint64_t d_ul = make_smem_desc_sw128(ul + kk * 32, 16, 1024);
+            const uint64_t d_a = make_smem_desc_sw128(bA + kk * 32, 16, 1024);
+            const uint64_t d_c = make_smem_desc_sw128(bC + kk * 32, 16, 1024);
+            umma_ss_f16(tHA, d_uh, d_a, idesc1, acc);
+            umma_ss_f16(tHA, d_ul, d_a, idesc1, 1u);
+            umma_ss_f16(tHC, d_uh, d_c, idesc1, acc);
+            umma_ss_f16(tHC, d_ul, d_c, idesc1, 1u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(h_full);
+        // ---- wait for P^T / Q^T from the epilogue warps
+        mbar_wait(p_full, tile_parity);
+        tc_fence_after();
+        // ---- GEMM2: X^T[:, 64p..64p+63] += P^T tile_A + Q^T tile_C, K = 128 rows
+        for (int p = 0; p < C::kPanels; ++p) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t bA = smem_u32(sStage + stage * C::kStageBytes), bC = bA + kPanelBytes;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t acc = (!first || ks > 0) ? 1u : 0u;
+            const uint64_t d_a = make_smem_desc_sw128(bA + ks * 2048, kPanelBytes, 1024);
+            const uint64_t d_c = make_smem_desc_sw128(bC + ks * 2048, kPanelBytes, 1024);
+            const uint32_t off = 32 * (ks >> 1) + 8 * (ks & 1);
+            umma_ts_f16(tX + 64 * p, tHA + off, d_a, idesc2, acc);
+            umma_ts_f16(tX + 64 * p, tHC + off, d_c, idesc2, 1u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        first = false;
+        tile_parity ^= 1;
+      }
+      umma_commit(x_full);
+    }
+  } else {
+    // ======================= epilogue warps =======================
+    const int q = warp & 3;                     // TMEM lane quarter this warp may touch
+    const int j = 32 * q + lane;                // projected column within the group
+    const int wpc = d_k >> 5;                   // warps per concept (d_k in {32, 64, 128})
+    const int q0 = (q / wpc) * wpc;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
+    const bool owner = (j % d_k) == 0;
+    float ssq = 0.f;
+    uint32_t tile_parity = 0;
+    for (int t = rb; t < num_tiles; t += nRB) {
+      mbar_wait(h_full, tile_parity);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t ha[32], hc[32];
+        tmem_ld32(lane_base + 256 + 32 * c, ha);
+        tmem_ld32(lane_base + 384 + 32 * c, hc);
+        tmem_ld_wait();
+        float pr[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pr[i] = __uint_as_float(ha[i]) * __uint_as_float(hc[i]);
+        // transpose-reduce: afterwards lane l holds sum over the warp's 32 lanes of column l
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < off; ++i) {
+            const float send = upper ? pr[i] : pr[i + off];
+            const float keep = upper ? pr[i + off] : pr[i];
+            pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        red[q * kRows + 32 * c + lane] = pr[0];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint32_t pk[16], qk[16];
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          float4 s4 = *reinterpret_cast<const float4*>(&red[q0 * kRows + 32 * c + 4 * i4]);
+          for (int w = 1; w < wpc; ++w) {
+            const float4 o = *reinterpret_cast<const float4*>(&red[(q0 + w) * kRows + 32 * c + 4 * i4]);
+            s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w;
+          }
+          const float g0 = fmaxf(s4.x, 0.f) * inv_scale, g1 = fmaxf(s4.y, 0.f) * inv_scale;
+          const float g2 = fmaxf(s4.z, 0.f) * inv_scale, g3 = fmaxf(s4.w, 0.f) * inv_scale;
+          if (owner) ssq += g0 * g0 + g1 * g1 + g2 * g2 + g3 * g3;
+          const int i = 4 * i4;
+          pk[2 * i4] = pack_h2_sat(g0 * __uint_as_float(hc[i]), g1 * __uint_as_float(hc[i + 1]));
+          pk[2 * i4 + 1] = pack_h2_sat(g2 * __uint_as_float(hc[i + 2]), g3 * __uint_as_float(hc[i + 3]));
+          qk[2 * i4] = pack_h2_sat(g0 * __uint_as_float(ha[i]), g1 * __uint_as_float(ha[i + 1]));
+          qk[2 * i4 + 1] = pack_h2_sat(g2 * __uint_as_float(ha[i + 2]), g3 * __uint_as_float(ha[i + 3]));
+        }
+        tmem_st16(lane_base + 256 + 32 * c, pk);   // P^T = g * HC^T (pairs with A rows)
+        tmem_st16(lane_base + 384 + 32 * c, qk);   // Q^T = g * HA^T (pairs with C rows)
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full);
+      tile_parity ^= 1;
+    }
+    // ---- final: X^T of this CTA -> partial buffer [cta][j][D]
+    mbar_wait(x_full, 0);
+    tc_fence_after();
+    float* dst = part + ((int64_t)blockIdx.x * kNG + j) * D;
+#pragma unroll 1
+    for (int cc = 0; cc < D / 32; ++cc) {
+      uint32_t v[32];
+      tmem_ld32(lane_base + 32 * cc, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(dst + 32 * cc + 4 * i) =
+            make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                        __uint_as_float(v[4 * i + 3]));
+    }
+    if (owner) ss_part[(int64_t)rb * (G * (kNG / d_k)) + g * (kNG / d_k) + j / d_k] = ssq;
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// sums[i*m + col] = inv_scale * sum_rb part[(rb*G + col/128)*128 + col%128][i] ; sums[d*m + k] = sum_rb ss_part
+__global__ void __launch_bounds__(256) tc_reduce_kernel(const float* __restrict__ part, const float* __restrict__ ss_part,
+                                                        int nRB, int G, int d, int m, int K, float inv_scale,
+                                                        float* __restrict__ sums) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int i0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int rb = 0; rb < nRB; ++rb) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int col = c0 + ty + 8 * r;
+      const int gg = col >> 7, jj = col & 127;
+      acc[r] += part[((int64_t)(rb * G + gg) * 128 + jj) * d + i0 + tx];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) tile[ty + 8 * r][tx] = acc[r];   // tile[col_local][i_local]
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int il = ty + 8 * r;
+    sums[(int64_t)(i0 + il) * m + c0 + tx] = tile[tx][il] * inv_scale;
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < K) {
+    float s = 0.f;
+    for (int rb = 0; rb < nRB; ++rb) s += ss_part[(int64_t)rb * K + threadIdx.x];
+    sums[(int64_t)d * m + threadIdx.x] = s;
+  }
+}
+
+__global__ void pack_f16_kernel(const float4* __restrict__ in, int64_t n4, float scale, uint2* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(in + i);
+    uint2 o;
+    o.x = pack_h2_sat(v.x * scale, v.y * scale);
+    o.y = pack_h2_sat(v.z * scale, v.w * scale);
+    out[i] = o;
+  }
+}
+__global__ void pack_f16_tail_kernel(const float* __restrict__ in, int64_t begin, int64_t count, float scale,
+                                     __half* __restrict__ out) {
+  const int64_t i = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < count) out[i] = __float2half_rn(fminf(fmaxf(in[i] * scale, -65504.f), 65504.f));
+}
+
+__global__ void __launch_bounds__(1024) absmax_kernel(const float* __restrict__ in, int64_t n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float best = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    best = fmaxf(best, fabsf(__ldg(in + i)));
+  best = warp_max(best);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_max(v);
+    if (threadIdx.x == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(v));   // v >= 0: int order == float order
+  }
+}
+
+struct TcPlan { int G, nRB, num_tiles; int64_t part_bytes, ss_bytes; };
+TcPlan plan_for(int64_t M, int d, int m, int K) {
+  TcPlan p;
+  p.G = m / kNG;
+  p.num_tiles = (int)((M + kRows - 1) / kRows);
+  int nrb = sm_count() / p.G;
+  if (nrb < 1) nrb = 1;
+  if (nrb > p.num_tiles) nrb = p.num_tiles;
+  p.nRB = nrb;
+  p.part_bytes = align_up((int64_t)p.nRB * p.G * kNG * d * 4, 256);
+  p.ss_bytes = align_up((int64_t)p.nRB * K * 4, 256);
+  return p;
+}
+}  // namespace
+
+bool tc_shape_supported(int d, int m, int K) {
+  if (K <= 0 || m % K != 0) return false;
+  const int d_k = m / K;
+  return (d == 128 || d == 256) && m % kNG == 0 && m <= d && (d_k == 32 || d_k == 64 || d_k == 128);
+}
+
+int64_t step_tc_workspace_bytes(int64_t M, int d, int m, int K) {
+  TcPlan p = plan_for(M, d, m, K);
+  return p.part_bytes + p.ss_bytes + 256;
+}
+
+int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_lo, int64_t M, int d, int m, int K,
+            float scaleA, float scaleC, float* sums, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  if (!tc_shape_supported(d, m, K)) return DRSA_ERR_SHAPE;
+  if (!aligned16(A16) || !aligned16(C16) || !aligned16(Ut_hi) || !aligned16(Ut_lo)) return DRSA_ERR_ALIGN;
+  if (M >= ((int64_t)1 << 31) * kRows / 2) return DRSA_ERR_SHAPE;
+  TcPlan p = plan_for(M, d, m, K);
+  if (workspace_bytes < p.part_bytes + p.ss_bytes + 256) return DRSA_ERR_WORKSPACE;
+  char* w = static_cast<char*>(workspace);
+  float* part = reinterpret_cast<float*>(w); w += p.part_bytes;
+  float* ss_part = reinterpret_cast<float*>(w); w += p.ss_bytes;
+  int* err = reinterpret_cast<int*>(w);
+
+  CUtensorMap tmA, tmC, tmUh, tmUl;
+  DRSA_TRY(make_tmap_f16_sw128(&tmA, A16, (uint64_t)M, (uint64_t)d, kRows));
+  DRSA_TRY(make_tmap_f16_sw128(&tmC, C16, (uint64_t)M, (uint64_t)d, kRows));
+  DRSA_TRY(make_tmap_f16_sw128(&tmUh, Ut_hi, (uint64_t)m, (uint64_t)d, kNG));
+  DRSA_TRY(make_tmap_f16_sw128(&tmUl, Ut_lo, (uint64_t)m, (uint64_t)d, kNG));
+
+  const float inv_scale = 1.0f / (scaleA * scaleC);
+  const int d_k = m / K;
+  const int grid = p.nRB * p.G;
+  if (d == 256) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      DRSA_CUDA(cudaFuncSetAttribute(drsa_tc_step_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg<256>::kSmemBytes));
+      attr_set = true;
+    }
+    drsa_tc_step_kernel<256><<<grid, kThreads, Cfg<256>::kSmemBytes, stream>>>(
+        tmA, tmC, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale, part, ss_part, err);
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      DRSA_CUDA(cudaFuncSetAttribute(drsa_tc_step_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg<128>::kSmemBytes));
+      attr_set = true;
+    }
+    drsa_tc_step_kernel<128><<<grid, kThreads, Cfg<128>::kSmemBytes, stream>>>(
+        tmA, tmC, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale, part, ss_part, err);
+  }
+  DRSA_LAUNCH_CHECK();
+  dim3 rgrid(m / 32, d / 32);
+  tc_reduce_kernel<<<rgrid, 256, 0, stream>>>(part, ss_part, p.nRB, p.G, d, m, K, inv_scale, sums);
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+int pack_f16(const float* in, int64_t count, float scale, void* out, cudaStream_t stream) {
+  if (!aligned16(in) || (reinterpret_cast<uintptr_t>(out) & 7u) != 0) return DRSA_ERR_ALIGN;
+  const int64_t n4 = count / 4;
+  if (n4 > 0) {
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pack_f16_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(in), n4, scale,
+                                                     reinterpret_cast<uint2*>(out));
+    DRSA_LAUNCH_CHECK();
+  }
+  if (count % 4) {
+    pack_f16_tail_kernel<<<1, 32, 0, stream>>>(in, n4 * 4, count, scale, static_cast<__half*>(out));
+    DRSA_LAUNCH_CHECK();
+  }
+  return DRSA_OK;
+}
+
+int absmax(const float* in, int64_t count, float* out, cudaStream_t stream) {
+  DRSA_CUDA(cudaMemsetAsync(out, 0, sizeof(float), stream));
+  int64_t blocks = (count + 1023) / 1024;
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  if (blocks < 1) blocks = 1;
+  absmax_kernel<<<(int)blocks, 1024, 0, stream>>>(in, count, out);
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+// ----------------------------------------------------------------------------- self tests
+// Exercise the two descriptor flavours the fused kernel relies on, each in isolation, against
+// a host computation of the same fp16 products:
+//   variant 0: SS MMA, A and B both K-major 128-byte-swizzled TMA boxes (GEMM1 building block)
+//   variant 1: TS MMA, A packed fp16 in TMEM (tcgen05.st), B an MN-major swizzled box (GEMM2)
+namespace {
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int variant,
+                     const __half* __restrict__ Pglob, float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kPanelBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kPanelBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_base = tmem_base + ((uint32_t)(32 * warp) << 16);
+
+  if (variant == 1) {
+    // every thread = one TMEM lane (row i of P); pack P[i][0..127] as fp16 pairs into columns 128..191
+    const __half* prow = Pglob + (int64_t)threadIdx.x * 128;
+    for (int c = 0; c < 4; ++c) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const __half2 h = __halves2half2(prow[32 * c + 2 * i], prow[32 * c + 2 * i + 1]);
+        pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      tmem_st16(lane_base + 128 + 16 * c, pk);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+
+  if (threadIdx.x == 0) {
+    if (variant == 0) {
+      mbar_expect_tx(&bars[0], 2 * kPanelBytes);
+      tma_load_2d(sA, &tmA, &bars[0], 0, 0);
+      tma_load_2d(sB, &tmB, &bars[0], 0, 0);
+      mbar_wait(&bars[0], 0);
+      tc_fence_after();
+      constexpr uint32_t idesc = make_idesc_f16(128, 128, 0, 0);
+      for (int kk = 0; kk < 4; ++kk)
+        umma_ss_f16(tmem_base, make_smem_desc_sw128(smem_u32(sA) + kk * 32, 16, 1024),
+                    make_smem_desc_sw128(smem_u32(sB) + kk * 32, 16, 1024), idesc, kk > 0);
+    } else {
+      mbar_expect_tx(&bars[0], kPanelBytes);
+      tma_load_2d(sB, &tmB, &bars[0], 0, 0);
+      mbar_wait(&bars[0], 0);
+      tc_fence_after();
+      constexpr uint32_t idesc = make_idesc_f16(128, 64, 0, 1);
+      for (int ks = 0; ks < 8; ++ks)
+        umma_ts_f16(tmem_base, tmem_base + 128 + 8 * ks, make_smem_desc_sw128(smem_u32(sB) + ks * 2048, kPanelBytes, 1024),
+                    idesc, ks > 0);
+    }
+    umma_commit(&bars[1]);
+  }
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+  const int ncol = variant == 0 ? 128 : 64;
+  for (int cc = 0; cc < ncol / 32; ++cc) {
+    uint32_t v[32];
+    tmem_ld32(lane_base + 32 * cc, v);
+    tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) out[(int64_t)threadIdx.x * ncol + 32 * cc + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<256>(tmem_base); }
+}
+}  // namespace
+
+int selftest_umma(int variant, float* max_err_host) {
+  if (variant < 0 || variant > 1 || max_err_host == nullptr) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  // host data: small integers / 8 so every product and partial sum is exact in fp32
+  std::vector<__half> hA(128 * 128), hB(128 * 64);
+  std::vector<float> fA(128 * 128), fB(128 * 64);
+  unsigned s = 12345u + variant;
+  auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (float)((int)((s >> 16) % 17) - 8) / 8.0f; };
+  for (size_t i = 0; i < hA.size(); ++i) { fA[i] = rnd(); hA[i] = __float2half(fA[i]); }
+  for (size_t i = 0; i < hB.size(); ++i) { fB[i] = rnd(); hB[i] = __float2half(fB[i]); }
+  __half *dA = nullptr, *dB = nullptr; float* dOut = nullptr;
+  DRSA_CUDA(cudaMalloc(&dA, hA.size() * 2));
+  DRSA_CUDA(cudaMalloc(&dB, hB.size() * 2));
+  DRSA_CUDA(cudaMalloc(&dOut, 128 * 128 * 4));
+  DRSA_CUDA(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+  DRSA_CUDA(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+  DRSA_CUDA(cudaMemset(dOut, 0, 128 * 128 * 4));
+  CUtensorMap tmA, tmB;
+  int ncol;
+  std::vector<float> ref;
+  if (variant == 0) {
+    // A [128 x 64] = first 64 columns of hA viewed as [128 x 128]; B [128 x 64] = hB
+    DRSA_TRY(make_tmap_f16_sw128(&tmA, dA, 128, 128, 128));
+    DRSA_TRY(make_tmap_f16_sw128(&tmB, dB, 128, 64, 128));
+    ncol = 128;
+    ref.assign(128 * 128, 0.f);
+    for (int i = 0; i < 128; ++i)
+      for (int j = 0; j < 128; ++j) {
+        float a = 0.f;
+        for (int k = 0; k < 64; ++k) a += fA[i * 128 + k] * fB[j * 64 + k];
+        ref[i * 128 + j] = a;
+      }
+  } else {
+    // P [128 x 128] = hA (row i = TMEM lane, K = 128); B [K = 128 rows x N = 64] = hB
+    DRSA_TRY(make_tmap_f16_sw128(&tmA, dA, 128, 128, 128));
+    DRSA_TRY(make_tmap_f16_sw128(&tmB, dB, 128, 64, 128));
+    ncol = 64;
+    ref.assign(128 * 64, 0.f);
+    for (int i = 0; i < 128; ++i)
+      for (int n = 0; n < 64; ++n) {
+        float a = 0.f;
+        for (int k = 0; k < 128; ++k) a += fA[i * 128 + k] * fB[k * 64 + n];
+        ref[i * 64 + n] = a;
+      }
+  }
+  const int smem_bytes = 2 * kPanelBytes + 256;
+  DRSA_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  umma_selftest_kernel<<<1, 128, smem_bytes>>>(tmA, tmB, variant, dA, dOut);
+  DRSA_LAUNCH_CHECK();
+  DRSA_CUDA(cudaDeviceSynchronize());
+  std::vector<float> got(128 * ncol);
+  DRSA_CUDA(cudaMemcpy(got.data(), dOut, got.size() * 4, cudaMemcpyDeviceToHost));
+  float worst = 0.f;
+  for (size_t i = 0; i < got.size(); ++i) {
+    const float e = std::fabs(got[i] - ref[i]);
+    if (!(e <= worst)) worst = std::isnan(e) ? 1e30f : e;
+  }
+  *max_err_host = worst;
+  cudaFree(dA); cudaFree(dB); cudaFree(dOut);
+  return DRSA_OK;
+}
+
+}  // namespace drsa

@@ -1,0 +1,161 @@
+// Small bandwidth-bound pieces around the two GEMM stages:
+//   * context vectors + gather from NCHW maps + sum of squares  (preprocessing.py:179-193, 234-256)
+//   * normalize_vectors with a global statistic                  (preprocessing.py:219-231)
+//   * per-instance concept relevances                            (explainer.py:206-242)
+#include "common.cuh"
+
+namespace drsa {
+
+namespace {
+// grid (N, ceil(L/32), ceil(d/32)), block 32x8.  Reads are coalesced along positions, writes along
+// channels (32x32 shared-memory transpose).
+__global__ void __launch_bounds__(256) context_gather_kernel(const float* __restrict__ a_map, const float* __restrict__ R_map,
+                                                             int d, int HW, const int64_t* __restrict__ idx, int L,
+                                                             float* __restrict__ act_out, float* __restrict__ ctx_out,
+                                                             double* __restrict__ sumsq) {
+  __shared__ float ta[32][33], tcx[32][33];
+  const int n = blockIdx.x, l0 = blockIdx.y * 32, c0 = blockIdx.z * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int l = l0 + tx;
+  int pos = -1;
+  if (l < L) pos = idx != nullptr ? (int)idx[(int64_t)n * L + l] : l;
+  float sa = 0.f, sc = 0.f;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = c0 + ty + 8 * r;
+    float a = 0.f, cx = 0.f;
+    if (pos >= 0 && c < d) {
+      const int64_t o = ((int64_t)n * d + c) * HW + pos;
+      a = __ldg(a_map + o);
+      cx = __ldg(R_map + o) / (a + 1e-7f);       // preprocessing.py:193
+      sa = fmaf(a, a, sa);
+      sc = fmaf(cx, cx, sc);
+    }
+    ta[ty + 8 * r][tx] = a;
+    tcx[ty + 8 * r][tx] = cx;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int ll = l0 + ty + 8 * r, c = c0 + tx;
+    if (ll < L && c < d) {
+      const int64_t o = ((int64_t)n * L + ll) * d + c;
+      act_out[o] = ta[tx][ty + 8 * r];
+      ctx_out[o] = tcx[tx][ty + 8 * r];
+    }
+  }
+  if (sumsq != nullptr) {
+    double da = warp_sum((double)sa), dc = warp_sum((double)sc);
+    if (tx == 0) { atomicAdd(&sumsq[0], da); atomicAdd(&sumsq[1], dc); }
+  }
+}
+
+__global__ void normalize_kernel(float* __restrict__ v, int64_t n, const double* __restrict__ sumsq, double inv_count,
+                                 float root4_d) {
+  const float E = sqrtf((float)(sumsq[0] * inv_count));     // sqrt(mean(v^2)), preprocessing.py:230
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    v[i] = (v[i] / E) / root4_d;                              // preprocessing.py:231
+}
+
+__global__ void context_vectors_kernel(const float* __restrict__ a, const float* __restrict__ R, int64_t n,
+                                       float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __ldg(R + i) / (__ldg(a + i) + 1e-7f);          // preprocessing.py:193
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ v, int64_t n, double* __restrict__ out) {
+  __shared__ double red[8];
+  float s = 0.f; double acc = 0.0; int cnt = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = __ldg(v + i);
+    s = fmaf(x, x, s);
+    if (++cnt == 64) { acc += (double)s; s = 0.f; cnt = 0; }   // bounded fp32 run, fp64 carry
+  }
+  acc += (double)s;
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(out, t);
+  }
+}
+
+// one warp per (b, k): sum over positions and the concept's columns of HA*HC
+__global__ void __launch_bounds__(256) subspace_rel_kernel(const float* __restrict__ HA, const float* __restrict__ HC,
+                                                           int64_t B, int64_t P, int m, int K, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= B * K) return;
+  const int64_t b = wid / K; const int k = (int)(wid % K); const int d_k = m / K;
+  float s = 0.f;
+  for (int64_t p = 0; p < P; ++p) {
+    const float* ha = HA + (b * P + p) * m + k * d_k;
+    const float* hc = HC + (b * P + p) * m + k * d_k;
+    for (int j = lane; j < d_k; j += 32) s = fmaf(ha[j], hc[j], s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) out[b * K + k] = s;
+}
+}  // namespace
+
+int context_gather(const float* a_map, const float* R_map, int64_t N, int d, int HW, const int64_t* idx, int L,
+                   float* act_out, float* ctx_out, double* sumsq, cudaStream_t stream) {
+  if (N > 2147483647LL) return DRSA_ERR_SHAPE;
+  dim3 grid((unsigned)N, cdiv(L, 32), cdiv(d, 32));
+  if (grid.y > 65535 || grid.z > 65535) return DRSA_ERR_SHAPE;
+  context_gather_kernel<<<grid, 256, 0, stream>>>(a_map, R_map, d, HW, idx, L, act_out, ctx_out, sumsq);
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+int normalize(float* v, int64_t rows, int d, const double* sumsq, int64_t count_global, cudaStream_t stream) {
+  const int64_t n = rows * d;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  normalize_kernel<<<(int)blocks, 256, 0, stream>>>(v, n, sumsq, 1.0 / (double)count_global,
+                                                     (float)pow((double)d, 0.25));
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+int context_vectors(const float* a, const float* R, int64_t count, float* out, cudaStream_t stream) {
+  int64_t blocks = (count + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  context_vectors_kernel<<<(int)blocks, 256, 0, stream>>>(a, R, count, out);
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+int sumsq(const float* v, int64_t count, double* out, cudaStream_t stream) {
+  DRSA_CUDA(cudaMemsetAsync(out, 0, sizeof(double), stream));
+  int64_t blocks = (count + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sumsq_kernel<<<(int)blocks, 256, 0, stream>>>(v, count, out);
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+int64_t subspace_relevances_workspace_bytes(int64_t B, int64_t P, int d, int m) {
+  (void)d;
+  return 2 * align_up(B * P * m * 4, 256);
+}
+
+int subspace_relevances(const float* act, const float* ctx, const float* U, int64_t B, int64_t P, int d, int m, int K,
+                        float* out, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  if (workspace_bytes < subspace_relevances_workspace_bytes(B, P, d, m)) return DRSA_ERR_WORKSPACE;
+  if (B * P > 2147483647LL) return DRSA_ERR_SHAPE;
+  float* HA = static_cast<float*>(workspace);
+  float* HC = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up(B * P * m * 4, 256));
+  GemmDesc g{};
+  g.M = (int)(B * P); g.N = m; g.K = d; g.lda = d; g.ldb = m; g.ldc = m; g.alpha = 1.f; g.splits = 1;
+  g.A = act; g.B = U; g.C = HA; DRSA_TRY(sgemm(g, stream));
+  g.A = ctx; g.C = HC;          DRSA_TRY(sgemm(g, stream));
+  const int64_t warps = B * K;
+  subspace_rel_kernel<<<cdiv(warps, 8), 256, 0, stream>>>(HA, HC, B, P, m, K, out);
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+}  // namespace drsa

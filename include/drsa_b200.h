@@ -1,0 +1,174 @@
+/*
+ * drsa_b200.h -- C ABI of libdrsa_b200.so, the sm_100a implementation of the
+ * DRSA / LRP explanation hot path of sharckhai/drsa-audio.
+ *
+ * The reference is pure Python and has no FFI of its own; every entry point below
+ * sits UNDER one of the reference's Python functions and names it (file:line are
+ * relative to the reference repository).  The Python package `cxai` in this
+ * repository keeps the reference's names and signatures and binds these symbols
+ * through ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C, no torch types: device pointers, sizes, a CUDA stream as void*.
+ *   - every function returns DRSA_OK (0) or a negative drsa_status; nothing throws.
+ *   - all work is asynchronous on `stream`; no function synchronises the host, so a
+ *     whole optimisation loop can be enqueued or captured in a CUDA graph.
+ *   - the library never allocates or frees device memory.  Callers pass workspaces
+ *     sized by the *_workspace_bytes() queries and keep every buffer alive until the
+ *     stream work has completed.
+ *   - there is no CPU fallback: on a device that is not sm_100 the compute entry
+ *     points return DRSA_ERR_ARCH.
+ *   - matrices are row-major fp32 unless stated otherwise.
+ */
+#ifndef DRSA_B200_H_
+#define DRSA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRSA_B200_VERSION 100
+
+typedef enum drsa_status {
+  DRSA_OK = 0,
+  DRSA_ERR_ARG = -1,        /* null pointer, non-positive size, bad enum            */
+  DRSA_ERR_SHAPE = -2,      /* shape not supported by the requested precision mode   */
+  DRSA_ERR_ARCH = -3,       /* device is not sm_100                                  */
+  DRSA_ERR_ALIGN = -4,      /* pointer / leading dimension not 16-byte aligned       */
+  DRSA_ERR_WORKSPACE = -5,  /* workspace too small                                   */
+  DRSA_ERR_CUDA = -6,       /* a CUDA runtime / driver call failed (see last_cuda)   */
+  DRSA_ERR_RANGE = -7       /* value outside the representable range of the mode     */
+} drsa_status;
+
+/* Arithmetic of the projection / gradient contractions (drsa.py:148-149 and the
+ * autograd backward of them, drsa.py:100). */
+typedef enum drsa_precision {
+  DRSA_PREC_FP32 = 0,       /* CUDA-core FFMA, fp32 throughout                        */
+  DRSA_PREC_TC_F16X2 = 1    /* tcgen05 kind::f16, fp32 accumulate in TMEM; A and C are
+                               stored once as scaled fp16, U is split hi+lo every step */
+} drsa_precision;
+
+const char* drsa_status_string(int status);
+int drsa_version(void);
+/* last cudaError_t seen by this thread inside the library (0 if none). */
+int drsa_last_cuda_error(void);
+/* DRSA_OK if `device` is an sm_100 part. */
+int drsa_check_device(int device);
+
+/* ------------------------------------------------------------------------------------
+ * Stage 2: DRSA subspace optimisation
+ *   reference: cxai/xai/drsa/drsa.py  SubspaceOptimizer.obj_val :123-155,
+ *              objective_fn :224-238, generalized_fmean :171-182, run :76-120,
+ *              orthogonalize :201-221
+ * ---------------------------------------------------------------------------------- */
+
+/* Data preparation for DRSA_PREC_TC_F16X2: out[i] = fp16(in[i] * scale) over M*d
+ * elements (scale is a power of two chosen by the caller so that max|in|*scale stays
+ * far below 65504).  Done once per optimiser because A and C are constant over the
+ * steps of drsa.py:84.  Returns DRSA_ERR_ALIGN unless both pointers are 16-byte
+ * aligned. */
+int drsa_pack_f16(const float* in, int64_t count, float scale, void* out_f16, void* stream);
+
+/* max |x| over `count` floats -> *out (one float).  Used to choose the pack scale. */
+int drsa_absmax(const float* in, int64_t count, float* out, void* stream);
+
+/* Bytes of workspace drsa_step needs for the given problem. */
+int64_t drsa_step_workspace_bytes(int64_t M, int d, int m, int K, int precision);
+
+/*
+ * One pass over the (activation, context) rows: the forward projection, the
+ * per-concept ReLU'd relevance and BOTH row-sums the update needs
+ *      sums[0 .. d*m)     X[i][j], j in concept k :  sum_r A[r][i] g_rk HC[r][j] + C[r][i] g_rk HA[r][j],
+ *                         g_rk = relu(s_rk), s_rk = sum_{j in k} HA[r][j] HC[r][j]      (un-normalised gradient)
+ *      sums[d*m .. d*m+K) sum_r relu(s_rk)^2
+ * i.e. drsa.py:148-155 fused with the backward of drsa.py:100.  The
+ * sums are additive over row shards, so under data parallelism the caller all-reduces
+ * `sums` (d*m+K floats) between drsa_step and drsa_finish_step.
+ *
+ *   A, C      [M, d]   fp32 (DRSA_PREC_FP32) or scaled fp16 from drsa_pack_f16 (TC mode)
+ *   U         [d, m]   fp32, m = K*d_k <= d               (FP32 mode; may be NULL in TC mode)
+ *   Ut_hi/lo  [m, d]   fp16 split of U^T written by drsa_finish_step / drsa_split_u
+ *                      (TC mode; may be NULL in FP32 mode)
+ *   data_scale          product scaleA*scaleC of the pack scales (1 in FP32 mode)
+ */
+int drsa_step(const void* A, const void* C, const float* U, const void* Ut_hi, const void* Ut_lo,
+              int64_t M, int d, int m, int K, int precision, float scaleA, float scaleC,
+              float* sums, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* U [d,m] fp32 -> Ut_hi, Ut_lo [m,d] fp16 with U^T = hi + lo (+ O(2^-22)). */
+int drsa_split_u(const float* U, int d, int m, void* Ut_hi, void* Ut_lo, void* stream);
+
+int64_t drsa_finish_workspace_bytes(int d, int m);
+
+/*
+ * Everything after the row pass (replicated on every rank):
+ *   q_k = sqrt(sums_k / M_global), obj = (mean_k sqrt(q_k))^2       drsa.py:236-237
+ *   obj_log[log_index] = obj                                          drsa.py:104
+ *   if U_out != NULL:
+ *     Y = U + sqrt(obj) / (K M q_k^1.5) * X_k      (ascent, unit step)  drsa.py:102
+ *     U_out = Y (Y^T Y)^(-1/2)                      (polar retraction)   drsa.py:201-221
+ *     Ut_hi/Ut_lo (optional) = fp16 split of U_out^T for the next TC step
+ * The polar factor is computed on the device by a scaled Newton-Schulz iteration in
+ * fp32 (at most `max_iters` sweeps, stops when ||Y^T Y - I||_F < tol*sqrt(m)); the
+ * reference uses an fp64 eigendecomposition on the host, both converge to the same
+ * (unique) polar factor.  status (4 ints, device): [0] = sweeps used, [1] = 1 if not
+ * converged, [2] = number of concepts with q_k == 0 (the reference yields NaN there),
+ * [3] = append cursor: when log_index < 0 the objective is stored at obj_log[status[3]++]
+ * so that a captured CUDA graph of one step can be replayed without changing arguments.
+ */
+int drsa_finish_step(const float* sums, int64_t M_global, const float* U, int d, int m, int K,
+                     float* U_out, void* Ut_hi, void* Ut_lo, float* obj_log, int64_t log_index,
+                     int max_iters, float tol, int* status, void* workspace,
+                     int64_t workspace_bytes, void* stream);
+
+/* orthogonalize(U) of drsa.py:201-221 on its own: U_out = Y (Y^T Y)^(-1/2). */
+int drsa_polar_retract(const float* Y, int d, int m, float* U_out, int max_iters, float tol,
+                       int* status, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Per-instance concept relevances, no ReLU, summed over positions
+ * (cxai/xai/explain/explainer.py:206-242): out[b][k] = sum_p sum_{j in k} (a U)_j (c U)_j
+ *   act, ctx [B, P, d] fp32, U [d, m], out [B, K]. */
+int drsa_subspace_relevances(const float* act, const float* ctx, const float* U, int64_t B,
+                             int64_t P, int d, int m, int K, float* out, void* workspace,
+                             int64_t workspace_bytes, void* stream);
+int64_t drsa_subspace_relevances_workspace_bytes(int64_t B, int64_t P, int d, int m);
+
+/* ------------------------------------------------------------------------------------
+ * Stage 1 helpers: context vectors and normalisation
+ *   reference: cxai/xai/drsa/preprocessing.py compute_context_vectors :179-193,
+ *              normalize_vectors :219-231, get_vectors_from_maps :234-256
+ * ---------------------------------------------------------------------------------- */
+
+/* Gather channel vectors from NCHW maps and form the context vector in one pass:
+ *   act_out[(n*L+l)][c] = a_map[n][c][pos]          pos = idx[n*L+l] (or l if idx==NULL, L==HW)
+ *   ctx_out[(n*L+l)][c] = R_map[n][c][pos] / (a_map[n][c][pos] + 1e-7)
+ * and accumulates sum(act^2), sum(ctx^2) into sumsq[0], sumsq[1] (fp64) for
+ * normalize_vectors.  (corrected [N*L, d] row layout) */
+int drsa_context_gather(const float* a_map, const float* R_map, int64_t N, int d, int HW,
+                        const int64_t* idx, int L, float* act_out, float* ctx_out, double* sumsq,
+                        void* stream);
+
+/* out = R / (a + 1e-7) element-wise over `count` floats (compute_context_vectors, any layout). */
+int drsa_context_vectors(const float* a, const float* R, int64_t count, float* out, void* stream);
+
+/* *out = sum v[i]^2 in fp64 (the statistic of normalize_vectors; all-reduce it across ranks). */
+int drsa_sumsq(const float* v, int64_t count, double* out, void* stream);
+
+/* v *= 1 / sqrt(sumsq / count_global) / d^0.25  (normalize_vectors with the global statistic). */
+int drsa_normalize(float* v, int64_t rows, int d, const double* sumsq, int64_t count_global,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Self tests of the tcgen05 / TMA building blocks (used by tests/ on the GPU box).
+ * Each returns DRSA_OK and writes max |error| against a CUDA-core computation of the
+ * same product into *max_err.
+ * ---------------------------------------------------------------------------------- */
+int drsa_selftest_umma(int variant, float* max_err_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRSA_B200_H_ */

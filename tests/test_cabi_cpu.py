@@ -1,0 +1,81 @@
+"""CPU-side checks of the C-ABI boundary: the library builds, loads, exports every symbol that
+include/drsa_b200.h declares, and refuses to compute without an sm_100 device (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import drsa_audio_b200
+from drsa_audio_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "drsa_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:drsa|lrp)_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.isfile(drsa_audio_b200.library_path()):
+        drsa_audio_b200.build()
+    return drsa_audio_b200.lib()
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    names = _declared()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/drsa_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in drsa_audio_b200/_lib.py"
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_version_and_status_strings(lib):
+    assert lib.drsa_version() == 100
+    assert lib.drsa_status_string(0) == b"ok"
+    assert b"sm_100" in lib.drsa_status_string(-3)
+
+
+def test_workspace_queries_need_no_gpu(lib):
+    assert lib.drsa_step_workspace_bytes(16000, 64, 64, 4, _lib.PREC_FP32) > 0
+    assert lib.drsa_step_workspace_bytes(640000, 256, 256, 4, _lib.PREC_TC_F16X2) > 0
+    assert lib.drsa_step_workspace_bytes(640000, 64, 64, 4, _lib.PREC_TC_F16X2) == -2     # shape unsupported
+    assert lib.drsa_step_workspace_bytes(0, 64, 64, 4, _lib.PREC_FP32) == -1
+    assert lib.drsa_step_workspace_bytes(100, 64, 63, 4, _lib.PREC_FP32) == -1            # m % K != 0
+    assert lib.drsa_finish_workspace_bytes(256, 256) > 0
+
+
+def test_compute_fails_loudly_without_sm100(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    st = lib.drsa_step(p, p, p, None, None, 8, 4, 4, 2, 0, 1.0, 1.0, p, p, 1 << 20, None)
+    assert st == -3
+    with pytest.raises(_lib.DRSAError):
+        _lib.check(st, "drsa_step")
+
+
+def test_python_mirror_refuses_cpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from cxai.xai.drsa.drsa import SubspaceOptimizer
+    with pytest.raises(_lib.DRSAError):
+        SubspaceOptimizer(torch.eye(8), torch.rand(16, 8), torch.rand(16, 8), None, num_concepts=2, device="cpu")
+    with pytest.raises(_lib.DRSAError):
+        SubspaceOptimizer(torch.eye(8), torch.rand(16, 8), torch.rand(16, 8), None, num_concepts=2, device="cuda")
+
+
+def test_pow2_scale():
+    from cxai.xai.drsa.drsa import _pow2_scale
+    for mx in (1e-6, 0.03, 0.25, 1.0, 77.0, 5e4, 3e9):
+        s = _pow2_scale(mx)
+        assert 128.0 <= mx * s < 256.0
+        assert s == 2.0 ** round(__import__("math").log2(s))
+    assert _pow2_scale(0.0) == 1.0

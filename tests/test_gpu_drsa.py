@@ -1,0 +1,235 @@
+"""GPU parity tests of the DRSA stage (run on the B200 box: pytest -m gpu).  Everything goes
+through the C ABI (ctypes) / the cxai mirror; the CPU oracle is the checker.
+
+Tolerances (BASELINE.json north_star): relative error <= 1e-4 on the objective at every step,
+principal angles between final subspaces <= 1e-3 rad."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import drsa_ref
+
+pytestmark = pytest.mark.gpu
+
+OBJ_TOL = 1e-4
+ANGLE_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def L():
+    from drsa_audio_b200 import _lib
+    return _lib
+
+
+def _dev(t):
+    return t.cuda().contiguous()
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _sums_gpu(L, A, C, U, K, prec):
+    lib = L.lib()
+    M, d = A.shape
+    m = U.shape[1]
+    code = L.PREC_TC_F16X2 if prec == "tc" else L.PREC_FP32
+    ws = torch.empty(int(L.check(lib.drsa_step_workspace_bytes(M, d, m, K, code))), dtype=torch.uint8, device="cuda")
+    sums = torch.full((d * m + K,), float("nan"), device="cuda")
+    Ad, Cd, Ud = _dev(A), _dev(C), _dev(U)
+    s = torch.cuda.current_stream().cuda_stream
+    if prec == "tc":
+        from cxai.xai.drsa.drsa import _pow2_scale
+        sA, sC = _pow2_scale(float(A.abs().max())), _pow2_scale(float(C.abs().max()))
+        A16 = torch.empty(M, d, dtype=torch.float16, device="cuda")
+        C16 = torch.empty(M, d, dtype=torch.float16, device="cuda")
+        L.check(lib.drsa_pack_f16(_ptr(Ad), Ad.numel(), sA, _ptr(A16), s))
+        L.check(lib.drsa_pack_f16(_ptr(Cd), Cd.numel(), sC, _ptr(C16), s))
+        hi = torch.empty(m, d, dtype=torch.float16, device="cuda")
+        lo = torch.empty(m, d, dtype=torch.float16, device="cuda")
+        L.check(lib.drsa_split_u(_ptr(Ud), d, m, _ptr(hi), _ptr(lo), s))
+        L.check(lib.drsa_step(_ptr(A16), _ptr(C16), None, _ptr(hi), _ptr(lo), M, d, m, K, code, sA, sC, _ptr(sums),
+                              _ptr(ws), ws.numel(), s), "drsa_step tc")
+    else:
+        L.check(lib.drsa_step(_ptr(Ad), _ptr(Cd), _ptr(Ud), None, None, M, d, m, K, code, 1.0, 1.0, _ptr(sums),
+                              _ptr(ws), ws.numel(), s), "drsa_step fp32")
+    torch.cuda.synchronize()
+    out = sums.cpu().double()
+    return out[: d * m].view(d, m), out[d * m:]
+
+
+# ------------------------------------------------------------------ building blocks
+@pytest.mark.parametrize("variant", [0, 1])
+def test_umma_selftest(L, variant):
+    """tcgen05 descriptors in isolation: 0 = SS K-major x K-major, 1 = TS (TMEM A) x MN-major B.
+    Inputs are small dyadic rationals, so the fp32 result must be exact."""
+    err = ctypes.c_float(-1.0)
+    L.check(L.lib().drsa_selftest_umma(variant, ctypes.byref(err)), "selftest")
+    assert err.value == 0.0, err.value
+
+
+@pytest.mark.parametrize("M,d,m,K", [(333, 32, 32, 2), (1000, 64, 64, 4), (777, 64, 32, 2), (4096, 128, 128, 4),
+                                     (2500, 256, 256, 4), (300, 96, 96, 3)])
+def test_row_sums_fp32_match_oracle(L, M, d, m, K):
+    A, C = drsa_ref.synth_pairs(M, d, 100 + d)
+    U = drsa_ref.synth_U0(d, m, 7)
+    X, ss = _sums_gpu(L, A, C, U, K, "fp32")
+    Xr, ssr = drsa_ref.step_sums(A.double(), C.double(), U.double(), K)
+    assert torch.linalg.norm(X - Xr) / torch.linalg.norm(Xr) < 2e-6
+    np.testing.assert_allclose(ss.numpy(), ssr.numpy(), rtol=2e-6)
+
+
+@pytest.mark.parametrize("M,d,m,K", [(128, 128, 128, 4), (1000, 128, 128, 2), (5000, 128, 128, 1), (4096, 256, 256, 4),
+                                     (20011, 256, 256, 8), (40000, 256, 256, 2), (3000, 256, 128, 2)])
+def test_row_sums_tensor_core_match_oracle(L, M, d, m, K):
+    """fused tcgen05 kernel vs fp64 oracle; fp16 storage of the rows bounds the error (2^-12 per
+    element, averaged over rows)."""
+    A, C = drsa_ref.synth_pairs(M, d, 200 + d + K)
+    U = drsa_ref.synth_U0(d, m, 9)
+    X, ss = _sums_gpu(L, A, C, U, K, "tc")
+    Xr, ssr = drsa_ref.step_sums(A.double(), C.double(), U.double(), K)
+    relX = float(torch.linalg.norm(X - Xr) / torch.linalg.norm(Xr))
+    assert relX < 2e-4, relX
+    np.testing.assert_allclose(ss.numpy(), ssr.numpy(), rtol=2e-4)
+
+
+def test_tensor_core_scale_invariance(L):
+    """power-of-two pre-scaling of the fp16 rows is undone exactly: unnormalised inputs 1000x larger
+    give row sums 1e6x / 1e12x larger."""
+    M, d, K = 2048, 128, 4
+    A, C = drsa_ref.synth_pairs(M, d, 5)
+    U = drsa_ref.synth_U0(d, d, 9)
+    X1, s1 = _sums_gpu(L, A, C, U, K, "tc")
+    X2, s2 = _sums_gpu(L, A * 1024.0, C * 1024.0, U, K, "tc")
+    np.testing.assert_allclose((X2 / 1024.0 ** 4).numpy(), X1.numpy(), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose((s2 / 1024.0 ** 4).numpy(), s1.numpy(), rtol=1e-6)
+
+
+@pytest.mark.parametrize("d,m", [(32, 32), (64, 64), (64, 32), (128, 128), (256, 256), (512, 512)])
+def test_polar_retraction_matches_reference_formula(d, m):
+    from cxai.xai.drsa.drsa import orthogonalize
+    g = torch.Generator().manual_seed(d + m)
+    U = drsa_ref.synth_U0(d, m, 3)
+    Y = U + 0.3 * torch.randn(d, m, generator=g) / d ** 0.5
+    got = orthogonalize(Y.cuda()).cpu()
+    want = drsa_ref.orthogonalize(Y.double())
+    assert float((got.double() - want).abs().max()) < 5e-6
+    G = got.double().T @ got.double()
+    assert float((G - torch.eye(m, dtype=torch.float64)).abs().max()) < 5e-6
+
+
+def test_polar_retraction_far_from_orthogonal():
+    from cxai.xai.drsa.drsa import orthogonalize
+    g = torch.Generator().manual_seed(1)
+    Y = torch.randn(64, 64, generator=g)           # condition number ~ 1e2-1e3
+    got = orthogonalize(Y.cuda(), max_iters=40).cpu().double()
+    want = drsa_ref.orthogonalize(Y.double())
+    assert float((got - want).abs().max()) < 1e-4
+
+
+# ------------------------------------------------------------------ trajectories vs golden vectors of the reference
+def _golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, f"drsa_{name}.npz"))
+    M, d, K = int(g["M"]), int(g["d"]), int(g["K"])
+    if "A" in g.files:
+        A, C = torch.from_numpy(g["A"]), torch.from_numpy(g["C"])
+    else:
+        A, C = drsa_ref.synth_pairs(M, d, int(g["seed"]))
+    return g, A, C, torch.from_numpy(g["U0"]), K
+
+
+@pytest.mark.parametrize("name,prec,graph", [("tiny", "fp32", False), ("ragged", "fp32", True), ("toy64", "fp32", True),
+                                             ("d128", "fp32", False), ("d256", "fp32", True), ("rect", "fp32", True),
+                                             ("d128", "tc", True), ("d256", "tc", True), ("d256", "tc", False)])
+def test_run_matches_reference_golden(golden_dir, name, prec, graph, tmp_path):
+    from cxai.xai.drsa.drsa import SubspaceOptimizer
+    g, A, C, U0, K = _golden(golden_dir, name)
+    steps = int(g["steps"])
+    opt = SubspaceOptimizer(U0, A, C, str(tmp_path), num_concepts=K, device="cuda", precision=prec,
+                            use_cuda_graph=graph)
+    opt.run(steps=steps)
+    objs = opt.obj_history
+    assert len(objs) == steps + 1
+    rel = np.max(np.abs(objs - g["objs"]) / np.abs(g["objs"]))
+    ang = drsa_ref.principal_angle(opt.U.cpu(), g["U_final"], K)
+    print(f"{name}/{prec}: rel obj {rel:.2e} angle {ang:.2e} sweeps {opt.last_status}")
+    assert rel < OBJ_TOL, rel
+    assert ang < ANGLE_TOL, ang
+    assert opt.last_status[1] == 0                      # retraction converged
+    # on-disk formats of drsa.py:157-168
+    import pickle
+    with open(tmp_path / "projection_matrix.pkl", "rb") as f:
+        Usaved = pickle.load(f)
+    assert Usaved.dtype == np.float32 and Usaved.shape == tuple(U0.shape)
+    lines = open(tmp_path / "train_stats.csv").read().splitlines()
+    assert lines[0] == ",loss" and len(lines) == steps + 2
+    UtU = opt.U.T @ opt.U
+    assert float((UtU - torch.eye(UtU.shape[0], device="cuda")).abs().max()) < 5e-6
+
+
+def test_obj_val_static_and_autograd(golden_dir):
+    from cxai.xai.drsa.drsa import SubspaceOptimizer, objective_fn
+    g, A, C, U0, K = _golden(golden_dir, "toy64")
+    U = U0.clone().cuda().requires_grad_(True)
+    obj = SubspaceOptimizer.obj_val(A.cuda(), C.cuda(), U, objective_fn, K, U0.shape[1] // K)
+    obj.backward()
+    assert abs(float(obj) - float(g["obj0"])) / float(g["obj0"]) < 1e-5
+    rel = np.linalg.norm(U.grad.cpu().numpy() - g["grad0"]) / np.linalg.norm(g["grad0"])
+    assert rel < 1e-5, rel
+
+
+def test_large_problem_properties(L):
+    """cfg-2-sized rows (M = 640k, d = 256, K = 4): the tensor-core row pass agrees with the fp32 path
+    on the same device, is additive over row shards, and a few steps increase the objective."""
+    M, d, K = 640_000, 256, 4
+    A, C = drsa_ref.synth_pairs(M, d, 20262, structured=False)
+    U = drsa_ref.synth_U0(d, d, 4)
+    Xt, st = _sums_gpu(L, A, C, U, K, "tc")
+    Xf, sf = _sums_gpu(L, A, C, U, K, "fp32")
+    assert float(torch.linalg.norm(Xt - Xf) / torch.linalg.norm(Xf)) < 1e-4
+    np.testing.assert_allclose(st.numpy(), sf.numpy(), rtol=1e-4)
+    half = M // 2 + 37
+    Xa, sa = _sums_gpu(L, A[:half], C[:half], U, K, "tc")
+    Xb, sb = _sums_gpu(L, A[half:], C[half:], U, K, "tc")
+    assert float(torch.linalg.norm(Xa + Xb - Xt) / torch.linalg.norm(Xt)) < 1e-5
+    from cxai.xai.drsa.drsa import SubspaceOptimizer
+    opt = SubspaceOptimizer(U, A, C, None, num_concepts=K, precision="tc")
+    opt.run(steps=8, save=False)
+    assert np.all(np.diff(opt.obj_history) > 0)
+    assert opt.last_status[1] == 0
+
+
+def test_subspace_relevances_and_context_helpers():
+    from cxai.xai.explain.explainer import compute_subspace_relevances
+    from cxai.xai.drsa import preprocessing as pp
+    g = torch.Generator().manual_seed(0)
+    B, P, d, K = 5, 16, 64, 4
+    a = torch.rand(B, P, d, generator=g); c = torch.randn(B, P, d, generator=g)
+    U = drsa_ref.synth_U0(d)
+    got = compute_subspace_relevances(a.cuda(), c.cuda(), U.cuda(), K).cpu()
+    want = drsa_ref.subspace_relevances(a, c, U, K)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-4, atol=1e-4)
+    # context vectors / normalisation / fused gather
+    amap = torch.relu(torch.randn(6, 40, 4, 8, generator=g)); Rmap = torch.randn(6, 40, 4, 8, generator=g) * (amap > 0)
+    cv = pp.compute_context_vectors(amap.cuda(), Rmap.cuda()).cpu()
+    np.testing.assert_array_equal(cv.numpy(), drsa_ref.compute_context_vectors(amap, Rmap).numpy())
+    nv = pp.normalize_vectors(amap.reshape(-1, 8).cuda()).cpu()
+    np.testing.assert_allclose(nv.numpy(), drsa_ref.normalize_vectors(amap.reshape(-1, 8)).numpy(), rtol=2e-6)
+    np.random.seed(3)
+    idcs = pp.sample_spatial_locations(6, (4, 8), 5)
+    np.random.seed(3)
+    idcs2 = np.stack([np.random.choice(32, 5, replace=False) for _ in range(6)])
+    np.testing.assert_array_equal(idcs, idcs2)
+    for idx in (None, idcs):
+        act, ctx = pp.gather_context_pairs(amap.cuda(), Rmap.cuda(), idx, normalize=True)
+        av = drsa_ref.vectors_from_maps_all(amap) if idx is None else drsa_ref.vectors_from_maps_fixed(amap, idx)
+        rv = drsa_ref.vectors_from_maps_all(Rmap) if idx is None else drsa_ref.vectors_from_maps_fixed(Rmap, idx)
+        np.testing.assert_allclose(act.cpu().numpy(), drsa_ref.normalize_vectors(av).numpy(), rtol=3e-6, atol=1e-8)
+        np.testing.assert_allclose(ctx.cpu().numpy(),
+                                   drsa_ref.normalize_vectors(drsa_ref.compute_context_vectors(av, rv)).numpy(),
+                                   rtol=3e-6, atol=1e-7)
+    v_ref = pp.get_vectors_from_maps(amap, idcs, layout="reference")
+    np.testing.assert_array_equal(v_ref.numpy(), drsa_ref.vectors_from_maps_ref(amap, idcs).numpy())
