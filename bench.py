@@ -113,14 +113,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                             # started early: nvidia-smi start-up must not land in the timed region
     opt = SubspaceOptimizer(U0, A, C, None, num_concepts=K, device=dev, precision=args.precision)
     opt._rows.split_u(opt.U)
     opt.reset_log(args.warmup + args.steps + 8)
     opt.enqueue_steps(max(args.warmup, 3))          # warm-up (also captures the CUDA graph)
     barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        t_wait = time.time() + 5.0
+        while not sampler.rows and time.time() < t_wait:
+            time.sleep(0.05)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -142,9 +146,19 @@ def run_ours(args):
         opt._rows.step(opt.U)
     k1.record()
     torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
     ms_kernel = k0.elapsed_time(k1) / args.steps
+    # ---- the replicated tail of a step alone (ascent + polar retraction)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    Utmp = opt.U.clone()
+    f0.record()
+    for _ in range(args.steps):
+        opt._rows.finish(Utmp, opt.M_global, None, 0, True, opt.retraction_iters, opt.retraction_tol)
+    f1.record()
+    torch.cuda.synchronize()
+    ms_finish = f0.elapsed_time(f1) / args.steps
     status = opt._rows.status.cpu().numpy().tolist()
+    lrp = None if args.no_lrp else lrp_throughput(args, dev, rank, world, barrier)
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the public API with HOST buffers: construct (H2D + pack) + run + D2H
     e2e_steps = args.e2e_steps
@@ -193,6 +207,8 @@ def run_ours(args):
                          "hbm_frac": (2.0 * M * d * elem / (ms_kernel * 1e-3) / 1e9) / peaks["hbm"],
                          "peak_source": peaks["source"] + "; sustained bf16 figure (kernel timed in a loop)",
                          "share_of_step": ms_kernel / ms_per_step},
+            "step_breakdown_ms": {"row_pass": ms_kernel, "ascent_and_retraction": ms_finish},
+            "lrp": lrp,
             "e2e": {"value": scale * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_steps,
                     "d2h_bytes_per_step": d2h / e2e_steps, "steps": e2e_steps,
                     "what": "SubspaceOptimizer(U0, A_host_pinned, C_host_pinned).run(steps) + U.cpu(): H2D of all rows, "
@@ -205,6 +221,65 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def build_cfg2_model(device):
+    """BASELINE cfg 2 CNN: arch A (getdrsadata.py:72-73) with the last block widened to 256 filters, BatchNorm,
+    input 128x256, PyTorch default init under torch.manual_seed(0), eval mode."""
+    import torch
+    from cxai.model.create_model import VGGType
+    torch.manual_seed(0)
+    net = VGGType(n_filters=[64, 64, 100, 128, 256], pool_kernels=[(2, 4), (2, 2), (2, 2), (2, 2), (2, 2)], n_dense=100,
+                  n_classes=10, dropout=0.3, block_depth=2, dense_depth=2, input_size=(128, 256), conv_bn=True,
+                  dense_bn=True)
+    return net.eval().to(device)
+
+
+def lrp_throughput(args, dev, rank, world, barrier):
+    """LRP context vectors / s: log-mel batch -> CNN forward -> LRP down to features[33] -> gather + c=R/(a+1e-7)
+    + normalise, through the public cxai API (get_intermediate + gather_context_pairs)."""
+    import torch
+    import torch.distributed as dist
+    from cxai.utils.constants import lrp_name_map_6s
+    from cxai.xai.explain.rules import NameMapComposite, SequentialMergeBatchNorm
+    from cxai.xai.drsa import preprocessing as pp
+    net = build_cfg2_model(dev)
+    comp = NameMapComposite(lrp_name_map_6s(), canonizers=[SequentialMergeBatchNorm()])
+    n = args.lrp_samples
+    g = torch.Generator(device=dev).manual_seed(20262 + rank)
+    x = (1.2 * torch.randn(n, 1, 128, 256, generator=g, device=dev) - 1.5).clamp(min=-4.0)
+    layer = net.features[33]
+
+    def once(xb):
+        a, R = pp.get_intermediate(net, xb, comp, layer, 0)
+        return pp.gather_context_pairs(a, R, None, normalize=True)
+
+    once(x[:64])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    act, ctx = once(x)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    # end to end from pinned host memory, result (vectors) read back
+    xh = x.cpu().pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    act, ctx = once(xh.to(dev, non_blocking=True))
+    _ = act[:1].cpu()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    P = act.shape[0] // n
+    flops = 2 * 1775.5e6 * n           # 2 x MACs of the widened arch A forward (SURVEY 8a) per sample
+    return {"metric": "LRP context vecs/s", "value": n * P * world / (ms * 1e-3), "unit": "vectors/s",
+            "samples_per_gpu": n, "positions": P, "d": int(act.shape[1]), "ms": ms,
+            "e2e_value": n * P * world / t_e2e, "h2d_bytes": int(xh.numel() * 4),
+            "forward_tflops": flops / (ms * 1e-3) / 1e12,
+            "kernel": "conv3x3_kernel (CUDA-core fp32 direct convolution, round-1 version)"}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one drsa_tc_step_kernel launch at cfg2 from the committed
@@ -289,7 +364,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32", "auto"])
@@ -297,6 +372,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=500)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lrp", action="store_true")
+    ap.add_argument("--lrp-samples", type=int, default=256)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -82,7 +82,7 @@ class _RowPass:
         self.prec_code = _L.PREC_TC_F16X2 if precision == "tc" else _L.PREC_FP32
         self.sums = torch.zeros(d * m + K, dtype=torch.float32, device=dev)
         self.status = torch.zeros(4, dtype=torch.int32, device=dev)
-        self.scaleA = self.scaleC = 1.0
+        self.scaleA = self.scaleC = self.pq_scale = 1.0
         self.Ut_hi = self.Ut_lo = None
         if self.M > 0:
             ws = _L.check(lib.drsa_step_workspace_bytes(self.M, d, m, K, self.prec_code), "drsa_step_workspace_bytes")
@@ -90,26 +90,30 @@ class _RowPass:
         if precision == "tc":
             self.Ut_hi = torch.empty(m, d, dtype=torch.float16, device=dev)
             self.Ut_lo = torch.empty(m, d, dtype=torch.float16, device=dev)
-            self.A, self.scaleA = self._pack(act)
-            self.C, self.scaleC = self._pack(ctx)
+            self.A, self.scaleA, rhoA = self._pack(act)
+            self.C, self.scaleC, rhoC = self._pack(ctx)
+            # |g*HC| <= pq * rhoA * rhoC^2 and |g*HA| <= pq * rhoA^2 * rhoC (rho = largest packed row norm):
+            # choose the power of two pq that keeps both below 2^15, so fp16 P/Q can never overflow
+            bound = max(rhoA * rhoC * rhoC, rhoA * rhoA * rhoC, 1e-30)
+            self.pq_scale = float(2.0 ** math.floor(math.log2(32768.0 / bound)))
         else:
             self.A, self.C = act, ctx
         wf = _L.check(lib.drsa_finish_workspace_bytes(d, m), "drsa_finish_workspace_bytes")
         self.ws_fin = torch.empty(int(wf), dtype=torch.uint8, device=dev)
 
     def _pack(self, x: torch.Tensor):
+        """fp16 copy of the rows, its power-of-two scale and the largest packed row norm."""
         if x.numel() == 0:
-            return torch.empty_like(x, dtype=torch.float16), 1.0
-        mx = torch.zeros(1, dtype=torch.float32, device=x.device)
-        _L.check(self.lib.drsa_absmax(_ptr(x), x.numel(), _ptr(mx), _stream()), "drsa_absmax")
-        scale = _pow2_scale(float(mx.item()))          # one host sync, once per optimiser
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            t = torch.tensor([scale], dtype=torch.float64, device=x.device)
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)   # same scale on every rank
-            scale = float(t.item())
+            return torch.empty_like(x, dtype=torch.float16), 1.0, 0.0
+        stats = torch.zeros(2, dtype=torch.float32, device=x.device)
+        _L.check(self.lib.drsa_absmax(_ptr(x), x.numel(), _ptr(stats[0:]), _stream()), "drsa_absmax")
+        _L.check(self.lib.drsa_rownorm_max(_ptr(x), x.size(0), x.size(1), _ptr(stats[1:]), _stream()),
+                 "drsa_rownorm_max")
+        mx, rho = (float(v) for v in stats.cpu())          # one host sync, once per optimiser
+        scale = _pow2_scale(mx)
         out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
         _L.check(self.lib.drsa_pack_f16(_ptr(x), x.numel(), scale, _ptr(out), _stream()), "drsa_pack_f16")
-        return out, scale
+        return out, scale, rho * scale
 
     def split_u(self, U: torch.Tensor):
         if self.precision == "tc":
@@ -122,7 +126,7 @@ class _RowPass:
             self.sums.zero_()
             return
         _L.check(self.lib.drsa_step(_ptr(self.A), _ptr(self.C), _ptr(U), _ptr(self.Ut_hi), _ptr(self.Ut_lo), self.M,
-                                    self.d, self.m, self.K, self.prec_code, self.scaleA, self.scaleC,
+                                    self.d, self.m, self.K, self.prec_code, self.scaleA, self.scaleC, self.pq_scale,
                                     _ptr(self.sums), _ptr(self.ws_step), self.ws_step.numel(), _stream()),
                  "drsa_step")
 

@@ -1,0 +1,321 @@
+"""LRP engine: forward pass of the log-mel CNN and the rule-modified backward pass on the CUDA library.
+
+This replaces what zennit does for the reference (``Gradient(model, composite)`` + hooks + autograd,
+see preprocessing.py:143-167 and attribute.py:98-107): the layer list of ``model.features`` /
+``model.classifier`` is compiled once into a plan of kernel calls, the forward keeps exactly the
+activations the backward needs, and the backward stops at the split layer when only the maps there are
+wanted (the reference propagates to the input even then).
+
+Semantics: rules return ``input * gradient`` so the quantity flowing between layers
+is the relevance itself; layers without a rule (ReLU, MaxPool2d, Dropout, flatten, canonised BatchNorm)
+use ordinary autograd: ReLU masks by ``output > 0``, MaxPool routes to the arg-max.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional
+
+import torch
+import torch.nn as nn
+
+from drsa_audio_b200 import _lib as _L
+from cxai.xai.explain import rules as R
+
+__all__ = ["LRPPlan", "lrp_intermediate", "lrp_input_relevance", "forward_logits"]
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Op:
+    __slots__ = ("kind", "name", "module", "rule", "relu", "w", "b", "w_mod", "wt_mod", "b_mod", "eps", "ones",
+                 "kh", "kw", "cin", "cout", "index")
+
+    def __init__(self, kind, name, module, index):
+        self.kind, self.name, self.module, self.index = kind, name, module, index
+        self.rule = None
+        self.relu = False
+
+
+class LRPPlan:
+    """Kernel plan for one (model, composite) pair.  Parameters are prepared once: BatchNorm folded
+    (SequentialMergeBatchNorm), rule-modified weights W', b' and the flipped copy for the transposed
+    convolution."""
+
+    def __init__(self, model: nn.Module, composite: R.Composite, device: torch.device):
+        if model.training:
+            raise _L.DRSAError("LRP needs model.eval() (BatchNorm running statistics are folded)")
+        self.device = device
+        self.ops: List[_Op] = []
+        self.module_to_op = {}
+        mods = [(f"features.{n}", m) for n, m in model.features.named_children()]
+        mods.append(("flatten", None))
+        mods += [(f"classifier.{n}", m) for n, m in model.classifier.named_children()]
+        i = 0
+        while i < len(mods):
+            name, m = mods[i]
+            if m is None:
+                op = _Op("flatten", name, None, len(self.ops))
+            elif isinstance(m, (nn.Conv2d, nn.Linear)):
+                op = _Op("conv" if isinstance(m, nn.Conv2d) else "dense", name, m, len(self.ops))
+                w = m.weight.detach().to(device, torch.float32)
+                b = (m.bias.detach().to(device, torch.float32) if m.bias is not None
+                     else torch.zeros(w.shape[0], device=device))
+                if isinstance(m, nn.Conv2d):
+                    if tuple(m.kernel_size) != (3, 3) or tuple(m.stride) != (1, 1) or m.padding not in ("same", 1, (1, 1)) \
+                            or m.groups != 1 or tuple(m.dilation) != (1, 1):
+                        raise _L.DRSAError(f"{name}: only 3x3 / stride 1 / 'same' convolutions are on this path")
+                nxt = mods[i + 1][1] if i + 1 < len(mods) else None
+                if isinstance(nxt, (nn.BatchNorm2d, nn.BatchNorm1d)):
+                    if not composite.merges_batchnorm:
+                        raise _L.DRSAError(f"{mods[i + 1][0]}: BatchNorm needs the SequentialMergeBatchNorm canonizer")
+                    scale = nxt.weight.detach().to(device) / torch.sqrt(nxt.running_var.detach().to(device) + nxt.eps)
+                    w = w * scale.view(-1, *([1] * (w.dim() - 1)))
+                    b = (b - nxt.running_mean.detach().to(device)) * scale + nxt.bias.detach().to(device)
+                    self.module_to_op[nxt] = None          # resolved below: output of BN == output of this op
+                op.w, op.b = w.contiguous(), b.contiguous()
+                op.cout, op.cin = w.shape[0], w.shape[1]
+                op.rule = composite.rule_for(name)
+                self._prepare_rule(op)
+            elif isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)):
+                op = _Op("identity", name, m, len(self.ops))       # folded into the previous op
+            elif isinstance(m, nn.ReLU):
+                op = _Op("relu", name, m, len(self.ops))
+            elif isinstance(m, nn.MaxPool2d):
+                op = _Op("pool", name, m, len(self.ops))
+                ks = m.kernel_size if isinstance(m.kernel_size, (tuple, list)) else (m.kernel_size, m.kernel_size)
+                st = m.stride if isinstance(m.stride, (tuple, list)) else (m.stride, m.stride)
+                if tuple(st) != tuple(ks) or m.padding not in (0, (0, 0)):
+                    raise _L.DRSAError(f"{name}: only non-overlapping max-pooling is on this path")
+                op.kh, op.kw = int(ks[0]), int(ks[1])
+            elif isinstance(m, nn.Dropout):
+                op = _Op("identity", name, m, len(self.ops))
+            else:
+                raise _L.DRSAError(f"{name}: layer type {type(m).__name__} is not on this path")
+            self.ops.append(op)
+            if m is not None:
+                self.module_to_op[m] = op
+            i += 1
+        # fuse ReLU into the producing conv/dense: the pre-activation is never needed (rules recompute z')
+        for k, op in enumerate(self.ops):
+            if op.kind in ("conv", "dense"):
+                j = k + 1
+                while j < len(self.ops) and self.ops[j].kind == "identity":
+                    j += 1
+                if j < len(self.ops) and self.ops[j].kind == "relu":
+                    op.relu = True
+
+    def _prepare_rule(self, op: _Op) -> None:
+        rule, w, b = op.rule, op.w, op.b
+        op.ones, op.eps = 0, 0.0
+        op.w_mod = op.b_mod = op.wt_mod = None
+        if rule is None or rule.kind == "pass":
+            return
+        op.eps = rule.stabilizer
+        if rule.kind == "epsilon":
+            wm, bm = w, b
+        elif rule.kind == "gamma":
+            wm, bm = w + rule.gamma * w.clamp(min=0), b + rule.gamma * b.clamp(min=0)
+        elif rule.kind == "zplus":
+            wm, bm = w.clamp(min=0), b.clamp(min=0)
+        elif rule.kind == "wsquare":
+            wm, bm, op.ones = w * w, b * b, 1
+        elif rule.kind == "flat":
+            wm, bm, op.ones = torch.ones_like(w), torch.ones_like(b), 1
+        else:
+            raise _L.DRSAError(f"{op.name}: rule {rule!r} is not implemented")
+        if op.kind == "dense" and rule.kind not in ("epsilon", "gamma", "zplus"):
+            raise _L.DRSAError(f"{op.name}: rule {rule!r} is only implemented for convolutions")
+        op.w_mod, op.b_mod = wm.contiguous(), bm.contiguous()
+        if op.kind == "conv":
+            op.wt_mod = torch.empty(op.cin, op.cout, 3, 3, device=w.device)
+            _L.check(_L.lib().lrp_conv3x3_flip_weights(_ptr(op.w_mod), op.cout, op.cin, _ptr(op.wt_mod), _stream()),
+                     "lrp_conv3x3_flip_weights")
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, keep_from: int = 0):
+        """Runs the network; returns (logits, saved) where saved[k] holds what op k needs in the backward
+        (its input, and the arg-max for pooling).  Only ops with index >= keep_from are kept."""
+        lib = _L.lib()
+        saved = [None] * len(self.ops)
+        outs = [None] * len(self.ops)
+        cur = x
+        for k, op in enumerate(self.ops):
+            keep = k >= keep_from
+            if op.kind == "conv":
+                N, Cin, H, W = cur.shape
+                y = torch.empty(N, op.cout, H, W, device=cur.device)
+                _L.check(lib.lrp_conv3x3_forward(_ptr(cur), _ptr(op.w), _ptr(op.b), N, Cin, op.cout, H, W,
+                                                 int(op.relu), _ptr(y), _stream()), op.name)
+                if keep:
+                    saved[k] = cur
+                cur = y
+            elif op.kind == "dense":
+                N, In = cur.shape
+                y = torch.empty(N, op.cout, device=cur.device)
+                _L.check(lib.lrp_dense_forward(_ptr(cur), _ptr(op.w), _ptr(op.b), N, In, op.cout, int(op.relu),
+                                               _ptr(y), _stream()), op.name)
+                if keep:
+                    saved[k] = cur
+                cur = y
+            elif op.kind == "pool":
+                N, Cc, H, W = cur.shape
+                Ho, Wo = H // op.kh, W // op.kw
+                y = torch.empty(N, Cc, Ho, Wo, device=cur.device)
+                am = torch.empty(N, Cc, Ho, Wo, dtype=torch.int32, device=cur.device)
+                _L.check(lib.lrp_maxpool_forward(_ptr(cur), N * Cc, H, W, op.kh, op.kw, _ptr(y), _ptr(am),
+                                                 _stream()), op.name)
+                if keep:
+                    saved[k] = (am, (N, Cc, H, W))
+                cur = y
+            elif op.kind == "flatten":
+                if keep:
+                    saved[k] = cur.shape
+                cur = cur.reshape(cur.size(0), -1)
+            elif op.kind == "relu":
+                if keep:
+                    saved[k] = cur            # ReLU already applied by the producer: output == input here
+            outs[k] = cur
+        return cur, saved, outs
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, Rel: torch.Tensor, saved, stop_after: int = -1) -> torch.Tensor:
+        """Propagates relevance from the logits down to the OUTPUT of op `stop_after` (-1: to the input)."""
+        lib = _L.lib()
+        for k in range(len(self.ops) - 1, stop_after, -1):
+            op = self.ops[k]
+            if op.kind == "dense":
+                if op.rule is None or op.rule.kind == "pass":
+                    if op.rule is None:
+                        raise _L.DRSAError(f"{op.name}: no LRP rule assigned")
+                    continue
+                x = saved[k]
+                N, In = x.shape
+                s_buf = torch.empty(N, op.cout, device=x.device)
+                R_in = torch.empty_like(x)
+                _L.check(lib.lrp_dense_epsilon_backward(_ptr(x), _ptr(op.w_mod), _ptr(op.b_mod), _ptr(Rel), N, In,
+                                                        op.cout, op.eps, _ptr(s_buf), _ptr(R_in), _stream()), op.name)
+                Rel = R_in
+            elif op.kind == "conv":
+                if op.rule is None:
+                    raise _L.DRSAError(f"{op.name}: no LRP rule assigned")
+                if op.rule.kind == "pass":
+                    continue
+                x = saved[k]
+                N, Cin, H, W = x.shape
+                s_buf = torch.empty(N, op.cout, H, W, device=x.device)
+                R_in = torch.empty_like(x)
+                _L.check(lib.lrp_conv3x3_backward(_ptr(x), _ptr(op.w_mod), _ptr(op.wt_mod), _ptr(op.b_mod), _ptr(Rel), N,
+                                                  Cin, op.cout, H, W, op.eps, op.ones, _ptr(s_buf), _ptr(R_in),
+                                                  _stream()), op.name)
+                Rel = R_in
+            elif op.kind == "relu":
+                a = saved[k]
+                Rel = Rel.contiguous()
+                _L.check(lib.lrp_relu_mask(_ptr(a), _ptr(Rel), Rel.numel(), _stream()), op.name)
+            elif op.kind == "pool":
+                am, shp = saved[k]
+                N, Cc, H, W = shp
+                R_in = torch.empty(shp, device=Rel.device)
+                _L.check(lib.lrp_maxpool_backward(_ptr(Rel.contiguous()), _ptr(am), N * Cc, H, W, op.kh, op.kw,
+                                                  _ptr(R_in), _stream()), op.name)
+                Rel = R_in
+            elif op.kind == "flatten":
+                Rel = Rel.reshape(saved[k])
+        return Rel
+
+    def check_nonneg_inputs(self):
+        """Gamma / ZPlus use the collapsed form that is valid for non-negative inputs only: every such
+        layer must be fed by a ReLU / pooling output (true for every name map of the reference)."""
+        seen_relu = False
+        for op in self.ops:
+            if op.kind in ("conv", "dense") and op.rule is not None and op.rule.kind in ("gamma", "zplus"):
+                if not seen_relu:
+                    raise _L.DRSAError(f"{op.name}: Gamma/ZPlus on a layer with signed input is not on this path "
+                                       "(use WSquare/Flat/Epsilon for the first layer, as the reference does)")
+            if op.kind == "relu" or (op.kind in ("conv", "dense") and op.relu):
+                seen_relu = True
+            elif op.kind in ("conv", "dense"):
+                seen_relu = False
+
+
+_PLAN_CACHE = {}
+
+
+def _plan(model, composite, device) -> LRPPlan:
+    key = (id(model), id(composite), str(device))
+    p = _PLAN_CACHE.get(key)
+    if p is None:
+        p = LRPPlan(model, composite, device)
+        p.check_nonneg_inputs()
+        _PLAN_CACHE.clear()
+        _PLAN_CACHE[key] = p
+    return p
+
+
+def _prep_input(input_batch: torch.Tensor) -> torch.Tensor:
+    if not torch.cuda.is_available():
+        raise _L.DRSAError("no CUDA device available and no fallback path exists")
+    x = input_batch.detach()
+    if not x.is_cuda:
+        x = x.cuda(non_blocking=True)
+    return x.to(torch.float32).contiguous()
+
+
+def forward_logits(model, input_batch, composite=None, batch_size: int = 64) -> torch.Tensor:
+    x = _prep_input(input_batch)
+    with torch.cuda.device(x.device):
+        plan = _plan(model, composite or R.NameMapComposite([], canonizers=[R.SequentialMergeBatchNorm()]), x.device)
+        outs = [plan.forward(x[i:i + batch_size], keep_from=len(plan.ops))[0] for i in range(0, x.size(0), batch_size)]
+    return torch.cat(outs, 0)
+
+
+def lrp_intermediate(model, input_batch, composite, layer, class_idx, attr_batch_size: int = 64,
+                     one_hot_encoded: bool = False, attr_output_fn: Optional[Callable] = None):
+    """(activation_maps, relevance_maps) at the output of ``layer`` (get_intermediate, preprocessing.py:106-176).
+    Minibatches of ``attr_batch_size`` like the reference; the backward stops at ``layer``."""
+    from cxai.xai.explain.attribute import lrp_output_modifier
+    x = _prep_input(input_batch)
+    fn = attr_output_fn or lrp_output_modifier(class_idx, one_hot_encoded=one_hot_encoded)
+    with torch.cuda.device(x.device):
+        plan = _plan(model, composite, x.device)
+        op = plan.module_to_op.get(layer)
+        if op is None:
+            # a BatchNorm folded into its conv: its output is the conv op's output
+            for k, o in enumerate(plan.ops):
+                if o.module is layer:
+                    op = o
+            if op is None:
+                raise _L.DRSAError("layer is not a module of model.features / model.classifier")
+        split = op.index
+        # a conv/dense whose ReLU was fused cannot expose its pre-activation
+        if plan.ops[split].kind in ("conv", "dense", "identity") and any(
+                o.kind in ("conv", "dense") and o.relu for o in plan.ops[max(0, split - 1):split + 1]):
+            nxt = split
+            while plan.ops[nxt].kind != "relu":
+                nxt += 1
+            raise _L.DRSAError(f"split at {plan.ops[split].name} (pre-activation) is not on this path; "
+                               f"use the ReLU {plan.ops[nxt].name} like the reference (layers 19/26/33)")
+        a_maps, r_maps = [], []
+        for i in range(0, x.size(0), attr_batch_size):
+            logits, saved, outs = plan.forward(x[i:i + attr_batch_size], keep_from=split + 1)
+            seed = fn(logits).contiguous()
+            r_maps.append(plan.backward(seed, saved, stop_after=split))
+            a_maps.append(outs[split])
+    return torch.cat(a_maps, 0), torch.cat(r_maps, 0)
+
+
+def lrp_input_relevance(model, input_batch, composite, attr_output_fn: Callable, batch_size: int = 64) -> torch.Tensor:
+    """Relevance at the input (compute_relevances, attribute.py:70-108)."""
+    x = _prep_input(input_batch)
+    with torch.cuda.device(x.device):
+        plan = _plan(model, composite, x.device)
+        out = []
+        for i in range(0, x.size(0), batch_size):
+            logits, saved, _ = plan.forward(x[i:i + batch_size], keep_from=0)
+            out.append(plan.backward(attr_output_fn(logits).contiguous(), saved, stop_after=-1))
+    return torch.cat(out, 0)

@@ -46,7 +46,8 @@ SIGNATURES = {
     "drsa_pack_f16": (_i32, [_vp, _i64, _f32, _vp, _vp]),
     "drsa_absmax": (_i32, [_vp, _i64, _vp, _vp]),
     "drsa_step_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32, _i32]),
-    "drsa_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _i64, _vp]),
+    "drsa_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _vp, _i64, _vp]),
+    "drsa_rownorm_max": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "drsa_split_u": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "drsa_finish_workspace_bytes": (_i64, [_i32, _i32]),
     "drsa_finish_step": (_i32, [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp,
@@ -58,6 +59,14 @@ SIGNATURES = {
     "drsa_context_vectors": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "drsa_sumsq": (_i32, [_vp, _i64, _vp, _vp]),
     "drsa_normalize": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp]),
+    "lrp_conv3x3_forward": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "lrp_conv3x3_flip_weights": (_i32, [_vp, _i32, _i32, _vp, _vp]),
+    "lrp_conv3x3_backward": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp]),
+    "lrp_maxpool_forward": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "lrp_maxpool_backward": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "lrp_dense_forward": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "lrp_dense_epsilon_backward": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp]),
+    "lrp_relu_mask": (_i32, [_vp, _vp, _i64, _vp]),
     "drsa_selftest_umma": (_i32, [_i32, _vp]),
 }
 

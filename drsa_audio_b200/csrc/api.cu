@@ -38,7 +38,23 @@ int step_fp32(const float* A, const float* C, const float* U, int64_t M, int d, 
 bool tc_shape_supported(int d, int m, int K);
 int64_t step_tc_workspace_bytes(int64_t M, int d, int m, int K);
 int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_lo, int64_t M, int d, int m, int K,
-            float scaleA, float scaleC, float* sums, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+            float scaleA, float scaleC, float pq_scale, float* sums, void* workspace, int64_t workspace_bytes,
+            cudaStream_t stream);
+int rownorm_max(const float* in, int64_t rows, int d, float* out, cudaStream_t stream);
+int conv3x3_forward(const float* x, const float* w, const float* b, int64_t N, int Cin, int Cout, int H, int W, int relu,
+                    float* y, cudaStream_t s);
+int conv3x3_backward(const float* x, const float* w_mod, const float* wt_mod, const float* b_mod, const float* R_out,
+                     int64_t N, int Cin, int Cout, int H, int W, float eps, int x_is_ones, float* s_buf, float* R_in,
+                     cudaStream_t s);
+int flip_weights(const float* w, int Cout, int Cin, float* wt, cudaStream_t s);
+int maxpool_forward(const float* x, int64_t NC, int H, int W, int kh, int kw, float* y, int32_t* argmax, cudaStream_t s);
+int maxpool_backward(const float* R_out, const int32_t* argmax, int64_t NC, int H, int W, int kh, int kw, float* R_in,
+                     cudaStream_t s);
+int dense_forward(const float* x, const float* w, const float* b, int64_t N, int In, int Out, int relu, float* y,
+                  cudaStream_t s);
+int dense_epsilon_backward(const float* x, const float* w, const float* b, const float* R_out, int64_t N, int In,
+                           int Out, float eps, float* s_buf, float* R_in, cudaStream_t s);
+int relu_mask(const float* a, float* R, int64_t count, cudaStream_t s);
 int pack_f16(const float* in, int64_t count, float scale, void* out, cudaStream_t stream);
 int absmax(const float* in, int64_t count, float* out, cudaStream_t stream);
 int64_t finish_workspace_bytes(int d, int m);
@@ -102,6 +118,12 @@ int drsa_absmax(const float* in, int64_t count, float* out, void* stream) {
   return absmax(in, count, out, static_cast<cudaStream_t>(stream));
 }
 
+int drsa_rownorm_max(const float* in, int64_t rows, int d, float* out, void* stream) {
+  if (in == nullptr || out == nullptr || rows <= 0 || d <= 0) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return rownorm_max(in, rows, d, out, static_cast<cudaStream_t>(stream));
+}
+
 int64_t drsa_step_workspace_bytes(int64_t M, int d, int m, int K, int precision) {
   if (!shape_ok(M, d, m, K)) return DRSA_ERR_ARG;
   if (precision == DRSA_PREC_FP32) return step_fp32_workspace_bytes(M, d, m, K);
@@ -113,7 +135,7 @@ int64_t drsa_step_workspace_bytes(int64_t M, int d, int m, int K, int precision)
 }
 
 int drsa_step(const void* A, const void* C, const float* U, const void* Ut_hi, const void* Ut_lo, int64_t M, int d,
-              int m, int K, int precision, float scaleA, float scaleC, float* sums, void* workspace,
+              int m, int K, int precision, float scaleA, float scaleC, float pq_scale, float* sums, void* workspace,
               int64_t workspace_bytes, void* stream) {
   if (A == nullptr || C == nullptr || sums == nullptr || workspace == nullptr || !shape_ok(M, d, m, K))
     return DRSA_ERR_ARG;
@@ -125,8 +147,9 @@ int drsa_step(const void* A, const void* C, const float* U, const void* Ut_hi, c
                      workspace_bytes, s);
   }
   if (precision == DRSA_PREC_TC_F16X2) {
-    if (Ut_hi == nullptr || Ut_lo == nullptr || !(scaleA > 0.f) || !(scaleC > 0.f)) return DRSA_ERR_ARG;
-    return step_tc(A, C, Ut_hi, Ut_lo, M, d, m, K, scaleA, scaleC, sums, workspace, workspace_bytes, s);
+    if (Ut_hi == nullptr || Ut_lo == nullptr || !(scaleA > 0.f) || !(scaleC > 0.f) || !(pq_scale > 0.f))
+      return DRSA_ERR_ARG;
+    return step_tc(A, C, Ut_hi, Ut_lo, M, d, m, K, scaleA, scaleC, pq_scale, sums, workspace, workspace_bytes, s);
   }
   return DRSA_ERR_ARG;
 }
@@ -205,6 +228,73 @@ int drsa_normalize(float* v, int64_t rows, int d, const double* sumsq, int64_t c
   if (v == nullptr || sumsq == nullptr || rows <= 0 || d <= 0 || count_global <= 0) return DRSA_ERR_ARG;
   DRSA_TRY(require_sm100());
   return normalize(v, rows, d, sumsq, count_global, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------- stage 1 (LRP)
+static bool conv_ok(int64_t N, int Cin, int Cout, int H, int W) { return N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0; }
+
+int lrp_conv3x3_forward(const float* x, const float* w, const float* b, int64_t N, int Cin, int Cout, int H, int W,
+                        int relu, float* y, void* stream) {
+  if (x == nullptr || w == nullptr || y == nullptr || !conv_ok(N, Cin, Cout, H, W)) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return conv3x3_forward(x, w, b, N, Cin, Cout, H, W, relu, y, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_conv3x3_flip_weights(const float* w, int Cout, int Cin, float* wt, void* stream) {
+  if (w == nullptr || wt == nullptr || Cout <= 0 || Cin <= 0) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return flip_weights(w, Cout, Cin, wt, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_conv3x3_backward(const float* x, const float* w_mod, const float* wt_mod, const float* b_mod, const float* R_out,
+                         int64_t N, int Cin, int Cout, int H, int W, float eps, int x_is_ones, float* s_buf,
+                         float* R_in, void* stream) {
+  if ((x == nullptr && !x_is_ones) || w_mod == nullptr || wt_mod == nullptr || R_out == nullptr || s_buf == nullptr ||
+      R_in == nullptr || !conv_ok(N, Cin, Cout, H, W))
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return conv3x3_backward(x, w_mod, wt_mod, b_mod, R_out, N, Cin, Cout, H, W, eps, x_is_ones, s_buf, R_in,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int lrp_maxpool_forward(const float* x, int64_t NC, int H, int W, int kh, int kw, float* y, int32_t* argmax,
+                        void* stream) {
+  if (x == nullptr || y == nullptr || argmax == nullptr || NC <= 0 || H <= 0 || W <= 0 || kh <= 0 || kw <= 0 ||
+      H / kh == 0 || W / kw == 0)
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return maxpool_forward(x, NC, H, W, kh, kw, y, argmax, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_maxpool_backward(const float* R_out, const int32_t* argmax, int64_t NC, int H, int W, int kh, int kw,
+                         float* R_in, void* stream) {
+  if (R_out == nullptr || argmax == nullptr || R_in == nullptr || NC <= 0 || H <= 0 || W <= 0 || kh <= 0 || kw <= 0)
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return maxpool_backward(R_out, argmax, NC, H, W, kh, kw, R_in, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_dense_forward(const float* x, const float* w, const float* b, int64_t N, int In, int Out, int relu, float* y,
+                      void* stream) {
+  if (x == nullptr || w == nullptr || y == nullptr || N <= 0 || In <= 0 || Out <= 0 || N > 2147483647LL)
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return dense_forward(x, w, b, N, In, Out, relu, y, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_dense_epsilon_backward(const float* x, const float* w, const float* b, const float* R_out, int64_t N, int In,
+                               int Out, float eps, float* s_buf, float* R_in, void* stream) {
+  if (x == nullptr || w == nullptr || R_out == nullptr || s_buf == nullptr || R_in == nullptr || N <= 0 || In <= 0 ||
+      Out <= 0 || N > 2147483647LL)
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return dense_epsilon_backward(x, w, b, R_out, N, In, Out, eps, s_buf, R_in, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_relu_mask(const float* a, float* R, int64_t count, void* stream) {
+  if (a == nullptr || R == nullptr || count <= 0) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return relu_mask(a, R, count, static_cast<cudaStream_t>(stream));
 }
 
 int drsa_selftest_umma(int variant, float* max_err_host) { return selftest_umma(variant, max_err_host); }

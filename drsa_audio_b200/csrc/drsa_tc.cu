@@ -100,7 +100,7 @@ template <int D>
 __global__ void __launch_bounds__(kThreads, 1)
 drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC,
                     const __grid_constant__ CUtensorMap tmUh, const __grid_constant__ CUtensorMap tmUl,
-                    int num_tiles, int G, int nRB, int d_k, float inv_scale, float* __restrict__ part,
+                    int num_tiles, int G, int nRB, int d_k, float inv_scale, float pq_scale, float* __restrict__ part,
                     float* __restrict__ ss_part, int* __restrict__ err_flag) {
   using C = Cfg<D>;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -258,9 +258,14 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const float4 o = *reinterpret_cast<const float4*>(&red[(q0 + w) * kRows + 32 * c + 4 * i4]);
             s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w;
           }
-          const float g0 = fmaxf(s4.x, 0.f) * inv_scale, g1 = fmaxf(s4.y, 0.f) * inv_scale;
-          const float g2 = fmaxf(s4.z, 0.f) * inv_scale, g3 = fmaxf(s4.w, 0.f) * inv_scale;
-          if (owner) ssq += g0 * g0 + g1 * g1 + g2 * g2 + g3 * g3;
+          // s is in packed scale (sA*sC*s_true): sums of squares are taken in true scale, the fp16
+          // operands P, Q of GEMM2 in packed scale times pq_scale (overflow-safe by construction)
+          float g0 = fmaxf(s4.x, 0.f), g1 = fmaxf(s4.y, 0.f), g2 = fmaxf(s4.z, 0.f), g3 = fmaxf(s4.w, 0.f);
+          if (owner) {
+            const float t0 = g0 * inv_scale, t1 = g1 * inv_scale, t2 = g2 * inv_scale, t3 = g3 * inv_scale;
+            ssq += t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3;
+          }
+          g0 *= pq_scale; g1 *= pq_scale; g2 *= pq_scale; g3 *= pq_scale;
           const int i = 4 * i4;
           pk[2 * i4] = pack_h2_sat(g0 * __uint_as_float(hc[i]), g1 * __uint_as_float(hc[i + 1]));
           pk[2 * i4 + 1] = pack_h2_sat(g2 * __uint_as_float(hc[i + 2]), g3 * __uint_as_float(hc[i + 3]));
@@ -302,7 +307,7 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 // sums[i*m + col] = inv_scale * sum_rb part[(rb*G + col/128)*128 + col%128][i] ; sums[d*m + k] = sum_rb ss_part
 __global__ void __launch_bounds__(256) tc_reduce_kernel(const float* __restrict__ part, const float* __restrict__ ss_part,
-                                                        int nRB, int G, int d, int m, int K, float inv_scale,
+                                                        int nRB, int G, int d, int m, int K, float x_scale,
                                                         float* __restrict__ sums) {
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(256) tc_reduce_kernel(const float* __restrict_
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int il = ty + 8 * r;
-    sums[(int64_t)(i0 + il) * m + c0 + tx] = tile[tx][il] * inv_scale;
+    sums[(int64_t)(i0 + il) * m + c0 + tx] = tile[tx][il] * x_scale;
   }
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < K) {
     float s = 0.f;
@@ -361,6 +366,20 @@ __global__ void __launch_bounds__(1024) absmax_kernel(const float* __restrict__ 
   }
 }
 
+// one warp per row: max_r ||in[r,:]||_2
+__global__ void __launch_bounds__(256) rownorm_max_kernel(const float* __restrict__ in, int64_t rows, int d,
+                                                          float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float best = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * nw + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * nw) {
+    float s = 0.f;
+    for (int j = lane; j < d; j += 32) { const float v = __ldg(in + r * d + j); s = fmaf(v, v, s); }
+    s = warp_sum(s);
+    best = fmaxf(best, s);
+  }
+  if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(sqrtf(best)));
+}
+
 struct TcPlan { int G, nRB, num_tiles; int64_t part_bytes, ss_bytes; };
 TcPlan plan_for(int64_t M, int d, int m, int K) {
   TcPlan p;
@@ -388,10 +407,10 @@ int64_t step_tc_workspace_bytes(int64_t M, int d, int m, int K) {
 }
 
 int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_lo, int64_t M, int d, int m, int K,
-            float scaleA, float scaleC, float* sums, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+            float scaleA, float scaleC, float pq_scale, float* sums, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
   if (!tc_shape_supported(d, m, K)) return DRSA_ERR_SHAPE;
   if (!aligned16(A16) || !aligned16(C16) || !aligned16(Ut_hi) || !aligned16(Ut_lo)) return DRSA_ERR_ALIGN;
-  if (M >= ((int64_t)1 << 31) * kRows / 2) return DRSA_ERR_SHAPE;
+  if (M >= ((int64_t)1 << 31)) return DRSA_ERR_SHAPE;
   TcPlan p = plan_for(M, d, m, K);
   if (workspace_bytes < p.part_bytes + p.ss_bytes + 256) return DRSA_ERR_WORKSPACE;
   char* w = static_cast<char*>(workspace);
@@ -416,7 +435,7 @@ int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_
       attr_set = true;
     }
     drsa_tc_step_kernel<256><<<grid, kThreads, Cfg<256>::kSmemBytes, stream>>>(
-        tmA, tmC, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale, part, ss_part, err);
+        tmA, tmC, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale, pq_scale, part, ss_part, err);
   } else {
     static bool attr_set = false;
     if (!attr_set) {
@@ -425,11 +444,12 @@ int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_
       attr_set = true;
     }
     drsa_tc_step_kernel<128><<<grid, kThreads, Cfg<128>::kSmemBytes, stream>>>(
-        tmA, tmC, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale, part, ss_part, err);
+        tmA, tmC, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale, pq_scale, part, ss_part, err);
   }
   DRSA_LAUNCH_CHECK();
   dim3 rgrid(m / 32, d / 32);
-  tc_reduce_kernel<<<rgrid, 256, 0, stream>>>(part, ss_part, p.nRB, p.G, d, m, K, inv_scale, sums);
+  // X' = pq_scale * (sA sC)^2 * X
+  tc_reduce_kernel<<<rgrid, 256, 0, stream>>>(part, ss_part, p.nRB, p.G, d, m, K, inv_scale * inv_scale / pq_scale, sums);
   DRSA_LAUNCH_CHECK();
   return DRSA_OK;
 }
@@ -457,6 +477,15 @@ int absmax(const float* in, int64_t count, float* out, cudaStream_t stream) {
   if (blocks > 148 * 2) blocks = 148 * 2;
   if (blocks < 1) blocks = 1;
   absmax_kernel<<<(int)blocks, 1024, 0, stream>>>(in, count, out);
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+int rownorm_max(const float* in, int64_t rows, int d, float* out, cudaStream_t stream) {
+  DRSA_CUDA(cudaMemsetAsync(out, 0, sizeof(float), stream));
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  rownorm_max_kernel<<<(int)blocks, 256, 0, stream>>>(in, rows, d, out);
   DRSA_LAUNCH_CHECK();
   return DRSA_OK;
 }

@@ -75,6 +75,11 @@ int drsa_pack_f16(const float* in, int64_t count, float scale, void* out_f16, vo
 /* max |x| over `count` floats -> *out (one float).  Used to choose the pack scale. */
 int drsa_absmax(const float* in, int64_t count, float* out, void* stream);
 
+/* max over rows of the Euclidean row norm of in [rows, d] -> *out.  With it the caller bounds
+ * |g * HC| <= pq_scale * rhoA * rhoC^2 and picks pq_scale so the fp16 P/Q operands of the
+ * gradient GEMM can never overflow. */
+int drsa_rownorm_max(const float* in, int64_t rows, int d, float* out, void* stream);
+
 /* Bytes of workspace drsa_step needs for the given problem. */
 int64_t drsa_step_workspace_bytes(int64_t M, int d, int m, int K, int precision);
 
@@ -92,11 +97,13 @@ int64_t drsa_step_workspace_bytes(int64_t M, int d, int m, int K, int precision)
  *   U         [d, m]   fp32, m = K*d_k <= d               (FP32 mode; may be NULL in TC mode)
  *   Ut_hi/lo  [m, d]   fp16 split of U^T written by drsa_finish_step / drsa_split_u
  *                      (TC mode; may be NULL in FP32 mode)
- *   data_scale          product scaleA*scaleC of the pack scales (1 in FP32 mode)
+ *   scaleA, scaleC      the pack scales of A and C (powers of two; 1 in FP32 mode)
+ *   pq_scale            power of two applied to g before P = g*HC, Q = g*HA are rounded to
+ *                       fp16 for the gradient GEMM (TC mode; undone exactly in the output)
  */
 int drsa_step(const void* A, const void* C, const float* U, const void* Ut_hi, const void* Ut_lo,
               int64_t M, int d, int m, int K, int precision, float scaleA, float scaleC,
-              float* sums, void* workspace, int64_t workspace_bytes, void* stream);
+              float pq_scale, float* sums, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* U [d,m] fp32 -> Ut_hi, Ut_lo [m,d] fp16 with U^T = hi + lo (+ O(2^-22)). */
 int drsa_split_u(const float* U, int d, int m, void* Ut_hi, void* Ut_lo, void* stream);
@@ -160,6 +167,52 @@ int drsa_sumsq(const float* v, int64_t count, double* out, void* stream);
 /* v *= 1 / sqrt(sumsq / count_global) / d^0.25  (normalize_vectors with the global statistic). */
 int drsa_normalize(float* v, int64_t rows, int d, const double* sumsq, int64_t count_global,
                    void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Stage 1: LRP pass through the log-mel CNN (zennit 0.5.1 rule semantics)
+ *   reference call sites: preprocessing.py:106-176 (get_intermediate),
+ *   explain/attribute.py:70-108 (compute_relevances); rules per utils/constants.py:27-51.
+ *   Activations are NCHW fp32 exactly as the reference stages them
+ *   (utils/dataloading.py:176).
+ * ---------------------------------------------------------------------------------- */
+
+/* y = relu?(conv3x3_same(x, w) + b); x [N,Cin,H,W], w [Cout,Cin,3,3], y [N,Cout,H,W]
+ * (nn.Conv2d of create_model.py:121-130, BatchNorm already folded into w, b). */
+int lrp_conv3x3_forward(const float* x, const float* w, const float* b, int64_t N, int Cin,
+                        int Cout, int H, int W, int relu, float* y, void* stream);
+
+/* wt [Cin,Cout,3,3] = w [Cout,Cin,3,3] with channels swapped and taps flipped: the weights
+ * of the transposed convolution used by lrp_conv3x3_backward. */
+int lrp_conv3x3_flip_weights(const float* w, int Cout, int Cin, float* wt, void* stream);
+
+/* Gamma / ZPlus-style rule for inputs x >= 0 (zennit Gamma collapsed):
+ *   z' = conv(x, w') + b',  s = R_out / stabilize(z', eps),  R_in = x * conv_transpose(s, w')
+ * w', b' are the caller's modified parameters (w + gamma*max(w,0) ...), wt' the flipped copy
+ * of w'.  `s_buf` [N,Cout,H,W] is scratch.  If x_is_ones != 0 the input is replaced by ones
+ * in the forward and the input factor is dropped (WSquare / Flat, where w' holds w^2 or
+ * ones); x may then be NULL. */
+int lrp_conv3x3_backward(const float* x, const float* w_mod, const float* wt_mod, const float* b_mod,
+                         const float* R_out, int64_t N, int Cin, int Cout, int H, int W, float eps,
+                         int x_is_ones, float* s_buf, float* R_in, void* stream);
+
+/* MaxPool2d(kh,kw) (stride = kernel, floor) forward with arg-max capture (first maximum in
+ * row-major window order, like PyTorch), and relevance routing to the arg-max (autograd
+ * semantics of an un-hooked MaxPool2d). */
+int lrp_maxpool_forward(const float* x, int64_t NC, int H, int W, int kh, int kw, float* y,
+                        int32_t* argmax, void* stream);
+int lrp_maxpool_backward(const float* R_out, const int32_t* argmax, int64_t NC, int H, int W, int kh,
+                         int kw, float* R_in, void* stream);
+
+/* Dense layer forward y = relu?(x w^T + b), x [N,In], w [Out,In]. */
+int lrp_dense_forward(const float* x, const float* w, const float* b, int64_t N, int In, int Out,
+                      int relu, float* y, void* stream);
+/* Epsilon rule: R_in = x * ( (R_out / stabilize(z, eps)) w ),  z = x w^T + b (recomputed
+ * into s_buf [N,Out]). */
+int lrp_dense_epsilon_backward(const float* x, const float* w, const float* b, const float* R_out,
+                               int64_t N, int In, int Out, float eps, float* s_buf, float* R_in,
+                               void* stream);
+/* R *= (a > 0): autograd of an un-hooked ReLU applied to the relevance flow. */
+int lrp_relu_mask(const float* a, float* R, int64_t count, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Self tests of the tcgen05 / TMA building blocks (used by tests/ on the GPU box).

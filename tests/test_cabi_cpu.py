@@ -55,7 +55,7 @@ def test_compute_fails_loudly_without_sm100(lib):
         pytest.skip("GPU present")
     buf = ctypes.create_string_buffer(64)
     p = ctypes.cast(buf, ctypes.c_void_p)
-    st = lib.drsa_step(p, p, p, None, None, 8, 4, 4, 2, 0, 1.0, 1.0, p, p, 1 << 20, None)
+    st = lib.drsa_step(p, p, p, None, None, 8, 4, 4, 2, 0, 1.0, 1.0, 1.0, p, p, 1 << 20, None)
     assert st == -3
     with pytest.raises(_lib.DRSAError):
         _lib.check(st, "drsa_step")

@@ -42,8 +42,11 @@ def _sums_gpu(L, A, C, U, K, prec):
     Ad, Cd, Ud = _dev(A), _dev(C), _dev(U)
     s = torch.cuda.current_stream().cuda_stream
     if prec == "tc":
+        import math
         from cxai.xai.drsa.drsa import _pow2_scale
         sA, sC = _pow2_scale(float(A.abs().max())), _pow2_scale(float(C.abs().max()))
+        rA, rC = float(A.norm(dim=1).max()) * sA, float(C.norm(dim=1).max()) * sC
+        pq = 2.0 ** math.floor(math.log2(32768.0 / max(rA * rC * rC, rA * rA * rC)))
         A16 = torch.empty(M, d, dtype=torch.float16, device="cuda")
         C16 = torch.empty(M, d, dtype=torch.float16, device="cuda")
         L.check(lib.drsa_pack_f16(_ptr(Ad), Ad.numel(), sA, _ptr(A16), s))
@@ -51,11 +54,11 @@ def _sums_gpu(L, A, C, U, K, prec):
         hi = torch.empty(m, d, dtype=torch.float16, device="cuda")
         lo = torch.empty(m, d, dtype=torch.float16, device="cuda")
         L.check(lib.drsa_split_u(_ptr(Ud), d, m, _ptr(hi), _ptr(lo), s))
-        L.check(lib.drsa_step(_ptr(A16), _ptr(C16), None, _ptr(hi), _ptr(lo), M, d, m, K, code, sA, sC, _ptr(sums),
-                              _ptr(ws), ws.numel(), s), "drsa_step tc")
+        L.check(lib.drsa_step(_ptr(A16), _ptr(C16), None, _ptr(hi), _ptr(lo), M, d, m, K, code, sA, sC, pq,
+                              _ptr(sums), _ptr(ws), ws.numel(), s), "drsa_step tc")
     else:
-        L.check(lib.drsa_step(_ptr(Ad), _ptr(Cd), _ptr(Ud), None, None, M, d, m, K, code, 1.0, 1.0, _ptr(sums),
-                              _ptr(ws), ws.numel(), s), "drsa_step fp32")
+        L.check(lib.drsa_step(_ptr(Ad), _ptr(Cd), _ptr(Ud), None, None, M, d, m, K, code, 1.0, 1.0, 1.0,
+                              _ptr(sums), _ptr(ws), ws.numel(), s), "drsa_step fp32")
     torch.cuda.synchronize()
     out = sums.cpu().double()
     return out[: d * m].view(d, m), out[d * m:]
@@ -90,10 +93,16 @@ def test_row_sums_tensor_core_match_oracle(L, M, d, m, K):
     A, C = drsa_ref.synth_pairs(M, d, 200 + d + K)
     U = drsa_ref.synth_U0(d, m, 9)
     X, ss = _sums_gpu(L, A, C, U, K, "tc")
+    # (1) kernel correctness: oracle on the SAME fp16-quantised rows (only P/Q rounding and summation order differ)
+    Xq, ssq = drsa_ref.step_sums(A.half().double(), C.half().double(), U.double(), K)
+    relq = float(torch.linalg.norm(X - Xq) / torch.linalg.norm(Xq))
+    assert relq < 1e-4, relq
+    np.testing.assert_allclose(ss.numpy(), ssq.numpy(), rtol=2e-5)
+    # (2) arithmetic mode vs the exact oracle: fp16 storage costs 2^-12 per element, averaged over rows
     Xr, ssr = drsa_ref.step_sums(A.double(), C.double(), U.double(), K)
     relX = float(torch.linalg.norm(X - Xr) / torch.linalg.norm(Xr))
-    assert relX < 2e-4, relX
-    np.testing.assert_allclose(ss.numpy(), ssr.numpy(), rtol=2e-4)
+    assert relX < (1e-3 if M < 4096 else 2e-4), relX
+    np.testing.assert_allclose(ss.numpy(), ssr.numpy(), rtol=1e-3 if M < 4096 else 2e-4)
 
 
 def test_tensor_core_scale_invariance(L):

@@ -1,0 +1,171 @@
+"""GPU parity tests of stage 1 (forward + LRP pass, context extraction) against the CPU oracle
+(oracle/lrp_ref.py, the general multi-pass restatement of zennit's rules; parity with zennit itself is
+unpinned, see that file's header).  Metric: norm-wise relative error per sample <= 1e-4."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import lrp_ref, drsa_ref
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _rel_per_sample(got, want):
+    got, want = got.double().cpu().flatten(1), want.double().cpu().flatten(1)
+    return float(((got - want).norm(dim=1) / want.norm(dim=1).clamp(min=1e-30)).max())
+
+
+def _L():
+    from drsa_audio_b200 import _lib
+    return _lib
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W", [(2, 1, 8, 64, 64), (3, 8, 16, 17, 33), (2, 64, 100, 16, 40), (1, 100, 128, 8, 8),
+                                            (2, 5, 7, 3, 5)])
+def test_conv3x3_forward_and_rule_backward(N, Cin, Cout, H, W):
+    L = _L(); lib = L.lib()
+    g = torch.Generator().manual_seed(Cin * Cout)
+    x = torch.rand(N, Cin, H, W, generator=g); x[x < 0.2] = 0
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
+    b = 0.1 * torch.randn(Cout, generator=g)
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    s = torch.cuda.current_stream().cuda_stream
+    for relu in (0, 1):
+        y = torch.empty(N, Cout, H, W, device="cuda")
+        L.check(lib.lrp_conv3x3_forward(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), N, Cin, Cout, H, W, relu, y.data_ptr(), s))
+        want = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+        if relu:
+            want = want.clamp(min=0)
+        assert _rel_per_sample(y, want) < 1e-5
+    # Gamma-style backward with modified weights vs the general 5-pass oracle
+    conv = torch.nn.Conv2d(Cin, Cout, 3, padding=1).double()
+    conv.weight.data.copy_(w); conv.bias.data.copy_(b)
+    z = conv(x.double()).detach()
+    Rout = (torch.randn(z.shape, generator=g).double() * (z > 0)).float()
+    gamma, eps = 0.3, 1e-7
+    want = lrp_ref.rule_backward(conv, "gamma", x.double(), Rout.double(), eps, gamma)
+    wm = (w + gamma * w.clamp(min=0)).cuda().contiguous(); bm = (b + gamma * b.clamp(min=0)).cuda().contiguous()
+    wt = torch.empty(Cin, Cout, 3, 3, device="cuda")
+    L.check(lib.lrp_conv3x3_flip_weights(wm.data_ptr(), Cout, Cin, wt.data_ptr(), s))
+    sbuf = torch.empty(N, Cout, H, W, device="cuda"); Rin = torch.empty(N, Cin, H, W, device="cuda")
+    L.check(lib.lrp_conv3x3_backward(xd.data_ptr(), wm.data_ptr(), wt.data_ptr(), bm.data_ptr(), Rout.cuda().data_ptr(), N, Cin,
+                                     Cout, H, W, eps, 0, sbuf.data_ptr(), Rin.data_ptr(), s))
+    assert _rel_per_sample(Rin, want) < TOL
+    # WSquare (input replaced by ones, no input factor)
+    want = lrp_ref.rule_backward(conv, "wsquare", x.double(), Rout.double(), eps)
+    w2 = (w * w).cuda().contiguous(); b2 = (b * b).cuda().contiguous()
+    L.check(lib.lrp_conv3x3_flip_weights(w2.data_ptr(), Cout, Cin, wt.data_ptr(), s))
+    L.check(lib.lrp_conv3x3_backward(None, w2.data_ptr(), wt.data_ptr(), b2.data_ptr(), Rout.cuda().data_ptr(), N, Cin, Cout, H,
+                                     W, eps, 1, sbuf.data_ptr(), Rin.data_ptr(), s))
+    assert _rel_per_sample(Rin, want) < TOL
+
+
+def test_maxpool_and_dense_blocks():
+    L = _L(); lib = L.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 5, 8, 12, generator=g); x[0, 0, :2, :4] = 1.5            # ties: first maximum wins
+    for kh, kw in ((2, 2), (2, 4)):
+        xd = x.cuda()
+        Ho, Wo = 8 // kh, 12 // kw
+        y = torch.empty(3, 5, Ho, Wo, device="cuda"); am = torch.empty(3, 5, Ho, Wo, dtype=torch.int32, device="cuda")
+        L.check(lib.lrp_maxpool_forward(xd.data_ptr(), 15, 8, 12, kh, kw, y.data_ptr(), am.data_ptr(), s))
+        want, idx = F.max_pool2d(x, (kh, kw), return_indices=True)
+        np.testing.assert_array_equal(y.cpu().numpy(), want.numpy())
+        np.testing.assert_array_equal(am.cpu().numpy(), idx.numpy().astype(np.int32))
+        Rout = torch.randn(3, 5, Ho, Wo, generator=g)
+        Rin = torch.empty(3, 5, 8, 12, device="cuda")
+        L.check(lib.lrp_maxpool_backward(Rout.cuda().data_ptr(), am.data_ptr(), 15, 8, 12, kh, kw, Rin.data_ptr(), s))
+        xi = x.clone().requires_grad_(True)
+        gr, = torch.autograd.grad(F.max_pool2d(xi, (kh, kw)), xi, Rout)
+        np.testing.assert_array_equal(Rin.cpu().numpy(), gr.numpy())
+    # dense forward + epsilon rule
+    lin = torch.nn.Linear(37, 11).double()
+    xv = torch.rand(9, 37, generator=g)
+    y = torch.empty(9, 11, device="cuda")
+    wd, bd = lin.weight.detach().float().cuda().contiguous(), lin.bias.detach().float().cuda().contiguous()
+    L.check(lib.lrp_dense_forward(xv.cuda().data_ptr(), wd.data_ptr(), bd.data_ptr(), 9, 37, 11, 1, y.data_ptr(), s))
+    np.testing.assert_allclose(y.cpu().numpy(), lin(xv.double()).clamp(min=0).detach().numpy(), rtol=1e-5, atol=1e-6)
+    Rout = torch.randn(9, 11, generator=g)
+    want = lrp_ref.rule_backward(lin, "epsilon", xv.double(), Rout.double(), 1e-7)
+    sbuf = torch.empty(9, 11, device="cuda"); Rin = torch.empty(9, 37, device="cuda")
+    L.check(lib.lrp_dense_epsilon_backward(xv.cuda().data_ptr(), wd.data_ptr(), bd.data_ptr(), Rout.cuda().data_ptr(), 9, 37, 11,
+                                           1e-7, sbuf.data_ptr(), Rin.data_ptr(), s))
+    assert _rel_per_sample(Rin, want) < TOL
+
+
+def test_get_intermediate_toy_cfg1():
+    """cfg 1: toy CNN on 64x64, LRP_NAME_MAP_TOY, split at features[13] -> maps [N,64,4,4]."""
+    from cxai.utils.constants import LRP_NAME_MAP_TOY
+    from cxai.xai.explain.rules import NameMapComposite
+    from cxai.xai.drsa.preprocessing import get_intermediate
+    net = lrp_ref.toy_model(seed=0, last=64)
+    x = lrp_ref.synth_logmel(70, 64, 64, 20261)               # 2 minibatches (64 + 6)
+    comp = NameMapComposite(LRP_NAME_MAP_TOY)
+    for cls, onehot in ((0, False), (1, True)):
+        a, R = get_intermediate(net, x, comp, net.features[13], cls, one_hot_encoded=onehot)
+        aw, Rw = lrp_ref.get_intermediate(net, x, LRP_NAME_MAP_TOY, net.features[13], cls, one_hot_encoded=onehot)
+        assert a.shape == (70, 64, 4, 4)
+        assert _rel_per_sample(a, aw) < 1e-5
+        assert _rel_per_sample(R, Rw) < TOL
+        assert float(a.min()) >= 0
+
+
+def test_compute_relevances_full_depth_and_bn_model():
+    """arch-A-style BatchNorm model (reduced resolution), production name map, relevance at the input
+    (the 'LRP relevance maps' parity surface) and maps at layers 19 / 26 / 33."""
+    from cxai.utils.constants import lrp_name_map_6s
+    from cxai.xai.explain.rules import NameMapComposite, SequentialMergeBatchNorm
+    from cxai.xai.explain.attribute import compute_relevances
+    from cxai.xai.drsa.preprocessing import get_intermediate
+    net = lrp_ref.genre_model(seed=0, last=64, input_size=(32, 64))
+    x = lrp_ref.synth_logmel(6, 32, 64, 20262)
+    nm = lrp_name_map_6s()
+    comp = NameMapComposite(nm, canonizers=[SequentialMergeBatchNorm()])
+    Rin = compute_relevances(net, x, comp, class_idx=3)
+    want = lrp_ref.lrp_pass(net, x, nm, lrp_ref.output_modifier(3))
+    assert Rin.shape == x.shape
+    assert _rel_per_sample(Rin, want["R_input"]) < TOL
+    for li in (19, 26, 33):
+        a, R = get_intermediate(net, x, comp, net.features[li], 3)
+        aw, Rw = lrp_ref.get_intermediate(net, x, nm, net.features[li], 3)
+        assert _rel_per_sample(a, aw) < 1e-5, li
+        assert _rel_per_sample(R, Rw) < TOL, li
+    # balanced batch of all classes (attribute.py:148-158)
+    net2 = lrp_ref.toy_model(seed=3, last=16)
+    from cxai.utils.constants import LRP_NAME_MAP_TOY
+    x2 = lrp_ref.synth_logmel(4, 64, 64, 9)
+    R2 = compute_relevances(net2, x2, NameMapComposite(LRP_NAME_MAP_TOY), num_classes=2)
+    w2 = lrp_ref.lrp_pass(net2, x2, LRP_NAME_MAP_TOY, lrp_ref.output_modifier(None, 2))
+    assert _rel_per_sample(R2, w2["R_input"]) < TOL
+
+
+def test_end_to_end_cfg1_pipeline():
+    """BASELINE cfg 1 end to end: toy CNN -> LRP context at features[13] (d = 64, P = 16) -> normalise ->
+    DRSA K = 4; the CUDA pipeline must follow the CPU oracle pipeline (objective 1e-4, angles 1e-3)."""
+    from cxai.utils.constants import LRP_NAME_MAP_TOY
+    from cxai.xai.explain.rules import NameMapComposite
+    from cxai.xai.drsa import preprocessing as pp
+    from cxai.xai.drsa.drsa import SubspaceOptimizer
+    net = lrp_ref.toy_model(seed=0, last=64)
+    N, K, steps = 250, 4, 40
+    x = lrp_ref.synth_logmel(N, 64, 64, 20261)
+    a, R = pp.get_intermediate(net, x, NameMapComposite(LRP_NAME_MAP_TOY), net.features[13], 0)
+    act, ctx = pp.gather_context_pairs(a, R, None, normalize=True)
+    aw, Rw = lrp_ref.get_intermediate(net, x, LRP_NAME_MAP_TOY, net.features[13], 0)
+    av = drsa_ref.vectors_from_maps_all(aw.float()); rv = drsa_ref.vectors_from_maps_all(Rw.float())
+    A = drsa_ref.normalize_vectors(av); C = drsa_ref.normalize_vectors(drsa_ref.compute_context_vectors(av, rv))
+    assert act.shape == (N * 16, 64)
+    assert _rel_per_sample(act, A) < 1e-4
+    U0 = drsa_ref.synth_U0(64, seed=5)
+    objs_ref, U_ref = drsa_ref.run_autograd(A, C, U0, K, steps)
+    opt = SubspaceOptimizer(U0, act, ctx, None, num_concepts=K)
+    opt.run(steps=steps, save=False)
+    rel = np.max(np.abs(opt.obj_history - objs_ref) / np.abs(objs_ref))
+    ang = drsa_ref.principal_angle(opt.U.cpu(), U_ref, K)
+    print(f"cfg1 e2e: objective rel err {rel:.2e}, angle {ang:.2e}")
+    assert rel < 1e-4 and ang < 1e-3
