@@ -215,7 +215,16 @@ int polar_from_Y(const PolarWs& p, int d, int m, float* U_out, void* Ut_hi, void
 }
 }  // namespace
 
-int64_t finish_workspace_bytes(int d, int m) { return polar_ws_bytes(d, m); }
+bool finish_fused_supported(int d, int m, int K);
+int64_t finish_fused_workspace_bytes(int d, int m);
+int finish_fused(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out, void* Ut_hi,
+                 void* Ut_lo, float* obj_log, int64_t log_index, int max_iters, float tol, int* status, void* workspace,
+                 int64_t workspace_bytes, const float* Y_in, cudaStream_t stream);
+
+int64_t finish_workspace_bytes(int d, int m) {
+  const int64_t a = polar_ws_bytes(d, m), b = finish_fused_workspace_bytes(d, m);
+  return a > b ? a : b;
+}
 
 int finish_step(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out,
                 void* Ut_hi, void* Ut_lo, float* obj_log, int64_t log_index, int max_iters, float tol,
@@ -234,6 +243,9 @@ int finish_step(const float* sums, int64_t M_global, const float* U, int d, int 
 
 int polar_retract(const float* Y, int d, int m, float* U_out, int max_iters, float tol, int* status,
                   void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  if (finish_fused_supported(d, m, 1))
+    return finish_fused(nullptr, 1, nullptr, d, m, 1, U_out, nullptr, nullptr, nullptr, 0, max_iters, tol, status,
+                        workspace, workspace_bytes, Y, stream);
   if (workspace_bytes < polar_ws_bytes(d, m)) return DRSA_ERR_WORKSPACE;
   PolarWs p = carve(workspace, d, m);
   DRSA_CUDA(cudaMemcpyAsync(p.Y, Y, (int64_t)d * m * 4, cudaMemcpyDeviceToDevice, stream));

@@ -1,0 +1,296 @@
+// The replicated tail of a DRSA step in ONE cooperative kernel: pooling scalars, ascent step and the
+// polar retraction (drsa.py:102, :201-221, :224-238).  Same arithmetic as retract.cu (scaled
+// Newton-Schulz, fp32) but without ~30 dependent launches: the d x m problem (<= 512 x 512) lives in L2,
+// every sweep is two tile-GEMM phases separated by grid-wide barriers, and the convergence decision is
+// taken on the device by all CTAs from the same residual, so there is no host round trip and no wasted
+// sweep.  Tiles are 32 x 32 per CTA (256 threads, 2 x 2 outputs per thread, k-chunks of 32 double
+// buffered through registers); d and m must be multiples of 32.
+#include <cooperative_groups.h>
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace drsa {
+
+namespace {
+constexpr int TS = 32;
+constexpr int LDS = 34;   // padded leading dimension (even: float2 reads stay 8-byte aligned)
+
+struct FusedParams {
+  const float* sums; double inv_M; const float* U; int d, m, K;
+  float* U_out; __half* Ut_hi; __half* Ut_lo; float* obj_log; long long log_index;
+  int max_iters; float tol2_m; int* status;
+  float* Y; float* X0; float* X1; float* G; float* rowsum; float* resid;   // resid[max_iters + 2]
+  int have_sums;   // 0: Y already holds the matrix to retract (drsa_polar_retract)
+};
+
+// C[32x32] (+)= sum_k A_k(i) B_k(j) with both operands given as "row k, column contiguous" views:
+//   MODE 0 (gram): A_k(i) = X[k*ld + i0 + i],  B_k(j) = X[k*ld + j0 + j]
+//   MODE 1 (mul) : A_k(i) = X[(i0 + i)*ldx + k], B_k(j) = T[k*ldt + j0 + j]
+template <int MODE>
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, int i0, const float* __restrict__ B,
+                                          int ldb, int j0, int Kdim, float (&acc)[2][2], float (*As)[LDS],
+                                          float (*Bs)[LDS]) {
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int lc = tid & 31, lr = tid >> 5;     // loader: column lc, rows lr + 8q
+  float ra[4], rb[4];
+  auto load = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int rr = lr + 8 * q;
+      if (MODE == 0) ra[q] = A[(int64_t)(k0 + rr) * lda + i0 + lc];          // As[k = rr][i = lc]
+      else           ra[q] = A[(int64_t)(i0 + rr) * lda + k0 + lc];          // As[k = lc][i = rr]
+      rb[q] = B[(int64_t)(k0 + rr) * ldb + j0 + lc];                          // Bs[k = rr][j = lc]
+    }
+  };
+  auto store = [&]() {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int rr = lr + 8 * q;
+      if (MODE == 0) As[rr][lc] = ra[q]; else As[lc][rr] = ra[q];
+      Bs[rr][lc] = rb[q];
+    }
+  };
+  acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = 0.f;
+  load(0);
+  for (int k0 = 0; k0 < Kdim; k0 += TS) {
+    __syncthreads();          // previous chunk fully consumed
+    store();
+    __syncthreads();
+    if (k0 + TS < Kdim) load(k0 + TS);
+#pragma unroll
+    for (int kk = 0; kk < TS; ++kk) {
+      const float2 a = *reinterpret_cast<const float2*>(&As[kk][2 * ty]);
+      const float2 b = *reinterpret_cast<const float2*>(&Bs[kk][2 * tx]);
+      acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
+      acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+    }
+  }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x < 8) t = red[threadIdx.x];
+  if (threadIdx.x < 32) t = warp_sum(t);
+  return t;   // valid in warp 0
+}
+
+__global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ __align__(16) float As[TS][LDS];
+  __shared__ __align__(16) float Bs[TS][LDS];
+  __shared__ float red[8];
+  __shared__ float coef[64];
+  __shared__ float bc[2];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int d = p.d, m = p.m;
+  const int64_t n = (int64_t)d * m;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + tid, gthreads = (int64_t)gridDim.x * blockDim.x;
+
+  // ---------------- phase 0: pooling scalars, objective log, Y = U + coef_k X_k
+  if (p.have_sums) {
+    const int K = p.K, d_k = m / K;
+    if (tid == 0) {
+      float acc = 0.f; int degenerate = 0;
+      for (int k = 0; k < K; ++k) {
+        const float q = sqrtf((float)((double)p.sums[n + k] * p.inv_M));
+        if (q == 0.f) ++degenerate;
+        acc += sqrtf(q);
+      }
+      const float root = acc / (float)K;
+      bc[0] = root;
+      if (blockIdx.x == 0) {
+        if (p.obj_log != nullptr) {
+          long long idx = p.log_index;
+          if (idx < 0) { idx = p.status[3]; p.status[3] = (int)idx + 1; }
+          p.obj_log[idx] = root * root;
+        }
+        if (p.status != nullptr) p.status[2] = degenerate;
+      }
+    }
+    __syncthreads();
+    if (p.U_out == nullptr) return;             // objective only (uniform across the grid)
+    const float root = bc[0];
+    for (int k = tid; k < K; k += blockDim.x) {
+      const float q = sqrtf((float)((double)p.sums[n + k] * p.inv_M));
+      coef[k & 63] = 0.f;
+      // K can exceed 64 only in exotic settings; recompute on the fly below in that case
+      if (K <= 64) coef[k] = (float)((double)root * p.inv_M / ((double)K * (double)q * sqrt((double)q)));
+    }
+    __syncthreads();
+    for (int64_t i = gtid; i < n; i += gthreads) {
+      const int k = (int)(i % m) / d_k;
+      float c;
+      if (K <= 64) c = coef[k];
+      else {
+        const float q = sqrtf((float)((double)p.sums[n + k] * p.inv_M));
+        c = (float)((double)root * p.inv_M / ((double)K * (double)q * sqrt((double)q)));
+      }
+      p.Y[i] = p.U[i] + c * p.sums[i];
+    }
+  }
+  for (int64_t i = gtid; i < m; i += gthreads) p.rowsum[i] = 0.f;
+  for (int64_t i = gtid; i < p.max_iters + 2; i += gthreads) p.resid[i] = 0.f;
+  grid.sync();
+
+  const int tm = m / TS, td = d / TS;
+  // ---------------- phase 1: G = Y^T Y, row sums of |G|
+  for (int t = blockIdx.x; t < tm * tm; t += gridDim.x) {
+    const int ti = t / tm, tj = t % tm;
+    float acc[2][2];
+    tile_gemm<0>(p.Y, m, ti * TS, p.Y, m, tj * TS, d, acc, As, Bs);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int gi = ti * TS + 2 * ty + a;
+      float rs = fabsf(acc[a][0]) + fabsf(acc[a][1]);
+      p.G[(int64_t)gi * m + tj * TS + 2 * tx] = acc[a][0];
+      p.G[(int64_t)gi * m + tj * TS + 2 * tx + 1] = acc[a][1];
+      // the 16 threads of a half-warp share the row gi
+      for (int o = 8; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+      if (tx == 0) atomicAdd(&p.rowsum[gi], rs);
+    }
+  }
+  grid.sync();
+  // ---------------- phase 2: c = ||G||_inf, X0 = Y / sqrt(c), G <- T_0 = 1.5 I - 0.5 G / c, resid[0]
+  {
+    float best = 0.f;
+    for (int i = tid; i < m; i += blockDim.x) best = fmaxf(best, p.rowsum[i]);
+    best = warp_max(best);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = best;
+    __syncthreads();
+    if (tid == 0) { float v = 0.f; for (int w = 0; w < 8; ++w) v = fmaxf(v, red[w]); bc[1] = v; }
+    __syncthreads();
+  }
+  const float c = bc[1];
+  const float inv_s = rsqrtf(c), inv_c = 1.f / c;
+  for (int64_t i = gtid; i < n; i += gthreads) p.X0[i] = p.Y[i] * inv_s;
+  {
+    float r = 0.f;
+    for (int64_t i = gtid; i < (int64_t)m * m; i += gthreads) {
+      const int rr = (int)(i / m), cc = (int)(i % m);
+      const float gv = p.G[i] * inv_c;
+      const float e = gv - (rr == cc ? 1.f : 0.f);
+      r = fmaf(e, e, r);
+      p.G[i] = (rr == cc ? 1.5f : 0.f) - 0.5f * gv;
+    }
+    const float tot = block_sum(r, red);
+    if (tid == 0) atomicAdd(&p.resid[0], tot);
+  }
+  grid.sync();
+
+  // ---------------- Newton-Schulz sweeps
+  int it = 0, converged = 0;
+  float* cur = p.X0;
+  float* nxt = p.X1;
+  while (true) {
+    const float res = *reinterpret_cast<volatile float*>(&p.resid[it]);
+    if (res < p.tol2_m) { converged = 1; break; }
+    if (it >= p.max_iters) break;
+    // nxt = cur * T
+    for (int t = blockIdx.x; t < td * tm; t += gridDim.x) {
+      const int tr = t / tm, tj = t % tm;
+      float acc[2][2];
+      tile_gemm<1>(cur, m, tr * TS, p.G, m, tj * TS, m, acc, As, Bs);
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int gi = tr * TS + 2 * ty + a;
+        *reinterpret_cast<float2*>(&nxt[(int64_t)gi * m + tj * TS + 2 * tx]) = make_float2(acc[a][0], acc[a][1]);
+      }
+    }
+    grid.sync();
+    // G = nxt^T nxt -> residual, T
+    float r = 0.f;
+    for (int t = blockIdx.x; t < tm * tm; t += gridDim.x) {
+      const int ti = t / tm, tj = t % tm;
+      float acc[2][2];
+      tile_gemm<0>(nxt, m, ti * TS, nxt, m, tj * TS, d, acc, As, Bs);
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int gi = ti * TS + 2 * ty + a;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int gj = tj * TS + 2 * tx + b;
+          const float e = acc[a][b] - (gi == gj ? 1.f : 0.f);
+          r = fmaf(e, e, r);
+          acc[a][b] = (gi == gj ? 1.5f : 0.f) - 0.5f * acc[a][b];
+        }
+        *reinterpret_cast<float2*>(&p.G[(int64_t)gi * m + tj * TS + 2 * tx]) = make_float2(acc[a][0], acc[a][1]);
+      }
+    }
+    {
+      const float tot = block_sum(r, red);
+      if (tid == 0) atomicAdd(&p.resid[it + 1], tot);
+    }
+    grid.sync();
+    float* tmp = cur; cur = nxt; nxt = tmp;
+    ++it;
+  }
+  // ---------------- output
+  if (blockIdx.x == 0 && tid == 0 && p.status != nullptr) { p.status[0] = it; p.status[1] = converged ? 0 : 1; }
+  for (int64_t i = gtid; i < n; i += gthreads) {
+    const float v = cur[i];
+    p.U_out[i] = v;
+    if (p.Ut_hi != nullptr) {
+      const int r = (int)(i / m), cc = (int)(i % m);
+      const __half hi = __float2half_rn(v);
+      p.Ut_hi[(int64_t)cc * d + r] = hi;
+      p.Ut_lo[(int64_t)cc * d + r] = __float2half_rn(v - __half2float(hi));
+    }
+  }
+}
+
+int64_t fused_ws_bytes(int d, int m, int max_iters) {
+  return align_up((int64_t)d * m * 4, 256) * 3 + align_up((int64_t)m * m * 4, 256) + align_up((int64_t)m * 4, 256) +
+         align_up((int64_t)(max_iters + 2) * 4, 256);
+}
+}  // namespace
+
+bool finish_fused_supported(int d, int m, int K) { return d % TS == 0 && m % TS == 0 && d >= TS && m >= TS && K >= 1; }
+
+int64_t finish_fused_workspace_bytes(int d, int m) { return fused_ws_bytes(d, m, 64); }
+
+// have_sums = 1: full finish step; have_sums = 0: retract the matrix already stored in Y_in (copied by the caller).
+int finish_fused(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out, void* Ut_hi,
+                 void* Ut_lo, float* obj_log, int64_t log_index, int max_iters, float tol, int* status, void* workspace,
+                 int64_t workspace_bytes, const float* Y_in, cudaStream_t stream) {
+  if (max_iters > 64) max_iters = 64;
+  if (workspace_bytes < fused_ws_bytes(d, m, 64)) return DRSA_ERR_WORKSPACE;
+  char* w = static_cast<char*>(workspace);
+  FusedParams p{};
+  const int64_t dm = align_up((int64_t)d * m * 4, 256);
+  p.Y = reinterpret_cast<float*>(w); w += dm;
+  p.X0 = reinterpret_cast<float*>(w); w += dm;
+  p.X1 = reinterpret_cast<float*>(w); w += dm;
+  p.G = reinterpret_cast<float*>(w); w += align_up((int64_t)m * m * 4, 256);
+  p.rowsum = reinterpret_cast<float*>(w); w += align_up((int64_t)m * 4, 256);
+  p.resid = reinterpret_cast<float*>(w);
+  p.sums = sums; p.inv_M = M_global > 0 ? 1.0 / (double)M_global : 0.0; p.U = U; p.d = d; p.m = m; p.K = K;
+  p.U_out = U_out; p.Ut_hi = static_cast<__half*>(Ut_hi); p.Ut_lo = static_cast<__half*>(Ut_lo);
+  p.obj_log = obj_log; p.log_index = log_index; p.max_iters = max_iters; p.tol2_m = tol * tol * (float)m;
+  p.status = status; p.have_sums = (Y_in == nullptr) ? 1 : 0;
+  if (Y_in != nullptr) DRSA_CUDA(cudaMemcpyAsync(p.Y, Y_in, (int64_t)d * m * 4, cudaMemcpyDeviceToDevice, stream));
+  int tiles = (d / TS) * (m / TS);
+  const int t2 = (m / TS) * (m / TS);
+  if (t2 > tiles) tiles = t2;
+  int grid = tiles;
+  static int max_coresident = 0;
+  if (max_coresident == 0) {
+    int per_sm = 0;
+    DRSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, finish_fused_kernel, 256, 0));
+    max_coresident = per_sm * sm_count();
+    if (max_coresident < 1) return DRSA_ERR_CUDA;
+  }
+  if (grid > max_coresident) grid = max_coresident;
+  if (U_out == nullptr) grid = 1;
+  void* args[] = {&p};
+  DRSA_CUDA(cudaLaunchCooperativeKernel((const void*)finish_fused_kernel, dim3(grid), dim3(256), args, 0, stream));
+  return DRSA_OK;
+}
+
+}  // namespace drsa

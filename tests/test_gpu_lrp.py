@@ -52,14 +52,15 @@ def test_conv3x3_forward_and_rule_backward(N, Cin, Cout, H, W):
     wt = torch.empty(Cin, Cout, 3, 3, device="cuda")
     L.check(lib.lrp_conv3x3_flip_weights(wm.data_ptr(), Cout, Cin, wt.data_ptr(), s))
     sbuf = torch.empty(N, Cout, H, W, device="cuda"); Rin = torch.empty(N, Cin, H, W, device="cuda")
-    L.check(lib.lrp_conv3x3_backward(xd.data_ptr(), wm.data_ptr(), wt.data_ptr(), bm.data_ptr(), Rout.cuda().data_ptr(), N, Cin,
+    Rd = Rout.cuda()
+    L.check(lib.lrp_conv3x3_backward(xd.data_ptr(), wm.data_ptr(), wt.data_ptr(), bm.data_ptr(), Rd.data_ptr(), N, Cin,
                                      Cout, H, W, eps, 0, sbuf.data_ptr(), Rin.data_ptr(), s))
     assert _rel_per_sample(Rin, want) < TOL
     # WSquare (input replaced by ones, no input factor)
     want = lrp_ref.rule_backward(conv, "wsquare", x.double(), Rout.double(), eps)
     w2 = (w * w).cuda().contiguous(); b2 = (b * b).cuda().contiguous()
     L.check(lib.lrp_conv3x3_flip_weights(w2.data_ptr(), Cout, Cin, wt.data_ptr(), s))
-    L.check(lib.lrp_conv3x3_backward(None, w2.data_ptr(), wt.data_ptr(), b2.data_ptr(), Rout.cuda().data_ptr(), N, Cin, Cout, H,
+    L.check(lib.lrp_conv3x3_backward(None, w2.data_ptr(), wt.data_ptr(), b2.data_ptr(), Rd.data_ptr(), N, Cin, Cout, H,
                                      W, eps, 1, sbuf.data_ptr(), Rin.data_ptr(), s))
     assert _rel_per_sample(Rin, want) < TOL
 
@@ -79,7 +80,8 @@ def test_maxpool_and_dense_blocks():
         np.testing.assert_array_equal(am.cpu().numpy(), idx.numpy().astype(np.int32))
         Rout = torch.randn(3, 5, Ho, Wo, generator=g)
         Rin = torch.empty(3, 5, 8, 12, device="cuda")
-        L.check(lib.lrp_maxpool_backward(Rout.cuda().data_ptr(), am.data_ptr(), 15, 8, 12, kh, kw, Rin.data_ptr(), s))
+        Rd = Rout.cuda()
+        L.check(lib.lrp_maxpool_backward(Rd.data_ptr(), am.data_ptr(), 15, 8, 12, kh, kw, Rin.data_ptr(), s))
         xi = x.clone().requires_grad_(True)
         gr, = torch.autograd.grad(F.max_pool2d(xi, (kh, kw)), xi, Rout)
         np.testing.assert_array_equal(Rin.cpu().numpy(), gr.numpy())
@@ -88,12 +90,14 @@ def test_maxpool_and_dense_blocks():
     xv = torch.rand(9, 37, generator=g)
     y = torch.empty(9, 11, device="cuda")
     wd, bd = lin.weight.detach().float().cuda().contiguous(), lin.bias.detach().float().cuda().contiguous()
-    L.check(lib.lrp_dense_forward(xv.cuda().data_ptr(), wd.data_ptr(), bd.data_ptr(), 9, 37, 11, 1, y.data_ptr(), s))
+    xvd = xv.cuda()
+    L.check(lib.lrp_dense_forward(xvd.data_ptr(), wd.data_ptr(), bd.data_ptr(), 9, 37, 11, 1, y.data_ptr(), s))
     np.testing.assert_allclose(y.cpu().numpy(), lin(xv.double()).clamp(min=0).detach().numpy(), rtol=1e-5, atol=1e-6)
     Rout = torch.randn(9, 11, generator=g)
     want = lrp_ref.rule_backward(lin, "epsilon", xv.double(), Rout.double(), 1e-7)
     sbuf = torch.empty(9, 11, device="cuda"); Rin = torch.empty(9, 37, device="cuda")
-    L.check(lib.lrp_dense_epsilon_backward(xv.cuda().data_ptr(), wd.data_ptr(), bd.data_ptr(), Rout.cuda().data_ptr(), 9, 37, 11,
+    Rd = Rout.cuda()
+    L.check(lib.lrp_dense_epsilon_backward(xvd.data_ptr(), wd.data_ptr(), bd.data_ptr(), Rd.data_ptr(), 9, 37, 11,
                                            1e-7, sbuf.data_ptr(), Rin.data_ptr(), s))
     assert _rel_per_sample(Rin, want) < TOL
 
