@@ -256,7 +256,7 @@ def lrp_throughput(args, dev, rank, world, barrier):
         a, R = pp.get_intermediate(net, xb, comp, layer, 0)
         return pp.gather_context_pairs(a, R, None, normalize=True)
 
-    once(x[:64])
+    once(x)                                     # warm-up with the full batch (allocator + plan cache)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -21,7 +21,7 @@
 // Operand staging: TMA (cp.async.bulk.tensor, 128-byte swizzle) into an mbarrier ring;
 // U^T of the CTA's column group stays resident in shared memory.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) + TMEM owner,
-// warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
+// warps 2..9 = epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter split the 4 row chunks).
 #include <cuda.h>
 #include <vector>
 #include <cmath>
@@ -71,7 +71,7 @@ using namespace tc;
 constexpr int kRows = 128;             // rows of A / C per tile (MMA N of GEMM1, K of GEMM2)
 constexpr int kNG = 128;               // projected columns per CTA (MMA M)
 constexpr int kPanelBytes = 128 * 128; // one [128 x 64] fp16 box, 128-byte rows
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;          // TMA warp, MMA warp, 8 epilogue warps
 constexpr int kRedBytes = 4 * kRows * 4;
 constexpr int kBarBytes = 256;
 
@@ -84,6 +84,13 @@ struct Cfg {
   static constexpr int kDataBytes = kUBytes + kStages * kStageBytes;
   static constexpr int kSmemBytes = kDataBytes + kRedBytes + kBarBytes;
 };
+
+// tcgen05 shared-memory descriptors split into a constant high word and a cheap low word
+// (see tc::make_smem_desc_sw128): hi = SBO 1024 B | version 1 | SWIZZLE_128B.
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t kdesc_lo(uint32_t smem_addr) { return (smem_addr >> 4) | (1u << 16); }           // LBO 16 B
+__device__ __forceinline__ uint32_t mndesc_lo(uint32_t smem_addr) { return (smem_addr >> 4) | ((uint32_t)(kPanelBytes >> 4) << 16); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
 
 __device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
   uint32_t r;
@@ -126,7 +133,7 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(u_full, 1); mbar_init(h_full, 1); mbar_init(p_full, 128); mbar_init(x_full, 1);
+    mbar_init(u_full, 1); mbar_init(h_full, 1); mbar_init(p_full, 256); mbar_init(x_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -172,15 +179,16 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int p = 0; p < C::kPanels; ++p) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t uh = smem_u32(sU_hi + p * kPanelBytes), ul = smem_u32(sU_lo + p * kPanelBytes);
-          const uint32_t bA = smem_u32(sStage + stage * C::kStageBytes), bC = bA + kPanelBytes;
+          // descriptors: the high word is constant, the low word is (address >> 4) | LBO field; advancing
+          // along K inside the 128-byte swizzle atom adds 32 B (>> 4 = 2) to the low word
+          const uint32_t uh = kdesc_lo(smem_u32(sU_hi + p * kPanelBytes)), ul = kdesc_lo(smem_u32(sU_lo + p * kPanelBytes));
+          const uint32_t bA = smem_u32(sStage + stage * C::kStageBytes);
+          const uint32_t dA = kdesc_lo(bA), dC = kdesc_lo(bA + kPanelBytes);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint32_t acc = (p | kk) ? 1u : 0u;
-            const uint64_t d_uh = make_smem_desc_sw128(uh + kk * 32, 16, 1024);
-            const uint64_t d_ul = make_smem_desc_sw128(ul + kk * 32, 16, 1024);
-            const uint64_t d_a = make_smem_desc_sw128(bA + kk * 32, 16, 1024);
-            const uint64_t d_c = make_smem_desc_sw128(bC + kk * 32, 16, 1024);
+            const uint64_t d_uh = desc64(uh + 2 * kk), d_ul = desc64(ul + 2 * kk);
+            const uint64_t d_a = desc64(dA + 2 * kk), d_c = desc64(dC + 2 * kk);
             umma_ss_f16(tHA, d_uh, d_a, idesc1, acc);
             umma_ss_f16(tHA, d_ul, d_a, idesc1, 1u);
             umma_ss_f16(tHC, d_uh, d_c, idesc1, acc);
@@ -197,15 +205,15 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int p = 0; p < C::kPanels; ++p) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t bA = smem_u32(sStage + stage * C::kStageBytes), bC = bA + kPanelBytes;
+          const uint32_t bA = smem_u32(sStage + stage * C::kStageBytes);
+          const uint32_t dA = mndesc_lo(bA), dC = mndesc_lo(bA + kPanelBytes);
+          const uint32_t first_acc = first ? 0u : 1u;
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t acc = (!first || ks > 0) ? 1u : 0u;
-            const uint64_t d_a = make_smem_desc_sw128(bA + ks * 2048, kPanelBytes, 1024);
-            const uint64_t d_c = make_smem_desc_sw128(bC + ks * 2048, kPanelBytes, 1024);
+            // MN-major: 16 rows of K = two 8-row swizzle atoms = 2048 B (>> 4 = 128)
             const uint32_t off = 32 * (ks >> 1) + 8 * (ks & 1);
-            umma_ts_f16(tX + 64 * p, tHA + off, d_a, idesc2, acc);
-            umma_ts_f16(tX + 64 * p, tHC + off, d_c, idesc2, 1u);
+            umma_ts_f16(tX + 64 * p, tHA + off, desc64(dA + 128 * ks), idesc2, ks > 0 ? 1u : first_acc);
+            umma_ts_f16(tX + 64 * p, tHC + off, desc64(dC + 128 * ks), idesc2, 1u);
           }
           umma_commit(&empty[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -218,18 +226,19 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     // ======================= epilogue warps =======================
     const int q = warp & 3;                     // TMEM lane quarter this warp may touch
+    const int half = (warp - 2) >> 2;           // two warps per quarter: each takes two of the four 32-row chunks
     const int j = 32 * q + lane;                // projected column within the group
     const int wpc = d_k >> 5;                   // warps per concept (d_k in {32, 64, 128})
     const int q0 = (q / wpc) * wpc;
     const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
-    const bool owner = (j % d_k) == 0;
+    const bool owner = (j % d_k) == 0;           // one thread per (concept, half) accumulates sum g^2
     float ssq = 0.f;
     uint32_t tile_parity = 0;
     for (int t = rb; t < num_tiles; t += nRB) {
       mbar_wait(h_full, tile_parity);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 2 * half; c < 2 * half + 2; ++c) {
         uint32_t ha[32], hc[32];
         tmem_ld32(lane_base + 256 + 32 * c, ha);
         tmem_ld32(lane_base + 384 + 32 * c, hc);
@@ -249,14 +258,17 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         red[q * kRows + 32 * c + lane] = pr[0];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");   // the 4 warps working on this chunk
         uint32_t pk[16], qk[16];
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
           float4 s4 = *reinterpret_cast<const float4*>(&red[q0 * kRows + 32 * c + 4 * i4]);
-          for (int w = 1; w < wpc; ++w) {
-            const float4 o = *reinterpret_cast<const float4*>(&red[(q0 + w) * kRows + 32 * c + 4 * i4]);
-            s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w;
+#pragma unroll
+          for (int w = 1; w < 4; ++w) {
+            if (w < wpc) {
+              const float4 o = *reinterpret_cast<const float4*>(&red[(q0 + w) * kRows + 32 * c + 4 * i4]);
+              s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w;
+            }
           }
           // s is in packed scale (sA*sC*s_true): sums of squares are taken in true scale, the fp16
           // operands P, Q of GEMM2 in packed scale times pq_scale (overflow-safe by construction)
@@ -285,7 +297,7 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     float* dst = part + ((int64_t)blockIdx.x * kNG + j) * D;
 #pragma unroll 1
-    for (int cc = 0; cc < D / 32; ++cc) {
+    for (int cc = half; cc < D / 32; cc += 2) {
       uint32_t v[32];
       tmem_ld32(lane_base + 32 * cc, v);
       tmem_ld_wait();
@@ -295,7 +307,7 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
                         __uint_as_float(v[4 * i + 3]));
     }
-    if (owner) ss_part[(int64_t)rb * (G * (kNG / d_k)) + g * (kNG / d_k) + j / d_k] = ssq;
+    if (owner) atomicAdd(&ss_part[(int64_t)rb * (G * (kNG / d_k)) + g * (kNG / d_k) + j / d_k], ssq);   // 2 adds: order-independent
     tc_fence_before();
   }
   __syncthreads();
@@ -427,6 +439,7 @@ int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_
   const float inv_scale = 1.0f / (scaleA * scaleC);
   const int d_k = m / K;
   const int grid = p.nRB * p.G;
+  DRSA_CUDA(cudaMemsetAsync(ss_part, 0, (size_t)p.nRB * K * 4, stream));
   if (d == 256) {
     static bool attr_set = false;
     if (!attr_set) {

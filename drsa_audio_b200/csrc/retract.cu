@@ -229,6 +229,9 @@ int64_t finish_workspace_bytes(int d, int m) {
 int finish_step(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out,
                 void* Ut_hi, void* Ut_lo, float* obj_log, int64_t log_index, int max_iters, float tol,
                 int* status, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  if (finish_fused_supported(d, m, K))       // one cooperative kernel instead of ~30 dependent launches
+    return finish_fused(sums, M_global, U, d, m, K, U_out, Ut_hi, Ut_lo, obj_log, log_index, max_iters, tol, status,
+                        workspace, workspace_bytes, nullptr, stream);
   if (workspace_bytes < polar_ws_bytes(d, m)) return DRSA_ERR_WORKSPACE;
   PolarWs p = carve(workspace, d, m);
   const int64_t n = (int64_t)d * m;

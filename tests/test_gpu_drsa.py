@@ -96,7 +96,7 @@ def test_row_sums_tensor_core_match_oracle(L, M, d, m, K):
     # (1) kernel correctness: oracle on the SAME fp16-quantised rows (only P/Q rounding and summation order differ)
     Xq, ssq = drsa_ref.step_sums(A.half().double(), C.half().double(), U.double(), K)
     relq = float(torch.linalg.norm(X - Xq) / torch.linalg.norm(Xq))
-    assert relq < (4e-4 if M < 4096 else 5e-5), relq      # fp16 rounding of P/Q: 2^-12 per element, averaged over rows
+    assert relq < (4e-4 if M < 4096 else 1.5e-4), relq      # fp16 rounding of P/Q: 2^-12 per element, averaged over rows
     np.testing.assert_allclose(ss.numpy(), ssq.numpy(), rtol=2e-5)
     # (2) arithmetic mode vs the exact oracle: fp16 storage costs 2^-12 per element, averaged over rows
     Xr, ssr = drsa_ref.step_sums(A.double(), C.double(), U.double(), K)
