@@ -68,6 +68,7 @@ SIGNATURES = {
     "lrp_dense_epsilon_backward": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp]),
     "lrp_relu_mask": (_i32, [_vp, _vp, _i64, _vp]),
     "drsa_selftest_umma": (_i32, [_i32, _vp]),
+    "drsa_debug_set_tc_profile": (_i32, [_vp]),
 }
 
 _lock = threading.Lock()

@@ -65,6 +65,7 @@ int polar_retract(const float* Y, int d, int m, float* U_out, int max_iters, flo
                   int64_t workspace_bytes, cudaStream_t stream);
 int split_u(const float* U, int d, int m, void* Ut_hi, void* Ut_lo, cudaStream_t stream);
 int selftest_umma(int variant, float* max_err_host);
+void set_tc_profile(long long* p);
 int64_t subspace_relevances_workspace_bytes(int64_t B, int64_t P, int d, int m);
 int subspace_relevances(const float* act, const float* ctx, const float* U, int64_t B, int64_t P, int d, int m, int K,
                         float* out, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
@@ -296,6 +297,8 @@ int lrp_relu_mask(const float* a, float* R, int64_t count, void* stream) {
   DRSA_TRY(require_sm100());
   return relu_mask(a, R, count, static_cast<cudaStream_t>(stream));
 }
+
+int drsa_debug_set_tc_profile(void* device_buf6) { set_tc_profile(static_cast<long long*>(device_buf6)); return DRSA_OK; }
 
 int drsa_selftest_umma(int variant, float* max_err_host) { return selftest_umma(variant, max_err_host); }
 

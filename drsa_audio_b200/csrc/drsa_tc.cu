@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC,
                     const __grid_constant__ CUtensorMap tmUh, const __grid_constant__ CUtensorMap tmUl,
                     int num_tiles, int G, int nRB, int d_k, float inv_scale, float pq_scale, float* __restrict__ part,
-                    float* __restrict__ ss_part, int* __restrict__ err_flag) {
+                    float* __restrict__ ss_part, int* __restrict__ err_flag, long long* __restrict__ prof) {
   using C = Cfg<D>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sU_hi = smem;
@@ -174,7 +174,9 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(u_full, 0);
       tc_fence_after();
       int stage = 0; uint32_t phase = 0, tile_parity = 0; bool first = true;
+      long long pa = 0, pb = 0, pc = 0, t0 = 0, t1 = 0, t2 = 0;
       for (int t = rb; t < num_tiles; t += nRB) {
+        if (prof) t0 = clock64();
         // ---- GEMM1: HA^T, HC^T [128 cols of U x 128 rows], K = D
         for (int p = 0; p < C::kPanels; ++p) {
           mbar_wait(&full[stage], phase);
@@ -198,9 +200,11 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(h_full);
+        if (prof) t1 = clock64();
         // ---- wait for P^T / Q^T from the epilogue warps
         mbar_wait(p_full, tile_parity);
         tc_fence_after();
+        if (prof) t2 = clock64();
         // ---- GEMM2: X^T[:, 64p..64p+63] += P^T tile_A + Q^T tile_C, K = 128 rows
         for (int p = 0; p < C::kPanels; ++p) {
           mbar_wait(&full[stage], phase);
@@ -220,8 +224,10 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         first = false;
         tile_parity ^= 1;
+        if (prof) { const long long t3 = clock64(); pa += t1 - t0; pb += t2 - t1; pc += t3 - t2; }
       }
       umma_commit(x_full);
+      if (prof && blockIdx.x == 0) { prof[0] = pa; prof[1] = pb; prof[2] = pc; }
     }
   } else {
     // ======================= epilogue warps =======================
@@ -234,9 +240,12 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool owner = (j % d_k) == 0;           // one thread per (concept, half) accumulates sum g^2
     float ssq = 0.f;
     uint32_t tile_parity = 0;
+    long long ea = 0, eb = 0, e0 = 0, e1 = 0;
     for (int t = rb; t < num_tiles; t += nRB) {
+      if (prof) e0 = clock64();
       mbar_wait(h_full, tile_parity);
       tc_fence_after();
+      if (prof) e1 = clock64();
 #pragma unroll 1
       for (int c = 2 * half; c < 2 * half + 2; ++c) {
         uint32_t ha[32], hc[32];
@@ -291,7 +300,9 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       mbar_arrive(p_full);
       tile_parity ^= 1;
+      if (prof) { ea += e1 - e0; eb += clock64() - e1; }
     }
+    if (prof && blockIdx.x == 0 && warp == 2 && lane == 0) { prof[3] = ea; prof[4] = eb; }
     // ---- final: X^T of this CTA -> partial buffer [cta][j][D]
     mbar_wait(x_full, 0);
     tc_fence_after();
@@ -392,6 +403,8 @@ __global__ void __launch_bounds__(256) rownorm_max_kernel(const float* __restric
   if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(sqrtf(best)));
 }
 
+long long* g_tc_prof = nullptr;   // debug: per-phase cycle counters of CTA 0 (drsa_debug_set_tc_profile)
+
 struct TcPlan { int G, nRB, num_tiles; int64_t part_bytes, ss_bytes; };
 TcPlan plan_for(int64_t M, int d, int m, int K) {
   TcPlan p;
@@ -448,7 +461,7 @@ int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_
       attr_set = true;
     }
     drsa_tc_step_kernel<256><<<grid, kThreads, Cfg<256>::kSmemBytes, stream>>>(
-        tmA, tmC, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale, pq_scale, part, ss_part, err);
+        tmA, tmC, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale, pq_scale, part, ss_part, err, g_tc_prof);
   } else {
     static bool attr_set = false;
     if (!attr_set) {
@@ -457,7 +470,7 @@ int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_
       attr_set = true;
     }
     drsa_tc_step_kernel<128><<<grid, kThreads, Cfg<128>::kSmemBytes, stream>>>(
-        tmA, tmC, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale, pq_scale, part, ss_part, err);
+        tmA, tmC, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale, pq_scale, part, ss_part, err, g_tc_prof);
   }
   DRSA_LAUNCH_CHECK();
   dim3 rgrid(m / 32, d / 32);
@@ -493,6 +506,8 @@ int absmax(const float* in, int64_t count, float* out, cudaStream_t stream) {
   DRSA_LAUNCH_CHECK();
   return DRSA_OK;
 }
+
+void set_tc_profile(long long* p) { g_tc_prof = p; }
 
 int rownorm_max(const float* in, int64_t rows, int d, float* out, cudaStream_t stream) {
   DRSA_CUDA(cudaMemsetAsync(out, 0, sizeof(float), stream));

@@ -221,6 +221,11 @@ int lrp_relu_mask(const float* a, float* R, int64_t count, void* stream);
  * ---------------------------------------------------------------------------------- */
 int drsa_selftest_umma(int variant, float* max_err_host);
 
+/* Diagnostics: when set to a device buffer of 6 int64, CTA 0 of the tensor-core row pass stores the SM
+ * cycles its MMA thread spent issuing GEMM1 [0], waiting for the epilogue [1], issuing GEMM2 [2] and its
+ * first epilogue warp spent waiting for GEMM1 [3] and working [4].  NULL switches it off (default). */
+int drsa_debug_set_tc_profile(void* device_buf6);
+
 #ifdef __cplusplus
 }
 #endif

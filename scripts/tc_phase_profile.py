@@ -1,0 +1,23 @@
+"""Per-phase cycle counters of the tensor-core row pass (CTA 0), cfg2 shape."""
+import sys, os, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from drsa_audio_b200 import _lib as L
+from cxai.xai.drsa.drsa import SubspaceOptimizer
+from bench import synth_rows_cuda
+M, d, K = 640000, 256, 4
+dev = torch.device("cuda")
+A, C = synth_rows_cuda(M, d, 1, dev)
+U0 = torch.linalg.qr(torch.randn(d, d))[0]
+opt = SubspaceOptimizer(U0, A, C, None, num_concepts=K, precision="tc", use_cuda_graph=False)
+opt._rows.split_u(opt.U)
+for _ in range(3): opt._rows.step(opt.U)
+buf = torch.zeros(6, dtype=torch.int64, device=dev)
+L.lib().drsa_debug_set_tc_profile(buf.data_ptr())
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); opt._rows.step(opt.U); e1.record(); torch.cuda.synchronize()
+L.lib().drsa_debug_set_tc_profile(None)
+tiles = -(-M // 128); nrb = 148 // 2; per = -(-tiles // nrb)
+v = buf.cpu().tolist()
+print(f"row pass {e0.elapsed_time(e1):.3f} ms, tiles per CTA ~{per}")
+for name, x in zip(["mma: GEMM1 issue", "mma: wait epilogue (incl. GEMM1 drain)", "mma: GEMM2 issue", "epi: wait GEMM1", "epi: work"], v):
+    print(f"  {name:42s} {x:10d} cycles total, {x/per:9.0f} per tile")
