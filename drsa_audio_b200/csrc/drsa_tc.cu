@@ -89,23 +89,19 @@ struct Cfg {
 // (see tc::make_smem_desc_sw128): hi = SBO 1024 B | version 1 | SWIZZLE_128B.
 constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t kdesc_lo(uint32_t smem_addr) { return (smem_addr >> 4) | (1u << 16); }           // LBO 16 B
-__device__ __forceinline__ uint32_t mndesc_lo(uint32_t smem_addr) { return (smem_addr >> 4) | ((uint32_t)(kPanelBytes >> 4) << 16); }
+__device__ __forceinline__ uint32_t mndesc_lo(uint32_t smem_addr) { return (smem_addr >> 4) | ((4096u >> 4) << 16); }            // LBO 4 KB: next 64-channel panel
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
 
 __device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
   uint32_t r;
-  asm("{\n\t.reg .b16 l, h;\n\t"
-      "cvt.rn.satfinite.f16.f32 l, %1;\n\t"
-      "cvt.rn.satfinite.f16.f32 h, %2;\n\t"
-      "mov.b32 %0, {l, h};\n\t}"
-      : "=r"(r)
-      : "f"(lo), "f"(hi));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // d = {hi : upper, lo : lower}
   return r;
 }
 
 template <int D>
 __global__ void __launch_bounds__(kThreads, 1)
 drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC,
+                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmC2,
                     const __grid_constant__ CUtensorMap tmUh, const __grid_constant__ CUtensorMap tmUl,
                     int num_tiles, int G, int nRB, int d_k, float inv_scale, float pq_scale, float* __restrict__ part,
                     float* __restrict__ ss_part, int* __restrict__ err_flag, long long* __restrict__ prof) {
@@ -151,17 +147,28 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_load_2d(sU_hi + p * kPanelBytes, &tmUh, u_full, 64 * p, g * kNG);
         tma_load_2d(sU_lo + p * kPanelBytes, &tmUl, u_full, 64 * p, g * kNG);
       }
+      tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmC2);
       int stage = 0; uint32_t phase = 0;
       for (int t = rb; t < num_tiles; t += nRB) {
-        for (int pass = 0; pass < 2; ++pass) {          // the row tile is streamed once per GEMM
+        // pass 1 (GEMM1): channel panels [128 rows x 64 ch], K-major operand
+        for (int p = 0; p < C::kPanels; ++p) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], C::kStageBytes);
+          uint8_t* dst = sStage + stage * C::kStageBytes;
+          tma_load_2d(dst, &tmA, &full[stage], 64 * p, t * kRows);
+          tma_load_2d(dst + kPanelBytes, &tmC, &full[stage], 64 * p, t * kRows);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        // pass 2 (GEMM2): row chunks [32 rows x D ch] as D/64 panels of 4 KB, MN-major operand with N = D
+        for (int rc = 0; rc < 4; ++rc) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], 2 * C::kPanels * 4096);
+          uint8_t* dst = sStage + stage * C::kStageBytes;
           for (int p = 0; p < C::kPanels; ++p) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], C::kStageBytes);
-            uint8_t* dst = sStage + stage * C::kStageBytes;
-            tma_load_2d(dst, &tmA, &full[stage], 64 * p, t * kRows);
-            tma_load_2d(dst + kPanelBytes, &tmC, &full[stage], 64 * p, t * kRows);
-            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            tma_load_2d(dst + p * 4096, &tmA2, &full[stage], 64 * p, t * kRows + 32 * rc);
+            tma_load_2d(dst + kPanelBytes + p * 4096, &tmC2, &full[stage], 64 * p, t * kRows + 32 * rc);
           }
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -169,7 +176,7 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ======================= MMA issuer =======================
     if (lane == 0) {
       constexpr uint32_t idesc1 = make_idesc_f16(kNG, kRows, 0, 0);   // U^T (K-major) x tile (K-major)
-      constexpr uint32_t idesc2 = make_idesc_f16(kNG, 64, 0, 1);      // P^T (TMEM)   x tile (MN-major)
+      constexpr uint32_t idesc2 = make_idesc_f16(kNG, D, 0, 1);       // P^T (TMEM)   x row chunk (MN-major, N = D)
       const uint32_t tX = tmem_base, tHA = tmem_base + 256, tHC = tmem_base + 384;
       mbar_wait(u_full, 0);
       tc_fence_after();
@@ -205,19 +212,19 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(p_full, tile_parity);
         tc_fence_after();
         if (prof) t2 = clock64();
-        // ---- GEMM2: X^T[:, 64p..64p+63] += P^T tile_A + Q^T tile_C, K = 128 rows
-        for (int p = 0; p < C::kPanels; ++p) {
+        // ---- GEMM2: X^T[:, 0..D) += P^T rows_A + Q^T rows_C, K = 128 rows in 4 chunks of 32.  One MMA covers all D
+        //      channels (N = D) so the TMEM-resident operand P^T is read once per k-step, not once per panel.
+        for (int rc = 0; rc < 4; ++rc) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t bA = smem_u32(sStage + stage * C::kStageBytes);
           const uint32_t dA = mndesc_lo(bA), dC = mndesc_lo(bA + kPanelBytes);
-          const uint32_t first_acc = first ? 0u : 1u;
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            // MN-major: 16 rows of K = two 8-row swizzle atoms = 2048 B (>> 4 = 128)
-            const uint32_t off = 32 * (ks >> 1) + 8 * (ks & 1);
-            umma_ts_f16(tX + 64 * p, tHA + off, desc64(dA + 128 * ks), idesc2, ks > 0 ? 1u : first_acc);
-            umma_ts_f16(tX + 64 * p, tHC + off, desc64(dC + 128 * ks), idesc2, 1u);
+          for (int h = 0; h < 2; ++h) {
+            // 16 rows of K = two 8-row swizzle atoms = 2048 B (>> 4 = 128); P^T k-step = 8 TMEM columns
+            const uint32_t off = 32 * rc + 8 * h;
+            umma_ts_f16(tX, tHA + off, desc64(dA + 128 * h), idesc2, (first && rc == 0 && h == 0) ? 0u : 1u);
+            umma_ts_f16(tX, tHC + off, desc64(dC + 128 * h), idesc2, 1u);
           }
           umma_commit(&empty[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -328,33 +335,35 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-// sums[i*m + col] = inv_scale * sum_rb part[(rb*G + col/128)*128 + col%128][i] ; sums[d*m + k] = sum_rb ss_part
-__global__ void __launch_bounds__(256) tc_reduce_kernel(const float* __restrict__ part, const float* __restrict__ ss_part,
-                                                        int nRB, int G, int d, int m, int K, float x_scale,
-                                                        float* __restrict__ sums) {
+// sums[i*m + col] = x_scale * sum_rb part[(rb*G + col/128)*128 + col%128][i] ; sums[d*m + k] = sum_rb ss_part.
+// One thread per output element (32 x 32 tile per CTA), the row-block loop unrolled so that many independent
+// L2 reads are in flight; fixed summation order (deterministic).
+__global__ void __launch_bounds__(1024) tc_reduce_kernel(const float* __restrict__ part, const float* __restrict__ ss_part,
+                                                         int nRB, int G, int d, int m, int K, float x_scale,
+                                                         float* __restrict__ sums) {
   __shared__ float tile[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 32
   const int i0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int rb = 0; rb < nRB; ++rb) {
+  const int col = c0 + ty;
+  const int gg = col >> 7, jj = col & 127;
+  const float* src = part + ((int64_t)gg * 128 + jj) * d + i0 + tx;
+  const int64_t stride = (int64_t)G * 128 * d;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int rb = 0;
+  for (; rb + 8 <= nRB; rb += 8) {
+    float v[8];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int col = c0 + ty + 8 * r;
-      const int gg = col >> 7, jj = col & 127;
-      acc[r] += part[((int64_t)(rb * G + gg) * 128 + jj) * d + i0 + tx];
-    }
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (rb + u) * stride);
+    a0 += v[0]; a1 += v[1]; a2 += v[2]; a3 += v[3];
+    a0 += v[4]; a1 += v[5]; a2 += v[6]; a3 += v[7];
   }
-#pragma unroll
-  for (int r = 0; r < 4; ++r) tile[ty + 8 * r][tx] = acc[r];   // tile[col_local][i_local]
+  for (; rb < nRB; ++rb) a0 += __ldg(src + rb * stride);
+  tile[ty][tx] = (a0 + a1) + (a2 + a3);      // tile[col_local][i_local]
   __syncthreads();
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int il = ty + 8 * r;
-    sums[(int64_t)(i0 + il) * m + c0 + tx] = tile[tx][il] * x_scale;
-  }
+  sums[(int64_t)(i0 + ty) * m + c0 + tx] = tile[tx][ty] * x_scale;
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < K) {
     float s = 0.f;
-    for (int rb = 0; rb < nRB; ++rb) s += ss_part[(int64_t)rb * K + threadIdx.x];
+    for (int r = 0; r < nRB; ++r) s += ss_part[(int64_t)r * K + threadIdx.x];
     sums[(int64_t)d * m + threadIdx.x] = s;
   }
 }
@@ -443,9 +452,11 @@ int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_
   float* ss_part = reinterpret_cast<float*>(w); w += p.ss_bytes;
   int* err = reinterpret_cast<int*>(w);
 
-  CUtensorMap tmA, tmC, tmUh, tmUl;
+  CUtensorMap tmA, tmC, tmA2, tmC2, tmUh, tmUl;
   DRSA_TRY(make_tmap_f16_sw128(&tmA, A16, (uint64_t)M, (uint64_t)d, kRows));
   DRSA_TRY(make_tmap_f16_sw128(&tmC, C16, (uint64_t)M, (uint64_t)d, kRows));
+  DRSA_TRY(make_tmap_f16_sw128(&tmA2, A16, (uint64_t)M, (uint64_t)d, 32));
+  DRSA_TRY(make_tmap_f16_sw128(&tmC2, C16, (uint64_t)M, (uint64_t)d, 32));
   DRSA_TRY(make_tmap_f16_sw128(&tmUh, Ut_hi, (uint64_t)m, (uint64_t)d, kNG));
   DRSA_TRY(make_tmap_f16_sw128(&tmUl, Ut_lo, (uint64_t)m, (uint64_t)d, kNG));
 
@@ -461,7 +472,7 @@ int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_
       attr_set = true;
     }
     drsa_tc_step_kernel<256><<<grid, kThreads, Cfg<256>::kSmemBytes, stream>>>(
-        tmA, tmC, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale, pq_scale, part, ss_part, err, g_tc_prof);
+        tmA, tmC, tmA2, tmC2, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale, pq_scale, part, ss_part, err, g_tc_prof);
   } else {
     static bool attr_set = false;
     if (!attr_set) {
@@ -470,12 +481,12 @@ int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_
       attr_set = true;
     }
     drsa_tc_step_kernel<128><<<grid, kThreads, Cfg<128>::kSmemBytes, stream>>>(
-        tmA, tmC, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale, pq_scale, part, ss_part, err, g_tc_prof);
+        tmA, tmC, tmA2, tmC2, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale, pq_scale, part, ss_part, err, g_tc_prof);
   }
   DRSA_LAUNCH_CHECK();
   dim3 rgrid(m / 32, d / 32);
   // X' = pq_scale * (sA sC)^2 * X
-  tc_reduce_kernel<<<rgrid, 256, 0, stream>>>(part, ss_part, p.nRB, p.G, d, m, K, inv_scale * inv_scale / pq_scale, sums);
+  tc_reduce_kernel<<<rgrid, 1024, 0, stream>>>(part, ss_part, p.nRB, p.G, d, m, K, inv_scale * inv_scale / pq_scale, sums);
   DRSA_LAUNCH_CHECK();
   return DRSA_OK;
 }
