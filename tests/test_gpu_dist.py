@@ -1,0 +1,55 @@
+"""2-GPU NCCL test of the row-sharded DRSA optimiser (skipped with fewer than 2 GPUs): two ranks each hold
+half of the rows; the trajectory must match the single-GPU run on all rows and the replicas of U must be
+bit-identical."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from oracle import drsa_ref
+    from cxai.xai.drsa.drsa import SubspaceOptimizer
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    M, d, K, steps = 20000, 128, 4, 12
+    A, C = drsa_ref.synth_pairs(M, d, 77)
+    U0 = drsa_ref.synth_U0(d, seed=78)
+    lo, hi = (0, 9000) if rank == 0 else (9000, M)           # uneven shards
+    out = {}
+    for prec in ("fp32", "tc"):
+        opt = SubspaceOptimizer(U0, A[lo:hi], C[lo:hi], None, num_concepts=K, device=f"cuda:{rank}", precision=prec)
+        opt.run(steps=steps, save=False)
+        gathered = [torch.zeros_like(opt.U) for _ in range(world)]
+        dist.all_gather(gathered, opt.U)
+        out[prec] = (opt.obj_history.copy(), opt.U.cpu(), float((gathered[0] - gathered[1]).abs().max()), opt.M_global)
+    if rank == 0:
+        objs_ref, U_ref = drsa_ref.run_autograd(A, C, U0, K, steps)
+        for prec, (objs, U, rep, Mg) in out.items():
+            ret[prec] = (float(np.max(np.abs(objs - objs_ref) / np.abs(objs_ref))), drsa_ref.principal_angle(U, U_ref, K), rep, Mg)
+    dist.destroy_process_group()
+
+
+def test_two_rank_row_sharding_matches_reference():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    port = 29600 + (os.getpid() % 1000)
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+        for prec in ("fp32", "tc"):
+            rel, ang, rep, Mg = ret[prec]
+            print(prec, rel, ang, rep)
+            assert Mg == 20000
+            assert rel < 1e-4 and ang < 1e-3
+            assert rep == 0.0
