@@ -33,12 +33,13 @@ def _stream():
 
 class _Op:
     __slots__ = ("kind", "name", "module", "rule", "relu", "w", "b", "w_mod", "wt_mod", "b_mod", "eps", "ones",
-                 "kh", "kw", "cin", "cout", "index")
+                 "kh", "kw", "cin", "cout", "index", "tc")
 
     def __init__(self, kind, name, module, index):
         self.kind, self.name, self.module, self.index = kind, name, module, index
         self.rule = None
         self.relu = False
+        self.tc = None          # lazily prepared tensor-core operands (hi/lo fp16 weights, padded bias)
 
 
 class LRPPlan:
@@ -50,6 +51,8 @@ class LRPPlan:
         if model.training:
             raise _L.DRSAError("LRP needs model.eval() (BatchNorm running statistics are folded)")
         self.device = device
+        self.use_tc = True          # run the layers below the split layer on the tcgen05 NHWC pipeline
+        self._tc_err = None
         self.ops: List[_Op] = []
         self.module_to_op = {}
         mods = [(f"features.{n}", m) for n, m in model.features.named_children()]
@@ -136,6 +139,112 @@ class LRPPlan:
             _L.check(_L.lib().lrp_conv3x3_flip_weights(_ptr(op.w_mod), op.cout, op.cin, _ptr(op.wt_mod), _stream()),
                      "lrp_conv3x3_flip_weights")
 
+    # ------------------------------------------------------------------ tensor-core forward prefix
+    @staticmethod
+    def _pad64(c: int) -> int:
+        return (c + 63) // 64 * 64
+
+    def _tc_prefix(self, x: torch.Tensor, keep_from: int) -> int:
+        """Number of leading ops that can run in the NHWC tcgen05 pipeline: nothing below `keep_from` has to
+        be kept for the backward, so those layers only need to hand over their final activation."""
+        if not self.use_tc or x.dim() != 4 or x.size(1) != 1:
+            return 0
+        lib = _L.lib()
+        B, _, H, W = x.shape
+        n, convs, last_good = 0, 0, 0
+        for k, op in enumerate(self.ops):
+            if k >= keep_from:
+                break
+            if op.kind == "conv":
+                if k == 0:
+                    if op.cin != 1:
+                        return 0
+                else:
+                    cin_p, cout_p = self._pad64(op.cin), self._pad64(op.cout)
+                    if cout_p > 256 or lib.lrp_tc_conv3x3_supported(B, cin_p, cout_p, H, W) != 0:
+                        break
+                convs += 1
+            elif op.kind == "pool":
+                if H % op.kh or W % op.kw:
+                    break
+                H, W = H // op.kh, W // op.kw
+            elif op.kind in ("identity", "relu"):
+                pass
+            else:
+                break
+            n = k + 1
+            if op.kind in ("conv", "pool") or (op.kind in ("identity", "relu")):
+                last_good = n
+        return last_good if convs >= 2 else 0
+
+    def _prepare_tc(self, op: _Op, first: bool) -> None:
+        if op.tc is not None:
+            return
+        lib = _L.lib()
+        dev = op.w.device
+        cout_p = self._pad64(op.cout)
+        bias = torch.zeros(cout_p, device=dev)
+        bias[: op.cout] = op.b
+        if first:
+            op.tc = {"w": op.w.reshape(op.cout, 9).contiguous(), "b": bias, "cout_p": cout_p}
+            return
+        cin_p = self._pad64(op.cin)
+        wt = torch.zeros(9, cout_p, cin_p, device=dev)
+        wt[:, : op.cout, : op.cin] = op.w.permute(2, 3, 0, 1).reshape(9, op.cout, op.cin)
+        hi = torch.empty(9, cout_p, cin_p, dtype=torch.float16, device=dev)
+        lo = torch.empty_like(hi)
+        _L.check(lib.lrp_tc_split_f16(_ptr(wt), wt.numel(), _ptr(hi), _ptr(lo), _stream()), "lrp_tc_split_f16")
+        op.tc = {"hi": hi, "lo": lo, "b": bias, "cin_p": cin_p, "cout_p": cout_p}
+
+    def _forward_tc(self, x: torch.Tensor, n_ops: int):
+        """Ops [0, n_ops) on the tensor-core pipeline; returns the activation after op n_ops-1 as NCHW fp32."""
+        lib = _L.lib()
+        B, _, H, W = x.shape
+        dev = x.device
+        if self._tc_err is None or self._tc_err.device != dev:
+            self._tc_err = torch.zeros(1, dtype=torch.int32, device=dev)
+        last_compute = max(k for k in range(n_ops) if self.ops[k].kind in ("conv", "pool"))
+        hi = lo = None
+        C = Cp = 1
+        out = None
+        for k in range(n_ops):
+            op = self.ops[k]
+            if op.kind == "conv":
+                self._prepare_tc(op, first=(k == 0))
+                cout_p = op.tc["cout_p"]
+                is_last = k == last_compute
+                if k == 0:
+                    yh = torch.empty(B, H, W, cout_p, dtype=torch.float16, device=dev)
+                    yl = torch.empty_like(yh)
+                    _L.check(lib.lrp_tc_conv3x3_first(_ptr(x), _ptr(op.tc["w"]), _ptr(op.tc["b"]), B, H, W, op.cout, cout_p,
+                                                      int(op.relu), _ptr(yh), _ptr(yl), _stream()), op.name)
+                    if is_last:
+                        out = torch.empty(B, op.cout, H, W, device=dev)
+                        _L.check(lib.lrp_tc_nhwc_to_nchw(_ptr(yh), _ptr(yl), B, H, W, cout_p, op.cout, _ptr(out), _stream()))
+                else:
+                    yh = yl = None
+                    if is_last:
+                        out = torch.empty(B, op.cout, H, W, device=dev)
+                    else:
+                        yh = torch.empty(B, H, W, cout_p, dtype=torch.float16, device=dev)
+                        yl = torch.empty_like(yh)
+                    _L.check(lib.lrp_tc_conv3x3_forward(_ptr(hi), _ptr(lo), _ptr(op.tc["hi"]), _ptr(op.tc["lo"]),
+                                                        _ptr(op.tc["b"]), B, H, W, op.tc["cin_p"], cout_p, op.cout,
+                                                        int(op.relu), _ptr(yh), _ptr(yl), _ptr(out) if is_last else None,
+                                                        _ptr(self._tc_err), _stream()), op.name)
+                hi, lo, C, Cp = yh, yl, op.cout, cout_p
+            elif op.kind == "pool":
+                Ho, Wo = H // op.kh, W // op.kw
+                yh = torch.empty(B, Ho, Wo, Cp, dtype=torch.float16, device=dev)
+                yl = torch.empty_like(yh)
+                _L.check(lib.lrp_tc_maxpool(_ptr(hi), _ptr(lo), B, H, W, Cp, op.kh, op.kw, _ptr(yh), _ptr(yl), _stream()),
+                         op.name)
+                hi, lo, H, W = yh, yl, Ho, Wo
+                if k == last_compute:
+                    out = torch.empty(B, C, H, W, device=dev)
+                    _L.check(lib.lrp_tc_nhwc_to_nchw(_ptr(hi), _ptr(lo), B, H, W, Cp, C, _ptr(out), _stream()))
+        return out
+
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, keep_from: int = 0):
         """Runs the network; returns (logits, saved) where saved[k] holds what op k needs in the backward
@@ -144,7 +253,14 @@ class LRPPlan:
         saved = [None] * len(self.ops)
         outs = [None] * len(self.ops)
         cur = x
+        n_tc = self._tc_prefix(x, keep_from)
+        if n_tc:
+            cur = self._forward_tc(x, n_tc)
+            for k in range(n_tc):
+                outs[k] = cur if k == n_tc - 1 else None
         for k, op in enumerate(self.ops):
+            if k < n_tc:
+                continue
             keep = k >= keep_from
             if op.kind == "conv":
                 N, Cin, H, W = cur.shape

@@ -67,6 +67,13 @@ SIGNATURES = {
     "lrp_dense_forward": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "lrp_dense_epsilon_backward": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp]),
     "lrp_relu_mask": (_i32, [_vp, _vp, _i64, _vp]),
+    "lrp_tc_conv3x3_supported": (_i32, [_i64, _i32, _i32, _i32, _i32]),
+    "lrp_tc_conv3x3_forward": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp,
+                                      _vp, _vp]),
+    "lrp_tc_conv3x3_first": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "lrp_tc_maxpool": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "lrp_tc_nhwc_to_nchw": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "lrp_tc_split_f16": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "drsa_selftest_umma": (_i32, [_i32, _vp]),
     "drsa_debug_set_tc_profile": (_i32, [_vp]),
 }

@@ -55,6 +55,17 @@ int dense_forward(const float* x, const float* w, const float* b, int64_t N, int
 int dense_epsilon_backward(const float* x, const float* w, const float* b, const float* R_out, int64_t N, int In,
                            int Out, float eps, float* s_buf, float* R_in, cudaStream_t s);
 int relu_mask(const float* a, float* R, int64_t count, cudaStream_t s);
+bool conv_tc_supported(int64_t B, int Cin_p, int Cout_p, int H, int W);
+int conv_tc_forward(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int64_t B,
+                    int H, int W, int Cin_p, int Cout_p, int Cout, int relu, void* y_hi, void* y_lo, float* y_nchw,
+                    int* err_flag, cudaStream_t stream);
+int conv_first_nhwc(const float* x, const float* w, const float* b, int64_t B, int H, int W, int Cout, int Cout_p,
+                    int relu, void* y_hi, void* y_lo, cudaStream_t stream);
+int maxpool_nhwc(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int kh, int kw, void* y_hi,
+                 void* y_lo, cudaStream_t stream);
+int nhwc_to_nchw(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int C, float* y,
+                 cudaStream_t stream);
+int split_f16(const float* in, int64_t count, void* hi, void* lo, cudaStream_t stream);
 int pack_f16(const float* in, int64_t count, float scale, void* out, cudaStream_t stream);
 int absmax(const float* in, int64_t count, float* out, cudaStream_t stream);
 int64_t finish_workspace_bytes(int d, int m);
@@ -296,6 +307,52 @@ int lrp_relu_mask(const float* a, float* R, int64_t count, void* stream) {
   if (a == nullptr || R == nullptr || count <= 0) return DRSA_ERR_ARG;
   DRSA_TRY(require_sm100());
   return relu_mask(a, R, count, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_tc_conv3x3_supported(int64_t B, int Cin_p, int Cout_p, int H, int W) {
+  return conv_tc_supported(B, Cin_p, Cout_p, H, W) ? DRSA_OK : DRSA_ERR_SHAPE;
+}
+
+int lrp_tc_conv3x3_forward(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                           int64_t B, int H, int W, int Cin_p, int Cout_p, int Cout, int relu, void* y_hi, void* y_lo,
+                           float* y_nchw, int* err_flag, void* stream) {
+  if (x_hi == nullptr || x_lo == nullptr || w_hi == nullptr || w_lo == nullptr || bias == nullptr || err_flag == nullptr ||
+      (y_hi == nullptr) != (y_lo == nullptr) || (y_hi == nullptr && y_nchw == nullptr) || Cout <= 0 || Cout > Cout_p)
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return conv_tc_forward(x_hi, x_lo, w_hi, w_lo, bias, B, H, W, Cin_p, Cout_p, Cout, relu, y_hi, y_lo, y_nchw, err_flag,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int lrp_tc_conv3x3_first(const float* x, const float* w, const float* b, int64_t B, int H, int W, int Cout, int Cout_p,
+                         int relu, void* y_hi, void* y_lo, void* stream) {
+  if (x == nullptr || w == nullptr || b == nullptr || y_hi == nullptr || y_lo == nullptr || B <= 0 || H <= 0 || W <= 0 ||
+      Cout <= 0 || Cout_p % 8 != 0 || Cout > Cout_p)
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return conv_first_nhwc(x, w, b, B, H, W, Cout, Cout_p, relu, y_hi, y_lo, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_tc_maxpool(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int kh, int kw, void* y_hi,
+                   void* y_lo, void* stream) {
+  if (x_hi == nullptr || x_lo == nullptr || y_hi == nullptr || y_lo == nullptr || B <= 0 || Cp % 8 != 0 || kh <= 0 ||
+      kw <= 0 || H / kh == 0 || W / kw == 0)
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return maxpool_nhwc(x_hi, x_lo, B, H, W, Cp, kh, kw, y_hi, y_lo, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_tc_nhwc_to_nchw(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int C, float* y,
+                        void* stream) {
+  if (x_hi == nullptr || x_lo == nullptr || y == nullptr || B <= 0 || C <= 0 || C > Cp) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return nhwc_to_nchw(x_hi, x_lo, B, H, W, Cp, C, y, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_tc_split_f16(const float* in, int64_t count, void* hi, void* lo, void* stream) {
+  if (in == nullptr || hi == nullptr || lo == nullptr || count <= 0) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return split_f16(in, count, hi, lo, static_cast<cudaStream_t>(stream));
 }
 
 int drsa_debug_set_tc_profile(void* device_buf6) { set_tc_profile(static_cast<long long*>(device_buf6)); return DRSA_OK; }

@@ -1,0 +1,443 @@
+// 3x3 'same' convolution as an implicit GEMM on the 5th-generation tensor cores (forward pass of the
+// log-mel CNN, create_model.py:100-137 as driven by preprocessing.py:156-162).
+//
+//   out[pixel][co] = sum_{tap, ci} in[pixel + tap][ci] * w[tap][co][ci]          M = 128 pixels, N = Cout, K = 9*Cin
+//
+// Layout: activations NHWC, stored as two fp16 planes hi + lo (x = hi + lo up to 2^-22), channels padded to
+// a multiple of 64; weights [tap][Cout][Cin] as hi + lo planes.  Three MMAs per k-step
+// (hi*hi + lo*hi + hi*lo) keep fp32-class accuracy (the LRP tolerance of 1e-4 does not survive single
+// fp16/TF32 operands through ten layers and the R/(z+eps) divisions).
+//
+// im2col is done by TMA: for tap (ky, kx) the A operand of a tile of 128 output pixels is the 4-D box
+// [nb, th, tw, 64 channels] at coordinates shifted by (ky-1, kx-1); out-of-bounds rows/columns are
+// zero-filled by the TMA unit, which IS the zero padding of the convolution.  The box lands in shared
+// memory as 128 rows of 128 bytes with the 128-byte swizzle, i.e. directly in the K-major operand layout
+// of tcgen05.mma.  Accumulators live in TMEM (double buffered when 2*Cout <= 512 columns); the epilogue
+// (4 warps, one pixel per thread) adds the bias, applies ReLU and writes the next layer's hi/lo planes.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue; persistent over tiles.
+#include <cuda.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace drsa {
+
+namespace {
+using namespace tc;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// NHWC fp16 [B, H, W, C] with a box of [nb, th, tw, 64 channels]
+int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t nb,
+                   uint32_t th, uint32_t tw) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return DRSA_ERR_CUDA;
+  cuuint64_t dims[4] = {C, W, H, B};
+  cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {64, tw, th, nb};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return DRSA_ERR_CUDA; }
+  return DRSA_OK;
+}
+
+constexpr int kTilePix = 128;
+constexpr int kABytes = kTilePix * 128;        // one [128 pixels x 64 ch] fp16 box
+constexpr int kConvThreads = 192;
+constexpr uint32_t kDescHiK = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint64_t kdesc(uint32_t smem_addr) {
+  return ((uint64_t)kDescHiK << 32) | ((smem_addr >> 4) | (1u << 16));
+}
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
+
+struct ConvGeom {
+  int B, H, W, Cin_p, Cout_p, Cout;      // padded channel counts (multiples of 64) and the real Cout
+  int nb, th, tw;                        // tile = nb images x th rows x tw columns = 128 pixels
+  int tiles_x, tiles_y, tiles_b, num_tiles;
+  int relu;
+};
+
+template <int kStages>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
+                  const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, ConvGeom g,
+                  const float* __restrict__ bias, __half* __restrict__ y_hi, __half* __restrict__ y_lo,
+                  float* __restrict__ y_nchw, int* __restrict__ err_flag) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int wbytes = g.Cout_p * 128;                 // one [Cout_p x 64] weight box
+  const int stage_bytes = 2 * kABytes + 2 * wbytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+  uint64_t* full = bars;                // [kStages]
+  uint64_t* empty = bars + 8;           // [kStages]
+  uint64_t* acc_full = bars + 16;       // [2]
+  uint64_t* acc_empty = bars + 18;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int acc_stages = (2 * g.Cout_p <= 512) ? 2 : 1;
+
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) atomicExch(err_flag, 1);
+    return;
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int kchunks = g.Cin_p / 64;
+  const int kiters = 9 * kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmXh); tma_prefetch_desc(&tmXl); tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        const int txi = tile % g.tiles_x, tyi = (tile / g.tiles_x) % g.tiles_y, tbi = tile / (g.tiles_x * g.tiles_y);
+        const int x0 = txi * g.tw, y0 = tyi * g.th, n0 = tbi * g.nb;
+        for (int it = 0; it < kiters; ++it) {
+          const int tap = it / kchunks, kc = it % kchunks;
+          const int ky = tap / 3, kx = tap % 3;
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], stage_bytes);
+          uint8_t* dst = smem + stage * stage_bytes;
+          tma_load_4d(dst, &tmXh, &full[stage], 64 * kc, x0 + kx - 1, y0 + ky - 1, n0);
+          tma_load_4d(dst + kABytes, &tmXl, &full[stage], 64 * kc, x0 + kx - 1, y0 + ky - 1, n0);
+          tma_load_2d(dst + 2 * kABytes, &tmWh, &full[stage], 64 * kc, tap * g.Cout_p);
+          tma_load_2d(dst + 2 * kABytes + wbytes, &tmWl, &full[stage], 64 * kc, tap * g.Cout_p);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(kTilePix, g.Cout_p, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + as * g.Cout_p;
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + stage * stage_bytes), a_lo = a_hi + kABytes;
+          const uint32_t w_hi = a_hi + 2 * kABytes, w_lo = w_hi + wbytes;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t dah = kdesc(a_hi + 32 * kk), dal = kdesc(a_lo + 32 * kk);
+            const uint64_t dwh = kdesc(w_hi + 32 * kk), dwl = kdesc(w_lo + 32 * kk);
+            umma_ss_f16(tacc, dah, dwh, idesc, (it | kk) ? 1u : 0u);
+            umma_ss_f16(tacc, dal, dwh, idesc, 1u);
+            umma_ss_f16(tacc, dah, dwl, idesc, 1u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[as]);
+        if (++as == acc_stages) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int pix = 32 * q + lane;                        // pixel of the tile = TMEM lane
+    const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      const int txi = tile % g.tiles_x, tyi = (tile / g.tiles_x) % g.tiles_y, tbi = tile / (g.tiles_x * g.tiles_y);
+      const int xx = pix % g.tw, yy = (pix / g.tw) % g.th, bi = pix / (g.tw * g.th);
+      const int x = txi * g.tw + xx, y = tyi * g.th + yy, n = tbi * g.nb + bi;
+      const bool valid = (x < g.W) && (y < g.H) && (n < g.B);
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+      const int64_t pbase = (((int64_t)n * g.H + y) * g.W + x) * g.Cout_p;
+#pragma unroll 1
+      for (int cc = 0; cc < g.Cout_p / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(lane_base + as * g.Cout_p + 32 * cc, v);
+        tmem_ld_wait();
+        if (valid) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float a = __uint_as_float(v[2 * i]) + __ldg(bias + 32 * cc + 2 * i);
+            float b = __uint_as_float(v[2 * i + 1]) + __ldg(bias + 32 * cc + 2 * i + 1);
+            if (g.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+            const __half2 h = __floats2half2_rn(a, b);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+            hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+            if (y_nchw != nullptr) {
+              const int c = 32 * cc + 2 * i;
+              if (c < g.Cout) y_nchw[(((int64_t)n * g.Cout + c) * g.H + y) * g.W + x] = a;
+              if (c + 1 < g.Cout) y_nchw[(((int64_t)n * g.Cout + c + 1) * g.H + y) * g.W + x] = b;
+            }
+          }
+          if (y_hi != nullptr) {
+            uint4* ph = reinterpret_cast<uint4*>(y_hi + pbase + 32 * cc);
+            uint4* pl = reinterpret_cast<uint4*>(y_lo + pbase + 32 * cc);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              ph[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+              pl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[as]);
+      if (++as == acc_stages) { as = 0; aphase ^= 1; }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// First layer (Cin = 1): bandwidth-bound, CUDA cores.  x [B,1,H,W] fp32 -> y NHWC hi/lo [B,H,W,Cout_p].
+// One thread per (pixel, group of 8 output channels).
+__global__ void __launch_bounds__(256) conv3x3_first_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                 const float* __restrict__ b, int64_t B, int H, int W,
+                                                                 int Cout, int Cout_p, int relu, __half* __restrict__ y_hi,
+                                                                 __half* __restrict__ y_lo) {
+  const int groups = Cout_p / 8;
+  const int64_t total = B * H * W * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int gq = (int)(i % groups);
+    const int64_t p = i / groups;
+    const int xx = (int)(p % W), yy = (int)((p / W) % H);
+    const int64_t n = p / ((int64_t)W * H);
+    float v[9];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int gy = yy + ky - 1, gx = xx + kx - 1;
+        v[ky * 3 + kx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(x + (n * H + gy) * W + gx) : 0.f;
+      }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float o[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = gq * 8 + 2 * j + e;
+        float acc = 0.f;
+        if (c < Cout) {
+          acc = __ldg(b + c);
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc = fmaf(v[t], __ldg(w + c * 9 + t), acc);
+          if (relu) acc = fmaxf(acc, 0.f);
+        }
+        o[e] = acc;
+      }
+      const __half2 h = __floats2half2_rn(o[0], o[1]);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(o[0] - hf.x, o[1] - hf.y);
+      hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    const int64_t o = p * Cout_p + gq * 8;
+    *reinterpret_cast<uint4*>(y_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(y_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// MaxPool2d(kh, kw), stride = kernel, on NHWC hi/lo planes; one thread per (output pixel, 8 channels).
+__global__ void __launch_bounds__(256) maxpool_nhwc_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo,
+                                                           int64_t B, int H, int W, int Cp, int kh, int kw,
+                                                           __half* __restrict__ y_hi, __half* __restrict__ y_lo) {
+  const int Ho = H / kh, Wo = W / kw, groups = Cp / 8;
+  const int64_t total = B * Ho * Wo * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int gq = (int)(i % groups);
+    const int64_t p = i / groups;
+    const int xo = (int)(p % Wo), yo = (int)((p / Wo) % Ho);
+    const int64_t n = p / ((int64_t)Wo * Ho);
+    float best[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) best[e] = -INFINITY;
+    for (int dy = 0; dy < kh; ++dy)
+      for (int dx = 0; dx < kw; ++dx) {
+        const int64_t o = (((n * H + yo * kh + dy) * W) + xo * kw + dx) * Cp + gq * 8;
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(x_hi + o));
+        const uint4 l = __ldg(reinterpret_cast<const uint4*>(x_lo + o));
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+          const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
+          best[2 * j] = fmaxf(best[2 * j], hf.x + lf.x);
+          best[2 * j + 1] = fmaxf(best[2 * j + 1], hf.y + lf.y);
+        }
+      }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2 h = __floats2half2_rn(best[2 * j], best[2 * j + 1]);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(best[2 * j] - hf.x, best[2 * j + 1] - hf.y);
+      hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    const int64_t o = p * Cp + gq * 8;
+    *reinterpret_cast<uint4*>(y_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(y_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// NHWC hi/lo -> NCHW fp32 (C real channels); 32x32 shared-memory transpose over (pixel, channel).
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo,
+                                                           int HW, int Cp, int C, float* __restrict__ y) {
+  __shared__ float t[32][33];
+  const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int p = p0 + ty + 8 * r, c = c0 + tx;
+    float v = 0.f;
+    if (p < HW && c < Cp) {
+      const int64_t o = ((int64_t)n * HW + p) * Cp + c;
+      v = __half2float(x_hi[o]) + __half2float(x_lo[o]);
+    }
+    t[ty + 8 * r][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = c0 + ty + 8 * r, p = p0 + tx;
+    if (c < C && p < HW) y[((int64_t)n * C + c) * HW + p] = t[tx][ty + 8 * r];
+  }
+}
+
+__global__ void split_f16_kernel(const float* __restrict__ in, int64_t n, __half* __restrict__ hi, __half* __restrict__ lo) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = in[i];
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+inline int eblocks(int64_t n) {
+  int64_t b = (n + 255) / 256;
+  return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
+}
+
+bool pick_tile(int B, int H, int W, int* nb, int* th, int* tw) {
+  (void)B;
+  // tw = largest power of two <= min(W, 128) that divides W; th, nb fill up to 128 pixels
+  int w = 1;
+  while (w * 2 <= W && w * 2 <= 128 && W % (w * 2) == 0) w *= 2;
+  if (W % w != 0) return false;
+  int rest = 128 / w, h = 1;
+  while (h * 2 <= rest && h * 2 <= H && H % (h * 2) == 0) h *= 2;
+  if (H % h != 0) return false;
+  int n = rest / h;
+  if (w * h * n != 128 || n > 256 || h > 256 || w > 256) return false;
+  *nb = n; *th = h; *tw = w;
+  return true;
+}
+}  // namespace
+
+bool conv_tc_supported(int64_t B, int Cin_p, int Cout_p, int H, int W) {
+  int nb, th, tw;
+  if (B <= 0 || Cin_p % 64 != 0 || Cout_p % 64 != 0 || Cout_p > 256 || Cin_p > 1024) return false;
+  return pick_tile((int)B, H, W, &nb, &th, &tw);
+}
+
+int conv_tc_forward(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int64_t B,
+                    int H, int W, int Cin_p, int Cout_p, int Cout, int relu, void* y_hi, void* y_lo, float* y_nchw,
+                    int* err_flag, cudaStream_t stream) {
+  ConvGeom g{};
+  if (!conv_tc_supported(B, Cin_p, Cout_p, H, W) || B > 2147483647LL / ((int64_t)H * W)) return DRSA_ERR_SHAPE;
+  g.B = (int)B; g.H = H; g.W = W; g.Cin_p = Cin_p; g.Cout_p = Cout_p; g.Cout = Cout; g.relu = relu;
+  pick_tile(g.B, H, W, &g.nb, &g.th, &g.tw);
+  g.tiles_x = W / g.tw; g.tiles_y = H / g.th; g.tiles_b = (g.B + g.nb - 1) / g.nb;
+  g.num_tiles = g.tiles_x * g.tiles_y * g.tiles_b;
+  CUtensorMap tmXh, tmXl, tmWh, tmWl;
+  DRSA_TRY(make_tmap_nhwc(&tmXh, x_hi, (uint64_t)B, H, W, Cin_p, g.nb, g.th, g.tw));
+  DRSA_TRY(make_tmap_nhwc(&tmXl, x_lo, (uint64_t)B, H, W, Cin_p, g.nb, g.th, g.tw));
+  DRSA_TRY(make_tmap_f16_sw128(&tmWh, w_hi, (uint64_t)9 * Cout_p, (uint64_t)Cin_p, (uint32_t)Cout_p));
+  DRSA_TRY(make_tmap_f16_sw128(&tmWl, w_lo, (uint64_t)9 * Cout_p, (uint64_t)Cin_p, (uint32_t)Cout_p));
+  const int stage_bytes = 2 * kABytes + 2 * Cout_p * 128;
+  int grid = sm_count();
+  if (grid > g.num_tiles) grid = g.num_tiles;
+  auto launch = [&](auto kernel, int stages) -> int {
+    const int smem_bytes = stages * stage_bytes + 256;
+    DRSA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmXh, tmXl, tmWh, tmWl, g, bias, static_cast<__half*>(y_hi),
+                                                        static_cast<__half*>(y_lo), y_nchw, err_flag);
+    DRSA_LAUNCH_CHECK();
+    return DRSA_OK;
+  };
+  if (Cout_p <= 64) return launch(conv3x3_tc_kernel<4>, 4);
+  if (Cout_p <= 128) return launch(conv3x3_tc_kernel<3>, 3);
+  return launch(conv3x3_tc_kernel<2>, 2);
+}
+
+int conv_first_nhwc(const float* x, const float* w, const float* b, int64_t B, int H, int W, int Cout, int Cout_p,
+                    int relu, void* y_hi, void* y_lo, cudaStream_t stream) {
+  conv3x3_first_nhwc_kernel<<<eblocks(B * H * W * (Cout_p / 8)), 256, 0, stream>>>(
+      x, w, b, B, H, W, Cout, Cout_p, relu, static_cast<__half*>(y_hi), static_cast<__half*>(y_lo));
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+int maxpool_nhwc(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int kh, int kw, void* y_hi,
+                 void* y_lo, cudaStream_t stream) {
+  maxpool_nhwc_kernel<<<eblocks(B * (H / kh) * (W / kw) * (Cp / 8)), 256, 0, stream>>>(
+      static_cast<const __half*>(x_hi), static_cast<const __half*>(x_lo), B, H, W, Cp, kh, kw,
+      static_cast<__half*>(y_hi), static_cast<__half*>(y_lo));
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+int nhwc_to_nchw(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int C, float* y,
+                 cudaStream_t stream) {
+  if (B > 65535) return DRSA_ERR_SHAPE;
+  dim3 grid(cdiv((int64_t)H * W, 32), cdiv(C, 32), (unsigned)B);
+  nhwc_to_nchw_kernel<<<grid, 256, 0, stream>>>(static_cast<const __half*>(x_hi), static_cast<const __half*>(x_lo),
+                                                H * W, Cp, C, y);
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+int split_f16(const float* in, int64_t count, void* hi, void* lo, cudaStream_t stream) {
+  split_f16_kernel<<<eblocks(count), 256, 0, stream>>>(in, count, static_cast<__half*>(hi), static_cast<__half*>(lo));
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+}  // namespace drsa

@@ -20,7 +20,9 @@ struct FusedParams {
   const float* sums; double inv_M; const float* U; int d, m, K;
   float* U_out; __half* Ut_hi; __half* Ut_lo; float* obj_log; long long log_index;
   int max_iters; float tol2_m; int* status;
-  float* Y; float* X0; float* X1; float* G; float* rowsum; float* resid;   // resid[max_iters + 2]
+  float* Y; float* X0; float* X1; float* G;
+  float* rowsum;   // [m/32][m] per-tile-column partial row sums of |G| (summed in fixed order: deterministic)
+  float* resid;    // [max_iters + 2][gridDim.x] per-CTA partial residuals (summed in fixed order)
   int have_sums;   // 0: Y already holds the matrix to retract (drsa_polar_retract)
 };
 
@@ -80,6 +82,19 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;   // valid in warp 0
 }
 
+// Sum of the per-CTA partials of one sweep, same order in every CTA and on every rank (bit-identical replicas).
+__device__ __forceinline__ float grid_total(const float* part, float* red) {
+  float v = 0.f;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) v += __ldcg(part + i);
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < 8; ++w) t += red[w];
+  return t;       // identical in every thread
+}
+
 __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
   cg::grid_group grid = cg::this_grid();
   __shared__ __align__(16) float As[TS][LDS];
@@ -118,8 +133,7 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
     const float root = bc[0];
     for (int k = tid; k < K; k += blockDim.x) {
       const float q = sqrtf((float)((double)p.sums[n + k] * p.inv_M));
-      coef[k & 63] = 0.f;
-      // K can exceed 64 only in exotic settings; recompute on the fly below in that case
+      // K > 64 is exotic: the factor is then recomputed on the fly below
       if (K <= 64) coef[k] = (float)((double)root * p.inv_M / ((double)K * (double)q * sqrt((double)q)));
     }
     __syncthreads();
@@ -134,8 +148,6 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
       p.Y[i] = p.U[i] + c * p.sums[i];
     }
   }
-  for (int64_t i = gtid; i < m; i += gthreads) p.rowsum[i] = 0.f;
-  for (int64_t i = gtid; i < p.max_iters + 2; i += gthreads) p.resid[i] = 0.f;
   grid.sync();
 
   const int tm = m / TS, td = d / TS;
@@ -152,14 +164,18 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
       p.G[(int64_t)gi * m + tj * TS + 2 * tx + 1] = acc[a][1];
       // the 16 threads of a half-warp share the row gi
       for (int o = 8; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
-      if (tx == 0) atomicAdd(&p.rowsum[gi], rs);
+      if (tx == 0) p.rowsum[(int64_t)tj * m + gi] = rs;     // every (tj, gi) is written by exactly one tile
     }
   }
   grid.sync();
   // ---------------- phase 2: c = ||G||_inf, X0 = Y / sqrt(c), G <- T_0 = 1.5 I - 0.5 G / c, resid[0]
   {
     float best = 0.f;
-    for (int i = tid; i < m; i += blockDim.x) best = fmaxf(best, p.rowsum[i]);
+    for (int i = tid; i < m; i += blockDim.x) {
+      float rs = 0.f;
+      for (int tj = 0; tj < tm; ++tj) rs += p.rowsum[(int64_t)tj * m + i];
+      best = fmaxf(best, rs);
+    }
     best = warp_max(best);
     __syncthreads();
     if ((tid & 31) == 0) red[tid >> 5] = best;
@@ -180,7 +196,7 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
       p.G[i] = (rr == cc ? 1.5f : 0.f) - 0.5f * gv;
     }
     const float tot = block_sum(r, red);
-    if (tid == 0) atomicAdd(&p.resid[0], tot);
+    if (tid == 0) p.resid[blockIdx.x] = tot;
   }
   grid.sync();
 
@@ -189,7 +205,7 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
   float* cur = p.X0;
   float* nxt = p.X1;
   while (true) {
-    const float res = *reinterpret_cast<volatile float*>(&p.resid[it]);
+    const float res = grid_total(p.resid + (int64_t)it * gridDim.x, red);
     if (res < p.tol2_m) { converged = 1; break; }
     if (it >= p.max_iters) break;
     // nxt = cur * T
@@ -225,7 +241,7 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
     }
     {
       const float tot = block_sum(r, red);
-      if (tid == 0) atomicAdd(&p.resid[it + 1], tot);
+      if (tid == 0) p.resid[(int64_t)(it + 1) * gridDim.x + blockIdx.x] = tot;
     }
     grid.sync();
     float* tmp = cur; cur = nxt; nxt = tmp;
@@ -246,8 +262,8 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
 }
 
 int64_t fused_ws_bytes(int d, int m, int max_iters) {
-  return align_up((int64_t)d * m * 4, 256) * 3 + align_up((int64_t)m * m * 4, 256) + align_up((int64_t)m * 4, 256) +
-         align_up((int64_t)(max_iters + 2) * 4, 256);
+  return align_up((int64_t)d * m * 4, 256) * 3 + align_up((int64_t)m * m * 4, 256) +
+         align_up((int64_t)(m / TS) * m * 4, 256) + align_up((int64_t)(max_iters + 2) * 1024 * 4, 256);
 }
 }  // namespace
 
@@ -268,7 +284,7 @@ int finish_fused(const float* sums, int64_t M_global, const float* U, int d, int
   p.X0 = reinterpret_cast<float*>(w); w += dm;
   p.X1 = reinterpret_cast<float*>(w); w += dm;
   p.G = reinterpret_cast<float*>(w); w += align_up((int64_t)m * m * 4, 256);
-  p.rowsum = reinterpret_cast<float*>(w); w += align_up((int64_t)m * 4, 256);
+  p.rowsum = reinterpret_cast<float*>(w); w += align_up((int64_t)(m / TS) * m * 4, 256);
   p.resid = reinterpret_cast<float*>(w);
   p.sums = sums; p.inv_M = M_global > 0 ? 1.0 / (double)M_global : 0.0; p.U = U; p.d = d; p.m = m; p.K = K;
   p.U_out = U_out; p.Ut_hi = static_cast<__half*>(Ut_hi); p.Ut_lo = static_cast<__half*>(Ut_lo);
@@ -287,6 +303,7 @@ int finish_fused(const float* sums, int64_t M_global, const float* U, int d, int
     if (max_coresident < 1) return DRSA_ERR_CUDA;
   }
   if (grid > max_coresident) grid = max_coresident;
+  if (grid > 1024) grid = 1024;            // resid partials are sized for <= 1024 CTAs
   if (U_out == nullptr) grid = 1;
   void* args[] = {&p};
   DRSA_CUDA(cudaLaunchCooperativeKernel((const void*)finish_fused_kernel, dim3(grid), dim3(256), args, 0, stream));

@@ -214,6 +214,36 @@ int lrp_dense_epsilon_backward(const float* x, const float* w, const float* b, c
 /* R *= (a > 0): autograd of an un-hooked ReLU applied to the relevance flow. */
 int lrp_relu_mask(const float* a, float* R, int64_t count, void* stream);
 
+/* ---- tensor-core forward pipeline (tcgen05 implicit GEMM, TMA im2col) ----------------------------------
+ * Activations are NHWC, split into two fp16 planes hi + lo with channels padded to a multiple of 64
+ * ([B,H,W,Cp] each); weights are [9 taps][Cout_p][Cin_p] hi + lo planes (lrp_tc_split_f16 of the padded,
+ * tap-major fp32 weights).  hi*hi + lo*hi + hi*lo keeps fp32-class accuracy. */
+
+/* DRSA_OK if lrp_tc_conv3x3_forward supports the shape (H, W must tile into 128-pixel boxes). */
+int lrp_tc_conv3x3_supported(int64_t B, int Cin_p, int Cout_p, int H, int W);
+
+/* y = relu?(conv3x3_same(x, w) + b).  Outputs: the hi/lo NHWC planes for the next layer (may be NULL) and/or
+ * an fp32 NCHW copy of the first `Cout` channels (may be NULL).  bias has Cout_p entries (zero padded).
+ * err_flag: device int set to 1 if the kernel detects a misaligned shared-memory window. */
+int lrp_tc_conv3x3_forward(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                           const float* bias, int64_t B, int H, int W, int Cin_p, int Cout_p, int Cout,
+                           int relu, void* y_hi, void* y_lo, float* y_nchw, int* err_flag, void* stream);
+
+/* First layer (Cin = 1, bandwidth bound, CUDA cores): x [B,1,H,W] fp32, w [Cout,9] -> NHWC hi/lo planes. */
+int lrp_tc_conv3x3_first(const float* x, const float* w, const float* b, int64_t B, int H, int W, int Cout,
+                         int Cout_p, int relu, void* y_hi, void* y_lo, void* stream);
+
+/* MaxPool2d(kh,kw), stride = kernel, on NHWC hi/lo planes. */
+int lrp_tc_maxpool(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int kh, int kw,
+                   void* y_hi, void* y_lo, void* stream);
+
+/* NHWC hi/lo planes -> NCHW fp32 with the first C channels (hand-over to the fp32 / LRP-backward path). */
+int lrp_tc_nhwc_to_nchw(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int C, float* y,
+                        void* stream);
+
+/* hi = fp16(in), lo = fp16(in - hi) over `count` floats. */
+int lrp_tc_split_f16(const float* in, int64_t count, void* hi, void* lo, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Self tests of the tcgen05 / TMA building blocks (used by tests/ on the GPU box).
  * Each returns DRSA_OK and writes max |error| against a CUDA-core computation of the

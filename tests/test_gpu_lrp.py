@@ -173,3 +173,90 @@ def test_end_to_end_cfg1_pipeline():
     ang = drsa_ref.principal_angle(opt.U.cpu(), U_ref, K)
     print(f"cfg1 e2e: objective rel err {rel:.2e}, angle {ang:.2e}")
     assert rel < 1e-4 and ang < 1e-3
+
+
+def _to_nhwc_split(x, Cp):
+    """[B,C,H,W] fp32 -> NHWC hi/lo fp16 planes with channels zero-padded to Cp."""
+    B, C, H, W = x.shape
+    t = torch.zeros(B, H, W, Cp)
+    t[..., :C] = x.permute(0, 2, 3, 1)
+    hi = t.half()
+    lo = (t - hi.float()).half()
+    return hi.cuda().contiguous(), lo.cuda().contiguous()
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W", [(3, 64, 64, 16, 64), (2, 64, 64, 4, 256), (5, 100, 128, 8, 8), (3, 128, 256, 4, 4),
+                                            (2, 256, 256, 8, 8), (70, 64, 100, 2, 2), (1, 64, 64, 128, 256)])
+def test_tc_conv3x3_forward_matches_fp64(B, Cin, Cout, H, W):
+    """tcgen05 implicit-GEMM convolution (TMA im2col, hi/lo split operands) vs an fp64 convolution."""
+    L = _L(); lib = L.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(B * Cin + Cout)
+    x = torch.rand(B, Cin, H, W, generator=g); x[x < 0.3] = 0
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
+    b = 0.1 * torch.randn(Cout, generator=g)
+    Cin_p, Cout_p = (Cin + 63) // 64 * 64, (Cout + 63) // 64 * 64
+    assert lib.lrp_tc_conv3x3_supported(B, Cin_p, Cout_p, H, W) == 0
+    xh, xl = _to_nhwc_split(x, Cin_p)
+    wt = torch.zeros(9, Cout_p, Cin_p)
+    wt[:, :Cout, :Cin] = w.permute(2, 3, 0, 1).reshape(9, Cout, Cin)
+    wtd = wt.cuda()
+    wh = torch.empty(9, Cout_p, Cin_p, dtype=torch.float16, device="cuda"); wl = torch.empty_like(wh)
+    L.check(lib.lrp_tc_split_f16(wtd.data_ptr(), wtd.numel(), wh.data_ptr(), wl.data_ptr(), s))
+    bias = torch.zeros(Cout_p); bias[:Cout] = b
+    bd = bias.cuda()
+    yh = torch.empty(B, H, W, Cout_p, dtype=torch.float16, device="cuda"); yl = torch.empty_like(yh)
+    yn = torch.full((B, Cout, H, W), float("nan"), device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    L.check(lib.lrp_tc_conv3x3_forward(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), bd.data_ptr(), B, H, W,
+                                       Cin_p, Cout_p, Cout, 1, yh.data_ptr(), yl.data_ptr(), yn.data_ptr(), err.data_ptr(), s))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    want = F.conv2d(x.double(), w.double(), b.double(), padding=1).clamp(min=0)
+    assert _rel_per_sample(yn, want) < 2e-6
+    y2 = (yh.float() + yl.float()).cpu()[..., :Cout].permute(0, 3, 1, 2)
+    assert _rel_per_sample(y2, want) < 2e-6
+    assert float((yh.float() + yl.float())[..., Cout:].abs().max()) == 0.0 if Cout_p > Cout else True
+
+
+def test_tc_first_conv_pool_and_layout_roundtrip():
+    L = _L(); lib = L.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(4)
+    B, H, W, Cout = 3, 16, 32, 64
+    x = lrp_ref.synth_logmel(B, H, W, 8)
+    w = torch.randn(Cout, 1, 3, 3, generator=g) / 3; b = 0.1 * torch.randn(Cout, generator=g)
+    xd, wd, bd = x.cuda(), w.reshape(Cout, 9).cuda().contiguous(), b.cuda()
+    yh = torch.empty(B, H, W, Cout, dtype=torch.float16, device="cuda"); yl = torch.empty_like(yh)
+    L.check(lib.lrp_tc_conv3x3_first(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), B, H, W, Cout, Cout, 1, yh.data_ptr(),
+                                     yl.data_ptr(), s))
+    want = F.conv2d(x.double(), w.double(), b.double(), padding=1).clamp(min=0)
+    got = (yh.float() + yl.float()).cpu().permute(0, 3, 1, 2)
+    assert _rel_per_sample(got, want) < 2e-6
+    ph = torch.empty(B, H // 2, W // 4, Cout, dtype=torch.float16, device="cuda"); pl = torch.empty_like(ph)
+    L.check(lib.lrp_tc_maxpool(yh.data_ptr(), yl.data_ptr(), B, H, W, Cout, 2, 4, ph.data_ptr(), pl.data_ptr(), s))
+    out = torch.empty(B, Cout, H // 2, W // 4, device="cuda")
+    L.check(lib.lrp_tc_nhwc_to_nchw(ph.data_ptr(), pl.data_ptr(), B, H // 2, W // 4, Cout, Cout, out.data_ptr(), s))
+    wantp = F.max_pool2d(got, (2, 4))
+    np.testing.assert_allclose(out.cpu().numpy(), wantp.numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_tc_prefix_equals_fp32_path_full_resolution():
+    """cfg-2 CNN at full 128x256 resolution: the tensor-core prefix and the CUDA-core path give the same maps."""
+    from cxai.utils.constants import lrp_name_map_6s
+    from cxai.xai.explain.rules import NameMapComposite, SequentialMergeBatchNorm
+    from cxai.xai.explain import lrp_engine
+    net = lrp_ref.genre_model(seed=0, last=256, input_size=(128, 256))
+    x = lrp_ref.synth_logmel(3, 128, 256, 20262).cuda()
+    comp = NameMapComposite(lrp_name_map_6s(), canonizers=[SequentialMergeBatchNorm()])
+    plan = lrp_engine._plan(net, comp, x.device)
+    from cxai.xai.drsa.preprocessing import get_intermediate
+    res = {}
+    for use_tc in (True, False):
+        plan.use_tc = use_tc
+        res[use_tc] = get_intermediate(net, x, comp, net.features[33], 2)
+    plan.use_tc = True
+    assert plan._tc_prefix(x, 34) == 34
+    assert res[True][0].shape == (3, 256, 8, 8)
+    assert _rel_per_sample(res[True][0], res[False][0]) < 1e-5
+    assert _rel_per_sample(res[True][1], res[False][1]) < 1e-4
