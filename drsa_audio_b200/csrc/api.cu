@@ -327,7 +327,7 @@ int lrp_tc_conv3x3_forward(const void* x_hi, const void* x_lo, const void* w_hi,
 int lrp_tc_conv3x3_first(const float* x, const float* w, const float* b, int64_t B, int H, int W, int Cout, int Cout_p,
                          int relu, void* y_hi, void* y_lo, void* stream) {
   if (x == nullptr || w == nullptr || b == nullptr || y_hi == nullptr || y_lo == nullptr || B <= 0 || H <= 0 || W <= 0 ||
-      Cout <= 0 || Cout_p % 8 != 0 || Cout > Cout_p)
+      Cout <= 0 || Cout_p % 32 != 0 || Cout > Cout_p || Cout_p > 1024)
     return DRSA_ERR_ARG;
   DRSA_TRY(require_sm100());
   return conv_first_nhwc(x, w, b, B, H, W, Cout, Cout_p, relu, y_hi, y_lo, static_cast<cudaStream_t>(stream));

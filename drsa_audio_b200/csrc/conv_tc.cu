@@ -81,7 +81,7 @@ struct ConvGeom {
   int relu;
 };
 
-template <int kStages>
+template <int kStages, bool kResW>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                   const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, ConvGeom g,
@@ -89,13 +89,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
                   float* __restrict__ y_nchw, int* __restrict__ err_flag) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int wbytes = g.Cout_p * 128;                 // one [Cout_p x 64] weight box
-  const int stage_bytes = 2 * kABytes + 2 * wbytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+  // kResW (Cin_p = Cout_p = 64): all 9 taps of the hi/lo weights (144 KB) stay resident in shared memory and the
+  // ring only carries the activation boxes; otherwise the weight boxes travel with the activations.
+  const int stage_bytes = kResW ? 2 * kABytes : 2 * kABytes + 2 * wbytes;
+  uint8_t* sW = smem + kStages * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (kResW ? 18 * wbytes : 0));
   uint64_t* full = bars;                // [kStages]
   uint64_t* empty = bars + 8;           // [kStages]
   uint64_t* acc_full = bars + 16;       // [2]
   uint64_t* acc_empty = bars + 18;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* w_full = bars + 20;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int acc_stages = (2 * g.Cout_p <= 512) ? 2 : 1;
 
@@ -106,6 +110,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    mbar_init(w_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -119,6 +124,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&tmXh); tma_prefetch_desc(&tmXl); tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
+      if (kResW) {
+        mbar_expect_tx(w_full, 18 * wbytes);
+        for (int tap = 0; tap < 9; ++tap) {
+          tma_load_2d(sW + (2 * tap) * wbytes, &tmWh, w_full, 0, tap * g.Cout_p);
+          tma_load_2d(sW + (2 * tap + 1) * wbytes, &tmWl, w_full, 0, tap * g.Cout_p);
+        }
+      }
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
         const int txi = tile % g.tiles_x, tyi = (tile / g.tiles_x) % g.tiles_y, tbi = tile / (g.tiles_x * g.tiles_y);
@@ -131,8 +143,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
           uint8_t* dst = smem + stage * stage_bytes;
           tma_load_4d(dst, &tmXh, &full[stage], 64 * kc, x0 + kx - 1, y0 + ky - 1, n0);
           tma_load_4d(dst + kABytes, &tmXl, &full[stage], 64 * kc, x0 + kx - 1, y0 + ky - 1, n0);
-          tma_load_2d(dst + 2 * kABytes, &tmWh, &full[stage], 64 * kc, tap * g.Cout_p);
-          tma_load_2d(dst + 2 * kABytes + wbytes, &tmWl, &full[stage], 64 * kc, tap * g.Cout_p);
+          if (!kResW) {
+            tma_load_2d(dst + 2 * kABytes, &tmWh, &full[stage], 64 * kc, tap * g.Cout_p);
+            tma_load_2d(dst + 2 * kABytes + wbytes, &tmWl, &full[stage], 64 * kc, tap * g.Cout_p);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -142,6 +156,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
       const uint32_t idesc = make_idesc_f16(kTilePix, g.Cout_p, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
+      if (kResW) { mbar_wait(w_full, 0); tc_fence_after(); }
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
         mbar_wait(&acc_empty[as], aphase ^ 1);
         tc_fence_after();
@@ -150,7 +165,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + stage * stage_bytes), a_lo = a_hi + kABytes;
-          const uint32_t w_hi = a_hi + 2 * kABytes, w_lo = w_hi + wbytes;
+          const uint32_t w_hi = kResW ? smem_u32(sW + 2 * (it / kchunks) * wbytes) : a_hi + 2 * kABytes, w_lo = w_hi + wbytes;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint64_t dah = kdesc(a_hi + 32 * kk), dal = kdesc(a_lo + 32 * kk);
@@ -226,16 +241,26 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
 }
 
 // First layer (Cin = 1): bandwidth-bound, CUDA cores.  x [B,1,H,W] fp32 -> y NHWC hi/lo [B,H,W,Cout_p].
-// One thread per (pixel, group of 8 output channels).
+// One thread per pixel and 32 output channels: the 9 taps sit in registers, the weights are read as float4
+// broadcasts from shared memory ([tap][channel]), each thread writes 64 contiguous bytes per plane.
 __global__ void __launch_bounds__(256) conv3x3_first_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                  const float* __restrict__ b, int64_t B, int H, int W,
                                                                  int Cout, int Cout_p, int relu, __half* __restrict__ y_hi,
                                                                  __half* __restrict__ y_lo) {
-  const int groups = Cout_p / 8;
+  extern __shared__ __align__(16) float sw[];      // [9][Cout_p] weights, then [Cout_p] bias
+  float* sb = sw + 9 * Cout_p;
+  for (int i = threadIdx.x; i < 9 * Cout_p; i += blockDim.x) {
+    const int t = i / Cout_p, c = i % Cout_p;
+    sw[i] = c < Cout ? __ldg(w + c * 9 + t) : 0.f;
+  }
+  for (int i = threadIdx.x; i < Cout_p; i += blockDim.x) sb[i] = i < Cout ? __ldg(b + i) : 0.f;
+  __syncthreads();
+  const int groups = Cout_p / 32;
   const int64_t total = B * H * W * groups;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int gq = (int)(i % groups);
-    const int64_t p = i / groups;
+    // consecutive threads take consecutive pixels (coalesced input reads); the channel group is the slow index
+    const int64_t p = i % (B * H * W);
+    const int gq = (int)(i / (B * H * W));
     const int xx = (int)(p % W), yy = (int)((p / W) % H);
     const int64_t n = p / ((int64_t)W * H);
     float v[9];
@@ -246,31 +271,42 @@ __global__ void __launch_bounds__(256) conv3x3_first_nhwc_kernel(const float* __
         const int gy = yy + ky - 1, gx = xx + kx - 1;
         v[ky * 3 + kx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(x + (n * H + gy) * W + gx) : 0.f;
       }
-    uint32_t hi[4], lo[4];
+    float acc[32];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float o[2];
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float4 bb = *reinterpret_cast<const float4*>(&sb[gq * 32 + 4 * c4]);
+      acc[4 * c4] = bb.x; acc[4 * c4 + 1] = bb.y; acc[4 * c4 + 2] = bb.z; acc[4 * c4 + 3] = bb.w;
+    }
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int c = gq * 8 + 2 * j + e;
-        float acc = 0.f;
-        if (c < Cout) {
-          acc = __ldg(b + c);
+    for (int t = 0; t < 9; ++t) {
 #pragma unroll
-          for (int t = 0; t < 9; ++t) acc = fmaf(v[t], __ldg(w + c * 9 + t), acc);
-          if (relu) acc = fmaxf(acc, 0.f);
-        }
-        o[e] = acc;
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 ww = *reinterpret_cast<const float4*>(&sw[t * Cout_p + gq * 32 + 4 * c4]);
+        acc[4 * c4] = fmaf(v[t], ww.x, acc[4 * c4]);
+        acc[4 * c4 + 1] = fmaf(v[t], ww.y, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(v[t], ww.z, acc[4 * c4 + 2]);
+        acc[4 * c4 + 3] = fmaf(v[t], ww.w, acc[4 * c4 + 3]);
       }
-      const __half2 h = __floats2half2_rn(o[0], o[1]);
+    }
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float a = acc[2 * j], c = acc[2 * j + 1];
+      if (relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+      const __half2 h = __floats2half2_rn(a, c);
       const float2 hf = __half22float2(h);
-      const __half2 l = __floats2half2_rn(o[0] - hf.x, o[1] - hf.y);
+      const __half2 l = __floats2half2_rn(a - hf.x, c - hf.y);
       hi[j] = *reinterpret_cast<const uint32_t*>(&h);
       lo[j] = *reinterpret_cast<const uint32_t*>(&l);
     }
-    const int64_t o = p * Cout_p + gq * 8;
-    *reinterpret_cast<uint4*>(y_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(y_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    const int64_t o = p * Cout_p + gq * 32;
+    uint4* ph = reinterpret_cast<uint4*>(y_hi + o);
+    uint4* pl = reinterpret_cast<uint4*>(y_lo + o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ph[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+      pl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+    }
   }
 }
 
@@ -391,25 +427,26 @@ int conv_tc_forward(const void* x_hi, const void* x_lo, const void* w_hi, const 
   DRSA_TRY(make_tmap_nhwc(&tmXl, x_lo, (uint64_t)B, H, W, Cin_p, g.nb, g.th, g.tw));
   DRSA_TRY(make_tmap_f16_sw128(&tmWh, w_hi, (uint64_t)9 * Cout_p, (uint64_t)Cin_p, (uint32_t)Cout_p));
   DRSA_TRY(make_tmap_f16_sw128(&tmWl, w_lo, (uint64_t)9 * Cout_p, (uint64_t)Cin_p, (uint32_t)Cout_p));
-  const int stage_bytes = 2 * kABytes + 2 * Cout_p * 128;
   int grid = sm_count();
   if (grid > g.num_tiles) grid = g.num_tiles;
-  auto launch = [&](auto kernel, int stages) -> int {
-    const int smem_bytes = stages * stage_bytes + 256;
+  auto launch = [&](auto kernel, int stages, bool resw) -> int {
+    const int stage_bytes = resw ? 2 * kABytes : 2 * kABytes + 2 * Cout_p * 128;
+    const int smem_bytes = stages * stage_bytes + (resw ? 18 * Cout_p * 128 : 0) + 256;
     DRSA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmXh, tmXl, tmWh, tmWl, g, bias, static_cast<__half*>(y_hi),
                                                         static_cast<__half*>(y_lo), y_nchw, err_flag);
     DRSA_LAUNCH_CHECK();
     return DRSA_OK;
   };
-  if (Cout_p <= 64) return launch(conv3x3_tc_kernel<4>, 4);
-  if (Cout_p <= 128) return launch(conv3x3_tc_kernel<3>, 3);
-  return launch(conv3x3_tc_kernel<2>, 2);
+  if (Cout_p == 64 && Cin_p == 64) return launch(conv3x3_tc_kernel<2, true>, 2, true);
+  if (Cout_p <= 64) return launch(conv3x3_tc_kernel<4, false>, 4, false);
+  if (Cout_p <= 128) return launch(conv3x3_tc_kernel<3, false>, 3, false);
+  return launch(conv3x3_tc_kernel<2, false>, 2, false);
 }
 
 int conv_first_nhwc(const float* x, const float* w, const float* b, int64_t B, int H, int W, int Cout, int Cout_p,
                     int relu, void* y_hi, void* y_lo, cudaStream_t stream) {
-  conv3x3_first_nhwc_kernel<<<eblocks(B * H * W * (Cout_p / 8)), 256, 0, stream>>>(
+  conv3x3_first_nhwc_kernel<<<eblocks(B * H * W * (Cout_p / 32)), 256, (size_t)10 * Cout_p * sizeof(float), stream>>>(
       x, w, b, B, H, W, Cout, Cout_p, relu, static_cast<__half*>(y_hi), static_cast<__half*>(y_lo));
   DRSA_LAUNCH_CHECK();
   return DRSA_OK;

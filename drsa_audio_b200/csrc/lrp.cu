@@ -176,6 +176,43 @@ __global__ void relu_mask_kernel(const float* __restrict__ a, float* __restrict_
     if (!(__ldg(a + i) > 0.f)) R[i] = 0.f;
 }
 
+// y[n][o] = sum_k x[n][k] w[o][k] for few outputs and long rows (the first classifier layer: 64 x 100 outputs,
+// K = 4096): one warp per output, both operands read with coalesced float4 loads, fixed reduction order.
+__global__ void __launch_bounds__(256) skinny_dense_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           int64_t N, int In, int Out, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= N * Out) return;
+  const int64_t n = wid / Out; const int o = (int)(wid % Out);
+  const float* xr = x + n * In; const float* wr = w + (int64_t)o * In;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if ((In & 3) == 0) {
+    const float4* x4 = reinterpret_cast<const float4*>(xr); const float4* w4 = reinterpret_cast<const float4*>(wr);
+    for (int k = lane; k < In / 4; k += 32) {
+      const float4 a = __ldg(x4 + k), b = __ldg(w4 + k);
+      a0 = fmaf(a.x, b.x, a0); a1 = fmaf(a.y, b.y, a1); a2 = fmaf(a.z, b.z, a2); a3 = fmaf(a.w, b.w, a3);
+    }
+  } else {
+    for (int k = lane; k < In; k += 32) a0 = fmaf(__ldg(xr + k), __ldg(wr + k), a0);
+  }
+  const float s = warp_sum((a0 + a1) + (a2 + a3));
+  if (lane == 0) y[wid] = s;
+}
+
+// z = x w^T without bias: skinny shapes go to the warp-per-output kernel, the rest to the tiled SGEMM
+int dense_matmul_xwT(const float* x, const float* w, int64_t N, int In, int Out, float* y, cudaStream_t s) {
+  if (N * Out <= 65536 && In >= 512) {
+    const int64_t warps = N * Out;
+    skinny_dense_kernel<<<(int)((warps + 7) / 8), 256, 0, s>>>(x, w, N, In, Out, y);
+    DRSA_LAUNCH_CHECK();
+    return DRSA_OK;
+  }
+  GemmDesc g{};
+  g.A = x; g.B = w; g.C = y; g.M = (int)N; g.N = Out; g.K = In; g.lda = In; g.ldb = In; g.ldc = Out;
+  g.transA = 0; g.transB = 1; g.alpha = 1.f; g.splits = 1;
+  return sgemm(g, s);
+}
+
 inline int eblocks(int64_t n) {
   int64_t b = (n + 255) / 256;
   return (int)(b > 148 * 8 ? 148 * 8 : (b < 1 ? 1 : b));
@@ -222,10 +259,7 @@ int maxpool_backward(const float* R_out, const int32_t* argmax, int64_t NC, int 
 
 int dense_forward(const float* x, const float* w, const float* b, int64_t N, int In, int Out, int relu, float* y,
                   cudaStream_t s) {
-  GemmDesc g{};
-  g.A = x; g.B = w; g.C = y; g.M = (int)N; g.N = Out; g.K = In; g.lda = In; g.ldb = In; g.ldc = Out;
-  g.transA = 0; g.transB = 1; g.alpha = 1.f; g.splits = 1;
-  DRSA_TRY(sgemm(g, s));
+  DRSA_TRY(dense_matmul_xwT(x, w, N, In, Out, y, s));
   bias_act_kernel<<<eblocks(N * Out), 256, 0, s>>>(y, b, N, Out, relu);
   DRSA_LAUNCH_CHECK();
   return DRSA_OK;
@@ -233,10 +267,7 @@ int dense_forward(const float* x, const float* w, const float* b, int64_t N, int
 
 int dense_epsilon_backward(const float* x, const float* w, const float* b, const float* R_out, int64_t N, int In,
                            int Out, float eps, float* s_buf, float* R_in, cudaStream_t s) {
-  GemmDesc g{};
-  g.A = x; g.B = w; g.C = s_buf; g.M = (int)N; g.N = Out; g.K = In; g.lda = In; g.ldb = In; g.ldc = Out;
-  g.transA = 0; g.transB = 1; g.alpha = 1.f; g.splits = 1;
-  DRSA_TRY(sgemm(g, s));                                            // z = x w^T
+  DRSA_TRY(dense_matmul_xwT(x, w, N, In, Out, s_buf, s));           // z = x w^T
   ratio_kernel<<<eblocks(N * Out), 256, 0, s>>>(s_buf, b, R_out, N, Out, eps);   // s = R / stabilize(z + b)
   DRSA_LAUNCH_CHECK();
   GemmDesc h{};
