@@ -201,7 +201,7 @@ def run_ours(args):
             "rows_per_s": M * world * 1000.0 / ms_per_step,
             "gpu_launches": int(args.steps * launches_per_step(opt2)),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tf_sustained"], "traffic": TRAFFIC_BYTES_PER_LAUNCH,
+                         "frac": achieved / peaks["tf_sustained"], "traffic": TRAFFIC_BYTES_PER_LAUNCH if (opt2.precision == "tc" and not args.rows) else None,
                          "kernel": "drsa_tc_step_kernel (+ tc_reduce_kernel)" if opt2.precision == "tc" else "sgemm_kernel chain",
                          "kernel_ms": ms_kernel, "algorithmic_flop_per_launch": flops,
                          "algorithmic_bytes_per_launch": 2.0 * M * d * elem,
@@ -269,6 +269,7 @@ def lrp_throughput(args, dev, rank, world, barrier):
     ms = float(ms.item())
     # end to end from pinned host memory, result (vectors) read back
     xh = x.cpu().pin_memory()
+    act, ctx = once(xh.to(dev, non_blocking=True))          # warm the pinned-copy path
     barrier()
     t0 = time.perf_counter()
     act, ctx = once(xh.to(dev, non_blocking=True))
@@ -281,12 +282,13 @@ def lrp_throughput(args, dev, rank, world, barrier):
             "samples_per_gpu": n, "positions": P, "d": int(act.shape[1]), "ms": ms,
             "e2e_value": n * P * world / t_e2e, "h2d_bytes": int(xh.numel() * 4),
             "forward_tflops": flops / (ms * 1e-3) / 1e12,
-            "kernel": "conv3x3_kernel (CUDA-core fp32 direct convolution, round-1 version)"}
+            "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM, TMA im2col, fp16 hi/lo operands) + NHWC pooling; "
+                      "dense head and pool routing on CUDA cores"}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one drsa_tc_step_kernel launch at cfg2 from the committed
 # ncu --set full capture (profiles/); None until a capture exists.
-TRAFFIC_BYTES_PER_LAUNCH = None
+TRAFFIC_BYTES_PER_LAUNCH = 661.3e6      # 655.7 MB read + ~5.6 MB written (profiles/r01_ncu_full_drsa_tc_step_kernel.csv)
 
 
 def launches_per_step(opt) -> int:
