@@ -51,8 +51,9 @@ class LRPPlan:
         if model.training:
             raise _L.DRSAError("LRP needs model.eval() (BatchNorm running statistics are folded)")
         self.device = device
-        self.use_tc = True          # run the layers below the split layer on the tcgen05 NHWC pipeline
+        self.use_tc = True          # run model.features on the tcgen05 NHWC pipeline when the shapes allow it
         self._tc_err = None
+        self._tc_ok_cache = {}
         self.ops: List[_Op] = []
         self.module_to_op = {}
         mods = [(f"features.{n}", m) for n, m in model.features.named_children()]
@@ -139,111 +140,142 @@ class LRPPlan:
             _L.check(_L.lib().lrp_conv3x3_flip_weights(_ptr(op.w_mod), op.cout, op.cin, _ptr(op.wt_mod), _stream()),
                      "lrp_conv3x3_flip_weights")
 
-    # ------------------------------------------------------------------ tensor-core forward prefix
+    # ------------------------------------------------------------------ tensor-core conv stack (NHWC)
     @staticmethod
     def _pad64(c: int) -> int:
         return (c + 63) // 64 * 64
 
-    def _tc_prefix(self, x: torch.Tensor, keep_from: int) -> int:
-        """Number of leading ops that can run in the NHWC tcgen05 pipeline: nothing below `keep_from` has to
-        be kept for the backward, so those layers only need to hand over their final activation."""
+    def _stack_end(self) -> int:
+        for k, op in enumerate(self.ops):
+            if op.kind == "flatten":
+                return k
+        return len(self.ops)
+
+    def _tc_stack_ok(self, x: torch.Tensor) -> bool:
+        """True if every layer of model.features can run on the NHWC tcgen05 pipeline for this input."""
         if not self.use_tc or x.dim() != 4 or x.size(1) != 1:
-            return 0
+            return False
+        key = tuple(x.shape)
+        if key in self._tc_ok_cache:
+            return self._tc_ok_cache[key]
         lib = _L.lib()
         B, _, H, W = x.shape
-        n, convs, last_good = 0, 0, 0
-        for k, op in enumerate(self.ops):
-            if k >= keep_from:
-                break
+        ok, convs = True, 0
+        for k, op in enumerate(self.ops[: self._stack_end()]):
             if op.kind == "conv":
                 if k == 0:
-                    if op.cin != 1:
-                        return 0
+                    ok = op.cin == 1
                 else:
                     cin_p, cout_p = self._pad64(op.cin), self._pad64(op.cout)
-                    if cout_p > 256 or lib.lrp_tc_conv3x3_supported(B, cin_p, cout_p, H, W) != 0:
-                        break
+                    ok = cin_p <= 256 and cout_p <= 256 and lib.lrp_tc_conv3x3_supported(B, cin_p, cout_p, H, W) == 0
+                    if op.rule is not None and op.rule.kind not in ("epsilon", "gamma", "zplus"):
+                        ok = False
                 convs += 1
             elif op.kind == "pool":
-                if H % op.kh or W % op.kw:
-                    break
-                H, W = H // op.kh, W // op.kw
-            elif op.kind in ("identity", "relu"):
-                pass
-            else:
+                ok = H % op.kh == 0 and W % op.kw == 0 and op.kh * op.kw <= 255
+                H, W = H // max(op.kh, 1), W // max(op.kw, 1)
+            elif op.kind not in ("identity", "relu"):
+                ok = False
+            if not ok:
                 break
-            n = k + 1
-            if op.kind in ("conv", "pool") or (op.kind in ("identity", "relu")):
-                last_good = n
-        return last_good if convs >= 2 else 0
+        ok = ok and convs >= 2 and self.ops[0].kind == "conv"
+        self._tc_ok_cache[key] = ok
+        return ok
+
+    def _split_planes(self, t: torch.Tensor):
+        hi = torch.empty(t.shape, dtype=torch.float16, device=t.device)
+        lo = torch.empty_like(hi)
+        _L.check(_L.lib().lrp_tc_split_f16(_ptr(t), t.numel(), _ptr(hi), _ptr(lo), _stream()), "lrp_tc_split_f16")
+        return hi, lo
 
     def _prepare_tc(self, op: _Op, first: bool) -> None:
+        """fp16 hi/lo operand planes of a conv layer: forward weights [9][Cout_p][Cin_p]; for the LRP backward the
+        rule-modified weights in the same layout and their flipped, channel-swapped copy [9][Cin_p][Cout_p]."""
         if op.tc is not None:
             return
-        lib = _L.lib()
         dev = op.w.device
         cout_p = self._pad64(op.cout)
-        bias = torch.zeros(cout_p, device=dev)
-        bias[: op.cout] = op.b
+
+        def padded_bias(b):
+            out = torch.zeros(cout_p, device=dev)
+            out[: op.cout] = b
+            return out
+
         if first:
-            op.tc = {"w": op.w.reshape(op.cout, 9).contiguous(), "b": bias, "cout_p": cout_p}
+            op.tc = {"w": op.w.reshape(op.cout, 9).contiguous(), "b": padded_bias(op.b), "cout_p": cout_p}
             return
         cin_p = self._pad64(op.cin)
-        wt = torch.zeros(9, cout_p, cin_p, device=dev)
-        wt[:, : op.cout, : op.cin] = op.w.permute(2, 3, 0, 1).reshape(9, op.cout, op.cin)
-        hi = torch.empty(9, cout_p, cin_p, dtype=torch.float16, device=dev)
-        lo = torch.empty_like(hi)
-        _L.check(lib.lrp_tc_split_f16(_ptr(wt), wt.numel(), _ptr(hi), _ptr(lo), _stream()), "lrp_tc_split_f16")
-        op.tc = {"hi": hi, "lo": lo, "b": bias, "cin_p": cin_p, "cout_p": cout_p}
 
-    def _forward_tc(self, x: torch.Tensor, n_ops: int):
-        """Ops [0, n_ops) on the tensor-core pipeline; returns the activation after op n_ops-1 as NCHW fp32."""
+        def taps(w):                     # [Cout, Cin, 3, 3] -> [9, Cout_p, Cin_p], tap = ky*3 + kx
+            t = torch.zeros(9, cout_p, cin_p, device=dev)
+            t[:, : op.cout, : op.cin] = w.permute(2, 3, 0, 1).reshape(9, op.cout, op.cin)
+            return t
+
+        hi, lo = self._split_planes(taps(op.w))
+        op.tc = {"hi": hi, "lo": lo, "b": padded_bias(op.b), "cin_p": cin_p, "cout_p": cout_p}
+        if op.w_mod is not None:
+            mh, ml = self._split_planes(taps(op.w_mod))
+            tt = torch.zeros(9, cin_p, cout_p, device=dev)      # transposed conv: tap' = 8 - tap, channels swapped
+            tt[:, : op.cin, : op.cout] = op.w_mod.permute(2, 3, 1, 0).reshape(9, op.cin, op.cout).flip(0)
+            th, tl = self._split_planes(tt)
+            op.tc.update({"m_hi": mh, "m_lo": ml, "m_b": padded_bias(op.b_mod), "t_hi": th, "t_lo": tl})
+
+    def _nhwc_to_nchw(self, t):
+        """(hi, lo, C, Cp, H, W) NHWC planes -> NCHW fp32 [B, C, H, W]."""
+        hi, lo, C, Cp, H, W = t
+        B = hi.size(0)
+        out = torch.empty(B, C, H, W, device=hi.device)
+        _L.check(_L.lib().lrp_tc_nhwc_to_nchw(_ptr(hi), _ptr(lo), B, H, W, Cp, C, _ptr(out), _stream()), "nhwc_to_nchw")
+        return out
+
+    def _forward_tc_stack(self, x: torch.Tensor, keep_from: int, saved, outs):
+        """model.features on the tensor cores.  Keeps, for ops >= keep_from, the NHWC input planes of every conv and
+        the arg-max of every pool; returns the features as NCHW fp32 for the dense head."""
         lib = _L.lib()
         B, _, H, W = x.shape
         dev = x.device
         if self._tc_err is None or self._tc_err.device != dev:
             self._tc_err = torch.zeros(1, dtype=torch.int32, device=dev)
-        last_compute = max(k for k in range(n_ops) if self.ops[k].kind in ("conv", "pool"))
-        hi = lo = None
-        C = Cp = 1
-        out = None
-        for k in range(n_ops):
+        end = self._stack_end()
+        cur = None                                   # (hi, lo, C, Cp, H, W)
+        for k in range(end):
             op = self.ops[k]
+            keep = k >= keep_from
             if op.kind == "conv":
                 self._prepare_tc(op, first=(k == 0))
                 cout_p = op.tc["cout_p"]
-                is_last = k == last_compute
+                yh = torch.empty(B, H, W, cout_p, dtype=torch.float16, device=dev)
+                yl = torch.empty_like(yh)
                 if k == 0:
-                    yh = torch.empty(B, H, W, cout_p, dtype=torch.float16, device=dev)
-                    yl = torch.empty_like(yh)
                     _L.check(lib.lrp_tc_conv3x3_first(_ptr(x), _ptr(op.tc["w"]), _ptr(op.tc["b"]), B, H, W, op.cout, cout_p,
                                                       int(op.relu), _ptr(yh), _ptr(yl), _stream()), op.name)
-                    if is_last:
-                        out = torch.empty(B, op.cout, H, W, device=dev)
-                        _L.check(lib.lrp_tc_nhwc_to_nchw(_ptr(yh), _ptr(yl), B, H, W, cout_p, op.cout, _ptr(out), _stream()))
+                    if keep:
+                        saved[k] = ("tc_first", x)
                 else:
-                    yh = yl = None
-                    if is_last:
-                        out = torch.empty(B, op.cout, H, W, device=dev)
-                    else:
-                        yh = torch.empty(B, H, W, cout_p, dtype=torch.float16, device=dev)
-                        yl = torch.empty_like(yh)
-                    _L.check(lib.lrp_tc_conv3x3_forward(_ptr(hi), _ptr(lo), _ptr(op.tc["hi"]), _ptr(op.tc["lo"]),
+                    _L.check(lib.lrp_tc_conv3x3_forward(_ptr(cur[0]), _ptr(cur[1]), _ptr(op.tc["hi"]), _ptr(op.tc["lo"]),
                                                         _ptr(op.tc["b"]), B, H, W, op.tc["cin_p"], cout_p, op.cout,
-                                                        int(op.relu), _ptr(yh), _ptr(yl), _ptr(out) if is_last else None,
-                                                        _ptr(self._tc_err), _stream()), op.name)
-                hi, lo, C, Cp = yh, yl, op.cout, cout_p
+                                                        int(op.relu), _ptr(yh), _ptr(yl), None, _ptr(self._tc_err),
+                                                        _stream()), op.name)
+                    if keep:
+                        saved[k] = ("tc_conv", cur)
+                cur = (yh, yl, op.cout, cout_p, H, W)
             elif op.kind == "pool":
                 Ho, Wo = H // op.kh, W // op.kw
+                C, Cp = cur[2], cur[3]
                 yh = torch.empty(B, Ho, Wo, Cp, dtype=torch.float16, device=dev)
                 yl = torch.empty_like(yh)
-                _L.check(lib.lrp_tc_maxpool(_ptr(hi), _ptr(lo), B, H, W, Cp, op.kh, op.kw, _ptr(yh), _ptr(yl), _stream()),
-                         op.name)
-                hi, lo, H, W = yh, yl, Ho, Wo
-                if k == last_compute:
-                    out = torch.empty(B, C, H, W, device=dev)
-                    _L.check(lib.lrp_tc_nhwc_to_nchw(_ptr(hi), _ptr(lo), B, H, W, Cp, C, _ptr(out), _stream()))
-        return out
+                am = torch.empty(B, Ho, Wo, Cp, dtype=torch.uint8, device=dev) if keep else None
+                _L.check(lib.lrp_tc_maxpool(_ptr(cur[0]), _ptr(cur[1]), B, H, W, Cp, op.kh, op.kw, _ptr(yh), _ptr(yl),
+                                            _ptr(am), _stream()), op.name)
+                if keep:
+                    saved[k] = ("tc_pool", am, (H, W, Cp))
+                H, W = Ho, Wo
+                cur = (yh, yl, C, Cp, H, W)
+            elif op.kind == "relu":
+                if keep:
+                    saved[k] = ("tc_relu", cur)          # ReLU is fused into the producer: output == input
+            outs[k] = ("nhwc", cur) if k >= keep_from - 1 else None
+        return self._nhwc_to_nchw(cur)
 
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, keep_from: int = 0):
@@ -253,11 +285,10 @@ class LRPPlan:
         saved = [None] * len(self.ops)
         outs = [None] * len(self.ops)
         cur = x
-        n_tc = self._tc_prefix(x, keep_from)
-        if n_tc:
-            cur = self._forward_tc(x, n_tc)
-            for k in range(n_tc):
-                outs[k] = cur if k == n_tc - 1 else None
+        n_tc = 0
+        if self._tc_stack_ok(x):
+            n_tc = self._stack_end()
+            cur = self._forward_tc_stack(x, keep_from, saved, outs)
         for k, op in enumerate(self.ops):
             if k < n_tc:
                 continue
@@ -300,16 +331,63 @@ class LRPPlan:
 
     # ------------------------------------------------------------------ backward
     def backward(self, Rel: torch.Tensor, saved, stop_after: int = -1) -> torch.Tensor:
-        """Propagates relevance from the logits down to the OUTPUT of op `stop_after` (-1: to the input)."""
+        """Propagates relevance from the logits down to the OUTPUT of op `stop_after` (-1: to the input).  Inside the
+        tensor-core conv stack the relevance travels as NHWC fp32 with padded channels."""
         lib = _L.lib()
+        nhwc = None            # (C, Cp, H, W) while Rel is NHWC fp32
         for k in range(len(self.ops) - 1, stop_after, -1):
             op = self.ops[k]
+            sv = saved[k]
+            is_tc = isinstance(sv, tuple) and len(sv) > 0 and isinstance(sv[0], str) and sv[0].startswith("tc_")
+            if is_tc and nhwc is None and sv[0] != "tc_first":
+                # entering the NHWC stack from the dense head: Rel is NCHW fp32 [B, C, H, W]
+                B, C, H, W = Rel.shape
+                Cp = self._pad64(C)
+                t = torch.empty(B, H, W, Cp, device=Rel.device)
+                _L.check(lib.lrp_tc_nchw_to_nhwc_f32(_ptr(Rel.contiguous()), B, H, W, C, Cp, _ptr(t), _stream()), "to_nhwc")
+                Rel, nhwc = t, (C, Cp, H, W)
+            if is_tc and sv[0] == "tc_pool":
+                am, (H, W, Cp) = sv[1], sv[2]
+                B = Rel.size(0)
+                R_in = torch.empty(B, H, W, Cp, device=Rel.device)
+                _L.check(lib.lrp_tc_maxpool_backward(_ptr(Rel), _ptr(am), B, H, W, Cp, op.kh, op.kw, _ptr(R_in), _stream()),
+                         op.name)
+                Rel, nhwc = R_in, (nhwc[0], Cp, H, W)
+                continue
+            if is_tc and sv[0] == "tc_relu":
+                if self._relu_needs_mask(k):
+                    a = sv[1]
+                    _L.check(lib.lrp_tc_relu_mask(_ptr(Rel), _ptr(a[0]), _ptr(a[1]), Rel.numel(), _stream()), op.name)
+                continue
+            if is_tc and sv[0] == "tc_conv":
+                if op.rule is None:
+                    raise _L.DRSAError(f"{op.name}: no LRP rule assigned")
+                xin = sv[1]                               # (hi, lo, C, Cp, H, W) input planes
+                B, H, W = Rel.size(0), xin[4], xin[5]
+                cin_p, cout_p = op.tc["cin_p"], op.tc["cout_p"]
+                sh = torch.empty(B, H, W, cout_p, dtype=torch.float16, device=Rel.device)
+                sl = torch.empty_like(sh)
+                _L.check(lib.lrp_tc_conv3x3_ratio(_ptr(xin[0]), _ptr(xin[1]), _ptr(op.tc["m_hi"]), _ptr(op.tc["m_lo"]),
+                                                  _ptr(op.tc["m_b"]), _ptr(Rel), B, H, W, cin_p, cout_p, op.eps, _ptr(sh),
+                                                  _ptr(sl), _ptr(self._tc_err), _stream()), op.name)
+                R_in = torch.empty(B, H, W, cin_p, device=Rel.device)
+                _L.check(lib.lrp_tc_conv3x3_inputmul(_ptr(sh), _ptr(sl), _ptr(op.tc["t_hi"]), _ptr(op.tc["t_lo"]), _ptr(xin[0]),
+                                                     _ptr(xin[1]), B, H, W, cout_p, cin_p, _ptr(R_in), _ptr(self._tc_err),
+                                                     _stream()), op.name)
+                Rel, nhwc = R_in, (op.cin, cin_p, H, W)
+                continue
+            if is_tc and sv[0] == "tc_first":
+                # leave the NHWC stack: the first conv (Cin = 1) runs on the CUDA-core kernels in NCHW
+                if nhwc is not None:
+                    Rel = self._rel_to_nchw(Rel, nhwc)
+                    nhwc = None
+                sv = sv[1]
             if op.kind == "dense":
-                if op.rule is None or op.rule.kind == "pass":
-                    if op.rule is None:
-                        raise _L.DRSAError(f"{op.name}: no LRP rule assigned")
+                if op.rule is None:
+                    raise _L.DRSAError(f"{op.name}: no LRP rule assigned")
+                if op.rule.kind == "pass":
                     continue
-                x = saved[k]
+                x = sv
                 N, In = x.shape
                 s_buf = torch.empty(N, op.cout, device=x.device)
                 R_in = torch.empty_like(x)
@@ -321,7 +399,7 @@ class LRPPlan:
                     raise _L.DRSAError(f"{op.name}: no LRP rule assigned")
                 if op.rule.kind == "pass":
                     continue
-                x = saved[k]
+                x = sv
                 N, Cin, H, W = x.shape
                 s_buf = torch.empty(N, op.cout, H, W, device=x.device)
                 R_in = torch.empty_like(x)
@@ -330,19 +408,41 @@ class LRPPlan:
                                                   _stream()), op.name)
                 Rel = R_in
             elif op.kind == "relu":
-                a = saved[k]
+                a = sv
                 Rel = Rel.contiguous()
                 _L.check(lib.lrp_relu_mask(_ptr(a), _ptr(Rel), Rel.numel(), _stream()), op.name)
             elif op.kind == "pool":
-                am, shp = saved[k]
+                am, shp = sv
                 N, Cc, H, W = shp
                 R_in = torch.empty(shp, device=Rel.device)
                 _L.check(lib.lrp_maxpool_backward(_ptr(Rel.contiguous()), _ptr(am), N * Cc, H, W, op.kh, op.kw,
                                                   _ptr(R_in), _stream()), op.name)
                 Rel = R_in
             elif op.kind == "flatten":
-                Rel = Rel.reshape(saved[k])
+                Rel = Rel.reshape(sv)
+        if nhwc is not None:
+            Rel = self._rel_to_nchw(Rel, nhwc)
         return Rel
+
+    def _rel_to_nchw(self, Rel: torch.Tensor, nhwc) -> torch.Tensor:
+        C, Cp, H, W = nhwc
+        B = Rel.size(0)
+        out = torch.empty(B, C, H, W, device=Rel.device)
+        _L.check(_L.lib().lrp_tc_nhwc_f32_to_nchw(_ptr(Rel), B, H, W, Cp, C, _ptr(out), _stream()), "to_nchw")
+        return out
+
+    def _relu_needs_mask(self, k: int) -> bool:
+        """The mask of an un-hooked ReLU is a no-op when the relevance arriving at its output was produced by an
+        input-multiplying rule on that very output (Gamma/ZPlus/Epsilon return x * (...), and pooling only routes
+        such values): then R is already zero wherever the activation is zero."""
+        for j in range(k + 1, len(self.ops)):
+            o = self.ops[j]
+            if o.kind in ("identity", "pool", "flatten", "relu"):
+                continue
+            if o.kind in ("conv", "dense"):
+                return not (o.rule is not None and o.rule.kind in ("epsilon", "gamma", "zplus"))
+            return True
+        return True
 
     def check_nonneg_inputs(self):
         """Gamma / ZPlus use the collapsed form that is valid for non-negative inputs only: every such
@@ -421,7 +521,8 @@ def lrp_intermediate(model, input_batch, composite, layer, class_idx, attr_batch
             logits, saved, outs = plan.forward(x[i:i + attr_batch_size], keep_from=split + 1)
             seed = fn(logits).contiguous()
             r_maps.append(plan.backward(seed, saved, stop_after=split))
-            a_maps.append(outs[split])
+            o = outs[split]
+            a_maps.append(plan._nhwc_to_nchw(o[1]) if isinstance(o, tuple) else o)
     return torch.cat(a_maps, 0), torch.cat(r_maps, 0)
 
 

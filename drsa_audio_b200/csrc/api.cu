@@ -61,11 +61,20 @@ int conv_tc_forward(const void* x_hi, const void* x_lo, const void* w_hi, const 
                     int* err_flag, cudaStream_t stream);
 int conv_first_nhwc(const float* x, const float* w, const float* b, int64_t B, int H, int W, int Cout, int Cout_p,
                     int relu, void* y_hi, void* y_lo, cudaStream_t stream);
+int conv_tc_run(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int64_t B,
+                int H, int W, int Cin_p, int Cout_p, int Cout, int relu, int epi, float eps, const float* aux_f32,
+                const void* aux_hi, const void* aux_lo, void* y_hi, void* y_lo, float* y_f32, float* y_nchw, int* err_flag,
+                cudaStream_t stream);
 int maxpool_nhwc(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int kh, int kw, void* y_hi,
-                 void* y_lo, cudaStream_t stream);
+                 void* y_lo, void* argmax_u8, cudaStream_t stream);
+int maxpool_nhwc_backward(const float* R_out, const void* argmax_u8, int64_t B, int H, int W, int Cp, int kh, int kw,
+                          float* R_in, cudaStream_t stream);
+int nhwc_f32_to_nchw(const float* x, int64_t B, int H, int W, int Cp, int C, float* y, cudaStream_t stream);
+int nchw_to_nhwc_f32(const float* x, int64_t B, int H, int W, int C, int Cp, float* y, cudaStream_t stream);
 int nhwc_to_nchw(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int C, float* y,
                  cudaStream_t stream);
 int split_f16(const float* in, int64_t count, void* hi, void* lo, cudaStream_t stream);
+int relu_mask_nhwc(float* R, const void* a_hi, const void* a_lo, int64_t count, cudaStream_t stream);
 int pack_f16(const float* in, int64_t count, float scale, void* out, cudaStream_t stream);
 int absmax(const float* in, int64_t count, float* out, cudaStream_t stream);
 int64_t finish_workspace_bytes(int d, int m);
@@ -334,12 +343,61 @@ int lrp_tc_conv3x3_first(const float* x, const float* w, const float* b, int64_t
 }
 
 int lrp_tc_maxpool(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int kh, int kw, void* y_hi,
-                   void* y_lo, void* stream) {
+                   void* y_lo, void* argmax_u8, void* stream) {
   if (x_hi == nullptr || x_lo == nullptr || y_hi == nullptr || y_lo == nullptr || B <= 0 || Cp % 8 != 0 || kh <= 0 ||
-      kw <= 0 || H / kh == 0 || W / kw == 0)
+      kw <= 0 || H / kh == 0 || W / kw == 0 || kh * kw > 255)
     return DRSA_ERR_ARG;
   DRSA_TRY(require_sm100());
-  return maxpool_nhwc(x_hi, x_lo, B, H, W, Cp, kh, kw, y_hi, y_lo, static_cast<cudaStream_t>(stream));
+  return maxpool_nhwc(x_hi, x_lo, B, H, W, Cp, kh, kw, y_hi, y_lo, argmax_u8, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_tc_maxpool_backward(const float* R_out, const void* argmax_u8, int64_t B, int H, int W, int Cp, int kh, int kw,
+                            float* R_in, void* stream) {
+  if (R_out == nullptr || argmax_u8 == nullptr || R_in == nullptr || B <= 0 || Cp % 4 != 0 || kh <= 0 || kw <= 0 ||
+      H % kh != 0 || W % kw != 0)
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return maxpool_nhwc_backward(R_out, argmax_u8, B, H, W, Cp, kh, kw, R_in, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_tc_conv3x3_ratio(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                         const float* R_out, int64_t B, int H, int W, int Cin_p, int Cout_p, float eps, void* s_hi,
+                         void* s_lo, int* err_flag, void* stream) {
+  if (x_hi == nullptr || x_lo == nullptr || w_hi == nullptr || w_lo == nullptr || bias == nullptr || R_out == nullptr ||
+      s_hi == nullptr || s_lo == nullptr || err_flag == nullptr)
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return conv_tc_run(x_hi, x_lo, w_hi, w_lo, bias, B, H, W, Cin_p, Cout_p, Cout_p, 0, 1, eps, R_out, nullptr, nullptr, s_hi,
+                     s_lo, nullptr, nullptr, err_flag, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_tc_conv3x3_inputmul(const void* s_hi, const void* s_lo, const void* wt_hi, const void* wt_lo, const void* x_hi,
+                            const void* x_lo, int64_t B, int H, int W, int Cout_p, int Cin_p, float* R_in, int* err_flag,
+                            void* stream) {
+  if (s_hi == nullptr || s_lo == nullptr || wt_hi == nullptr || wt_lo == nullptr || x_hi == nullptr || x_lo == nullptr ||
+      R_in == nullptr || err_flag == nullptr)
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return conv_tc_run(s_hi, s_lo, wt_hi, wt_lo, nullptr, B, H, W, Cout_p, Cin_p, Cin_p, 0, 2, 0.f, nullptr, x_hi, x_lo, nullptr,
+                     nullptr, R_in, nullptr, err_flag, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_tc_relu_mask(float* R, const void* a_hi, const void* a_lo, int64_t count, void* stream) {
+  if (R == nullptr || a_hi == nullptr || a_lo == nullptr || count <= 0) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return relu_mask_nhwc(R, a_hi, a_lo, count, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_tc_nhwc_f32_to_nchw(const float* x, int64_t B, int H, int W, int Cp, int C, float* y, void* stream) {
+  if (x == nullptr || y == nullptr || B <= 0 || C <= 0 || C > Cp) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return nhwc_f32_to_nchw(x, B, H, W, Cp, C, y, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_tc_nchw_to_nhwc_f32(const float* x, int64_t B, int H, int W, int C, int Cp, float* y, void* stream) {
+  if (x == nullptr || y == nullptr || B <= 0 || C <= 0 || C > Cp) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return nchw_to_nhwc_f32(x, B, H, W, C, Cp, y, static_cast<cudaStream_t>(stream));
 }
 
 int lrp_tc_nhwc_to_nchw(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int C, float* y,

@@ -79,14 +79,17 @@ struct ConvGeom {
   int nb, th, tw;                        // tile = nb images x th rows x tw columns = 128 pixels
   int tiles_x, tiles_y, tiles_b, num_tiles;
   int relu;
+  int epi;      // 0: y = relu?(acc + b); 1: y = aux_f32 / stabilize(acc + b, eps); 2: y = (aux_hi + aux_lo) * acc
+  float eps;
 };
 
 template <int kStages, bool kResW>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                   const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, ConvGeom g,
-                  const float* __restrict__ bias, __half* __restrict__ y_hi, __half* __restrict__ y_lo,
-                  float* __restrict__ y_nchw, int* __restrict__ err_flag) {
+                  const float* __restrict__ bias, const float* __restrict__ aux_f32, const __half* __restrict__ aux_hi,
+                  const __half* __restrict__ aux_lo, __half* __restrict__ y_hi, __half* __restrict__ y_lo,
+                  float* __restrict__ y_f32, float* __restrict__ y_nchw, int* __restrict__ err_flag) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int wbytes = g.Cout_p * 128;                 // one [Cout_p x 64] weight box
   // kResW (Cin_p = Cout_p = 64): all 9 taps of the hi/lo weights (144 KB) stay resident in shared memory and the
@@ -200,26 +203,70 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
         tmem_ld32(lane_base + as * g.Cout_p + 32 * cc, v);
         tmem_ld_wait();
         if (valid) {
-          uint32_t hi[16], lo[16];
+          float a[32];
+          const int64_t o = pbase + 32 * cc;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float a = __uint_as_float(v[2 * i]) + __ldg(bias + 32 * cc + 2 * i);
-            float b = __uint_as_float(v[2 * i + 1]) + __ldg(bias + 32 * cc + 2 * i + 1);
-            if (g.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-            const __half2 h = __floats2half2_rn(a, b);
-            const float2 hf = __half22float2(h);
-            const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-            hi[i] = *reinterpret_cast<const uint32_t*>(&h);
-            lo[i] = *reinterpret_cast<const uint32_t*>(&l);
-            if (y_nchw != nullptr) {
-              const int c = 32 * cc + 2 * i;
-              if (c < g.Cout) y_nchw[(((int64_t)n * g.Cout + c) * g.H + y) * g.W + x] = a;
-              if (c + 1 < g.Cout) y_nchw[(((int64_t)n * g.Cout + c + 1) * g.H + y) * g.W + x] = b;
+          for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(v[i]);
+          if (g.epi != 2) {
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + 32 * cc) + i4);
+              a[4 * i4] += bb.x; a[4 * i4 + 1] += bb.y; a[4 * i4 + 2] += bb.z; a[4 * i4 + 3] += bb.w;
             }
           }
+          if (g.epi == 0) {
+            if (g.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) a[i] = fmaxf(a[i], 0.f);
+            }
+          } else if (g.epi == 1) {            // s = R_out / stabilize(z', eps)
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+              const float4 r = __ldg(reinterpret_cast<const float4*>(aux_f32 + o) + i4);
+              a[4 * i4] = r.x / stabilize(a[4 * i4], g.eps);
+              a[4 * i4 + 1] = r.y / stabilize(a[4 * i4 + 1], g.eps);
+              a[4 * i4 + 2] = r.z / stabilize(a[4 * i4 + 2], g.eps);
+              a[4 * i4 + 3] = r.w / stabilize(a[4 * i4 + 3], g.eps);
+            }
+          } else {                            // R_in = x * c
+#pragma unroll
+            for (int i8 = 0; i8 < 4; ++i8) {
+              const uint4 h = __ldg(reinterpret_cast<const uint4*>(aux_hi + o) + i8);
+              const uint4 l = __ldg(reinterpret_cast<const uint4*>(aux_lo + o) + i8);
+              const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+                const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
+                a[8 * i8 + 2 * j] *= hf.x + lf.x;
+                a[8 * i8 + 2 * j + 1] *= hf.y + lf.y;
+              }
+            }
+          }
+          if (y_nchw != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = 32 * cc + i;
+              if (c < g.Cout) y_nchw[(((int64_t)n * g.Cout + c) * g.H + y) * g.W + x] = a[i];
+            }
+          }
+          if (y_f32 != nullptr) {
+            float4* pf = reinterpret_cast<float4*>(y_f32 + o);
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) pf[i4] = make_float4(a[4 * i4], a[4 * i4 + 1], a[4 * i4 + 2], a[4 * i4 + 3]);
+          }
           if (y_hi != nullptr) {
-            uint4* ph = reinterpret_cast<uint4*>(y_hi + pbase + 32 * cc);
-            uint4* pl = reinterpret_cast<uint4*>(y_lo + pbase + 32 * cc);
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const __half2 h = __floats2half2_rn(a[2 * i], a[2 * i + 1]);
+              const float2 hf = __half22float2(h);
+              const __half2 l = __floats2half2_rn(a[2 * i] - hf.x, a[2 * i + 1] - hf.y);
+              hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+              lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            uint4* ph = reinterpret_cast<uint4*>(y_hi + o);
+            uint4* pl = reinterpret_cast<uint4*>(y_lo + o);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               ph[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
@@ -313,7 +360,8 @@ __global__ void __launch_bounds__(256) conv3x3_first_nhwc_kernel(const float* __
 // MaxPool2d(kh, kw), stride = kernel, on NHWC hi/lo planes; one thread per (output pixel, 8 channels).
 __global__ void __launch_bounds__(256) maxpool_nhwc_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo,
                                                            int64_t B, int H, int W, int Cp, int kh, int kw,
-                                                           __half* __restrict__ y_hi, __half* __restrict__ y_lo) {
+                                                           __half* __restrict__ y_hi, __half* __restrict__ y_lo,
+                                                           uint8_t* __restrict__ amax) {
   const int Ho = H / kh, Wo = W / kw, groups = Cp / 8;
   const int64_t total = B * Ho * Wo * groups;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -322,8 +370,9 @@ __global__ void __launch_bounds__(256) maxpool_nhwc_kernel(const __half* __restr
     const int xo = (int)(p % Wo), yo = (int)((p / Wo) % Ho);
     const int64_t n = p / ((int64_t)Wo * Ho);
     float best[8];
+    unsigned char bidx[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) best[e] = -INFINITY;
+    for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; bidx[e] = 0; }
     for (int dy = 0; dy < kh; ++dy)
       for (int dx = 0; dx < kw; ++dx) {
         const int64_t o = (((n * H + yo * kh + dy) * W) + xo * kw + dx) * Cp + gq * 8;
@@ -334,10 +383,18 @@ __global__ void __launch_bounds__(256) maxpool_nhwc_kernel(const __half* __restr
         for (int j = 0; j < 4; ++j) {
           const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
           const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
-          best[2 * j] = fmaxf(best[2 * j], hf.x + lf.x);
-          best[2 * j + 1] = fmaxf(best[2 * j + 1], hf.y + lf.y);
+          const float v0 = hf.x + lf.x, v1 = hf.y + lf.y;
+          // strict '>' keeps the first maximum in row-major window order (PyTorch's choice)
+          if (v0 > best[2 * j]) { best[2 * j] = v0; bidx[2 * j] = (unsigned char)(dy * kw + dx); }
+          if (v1 > best[2 * j + 1]) { best[2 * j + 1] = v1; bidx[2 * j + 1] = (unsigned char)(dy * kw + dx); }
         }
       }
+    if (amax != nullptr) {
+      uint2 packed;
+      packed.x = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | ((uint32_t)bidx[3] << 24);
+      packed.y = bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | ((uint32_t)bidx[7] << 24);
+      *reinterpret_cast<uint2*>(amax + p * Cp + gq * 8) = packed;
+    }
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -350,6 +407,68 @@ __global__ void __launch_bounds__(256) maxpool_nhwc_kernel(const __half* __restr
     const int64_t o = p * Cp + gq * 8;
     *reinterpret_cast<uint4*>(y_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(y_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// Relevance routing of an un-hooked MaxPool2d on NHWC fp32: R_in[window arg-max] = R_out, zeros elsewhere.
+__global__ void __launch_bounds__(256) maxpool_nhwc_bwd_kernel(const float* __restrict__ R_out, const uint8_t* __restrict__ amax,
+                                                               int64_t B, int H, int W, int Cp, int kh, int kw,
+                                                               float* __restrict__ R_in) {
+  const int Ho = H / kh, Wo = W / kw, groups = Cp / 4;
+  const int64_t total = B * Ho * Wo * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int gq = (int)(i % groups);
+    const int64_t p = i / groups;
+    const int xo = (int)(p % Wo), yo = (int)((p / Wo) % Ho);
+    const int64_t n = p / ((int64_t)Wo * Ho);
+    const float4 r = __ldg(reinterpret_cast<const float4*>(R_out + p * Cp + gq * 4));
+    const uchar4 am = *reinterpret_cast<const uchar4*>(amax + p * Cp + gq * 4);
+    const float rv[4] = {r.x, r.y, r.z, r.w};
+    const unsigned char av[4] = {am.x, am.y, am.z, am.w};
+    for (int dy = 0; dy < kh; ++dy)
+      for (int dx = 0; dx < kw; ++dx) {
+        const int widx = dy * kw + dx;
+        float4 o;
+        o.x = av[0] == widx ? rv[0] : 0.f; o.y = av[1] == widx ? rv[1] : 0.f;
+        o.z = av[2] == widx ? rv[2] : 0.f; o.w = av[3] == widx ? rv[3] : 0.f;
+        *reinterpret_cast<float4*>(R_in + (((n * H + yo * kh + dy) * W) + xo * kw + dx) * Cp + gq * 4) = o;
+      }
+  }
+}
+
+// NHWC fp32 [B,H,W,Cp] <-> NCHW fp32 [B,C,H,W] (32x32 shared-memory transposes; padded channels are zero-filled)
+__global__ void __launch_bounds__(256) nhwc_f32_to_nchw_kernel(const float* __restrict__ x, int HW, int Cp, int C,
+                                                               float* __restrict__ y) {
+  __shared__ float t[32][33];
+  const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int p = p0 + ty + 8 * r, c = c0 + tx;
+    t[ty + 8 * r][tx] = (p < HW && c < Cp) ? x[((int64_t)n * HW + p) * Cp + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = c0 + ty + 8 * r, p = p0 + tx;
+    if (c < C && p < HW) y[((int64_t)n * C + c) * HW + p] = t[tx][ty + 8 * r];
+  }
+}
+__global__ void __launch_bounds__(256) nchw_to_nhwc_f32_kernel(const float* __restrict__ x, int HW, int C, int Cp,
+                                                               float* __restrict__ y) {
+  __shared__ float t[32][33];
+  const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = c0 + ty + 8 * r, p = p0 + tx;
+    t[ty + 8 * r][tx] = (c < C && p < HW) ? x[((int64_t)n * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int p = p0 + ty + 8 * r, c = c0 + tx;
+    if (p < HW && c < Cp) y[((int64_t)n * HW + p) * Cp + c] = t[tx][ty + 8 * r];
   }
 }
 
@@ -375,6 +494,13 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __half* __restr
     const int c = c0 + ty + 8 * r, p = p0 + tx;
     if (c < C && p < HW) y[((int64_t)n * C + c) * HW + p] = t[tx][ty + 8 * r];
   }
+}
+
+// R = 0 where the ReLU output a = hi + lo is not positive (autograd of an un-hooked ReLU, NHWC)
+__global__ void relu_mask_nhwc_kernel(float* __restrict__ R, const __half* __restrict__ a_hi, const __half* __restrict__ a_lo,
+                                      int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (!(__half2float(a_hi[i]) + __half2float(a_lo[i]) > 0.f)) R[i] = 0.f;
 }
 
 __global__ void split_f16_kernel(const float* __restrict__ in, int64_t n, __half* __restrict__ hi, __half* __restrict__ lo) {
@@ -413,12 +539,13 @@ bool conv_tc_supported(int64_t B, int Cin_p, int Cout_p, int H, int W) {
   return pick_tile((int)B, H, W, &nb, &th, &tw);
 }
 
-int conv_tc_forward(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int64_t B,
-                    int H, int W, int Cin_p, int Cout_p, int Cout, int relu, void* y_hi, void* y_lo, float* y_nchw,
-                    int* err_flag, cudaStream_t stream) {
+int conv_tc_run(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int64_t B,
+                int H, int W, int Cin_p, int Cout_p, int Cout, int relu, int epi, float eps, const float* aux_f32,
+                const void* aux_hi, const void* aux_lo, void* y_hi, void* y_lo, float* y_f32, float* y_nchw, int* err_flag,
+                cudaStream_t stream) {
   ConvGeom g{};
   if (!conv_tc_supported(B, Cin_p, Cout_p, H, W) || B > 2147483647LL / ((int64_t)H * W)) return DRSA_ERR_SHAPE;
-  g.B = (int)B; g.H = H; g.W = W; g.Cin_p = Cin_p; g.Cout_p = Cout_p; g.Cout = Cout; g.relu = relu;
+  g.B = (int)B; g.H = H; g.W = W; g.Cin_p = Cin_p; g.Cout_p = Cout_p; g.Cout = Cout; g.relu = relu; g.epi = epi; g.eps = eps;
   pick_tile(g.B, H, W, &g.nb, &g.th, &g.tw);
   g.tiles_x = W / g.tw; g.tiles_y = H / g.th; g.tiles_b = (g.B + g.nb - 1) / g.nb;
   g.num_tiles = g.tiles_x * g.tiles_y * g.tiles_b;
@@ -433,8 +560,10 @@ int conv_tc_forward(const void* x_hi, const void* x_lo, const void* w_hi, const 
     const int stage_bytes = resw ? 2 * kABytes : 2 * kABytes + 2 * Cout_p * 128;
     const int smem_bytes = stages * stage_bytes + (resw ? 18 * Cout_p * 128 : 0) + 256;
     DRSA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmXh, tmXl, tmWh, tmWl, g, bias, static_cast<__half*>(y_hi),
-                                                        static_cast<__half*>(y_lo), y_nchw, err_flag);
+    kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmXh, tmXl, tmWh, tmWl, g, bias, aux_f32,
+                                                        static_cast<const __half*>(aux_hi), static_cast<const __half*>(aux_lo),
+                                                        static_cast<__half*>(y_hi), static_cast<__half*>(y_lo), y_f32, y_nchw,
+                                                        err_flag);
     DRSA_LAUNCH_CHECK();
     return DRSA_OK;
   };
@@ -442,6 +571,13 @@ int conv_tc_forward(const void* x_hi, const void* x_lo, const void* w_hi, const 
   if (Cout_p <= 64) return launch(conv3x3_tc_kernel<4, false>, 4, false);
   if (Cout_p <= 128) return launch(conv3x3_tc_kernel<3, false>, 3, false);
   return launch(conv3x3_tc_kernel<2, false>, 2, false);
+}
+
+int conv_tc_forward(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int64_t B,
+                    int H, int W, int Cin_p, int Cout_p, int Cout, int relu, void* y_hi, void* y_lo, float* y_nchw,
+                    int* err_flag, cudaStream_t stream) {
+  return conv_tc_run(x_hi, x_lo, w_hi, w_lo, bias, B, H, W, Cin_p, Cout_p, Cout, relu, 0, 0.f, nullptr, nullptr, nullptr, y_hi,
+                     y_lo, nullptr, y_nchw, err_flag, stream);
 }
 
 int conv_first_nhwc(const float* x, const float* w, const float* b, int64_t B, int H, int W, int Cout, int Cout_p,
@@ -453,10 +589,34 @@ int conv_first_nhwc(const float* x, const float* w, const float* b, int64_t B, i
 }
 
 int maxpool_nhwc(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int kh, int kw, void* y_hi,
-                 void* y_lo, cudaStream_t stream) {
+                 void* y_lo, void* argmax_u8, cudaStream_t stream) {
   maxpool_nhwc_kernel<<<eblocks(B * (H / kh) * (W / kw) * (Cp / 8)), 256, 0, stream>>>(
       static_cast<const __half*>(x_hi), static_cast<const __half*>(x_lo), B, H, W, Cp, kh, kw,
-      static_cast<__half*>(y_hi), static_cast<__half*>(y_lo));
+      static_cast<__half*>(y_hi), static_cast<__half*>(y_lo), static_cast<uint8_t*>(argmax_u8));
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+int maxpool_nhwc_backward(const float* R_out, const void* argmax_u8, int64_t B, int H, int W, int Cp, int kh, int kw,
+                          float* R_in, cudaStream_t stream) {
+  maxpool_nhwc_bwd_kernel<<<eblocks(B * (H / kh) * (W / kw) * (Cp / 4)), 256, 0, stream>>>(
+      R_out, static_cast<const uint8_t*>(argmax_u8), B, H, W, Cp, kh, kw, R_in);
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+int nhwc_f32_to_nchw(const float* x, int64_t B, int H, int W, int Cp, int C, float* y, cudaStream_t stream) {
+  if (B > 65535) return DRSA_ERR_SHAPE;
+  dim3 grid(cdiv((int64_t)H * W, 32), cdiv(C, 32), (unsigned)B);
+  nhwc_f32_to_nchw_kernel<<<grid, 256, 0, stream>>>(x, H * W, Cp, C, y);
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+int nchw_to_nhwc_f32(const float* x, int64_t B, int H, int W, int C, int Cp, float* y, cudaStream_t stream) {
+  if (B > 65535) return DRSA_ERR_SHAPE;
+  dim3 grid(cdiv((int64_t)H * W, 32), cdiv(Cp, 32), (unsigned)B);
+  nchw_to_nhwc_f32_kernel<<<grid, 256, 0, stream>>>(x, H * W, C, Cp, y);
   DRSA_LAUNCH_CHECK();
   return DRSA_OK;
 }
@@ -467,6 +627,13 @@ int nhwc_to_nchw(const void* x_hi, const void* x_lo, int64_t B, int H, int W, in
   dim3 grid(cdiv((int64_t)H * W, 32), cdiv(C, 32), (unsigned)B);
   nhwc_to_nchw_kernel<<<grid, 256, 0, stream>>>(static_cast<const __half*>(x_hi), static_cast<const __half*>(x_lo),
                                                 H * W, Cp, C, y);
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+int relu_mask_nhwc(float* R, const void* a_hi, const void* a_lo, int64_t count, cudaStream_t stream) {
+  relu_mask_nhwc_kernel<<<eblocks(count), 256, 0, stream>>>(R, static_cast<const __half*>(a_hi),
+                                                            static_cast<const __half*>(a_lo), count);
   DRSA_LAUNCH_CHECK();
   return DRSA_OK;
 }

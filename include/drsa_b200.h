@@ -233,9 +233,29 @@ int lrp_tc_conv3x3_forward(const void* x_hi, const void* x_lo, const void* w_hi,
 int lrp_tc_conv3x3_first(const float* x, const float* w, const float* b, int64_t B, int H, int W, int Cout,
                          int Cout_p, int relu, void* y_hi, void* y_lo, void* stream);
 
-/* MaxPool2d(kh,kw), stride = kernel, on NHWC hi/lo planes. */
+/* MaxPool2d(kh,kw), stride = kernel, on NHWC hi/lo planes.  argmax_u8 (optional) [B,Ho,Wo,Cp] receives the
+ * window index dy*kw+dx of the first maximum (PyTorch's tie rule) for the relevance routing. */
 int lrp_tc_maxpool(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int kh, int kw,
-                   void* y_hi, void* y_lo, void* stream);
+                   void* y_hi, void* y_lo, void* argmax_u8, void* stream);
+/* R_in [B,H,W,Cp] fp32 = R_out [B,Ho,Wo,Cp] routed to the arg-max of every window, zeros elsewhere. */
+int lrp_tc_maxpool_backward(const float* R_out, const void* argmax_u8, int64_t B, int H, int W, int Cp, int kh,
+                            int kw, float* R_in, void* stream);
+
+/* Rule-modified forward of a Gamma / ZPlus / Epsilon conv layer on the tensor cores:
+ *   s = R_out / stabilize(conv(x, w') + b', eps)       x, s NHWC hi/lo; R_out NHWC fp32 [B,H,W,Cout_p]. */
+int lrp_tc_conv3x3_ratio(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                         const float* bias, const float* R_out, int64_t B, int H, int W, int Cin_p,
+                         int Cout_p, float eps, void* s_hi, void* s_lo, int* err_flag, void* stream);
+/* Backward-data step with the input factor: R_in = x * conv(s, wt') where wt' = flipped, channel-swapped w'
+ * ([9][Cin_p][Cout_p] hi/lo planes); R_in NHWC fp32 [B,H,W,Cin_p]. */
+int lrp_tc_conv3x3_inputmul(const void* s_hi, const void* s_lo, const void* wt_hi, const void* wt_lo,
+                            const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cout_p,
+                            int Cin_p, float* R_in, int* err_flag, void* stream);
+/* R *= (a_hi + a_lo > 0) on NHWC tensors (un-hooked ReLU). */
+int lrp_tc_relu_mask(float* R, const void* a_hi, const void* a_lo, int64_t count, void* stream);
+/* Layout hand-over of relevance maps between the NHWC tensor-core stack and the NCHW API surface. */
+int lrp_tc_nhwc_f32_to_nchw(const float* x, int64_t B, int H, int W, int Cp, int C, float* y, void* stream);
+int lrp_tc_nchw_to_nhwc_f32(const float* x, int64_t B, int H, int W, int C, int Cp, float* y, void* stream);
 
 /* NHWC hi/lo planes -> NCHW fp32 with the first C channels (hand-over to the fp32 / LRP-backward path). */
 int lrp_tc_nhwc_to_nchw(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int C, float* y,

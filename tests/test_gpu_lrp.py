@@ -263,8 +263,63 @@ def test_tc_first_conv_pool_and_layout_roundtrip():
     np.testing.assert_allclose(out.cpu().numpy(), wantp.numpy(), rtol=1e-6, atol=1e-7)
 
 
+def test_tc_rule_backward_kernels_match_oracle():
+    """tensor-core ratio + input-multiply passes (the collapsed Gamma rule) vs the general 5-pass oracle."""
+    L = _L(); lib = L.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(11)
+    B, Cin, Cout, H, W = 3, 64, 100, 8, 16
+    Cin_p, Cout_p = 64, 128
+    x = torch.rand(B, Cin, H, W, generator=g); x[x < 0.3] = 0
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
+    b = 0.1 * torch.randn(Cout, generator=g)
+    conv = torch.nn.Conv2d(Cin, Cout, 3, padding=1).double()
+    conv.weight.data.copy_(w); conv.bias.data.copy_(b)
+    z = conv(x.double()).detach()
+    Rout = (torch.randn(z.shape, generator=g).double() * (z > 0)).float()
+    gamma, eps = 0.3, 1e-7
+    want = lrp_ref.rule_backward(conv, "gamma", x.double(), Rout.double(), eps, gamma)
+    wm = w + gamma * w.clamp(min=0); bm = b + gamma * b.clamp(min=0)
+
+    def planes(t):
+        td = t.cuda().contiguous()
+        hi = torch.empty(td.shape, dtype=torch.float16, device="cuda"); lo = torch.empty_like(hi)
+        L.check(lib.lrp_tc_split_f16(td.data_ptr(), td.numel(), hi.data_ptr(), lo.data_ptr(), s))
+        return hi, lo
+    wt = torch.zeros(9, Cout_p, Cin_p); wt[:, :Cout, :Cin] = wm.permute(2, 3, 0, 1).reshape(9, Cout, Cin)
+    tt = torch.zeros(9, Cin_p, Cout_p); tt[:, :Cin, :Cout] = wm.permute(2, 3, 1, 0).reshape(9, Cin, Cout).flip(0)
+    mh, ml = planes(wt); th, tl = planes(tt)
+    bias = torch.zeros(Cout_p); bias[:Cout] = bm; bd = bias.cuda()
+    xh, xl = _to_nhwc_split(x, Cin_p)
+    Rn = torch.zeros(B, H, W, Cout_p); Rn[..., :Cout] = Rout.permute(0, 2, 3, 1); Rd = Rn.cuda().contiguous()
+    sh = torch.empty(B, H, W, Cout_p, dtype=torch.float16, device="cuda"); sl = torch.empty_like(sh)
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    L.check(lib.lrp_tc_conv3x3_ratio(xh.data_ptr(), xl.data_ptr(), mh.data_ptr(), ml.data_ptr(), bd.data_ptr(), Rd.data_ptr(), B, H,
+                                     W, Cin_p, Cout_p, eps, sh.data_ptr(), sl.data_ptr(), err.data_ptr(), s))
+    Rin = torch.empty(B, H, W, Cin_p, device="cuda")
+    L.check(lib.lrp_tc_conv3x3_inputmul(sh.data_ptr(), sl.data_ptr(), th.data_ptr(), tl.data_ptr(), xh.data_ptr(), xl.data_ptr(), B,
+                                        H, W, Cout_p, Cin_p, Rin.data_ptr(), err.data_ptr(), s))
+    out = torch.empty(B, Cin, H, W, device="cuda")
+    L.check(lib.lrp_tc_nhwc_f32_to_nchw(Rin.data_ptr(), B, H, W, Cin_p, Cin, out.data_ptr(), s))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    assert _rel_per_sample(out, want) < TOL
+    # NHWC pooling with arg-max capture and relevance routing vs autograd
+    a = torch.rand(2, 8, 6, 64, generator=g)
+    ah, al = a.half().cuda(), (a - a.half().float()).half().cuda()
+    ph = torch.empty(2, 4, 3, 64, dtype=torch.float16, device="cuda"); pl = torch.empty_like(ph)
+    am = torch.empty(2, 4, 3, 64, dtype=torch.uint8, device="cuda")
+    L.check(lib.lrp_tc_maxpool(ah.data_ptr(), al.data_ptr(), 2, 8, 6, 64, 2, 2, ph.data_ptr(), pl.data_ptr(), am.data_ptr(), s))
+    Ro = torch.randn(2, 4, 3, 64, generator=g).cuda()
+    Ri = torch.empty(2, 8, 6, 64, device="cuda")
+    L.check(lib.lrp_tc_maxpool_backward(Ro.data_ptr(), am.data_ptr(), 2, 8, 6, 64, 2, 2, Ri.data_ptr(), s))
+    a_rec = (ah.float() + al.float()).cpu().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    gr, = torch.autograd.grad(F.max_pool2d(a_rec, 2), a_rec, Ro.cpu().permute(0, 3, 1, 2))
+    np.testing.assert_array_equal(Ri.cpu().permute(0, 3, 1, 2).numpy(), gr.numpy())
+
+
 def test_tc_prefix_equals_fp32_path_full_resolution():
-    """cfg-2 CNN at full 128x256 resolution: the tensor-core prefix and the CUDA-core path give the same maps."""
+    """cfg-2 CNN at full 128x256 resolution: the tensor-core stack and the CUDA-core path give the same maps."""
     from cxai.utils.constants import lrp_name_map_6s
     from cxai.xai.explain.rules import NameMapComposite, SequentialMergeBatchNorm
     from cxai.xai.explain import lrp_engine
@@ -278,7 +333,7 @@ def test_tc_prefix_equals_fp32_path_full_resolution():
         plan.use_tc = use_tc
         res[use_tc] = get_intermediate(net, x, comp, net.features[33], 2)
     plan.use_tc = True
-    assert plan._tc_prefix(x, 34) == 34
+    assert plan._tc_stack_ok(x)
     assert res[True][0].shape == (3, 256, 8, 8)
     assert _rel_per_sample(res[True][0], res[False][0]) < 1e-5
     _assert_relevance_close_up_to_pool_ties(res[True][0], res[True][1], res[False][1], (2, 2))
