@@ -256,7 +256,7 @@ def test_tc_first_conv_pool_and_layout_roundtrip():
     got = (yh.float() + yl.float()).cpu().permute(0, 3, 1, 2)
     assert _rel_per_sample(got, want) < 2e-6
     ph = torch.empty(B, H // 2, W // 4, Cout, dtype=torch.float16, device="cuda"); pl = torch.empty_like(ph)
-    L.check(lib.lrp_tc_maxpool(yh.data_ptr(), yl.data_ptr(), B, H, W, Cout, 2, 4, ph.data_ptr(), pl.data_ptr(), s))
+    L.check(lib.lrp_tc_maxpool(yh.data_ptr(), yl.data_ptr(), B, H, W, Cout, 2, 4, ph.data_ptr(), pl.data_ptr(), None, s))
     out = torch.empty(B, Cout, H // 2, W // 4, device="cuda")
     L.check(lib.lrp_tc_nhwc_to_nchw(ph.data_ptr(), pl.data_ptr(), B, H // 2, W // 4, Cout, Cout, out.data_ptr(), s))
     wantp = F.max_pool2d(got, (2, 4))
