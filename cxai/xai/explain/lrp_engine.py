@@ -321,7 +321,7 @@ class LRPPlan:
                 cur = y
             elif op.kind == "flatten":
                 if keep:
-                    saved[k] = cur.shape
+                    saved[k] = ("flat", cur.shape, cur)      # the features also bound |s| of the conv stack below
                 cur = cur.reshape(cur.size(0), -1)
             elif op.kind == "relu":
                 if keep:
@@ -335,6 +335,9 @@ class LRPPlan:
         tensor-core conv stack the relevance travels as NHWC fp32 with padded channels."""
         lib = _L.lib()
         nhwc = None            # (C, Cp, H, W) while Rel is NHWC fp32
+        feat = None            # output of model.features (NCHW fp32), set when the flatten op is crossed
+        bound = None           # per-sample bound on |s| of the next tensor-core layer (device, [B])
+        cmax = None
         for k in range(len(self.ops) - 1, stop_after, -1):
             op = self.ops[k]
             sv = saved[k]
@@ -343,8 +346,15 @@ class LRPPlan:
                 # entering the NHWC stack from the dense head: Rel is NCHW fp32 [B, C, H, W]
                 B, C, H, W = Rel.shape
                 Cp = self._pad64(C)
+                Rel = Rel.contiguous()
+                cmax = torch.zeros(len(self.ops) + 1, B, device=Rel.device)
+                if feat is not None and feat.shape == Rel.shape:
+                    # R = a * c at the output of the stack: max |c| bounds |s| of the first rule layer below
+                    bound = cmax[len(self.ops)]
+                    _L.check(lib.lrp_tc_sample_absmax_ratio(_ptr(Rel), _ptr(feat), B, C * H * W, _ptr(bound), _stream()),
+                             "absmax_ratio")
                 t = torch.empty(B, H, W, Cp, device=Rel.device)
-                _L.check(lib.lrp_tc_nchw_to_nhwc_f32(_ptr(Rel.contiguous()), B, H, W, C, Cp, _ptr(t), _stream()), "to_nhwc")
+                _L.check(lib.lrp_tc_nchw_to_nhwc_f32(_ptr(Rel), B, H, W, C, Cp, _ptr(t), _stream()), "to_nhwc")
                 Rel, nhwc = t, (C, Cp, H, W)
             if is_tc and sv[0] == "tc_pool":
                 am, (H, W, Cp) = sv[1], sv[2]
@@ -368,13 +378,14 @@ class LRPPlan:
                 sh = torch.empty(B, H, W, cout_p, dtype=torch.float16, device=Rel.device)
                 sl = torch.empty_like(sh)
                 _L.check(lib.lrp_tc_conv3x3_ratio(_ptr(xin[0]), _ptr(xin[1]), _ptr(op.tc["m_hi"]), _ptr(op.tc["m_lo"]),
-                                                  _ptr(op.tc["m_b"]), _ptr(Rel), B, H, W, cin_p, cout_p, op.eps, _ptr(sh),
-                                                  _ptr(sl), _ptr(self._tc_err), _stream()), op.name)
+                                                  _ptr(op.tc["m_b"]), _ptr(Rel), B, H, W, cin_p, cout_p, op.eps, _ptr(bound),
+                                                  _ptr(sh), _ptr(sl), _ptr(self._tc_err), _stream()), op.name)
                 R_in = torch.empty(B, H, W, cin_p, device=Rel.device)
+                nxt = cmax[k]
                 _L.check(lib.lrp_tc_conv3x3_inputmul(_ptr(sh), _ptr(sl), _ptr(op.tc["t_hi"]), _ptr(op.tc["t_lo"]), _ptr(xin[0]),
-                                                     _ptr(xin[1]), B, H, W, cout_p, cin_p, _ptr(R_in), _ptr(self._tc_err),
-                                                     _stream()), op.name)
-                Rel, nhwc = R_in, (op.cin, cin_p, H, W)
+                                                     _ptr(xin[1]), B, H, W, cout_p, cin_p, _ptr(bound), _ptr(nxt), _ptr(R_in),
+                                                     _ptr(self._tc_err), _stream()), op.name)
+                Rel, nhwc, bound = R_in, (op.cin, cin_p, H, W), nxt
                 continue
             if is_tc and sv[0] == "tc_first":
                 # leave the NHWC stack: the first conv (Cin = 1) runs on the CUDA-core kernels in NCHW
@@ -419,7 +430,8 @@ class LRPPlan:
                                                   _ptr(R_in), _stream()), op.name)
                 Rel = R_in
             elif op.kind == "flatten":
-                Rel = Rel.reshape(sv)
+                Rel = Rel.reshape(sv[1])
+                feat = sv[2]
         if nhwc is not None:
             Rel = self._rel_to_nchw(Rel, nhwc)
         return Rel
@@ -459,6 +471,24 @@ class LRPPlan:
                 seen_relu = False
 
 
+    def tc_failed(self) -> bool:
+        """True (and the tensor-core stack is switched off for this plan) if a tensor-core kernel raised its error
+        flag: a value left the fp16 range of the split planes.  The caller reruns on the fp32 CUDA-core kernels."""
+        if self._tc_err is None or not self.use_tc:
+            return False
+        code = int(self._tc_err.item())
+        if code == 0:
+            return False
+        if code == 1:
+            raise _L.DRSAError("tensor-core convolution: misaligned shared-memory window")
+        import warnings
+        warnings.warn("LRP: activations or relevance quotients exceed the fp16 range of the split-precision tensor-core "
+                      "path; rerunning this model on the fp32 CUDA-core kernels")
+        self.use_tc = False
+        self._tc_err.zero_()
+        return True
+
+
 _PLAN_CACHE = {}
 
 
@@ -486,7 +516,10 @@ def forward_logits(model, input_batch, composite=None, batch_size: int = 64) -> 
     x = _prep_input(input_batch)
     with torch.cuda.device(x.device):
         plan = _plan(model, composite or R.NameMapComposite([], canonizers=[R.SequentialMergeBatchNorm()]), x.device)
-        outs = [plan.forward(x[i:i + batch_size], keep_from=len(plan.ops))[0] for i in range(0, x.size(0), batch_size)]
+        while True:
+            outs = [plan.forward(x[i:i + batch_size], keep_from=len(plan.ops))[0] for i in range(0, x.size(0), batch_size)]
+            if not plan.tc_failed():
+                break
     return torch.cat(outs, 0)
 
 
@@ -516,13 +549,16 @@ def lrp_intermediate(model, input_batch, composite, layer, class_idx, attr_batch
                 nxt += 1
             raise _L.DRSAError(f"split at {plan.ops[split].name} (pre-activation) is not on this path; "
                                f"use the ReLU {plan.ops[nxt].name} like the reference (layers 19/26/33)")
-        a_maps, r_maps = [], []
-        for i in range(0, x.size(0), attr_batch_size):
-            logits, saved, outs = plan.forward(x[i:i + attr_batch_size], keep_from=split + 1)
-            seed = fn(logits).contiguous()
-            r_maps.append(plan.backward(seed, saved, stop_after=split))
-            o = outs[split]
-            a_maps.append(plan._nhwc_to_nchw(o[1]) if isinstance(o, tuple) else o)
+        while True:
+            a_maps, r_maps = [], []
+            for i in range(0, x.size(0), attr_batch_size):
+                logits, saved, outs = plan.forward(x[i:i + attr_batch_size], keep_from=split + 1)
+                seed = fn(logits).contiguous()
+                r_maps.append(plan.backward(seed, saved, stop_after=split))
+                o = outs[split]
+                a_maps.append(plan._nhwc_to_nchw(o[1]) if isinstance(o, tuple) else o)
+            if not plan.tc_failed():
+                break
     return torch.cat(a_maps, 0), torch.cat(r_maps, 0)
 
 
@@ -531,8 +567,11 @@ def lrp_input_relevance(model, input_batch, composite, attr_output_fn: Callable,
     x = _prep_input(input_batch)
     with torch.cuda.device(x.device):
         plan = _plan(model, composite, x.device)
-        out = []
-        for i in range(0, x.size(0), batch_size):
-            logits, saved, _ = plan.forward(x[i:i + batch_size], keep_from=0)
-            out.append(plan.backward(attr_output_fn(logits).contiguous(), saved, stop_after=-1))
+        while True:
+            out = []
+            for i in range(0, x.size(0), batch_size):
+                logits, saved, _ = plan.forward(x[i:i + batch_size], keep_from=0)
+                out.append(plan.backward(attr_output_fn(logits).contiguous(), saved, stop_after=-1))
+            if not plan.tc_failed():
+                break
     return torch.cat(out, 0)

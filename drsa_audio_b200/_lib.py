@@ -73,8 +73,11 @@ SIGNATURES = {
     "lrp_tc_conv3x3_first": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "lrp_tc_maxpool": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "lrp_tc_maxpool_backward": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
-    "lrp_tc_conv3x3_ratio": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
-    "lrp_tc_conv3x3_inputmul": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "lrp_tc_conv3x3_ratio": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp,
+                                    _vp]),
+    "lrp_tc_conv3x3_inputmul": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp,
+                                       _vp]),
+    "lrp_tc_sample_absmax_ratio": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "lrp_tc_relu_mask": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "lrp_tc_nhwc_f32_to_nchw": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "lrp_tc_nchw_to_nhwc_f32": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),

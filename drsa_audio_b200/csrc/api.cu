@@ -63,8 +63,9 @@ int conv_first_nhwc(const float* x, const float* w, const float* b, int64_t B, i
                     int relu, void* y_hi, void* y_lo, cudaStream_t stream);
 int conv_tc_run(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int64_t B,
                 int H, int W, int Cin_p, int Cout_p, int Cout, int relu, int epi, float eps, const float* aux_f32,
-                const void* aux_hi, const void* aux_lo, void* y_hi, void* y_lo, float* y_f32, float* y_nchw, int* err_flag,
-                cudaStream_t stream);
+                const void* aux_hi, const void* aux_lo, void* y_hi, void* y_lo, float* y_f32, float* y_nchw,
+                const float* scale_ref, float* cmax_out, int* err_flag, cudaStream_t stream);
+int sample_absmax_ratio(const float* R, const float* x, int64_t B, int64_t per, float* out, cudaStream_t stream);
 int maxpool_nhwc(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int kh, int kw, void* y_hi,
                  void* y_lo, void* argmax_u8, cudaStream_t stream);
 int maxpool_nhwc_backward(const float* R_out, const void* argmax_u8, int64_t B, int H, int W, int Cp, int kh, int kw,
@@ -361,25 +362,31 @@ int lrp_tc_maxpool_backward(const float* R_out, const void* argmax_u8, int64_t B
 }
 
 int lrp_tc_conv3x3_ratio(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
-                         const float* R_out, int64_t B, int H, int W, int Cin_p, int Cout_p, float eps, void* s_hi,
-                         void* s_lo, int* err_flag, void* stream) {
+                         const float* R_out, int64_t B, int H, int W, int Cin_p, int Cout_p, float eps,
+                         const float* scale_ref, void* s_hi, void* s_lo, int* err_flag, void* stream) {
   if (x_hi == nullptr || x_lo == nullptr || w_hi == nullptr || w_lo == nullptr || bias == nullptr || R_out == nullptr ||
       s_hi == nullptr || s_lo == nullptr || err_flag == nullptr)
     return DRSA_ERR_ARG;
   DRSA_TRY(require_sm100());
   return conv_tc_run(x_hi, x_lo, w_hi, w_lo, bias, B, H, W, Cin_p, Cout_p, Cout_p, 0, 1, eps, R_out, nullptr, nullptr, s_hi,
-                     s_lo, nullptr, nullptr, err_flag, static_cast<cudaStream_t>(stream));
+                     s_lo, nullptr, nullptr, scale_ref, nullptr, err_flag, static_cast<cudaStream_t>(stream));
 }
 
 int lrp_tc_conv3x3_inputmul(const void* s_hi, const void* s_lo, const void* wt_hi, const void* wt_lo, const void* x_hi,
-                            const void* x_lo, int64_t B, int H, int W, int Cout_p, int Cin_p, float* R_in, int* err_flag,
-                            void* stream) {
+                            const void* x_lo, int64_t B, int H, int W, int Cout_p, int Cin_p, const float* scale_ref,
+                            float* cmax_out, float* R_in, int* err_flag, void* stream) {
   if (s_hi == nullptr || s_lo == nullptr || wt_hi == nullptr || wt_lo == nullptr || x_hi == nullptr || x_lo == nullptr ||
       R_in == nullptr || err_flag == nullptr)
     return DRSA_ERR_ARG;
   DRSA_TRY(require_sm100());
   return conv_tc_run(s_hi, s_lo, wt_hi, wt_lo, nullptr, B, H, W, Cout_p, Cin_p, Cin_p, 0, 2, 0.f, nullptr, x_hi, x_lo, nullptr,
-                     nullptr, R_in, nullptr, err_flag, static_cast<cudaStream_t>(stream));
+                     nullptr, R_in, nullptr, scale_ref, cmax_out, err_flag, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_tc_sample_absmax_ratio(const float* R, const float* x, int64_t B, int64_t per_sample, float* out, void* stream) {
+  if (R == nullptr || x == nullptr || out == nullptr || B <= 0 || per_sample <= 0) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return sample_absmax_ratio(R, x, B, per_sample, out, static_cast<cudaStream_t>(stream));
 }
 
 int lrp_tc_relu_mask(float* R, const void* a_hi, const void* a_lo, int64_t count, void* stream) {

@@ -74,6 +74,19 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// Power-of-two scale for the fp16 hi/lo planes of s = R / z.  Relevance shrinks by orders of magnitude on the way
+// down (biases absorb it), so the unscaled quotient leaves the fp16 range (min subnormal 6e-8) after a few
+// layers.  `bound` is a rigorous per-sample bound on |s|: |s| = |R|/z' = a|c|/z' <= |c| because z' >= z >= a for
+// Gamma / ZPlus / Epsilon on non-negative input, c being the un-multiplied relevance of the layer above.  The
+// scale maps it to [2^11, 2^12), a factor 16 below the fp16 maximum; the pair error is then <= 2^-25 absolute.
+__device__ __forceinline__ float pow2_scale(float bound) {
+  if (!(bound > 0.f) || !(bound < 3.0e38f)) return 1.f;
+  const int e = (int)((__float_as_uint(bound) >> 23) & 0xffu) - 127;
+  int k = 11 - e;
+  k = k < -100 ? -100 : (k > 100 ? 100 : k);
+  return __uint_as_float((uint32_t)(k + 127) << 23);
+}
+
 struct ConvGeom {
   int B, H, W, Cin_p, Cout_p, Cout;      // padded channel counts (multiples of 64) and the real Cout
   int nb, th, tw;                        // tile = nb images x th rows x tw columns = 128 pixels
@@ -89,7 +102,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
                   const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, ConvGeom g,
                   const float* __restrict__ bias, const float* __restrict__ aux_f32, const __half* __restrict__ aux_hi,
                   const __half* __restrict__ aux_lo, __half* __restrict__ y_hi, __half* __restrict__ y_lo,
-                  float* __restrict__ y_f32, float* __restrict__ y_nchw, int* __restrict__ err_flag) {
+                  float* __restrict__ y_f32, float* __restrict__ y_nchw, const float* __restrict__ scale_ref,
+                  float* __restrict__ cmax_out, int* __restrict__ err_flag) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int wbytes = g.Cout_p * 128;                 // one [Cout_p x 64] weight box
   // kResW (Cin_p = Cout_p = 64): all 9 taps of the hi/lo weights (144 KB) stay resident in shared memory and the
@@ -189,11 +203,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
     const int pix = 32 * q + lane;                        // pixel of the tile = TMEM lane
     const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
     int as = 0; uint32_t aphase = 0;
+    bool ovf = false;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
       const int txi = tile % g.tiles_x, tyi = (tile / g.tiles_x) % g.tiles_y, tbi = tile / (g.tiles_x * g.tiles_y);
       const int xx = pix % g.tw, yy = (pix / g.tw) % g.th, bi = pix / (g.tw * g.th);
       const int x = txi * g.tw + xx, y = tyi * g.th + yy, n = tbi * g.nb + bi;
       const bool valid = (x < g.W) && (y < g.H) && (n < g.B);
+      // per-sample power-of-two scale of the fp16 planes that carry s = R / z (see pow2_scale)
+      const float sc = (scale_ref != nullptr && valid) ? pow2_scale(__ldg(scale_ref + n)) : 1.f;
+      const float isc = 1.f / sc;
+      float cm = 0.f;
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const int64_t pbase = (((int64_t)n * g.H + y) * g.W + x) * g.Cout_p;
@@ -223,12 +242,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
 #pragma unroll
             for (int i4 = 0; i4 < 8; ++i4) {
               const float4 r = __ldg(reinterpret_cast<const float4*>(aux_f32 + o) + i4);
-              a[4 * i4] = r.x / stabilize(a[4 * i4], g.eps);
-              a[4 * i4 + 1] = r.y / stabilize(a[4 * i4 + 1], g.eps);
-              a[4 * i4 + 2] = r.z / stabilize(a[4 * i4 + 2], g.eps);
-              a[4 * i4 + 3] = r.w / stabilize(a[4 * i4 + 3], g.eps);
+              a[4 * i4] = r.x / stabilize(a[4 * i4], g.eps) * sc;
+              a[4 * i4 + 1] = r.y / stabilize(a[4 * i4 + 1], g.eps) * sc;
+              a[4 * i4 + 2] = r.z / stabilize(a[4 * i4 + 2], g.eps) * sc;
+              a[4 * i4 + 3] = r.w / stabilize(a[4 * i4 + 3], g.eps) * sc;
             }
-          } else {                            // R_in = x * c
+          } else {                            // c = conv(s, wt') / scale;  R_in = x * c
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { a[i] *= isc; cm = fmaxf(cm, fabsf(a[i])); }
 #pragma unroll
             for (int i8 = 0; i8 < 4; ++i8) {
               const uint4 h = __ldg(reinterpret_cast<const uint4*>(aux_hi + o) + i8);
@@ -257,6 +278,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
           }
           if (y_hi != nullptr) {
             uint32_t hi[16], lo[16];
+            float am = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) am = fmaxf(am, fabsf(a[i]));
+            ovf = ovf || !(am < 60000.f);           // fp16 range of the hi plane
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const __half2 h = __floats2half2_rn(a[2 * i], a[2 * i + 1]);
@@ -278,7 +303,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
       tc_fence_before();
       mbar_arrive(&acc_empty[as]);
       if (++as == acc_stages) { as = 0; aphase ^= 1; }
+      if (cmax_out != nullptr) {              // per-sample max |c|: the bound on |s| of the layer below
+        uint32_t bits = valid ? __float_as_uint(cm) : 0u;
+        const int n0 = __shfl_sync(0xffffffffu, n, 0);
+        if (__all_sync(0xffffffffu, n == n0)) {
+          bits = __reduce_max_sync(0xffffffffu, bits);
+          if (lane == 0 && bits != 0u && n0 < g.B) atomicMax(reinterpret_cast<unsigned int*>(cmax_out) + n0, bits);
+        } else if (bits != 0u) {
+          atomicMax(reinterpret_cast<unsigned int*>(cmax_out) + n, bits);
+        }
+      }
     }
+    if (ovf) atomicExch(err_flag, 2);
   }
   __syncthreads();
   if (warp == 1) {
@@ -512,6 +548,27 @@ __global__ void split_f16_kernel(const float* __restrict__ in, int64_t n, __half
   }
 }
 
+// out[n] = max_i |R[n,i]| / x[n,i] over x > 0: the bound on |s| for the first Gamma layer below the dense head
+// (R = x * c there, so this is max |c|).  One CTA per sample.
+__global__ void __launch_bounds__(256) sample_absmax_ratio_kernel(const float* __restrict__ R, const float* __restrict__ x,
+                                                                  int64_t per, float* __restrict__ out) {
+  __shared__ float red[8];
+  const int64_t base = (int64_t)blockIdx.x * per;
+  float m = 0.f;
+  for (int64_t i = threadIdx.x; i < per; i += blockDim.x) {
+    const float xv = x[base + i];
+    if (xv > 0.f) m = fmaxf(m, fabsf(R[base + i]) / xv);
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    m = warp_max(m);
+    if (threadIdx.x == 0) out[blockIdx.x] = m;
+  }
+}
+
 inline int eblocks(int64_t n) {
   int64_t b = (n + 255) / 256;
   return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
@@ -541,8 +598,8 @@ bool conv_tc_supported(int64_t B, int Cin_p, int Cout_p, int H, int W) {
 
 int conv_tc_run(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int64_t B,
                 int H, int W, int Cin_p, int Cout_p, int Cout, int relu, int epi, float eps, const float* aux_f32,
-                const void* aux_hi, const void* aux_lo, void* y_hi, void* y_lo, float* y_f32, float* y_nchw, int* err_flag,
-                cudaStream_t stream) {
+                const void* aux_hi, const void* aux_lo, void* y_hi, void* y_lo, float* y_f32, float* y_nchw,
+                const float* scale_ref, float* cmax_out, int* err_flag, cudaStream_t stream) {
   ConvGeom g{};
   if (!conv_tc_supported(B, Cin_p, Cout_p, H, W) || B > 2147483647LL / ((int64_t)H * W)) return DRSA_ERR_SHAPE;
   g.B = (int)B; g.H = H; g.W = W; g.Cin_p = Cin_p; g.Cout_p = Cout_p; g.Cout = Cout; g.relu = relu; g.epi = epi; g.eps = eps;
@@ -563,7 +620,7 @@ int conv_tc_run(const void* x_hi, const void* x_lo, const void* w_hi, const void
     kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmXh, tmXl, tmWh, tmWl, g, bias, aux_f32,
                                                         static_cast<const __half*>(aux_hi), static_cast<const __half*>(aux_lo),
                                                         static_cast<__half*>(y_hi), static_cast<__half*>(y_lo), y_f32, y_nchw,
-                                                        err_flag);
+                                                        scale_ref, cmax_out, err_flag);
     DRSA_LAUNCH_CHECK();
     return DRSA_OK;
   };
@@ -577,7 +634,7 @@ int conv_tc_forward(const void* x_hi, const void* x_lo, const void* w_hi, const 
                     int H, int W, int Cin_p, int Cout_p, int Cout, int relu, void* y_hi, void* y_lo, float* y_nchw,
                     int* err_flag, cudaStream_t stream) {
   return conv_tc_run(x_hi, x_lo, w_hi, w_lo, bias, B, H, W, Cin_p, Cout_p, Cout, relu, 0, 0.f, nullptr, nullptr, nullptr, y_hi,
-                     y_lo, nullptr, y_nchw, err_flag, stream);
+                     y_lo, nullptr, y_nchw, nullptr, nullptr, err_flag, stream);
 }
 
 int conv_first_nhwc(const float* x, const float* w, const float* b, int64_t B, int H, int W, int Cout, int Cout_p,
@@ -634,6 +691,13 @@ int nhwc_to_nchw(const void* x_hi, const void* x_lo, int64_t B, int H, int W, in
 int relu_mask_nhwc(float* R, const void* a_hi, const void* a_lo, int64_t count, cudaStream_t stream) {
   relu_mask_nhwc_kernel<<<eblocks(count), 256, 0, stream>>>(R, static_cast<const __half*>(a_hi),
                                                             static_cast<const __half*>(a_lo), count);
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+int sample_absmax_ratio(const float* R, const float* x, int64_t B, int64_t per, float* out, cudaStream_t stream) {
+  if (B > 2147483647LL) return DRSA_ERR_SHAPE;
+  sample_absmax_ratio_kernel<<<(unsigned)B, 256, 0, stream>>>(R, x, per, out);
   DRSA_LAUNCH_CHECK();
   return DRSA_OK;
 }

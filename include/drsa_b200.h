@@ -224,7 +224,8 @@ int lrp_tc_conv3x3_supported(int64_t B, int Cin_p, int Cout_p, int H, int W);
 
 /* y = relu?(conv3x3_same(x, w) + b).  Outputs: the hi/lo NHWC planes for the next layer (may be NULL) and/or
  * an fp32 NCHW copy of the first `Cout` channels (may be NULL).  bias has Cout_p entries (zero padded).
- * err_flag: device int set to 1 if the kernel detects a misaligned shared-memory window. */
+ * err_flag: device int set to 1 if the kernel detects a misaligned shared-memory window, 2 if an output value
+ * does not fit the fp16 range of the hi plane (|y| >= 60000). */
 int lrp_tc_conv3x3_forward(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
                            const float* bias, int64_t B, int H, int W, int Cin_p, int Cout_p, int Cout,
                            int relu, void* y_hi, void* y_lo, float* y_nchw, int* err_flag, void* stream);
@@ -242,15 +243,26 @@ int lrp_tc_maxpool_backward(const float* R_out, const void* argmax_u8, int64_t B
                             int kw, float* R_in, void* stream);
 
 /* Rule-modified forward of a Gamma / ZPlus / Epsilon conv layer on the tensor cores:
- *   s = R_out / stabilize(conv(x, w') + b', eps)       x, s NHWC hi/lo; R_out NHWC fp32 [B,H,W,Cout_p]. */
+ *   s = 2^k(n) * R_out / stabilize(conv(x, w') + b', eps)       x, s NHWC hi/lo; R_out NHWC fp32 [B,H,W,Cout_p].
+ * scale_ref (device, [B], may be NULL = no scaling): per-sample bound on |R_out / z'|; the power of two 2^k(n)
+ * derived from it keeps s inside the fp16 range of the hi/lo planes however small the relevance has become
+ * (it shrinks by orders of magnitude on the way down).  err_flag is set to 2 if a value leaves that range. */
 int lrp_tc_conv3x3_ratio(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
                          const float* bias, const float* R_out, int64_t B, int H, int W, int Cin_p,
-                         int Cout_p, float eps, void* s_hi, void* s_lo, int* err_flag, void* stream);
-/* Backward-data step with the input factor: R_in = x * conv(s, wt') where wt' = flipped, channel-swapped w'
- * ([9][Cin_p][Cout_p] hi/lo planes); R_in NHWC fp32 [B,H,W,Cin_p]. */
+                         int Cout_p, float eps, const float* scale_ref, void* s_hi, void* s_lo, int* err_flag,
+                         void* stream);
+/* Backward-data step with the input factor: c = 2^-k(n) * conv(s, wt'), R_in = x * c, where wt' = flipped,
+ * channel-swapped w' ([9][Cin_p][Cout_p] hi/lo planes); R_in NHWC fp32 [B,H,W,Cin_p].  scale_ref: the same
+ * array the ratio pass was given.  cmax_out (device, [B], zeroed by the caller, may be NULL) receives
+ * max |c| per sample = the scale_ref of the next layer below. */
 int lrp_tc_conv3x3_inputmul(const void* s_hi, const void* s_lo, const void* wt_hi, const void* wt_lo,
                             const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cout_p,
-                            int Cin_p, float* R_in, int* err_flag, void* stream);
+                            int Cin_p, const float* scale_ref, float* cmax_out, float* R_in, int* err_flag,
+                            void* stream);
+/* out[n] = max_i |R[n,i]| / x[n,i] over x[n,i] > 0 (R, x: [B, per_sample] fp32): scale_ref of the first
+ * tensor-core layer below the dense head, where R = x * c. */
+int lrp_tc_sample_absmax_ratio(const float* R, const float* x, int64_t B, int64_t per_sample, float* out,
+                               void* stream);
 /* R *= (a_hi + a_lo > 0) on NHWC tensors (un-hooked ReLU). */
 int lrp_tc_relu_mask(float* R, const void* a_hi, const void* a_lo, int64_t count, void* stream);
 /* Layout hand-over of relevance maps between the NHWC tensor-core stack and the NCHW API surface. */

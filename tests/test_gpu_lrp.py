@@ -295,15 +295,49 @@ def test_tc_rule_backward_kernels_match_oracle():
     sh = torch.empty(B, H, W, Cout_p, dtype=torch.float16, device="cuda"); sl = torch.empty_like(sh)
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
     L.check(lib.lrp_tc_conv3x3_ratio(xh.data_ptr(), xl.data_ptr(), mh.data_ptr(), ml.data_ptr(), bd.data_ptr(), Rd.data_ptr(), B, H,
-                                     W, Cin_p, Cout_p, eps, sh.data_ptr(), sl.data_ptr(), err.data_ptr(), s))
+                                     W, Cin_p, Cout_p, eps, None, sh.data_ptr(), sl.data_ptr(), err.data_ptr(), s))
     Rin = torch.empty(B, H, W, Cin_p, device="cuda")
+    cmax = torch.zeros(B, device="cuda")
     L.check(lib.lrp_tc_conv3x3_inputmul(sh.data_ptr(), sl.data_ptr(), th.data_ptr(), tl.data_ptr(), xh.data_ptr(), xl.data_ptr(), B,
-                                        H, W, Cout_p, Cin_p, Rin.data_ptr(), err.data_ptr(), s))
+                                        H, W, Cout_p, Cin_p, None, cmax.data_ptr(), Rin.data_ptr(), err.data_ptr(), s))
     out = torch.empty(B, Cin, H, W, device="cuda")
     L.check(lib.lrp_tc_nhwc_f32_to_nchw(Rin.data_ptr(), B, H, W, Cin_p, Cin, out.data_ptr(), s))
     torch.cuda.synchronize()
     assert int(err.item()) == 0
     assert _rel_per_sample(out, want) < TOL
+    # cmax = per-sample max |c| with c = conv_transpose(s, w') (the bound handed to the layer below)
+    z_mod = F.conv2d(x.double(), wm.double(), bm.double(), padding=1)
+    s_want = Rout.double() / (z_mod + torch.where(z_mod >= 0, eps, -eps))
+    c_want = F.conv_transpose2d(s_want, wm.double(), padding=1).abs()
+    np.testing.assert_allclose(cmax.cpu().numpy(), c_want.amax(dim=(1, 2, 3)).numpy(), rtol=1e-3)
+    # relevance far below the fp16 range (it shrinks by orders of magnitude on the way down the network), very
+    # different per sample: the per-sample power-of-two scale keeps full accuracy
+    fac = torch.tensor([1e-11, 3e-20, 7.0]).view(B, 1, 1, 1)
+    Rd2 = (Rn * fac).cuda().contiguous()
+    bound = ((s_want * fac).abs().amax(dim=(1, 2, 3)) * 1.5).float().cuda()
+    L.check(lib.lrp_tc_conv3x3_ratio(xh.data_ptr(), xl.data_ptr(), mh.data_ptr(), ml.data_ptr(), bd.data_ptr(), Rd2.data_ptr(), B,
+                                     H, W, Cin_p, Cout_p, eps, bound.data_ptr(), sh.data_ptr(), sl.data_ptr(), err.data_ptr(), s))
+    assert float(sh.float().abs().max()) >= 1024.0                      # planes sit high in the fp16 range
+    cmax.zero_()
+    L.check(lib.lrp_tc_conv3x3_inputmul(sh.data_ptr(), sl.data_ptr(), th.data_ptr(), tl.data_ptr(), xh.data_ptr(), xl.data_ptr(), B,
+                                        H, W, Cout_p, Cin_p, bound.data_ptr(), cmax.data_ptr(), Rin.data_ptr(), err.data_ptr(), s))
+    L.check(lib.lrp_tc_nhwc_f32_to_nchw(Rin.data_ptr(), B, H, W, Cin_p, Cin, out.data_ptr(), s))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    assert _rel_per_sample(out, want * fac.double()) < TOL
+    np.testing.assert_allclose(cmax.cpu().numpy(), (c_want * fac.double()).amax(dim=(1, 2, 3)).float().numpy(), rtol=1e-3)
+    # a bound that is far too small drives s out of the fp16 range: the kernel must flag it, not return garbage silently
+    tiny = (bound * 1e-4).contiguous()
+    L.check(lib.lrp_tc_conv3x3_ratio(xh.data_ptr(), xl.data_ptr(), mh.data_ptr(), ml.data_ptr(), bd.data_ptr(), Rd2.data_ptr(), B,
+                                     H, W, Cin_p, Cout_p, eps, tiny.data_ptr(), sh.data_ptr(), sl.data_ptr(), err.data_ptr(), s))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 2
+    # per-sample max |R / x| over x > 0 (entry bound below the dense head)
+    xr = torch.rand(4, 300, generator=g); xr[xr < 0.4] = 0
+    cr = torch.randn(4, 300, generator=g) * torch.tensor([1.0, 1e-9, 50.0, 0.0]).view(4, 1)
+    Rr = (xr * cr).cuda(); xrd = xr.cuda(); ob = torch.empty(4, device="cuda")
+    L.check(lib.lrp_tc_sample_absmax_ratio(Rr.data_ptr(), xrd.data_ptr(), 4, 300, ob.data_ptr(), s))
+    np.testing.assert_allclose(ob.cpu().numpy(), (cr.abs() * (xr > 0)).amax(dim=1).numpy(), rtol=1e-5)
     # NHWC pooling with arg-max capture and relevance routing vs autograd
     a = torch.rand(2, 8, 6, 64, generator=g)
     ah, al = a.half().cuda(), (a - a.half().float()).half().cuda()
