@@ -92,6 +92,10 @@ __device__ __forceinline__ uint32_t kdesc_lo(uint32_t smem_addr) { return (smem_
 __device__ __forceinline__ uint32_t mndesc_lo(uint32_t smem_addr) { return (smem_addr >> 4) | ((4096u >> 4) << 16); }            // LBO 4 KB: next 64-channel panel
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
 
+// Order in which the 32-row chunks of a tile are handed from the epilogue to GEMM2: the two epilogue halves work on
+// chunks {0,1} and {2,3} concurrently, so chunks 0 and 2 are ready first.
+__device__ __forceinline__ int chunk_order(int i) { return ((i & 1) << 1) | (i >> 1); }
+
 __device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // d = {hi : upper, lo : lower}
@@ -116,9 +120,9 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty = bars + 8;       // [kStages]
   uint64_t* u_full = bars + 16;
   uint64_t* h_full = bars + 17;
-  uint64_t* p_full = bars + 18;
-  uint64_t* x_full = bars + 19;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* x_full = bars + 18;
+  uint64_t* p_full = bars + 20;     // [4]: one per 32-row chunk, so GEMM2 can trail the epilogue chunk by chunk
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x % G, rb = blockIdx.x / G;
@@ -129,7 +133,8 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(u_full, 1); mbar_init(h_full, 1); mbar_init(p_full, 256); mbar_init(x_full, 1);
+    mbar_init(u_full, 1); mbar_init(h_full, 1); mbar_init(x_full, 1);
+    for (int c = 0; c < 4; ++c) mbar_init(&p_full[c], 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -160,7 +165,8 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         // pass 2 (GEMM2): row chunks [32 rows x D ch] as D/64 panels of 4 KB, MN-major operand with N = D
-        for (int rc = 0; rc < 4; ++rc) {
+        for (int rq = 0; rq < 4; ++rq) {
+          const int rc = chunk_order(rq);
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], 2 * C::kPanels * 4096);
           uint8_t* dst = sStage + stage * C::kStageBytes;
@@ -175,7 +181,9 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc_f16(kNG, kRows, 0, 0);   // U^T (K-major) x tile (K-major)
+      // GEMM1: one MMA covers the A rows and the C rows of the tile (N = 256: the C panel follows the A panel in
+      // shared memory, so the stacked [A; C] tile is one K-major operand) -- U^T is read once per k-step, not twice
+      constexpr uint32_t idesc1 = make_idesc_f16(kNG, 2 * kRows, 0, 0);
       constexpr uint32_t idesc2 = make_idesc_f16(kNG, D, 0, 1);       // P^T (TMEM)   x row chunk (MN-major, N = D)
       const uint32_t tX = tmem_base, tHA = tmem_base + 256, tHC = tmem_base + 384;
       mbar_wait(u_full, 0);
@@ -192,29 +200,26 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // along K inside the 128-byte swizzle atom adds 32 B (>> 4 = 2) to the low word
           const uint32_t uh = kdesc_lo(smem_u32(sU_hi + p * kPanelBytes)), ul = kdesc_lo(smem_u32(sU_lo + p * kPanelBytes));
           const uint32_t bA = smem_u32(sStage + stage * C::kStageBytes);
-          const uint32_t dA = kdesc_lo(bA), dC = kdesc_lo(bA + kPanelBytes);
+          const uint32_t dAC = kdesc_lo(bA);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint32_t acc = (p | kk) ? 1u : 0u;
-            const uint64_t d_uh = desc64(uh + 2 * kk), d_ul = desc64(ul + 2 * kk);
-            const uint64_t d_a = desc64(dA + 2 * kk), d_c = desc64(dC + 2 * kk);
-            umma_ss_f16(tHA, d_uh, d_a, idesc1, acc);
-            umma_ss_f16(tHA, d_ul, d_a, idesc1, 1u);
-            umma_ss_f16(tHC, d_uh, d_c, idesc1, acc);
-            umma_ss_f16(tHC, d_ul, d_c, idesc1, 1u);
+            const uint64_t d_ac = desc64(dAC + 2 * kk);
+            umma_ss_f16(tHA, desc64(uh + 2 * kk), d_ac, idesc1, acc);
+            umma_ss_f16(tHA, desc64(ul + 2 * kk), d_ac, idesc1, 1u);
           }
           umma_commit(&empty[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(h_full);
         if (prof) t1 = clock64();
-        // ---- wait for P^T / Q^T from the epilogue warps
-        mbar_wait(p_full, tile_parity);
-        tc_fence_after();
-        if (prof) t2 = clock64();
+        if (prof) t2 = t1;
         // ---- GEMM2: X^T[:, 0..D) += P^T rows_A + Q^T rows_C, K = 128 rows in 4 chunks of 32.  One MMA covers all D
         //      channels (N = D) so the TMEM-resident operand P^T is read once per k-step, not once per panel.
-        for (int rc = 0; rc < 4; ++rc) {
+        for (int rq = 0; rq < 4; ++rq) {
+          const int rc = chunk_order(rq);
+          mbar_wait(&p_full[rc], tile_parity);      // P^T / Q^T of this chunk written by its 4 epilogue warps
+          if (prof && rq == 0) t2 = clock64();
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t bA = smem_u32(sStage + stage * C::kStageBytes);
@@ -223,7 +228,7 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int h = 0; h < 2; ++h) {
             // 16 rows of K = two 8-row swizzle atoms = 2048 B (>> 4 = 128); P^T k-step = 8 TMEM columns
             const uint32_t off = 32 * rc + 8 * h;
-            umma_ts_f16(tX, tHA + off, desc64(dA + 128 * h), idesc2, (first && rc == 0 && h == 0) ? 0u : 1u);
+            umma_ts_f16(tX, tHA + off, desc64(dA + 128 * h), idesc2, (first && rq == 0 && h == 0) ? 0u : 1u);
             umma_ts_f16(tX, tHC + off, desc64(dC + 128 * h), idesc2, 1u);
           }
           umma_commit(&empty[stage]);
@@ -302,10 +307,10 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         tmem_st16(lane_base + 256 + 32 * c, pk);   // P^T = g * HC^T (pairs with A rows)
         tmem_st16(lane_base + 384 + 32 * c, qk);   // Q^T = g * HA^T (pairs with C rows)
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[c]);
       }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(p_full);
       tile_parity ^= 1;
       if (prof) { ea += e1 - e0; eb += clock64() - e1; }
     }
