@@ -188,11 +188,13 @@ def run_ours(args):
         value = scale * 1000.0 / ms_per_step
         flops = 8.0 * M * d * m
         achieved = flops / (ms_kernel * 1e-3) / 1e12
-        elem = 2 if opt2.precision == "tc" else 4
+        is_tc = opt2.precision in ("tc", "tc_split")
+        mma_factor = {"tc": 1.0, "tc_split": 1.5}.get(opt2.precision, 1.0)
+        elem = 2 if is_tc else 4
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16 operands (U split hi+lo) / f32 accumulate" if opt2.precision == "tc" else "f32",
+            "vs_baseline": None, "dtype": {"tc": "f16 operands / f32 accumulate", "tc_split": "f16 operands (U split hi+lo) / f32 accumulate"}.get(opt2.precision, "f32"),
             "data": "synthetic",
             "config": {"workload": "cfg2" if not args.rows else f"custom rows={M}", "rows_per_gpu": M, "d": d, "m": m, "K": K,
                        "d_k": m // K, "precision": opt2.precision, "cuda_graph": bool(opt2.use_cuda_graph),
@@ -201,11 +203,11 @@ def run_ours(args):
             "rows_per_s": M * world * 1000.0 / ms_per_step,
             "gpu_launches": int(args.steps * launches_per_step(opt2)),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tf_sustained"], "traffic": TRAFFIC_BYTES_PER_LAUNCH if (opt2.precision == "tc" and not args.rows) else None,
-                         "kernel": "drsa_tc_step_kernel (+ tc_reduce_kernel)" if opt2.precision == "tc" else "sgemm_kernel chain",
+                         "frac": achieved / peaks["tf_sustained"], "traffic": TRAFFIC_BYTES_PER_LAUNCH if (is_tc and not args.rows) else None,
+                         "kernel": "drsa_tc_step_kernel (+ tc_reduce_kernel)" if is_tc else "sgemm_kernel chain",
                          "kernel_ms": ms_kernel, "algorithmic_flop_per_launch": flops,
                          "algorithmic_bytes_per_launch": 2.0 * M * d * elem,
-                         "executed_mma_flop_per_launch": flops * 1.5 if opt2.precision == "tc" else flops,
+                         "executed_mma_flop_per_launch": flops * mma_factor,
                          "hbm_frac": (2.0 * M * d * elem / (ms_kernel * 1e-3) / 1e9) / peaks["hbm"],
                          "peak_source": peaks["source"] + "; sustained bf16 figure (kernel timed in a loop)",
                          "share_of_step": ms_kernel / ms_per_step},
@@ -293,7 +295,7 @@ TRAFFIC_BYTES_PER_LAUNCH = 661.3e6      # 655.7 MB read + ~5.6 MB written (profi
 
 def launches_per_step(opt) -> int:
     """Kernels of libdrsa_b200.so launched per DRSA step (counted from the host code in csrc/)."""
-    row = 2 if opt.precision == "tc" else 8 * max(1, -(-opt.act_vecs.size(0) // (1 << 18)))
+    row = 2 if opt.precision in ("tc", "tc_split") else 8 * max(1, -(-opt.act_vecs.size(0) // (1 << 18)))
     return row + 1                      # row pass (+ partial reduce) and the fused cooperative finish kernel
 
 
@@ -370,7 +372,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="tc", choices=["tc", "fp32", "auto"])
+    ap.add_argument("--precision", default="tc", choices=["tc", "tc_split", "fp32", "auto"])
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (default: cfg2 = 640000)")
     ap.add_argument("--e2e-steps", type=int, default=500)
     ap.add_argument("--cpu-budget", type=float, default=15.0)

@@ -71,15 +71,17 @@ class _RowPass:
         self.lib = lib
         self.M, self.d, self.m, self.K = int(act.shape[0]), d, m, K
         dev = act.device
-        tc_ok = lib.drsa_step_workspace_bytes(max(self.M, 1), d, m, K, _L.PREC_TC_F16X2) >= 0
+        tc_ok = lib.drsa_step_workspace_bytes(max(self.M, 1), d, m, K, _L.PREC_TC_F16) >= 0
         if precision == "auto":
             precision = "tc" if (tc_ok and self.M >= 8192) else "fp32"
-        if precision == "tc" and not tc_ok:
-            raise _L.DRSAError(f"precision='tc' does not support d={d}, m={m}, K={K}")
-        if precision not in ("tc", "fp32"):
-            raise ValueError("precision must be 'auto', 'tc' or 'fp32'")
+        if precision in ("tc", "tc_split") and not tc_ok:
+            raise _L.DRSAError(f"precision='{precision}' does not support d={d}, m={m}, K={K}")
+        if precision not in ("tc", "tc_split", "fp32"):
+            raise ValueError("precision must be 'auto', 'tc', 'tc_split' or 'fp32'")
         self.precision = precision
-        self.prec_code = _L.PREC_TC_F16X2 if precision == "tc" else _L.PREC_FP32
+        self.prec_code = {"tc": _L.PREC_TC_F16, "tc_split": _L.PREC_TC_F16X2, "fp32": _L.PREC_FP32}[precision]
+        self.is_tc = precision != "fp32"
+        self.u_rounded = 1 if precision == "tc" else 0
         self.sums = torch.zeros(d * m + K, dtype=torch.float32, device=dev)
         self.status = torch.zeros(4, dtype=torch.int32, device=dev)
         self.scaleA = self.scaleC = self.pq_scale = 1.0
@@ -87,9 +89,10 @@ class _RowPass:
         if self.M > 0:
             ws = _L.check(lib.drsa_step_workspace_bytes(self.M, d, m, K, self.prec_code), "drsa_step_workspace_bytes")
             self.ws_step = torch.empty(max(int(ws), 256), dtype=torch.uint8, device=dev)
-        if precision == "tc":
+        if self.is_tc:
             self.Ut_hi = torch.empty(m, d, dtype=torch.float16, device=dev)
-            self.Ut_lo = torch.empty(m, d, dtype=torch.float16, device=dev)
+            if precision == "tc_split":
+                self.Ut_lo = torch.empty(m, d, dtype=torch.float16, device=dev)
             self.A, self.scaleA, rhoA = self._pack(act)
             self.C, self.scaleC, rhoC = self._pack(ctx)
             # |g*HC| <= pq * rhoA * rhoC^2 and |g*HA| <= pq * rhoA^2 * rhoC (rho = largest packed row norm):
@@ -116,7 +119,7 @@ class _RowPass:
         return out, scale, rho * scale
 
     def split_u(self, U: torch.Tensor):
-        if self.precision == "tc":
+        if self.is_tc:
             _L.check(self.lib.drsa_split_u(_ptr(U), self.d, self.m, _ptr(self.Ut_hi), _ptr(self.Ut_lo), _stream()),
                      "drsa_split_u")
 
@@ -135,7 +138,7 @@ class _RowPass:
         _L.check(self.lib.drsa_finish_step(_ptr(self.sums), M_global, _ptr(U), self.d, self.m, self.K,
                                            _ptr(U) if update else None,
                                            _ptr(self.Ut_hi) if update else None, _ptr(self.Ut_lo) if update else None,
-                                           _ptr(obj_log), log_index, max_iters, tol, _ptr(self.status),
+                                           _ptr(obj_log), log_index, max_iters, tol, self.u_rounded, _ptr(self.status),
                                            _ptr(self.ws_fin), self.ws_fin.numel(), _stream()),
                  "drsa_finish_step")
 
@@ -148,7 +151,9 @@ class SubspaceOptimizer:
     ``obj_val``, ``save_model`` and ``save_train_stats``.
 
     Extra keyword arguments (all optional, defaults keep the reference behaviour):
-        precision: 'auto' | 'tc' | 'fp32' -- arithmetic of the row pass (see include/drsa_b200.h).
+        precision: 'auto' | 'tc' | 'tc_split' | 'fp32' -- arithmetic of the row pass (see include/drsa_b200.h):
+            'tc' = tcgen05 with U rounded to fp16 once per step and a first-order corrected objective,
+            'tc_split' = tcgen05 with U split hi + lo (1.5x the MMA work), 'fp32' = CUDA cores.
         process_group: torch.distributed group over which the rows are sharded; ``activation_vecs``
             / ``context_vecs`` are then this rank's slice.  Defaults to the world group if
             torch.distributed is initialised.

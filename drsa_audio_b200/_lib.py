@@ -13,6 +13,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 PREC_FP32 = 0
 PREC_TC_F16X2 = 1
+PREC_TC_F16 = 2
 
 
 class DRSAError(RuntimeError):
@@ -50,7 +51,7 @@ SIGNATURES = {
     "drsa_rownorm_max": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "drsa_split_u": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "drsa_finish_workspace_bytes": (_i64, [_i32, _i32]),
-    "drsa_finish_step": (_i32, [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp,
+    "drsa_finish_step": (_i32, [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp,
                                 _i64, _vp]),
     "drsa_polar_retract": (_i32, [_vp, _i32, _i32, _vp, _i32, _f32, _vp, _vp, _i64, _vp]),
     "drsa_subspace_relevances": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
@@ -85,6 +86,7 @@ SIGNATURES = {
     "lrp_tc_split_f16": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "drsa_selftest_umma": (_i32, [_i32, _vp]),
     "drsa_debug_set_tc_profile": (_i32, [_vp]),
+    "drsa_debug_tc_kernel_attrs": (_i32, [_i32, _i32, _vp]),
 }
 
 _lock = threading.Lock()

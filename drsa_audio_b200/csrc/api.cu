@@ -38,7 +38,7 @@ int step_fp32(const float* A, const float* C, const float* U, int64_t M, int d, 
 bool tc_shape_supported(int d, int m, int K);
 int64_t step_tc_workspace_bytes(int64_t M, int d, int m, int K);
 int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_lo, int64_t M, int d, int m, int K,
-            float scaleA, float scaleC, float pq_scale, float* sums, void* workspace, int64_t workspace_bytes,
+            float scaleA, float scaleC, float pq_scale, bool split_u, float* sums, void* workspace, int64_t workspace_bytes,
             cudaStream_t stream);
 int rownorm_max(const float* in, int64_t rows, int d, float* out, cudaStream_t stream);
 int conv3x3_forward(const float* x, const float* w, const float* b, int64_t N, int Cin, int Cout, int H, int W, int relu,
@@ -80,13 +80,14 @@ int pack_f16(const float* in, int64_t count, float scale, void* out, cudaStream_
 int absmax(const float* in, int64_t count, float* out, cudaStream_t stream);
 int64_t finish_workspace_bytes(int d, int m);
 int finish_step(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out, void* Ut_hi,
-                void* Ut_lo, float* obj_log, int64_t log_index, int max_iters, float tol, int* status,
+                void* Ut_lo, float* obj_log, int64_t log_index, int max_iters, float tol, int u_rounded, int* status,
                 void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 int polar_retract(const float* Y, int d, int m, float* U_out, int max_iters, float tol, int* status, void* workspace,
                   int64_t workspace_bytes, cudaStream_t stream);
 int split_u(const float* U, int d, int m, void* Ut_hi, void* Ut_lo, cudaStream_t stream);
 int selftest_umma(int variant, float* max_err_host);
 void set_tc_profile(long long* p);
+int tc_kernel_attrs(int d, int split, int* out5);
 int64_t subspace_relevances_workspace_bytes(int64_t B, int64_t P, int d, int m);
 int subspace_relevances(const float* act, const float* ctx, const float* U, int64_t B, int64_t P, int d, int m, int K,
                         float* out, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
@@ -149,7 +150,7 @@ int drsa_rownorm_max(const float* in, int64_t rows, int d, float* out, void* str
 int64_t drsa_step_workspace_bytes(int64_t M, int d, int m, int K, int precision) {
   if (!shape_ok(M, d, m, K)) return DRSA_ERR_ARG;
   if (precision == DRSA_PREC_FP32) return step_fp32_workspace_bytes(M, d, m, K);
-  if (precision == DRSA_PREC_TC_F16X2) {
+  if (precision == DRSA_PREC_TC_F16X2 || precision == DRSA_PREC_TC_F16) {
     if (!tc_shape_supported(d, m, K)) return DRSA_ERR_SHAPE;
     return step_tc_workspace_bytes(M, d, m, K);
   }
@@ -168,16 +169,17 @@ int drsa_step(const void* A, const void* C, const float* U, const void* Ut_hi, c
     return step_fp32(static_cast<const float*>(A), static_cast<const float*>(C), U, M, d, m, K, sums, workspace,
                      workspace_bytes, s);
   }
-  if (precision == DRSA_PREC_TC_F16X2) {
-    if (Ut_hi == nullptr || Ut_lo == nullptr || !(scaleA > 0.f) || !(scaleC > 0.f) || !(pq_scale > 0.f))
+  if (precision == DRSA_PREC_TC_F16X2 || precision == DRSA_PREC_TC_F16) {
+    const bool split = precision == DRSA_PREC_TC_F16X2;
+    if (Ut_hi == nullptr || (split && Ut_lo == nullptr) || !(scaleA > 0.f) || !(scaleC > 0.f) || !(pq_scale > 0.f))
       return DRSA_ERR_ARG;
-    return step_tc(A, C, Ut_hi, Ut_lo, M, d, m, K, scaleA, scaleC, pq_scale, sums, workspace, workspace_bytes, s);
+    return step_tc(A, C, Ut_hi, Ut_lo, M, d, m, K, scaleA, scaleC, pq_scale, split, sums, workspace, workspace_bytes, s);
   }
   return DRSA_ERR_ARG;
 }
 
 int drsa_split_u(const float* U, int d, int m, void* Ut_hi, void* Ut_lo, void* stream) {
-  if (U == nullptr || Ut_hi == nullptr || Ut_lo == nullptr || d <= 0 || m <= 0) return DRSA_ERR_ARG;
+  if (U == nullptr || Ut_hi == nullptr || d <= 0 || m <= 0) return DRSA_ERR_ARG;
   DRSA_TRY(require_sm100());
   return split_u(U, d, m, Ut_hi, Ut_lo, static_cast<cudaStream_t>(stream));
 }
@@ -189,15 +191,16 @@ int64_t drsa_finish_workspace_bytes(int d, int m) {
 
 int drsa_finish_step(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out,
                      void* Ut_hi, void* Ut_lo, float* obj_log, int64_t log_index, int max_iters, float tol,
-                     int* status, void* workspace, int64_t workspace_bytes, void* stream) {
+                     int u_rounded, int* status, void* workspace, int64_t workspace_bytes, void* stream) {
   if (sums == nullptr || !shape_ok(M_global, d, m, K) || workspace == nullptr) return DRSA_ERR_ARG;
   if (U_out != nullptr && (U == nullptr || max_iters < 1 || !(tol > 0.f))) return DRSA_ERR_ARG;
-  if ((Ut_hi == nullptr) != (Ut_lo == nullptr)) return DRSA_ERR_ARG;
+  if (Ut_lo != nullptr && Ut_hi == nullptr) return DRSA_ERR_ARG;
+  if (u_rounded && U == nullptr) return DRSA_ERR_ARG;
   if (K > 1024) return DRSA_ERR_SHAPE;
   if (obj_log != nullptr && log_index < 0 && status == nullptr) return DRSA_ERR_ARG;
   DRSA_TRY(require_sm100());
-  return finish_step(sums, M_global, U, d, m, K, U_out, Ut_hi, Ut_lo, obj_log, log_index, max_iters, tol, status,
-                     workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+  return finish_step(sums, M_global, U, d, m, K, U_out, Ut_hi, Ut_lo, obj_log, log_index, max_iters, tol, u_rounded,
+                     status, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int drsa_polar_retract(const float* Y, int d, int m, float* U_out, int max_iters, float tol, int* status,
@@ -418,6 +421,11 @@ int lrp_tc_split_f16(const float* in, int64_t count, void* hi, void* lo, void* s
   if (in == nullptr || hi == nullptr || lo == nullptr || count <= 0) return DRSA_ERR_ARG;
   DRSA_TRY(require_sm100());
   return split_f16(in, count, hi, lo, static_cast<cudaStream_t>(stream));
+}
+
+int drsa_debug_tc_kernel_attrs(int d, int split, int* out5) {
+  if (out5 == nullptr || (d != 128 && d != 256)) return DRSA_ERR_ARG;
+  return tc_kernel_attrs(d, split, out5);
 }
 
 int drsa_debug_set_tc_profile(void* device_buf6) { set_tc_profile(static_cast<long long*>(device_buf6)); return DRSA_OK; }

@@ -68,19 +68,19 @@ int make_tmap_f16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint6
 namespace {
 using namespace tc;
 
-constexpr int kRows = 128;             // rows of A / C per tile (MMA N of GEMM1, K of GEMM2)
+constexpr int kSub = 64;               // rows of A / C per subtile (half the MMA N of GEMM1, the K of GEMM2)
 constexpr int kNG = 128;               // projected columns per CTA (MMA M)
 constexpr int kPanelBytes = 128 * 128; // one [128 x 64] fp16 box, 128-byte rows
-constexpr int kThreads = 320;          // TMA warp, MMA warp, 8 epilogue warps
-constexpr int kRedBytes = 4 * kRows * 4;
+constexpr int kThreads = 576;          // TMA warp, MMA warp, 2 sets of 8 epilogue warps (even / odd subtiles)
+constexpr int kRedBytes = 2 * 4 * kSub * 4;
 constexpr int kBarBytes = 256;
 
-template <int D>
+template <int D, bool kSplitU>
 struct Cfg {
   static constexpr int kPanels = D / 64;
-  static constexpr int kUBytes = 2 * kPanels * kPanelBytes;   // U^T hi + lo of this column group
-  static constexpr int kStageBytes = 2 * kPanelBytes;         // A panel + C panel
-  static constexpr int kStages = (D >= 256) ? 3 : 4;
+  static constexpr int kUBytes = (kSplitU ? 2 : 1) * kPanels * kPanelBytes;   // U^T (hi, or hi + lo) of this column group
+  static constexpr int kStageBytes = 2 * kPanelBytes;         // GEMM1: two [A64;C64] panels, GEMM2: 32 rows of A and of C
+  static constexpr int kStages = (D >= 256) ? (kSplitU ? 3 : 5) : (kSplitU ? 5 : 6);
   static constexpr int kDataBytes = kUBytes + kStages * kStageBytes;
   static constexpr int kSmemBytes = kDataBytes + kRedBytes + kBarBytes;
 };
@@ -92,36 +92,37 @@ __device__ __forceinline__ uint32_t kdesc_lo(uint32_t smem_addr) { return (smem_
 __device__ __forceinline__ uint32_t mndesc_lo(uint32_t smem_addr) { return (smem_addr >> 4) | ((4096u >> 4) << 16); }            // LBO 4 KB: next 64-channel panel
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
 
-// Order in which the 32-row chunks of a tile are handed from the epilogue to GEMM2: the two epilogue halves work on
-// chunks {0,1} and {2,3} concurrently, so chunks 0 and 2 are ready first.
-__device__ __forceinline__ int chunk_order(int i) { return ((i & 1) << 1) | (i >> 1); }
-
 __device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // d = {hi : upper, lo : lower}
   return r;
 }
 
-template <int D>
+// Schedule (per CTA, subtiles i = 0, 1, ... of 64 rows; H has two TMEM buffers of 128 columns):
+//     MMA thread :  G1(0) G1(1) G2(0) G1(2) G2(1) G1(3) G2(2) ...          (tensor pipe executes in issue order)
+//     epilogue   :        E(0)        E(1)        E(2)   ...               E(i) starts when G1(i) completes
+// so the epilogue of subtile i runs under GEMM1 of subtile i+1 and the tensor pipe never waits for it as long as
+// E(i) is shorter than G1(i+1) + G2(i-1).  H[i & 1] is free for G1(i) because G2(i-2), issued earlier, has read it.
+template <int D, bool kSplitU>
 __global__ void __launch_bounds__(kThreads, 1)
 drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmC2,
                     const __grid_constant__ CUtensorMap tmUh, const __grid_constant__ CUtensorMap tmUl,
-                    int num_tiles, int G, int nRB, int d_k, float inv_scale, float pq_scale, float* __restrict__ part,
+                    int n_sub, int G, int nRB, int d_k, float inv_scale, float pq_scale, float* __restrict__ part,
                     float* __restrict__ ss_part, int* __restrict__ err_flag, long long* __restrict__ prof) {
-  using C = Cfg<D>;
+  using C = Cfg<D, kSplitU>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sU_hi = smem;
   uint8_t* sU_lo = smem + C::kPanels * kPanelBytes;
   uint8_t* sStage = smem + C::kUBytes;
-  float* red = reinterpret_cast<float*>(smem + C::kDataBytes);
+  float* red = reinterpret_cast<float*>(smem + C::kDataBytes);      // [2 buffers][4 lane quarters][64 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kDataBytes + kRedBytes);
   uint64_t* full = bars;            // [kStages]
   uint64_t* empty = bars + 8;       // [kStages]
   uint64_t* u_full = bars + 16;
-  uint64_t* h_full = bars + 17;
-  uint64_t* x_full = bars + 18;
-  uint64_t* p_full = bars + 20;     // [4]: one per 32-row chunk, so GEMM2 can trail the epilogue chunk by chunk
+  uint64_t* x_full = bars + 17;
+  uint64_t* h_full = bars + 18;     // [2]: H buffer written by GEMM1
+  uint64_t* p_full = bars + 20;     // [2 buffers][2 chunks]: P^T / Q^T of a 32-row chunk written by its 4 epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -133,7 +134,7 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(u_full, 1); mbar_init(h_full, 1); mbar_init(x_full, 1);
+    mbar_init(u_full, 1); mbar_init(x_full, 1); mbar_init(&h_full[0], 1); mbar_init(&h_full[1], 1);
     for (int c = 0; c < 4; ++c) mbar_init(&p_full[c], 128);
     fence_barrier_init();
   }
@@ -150,168 +151,189 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_expect_tx(u_full, C::kUBytes);
       for (int p = 0; p < C::kPanels; ++p) {
         tma_load_2d(sU_hi + p * kPanelBytes, &tmUh, u_full, 64 * p, g * kNG);
-        tma_load_2d(sU_lo + p * kPanelBytes, &tmUl, u_full, 64 * p, g * kNG);
+        if (kSplitU) tma_load_2d(sU_lo + p * kPanelBytes, &tmUl, u_full, 64 * p, g * kNG);
       }
       tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmC2);
       int stage = 0; uint32_t phase = 0;
-      for (int t = rb; t < num_tiles; t += nRB) {
-        // pass 1 (GEMM1): channel panels [128 rows x 64 ch], K-major operand
-        for (int p = 0; p < C::kPanels; ++p) {
+      // GEMM1 operand: per 64-channel panel the stacked tile [A rows r0..r0+63 ; C rows r0..r0+63] (K-major), two panels per stage
+      auto load_g1 = [&](int sub) {
+        for (int hs = 0; hs < C::kPanels / 2; ++hs) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], C::kStageBytes);
           uint8_t* dst = sStage + stage * C::kStageBytes;
-          tma_load_2d(dst, &tmA, &full[stage], 64 * p, t * kRows);
-          tma_load_2d(dst + kPanelBytes, &tmC, &full[stage], 64 * p, t * kRows);
+#pragma unroll
+          for (int pp = 0; pp < 2; ++pp) {
+            tma_load_2d(dst + pp * kPanelBytes, &tmA, &full[stage], 64 * (2 * hs + pp), sub * kSub);
+            tma_load_2d(dst + pp * kPanelBytes + kPanelBytes / 2, &tmC, &full[stage], 64 * (2 * hs + pp), sub * kSub);
+          }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        // pass 2 (GEMM2): row chunks [32 rows x D ch] as D/64 panels of 4 KB, MN-major operand with N = D
-        for (int rq = 0; rq < 4; ++rq) {
-          const int rc = chunk_order(rq);
+      };
+      // GEMM2 operand: row chunks [32 rows x D ch] of A and of C as D/64 panels of 4 KB each (MN-major, N = D)
+      auto load_g2 = [&](int sub) {
+        for (int c = 0; c < 2; ++c) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], 2 * C::kPanels * 4096);
           uint8_t* dst = sStage + stage * C::kStageBytes;
           for (int p = 0; p < C::kPanels; ++p) {
-            tma_load_2d(dst + p * 4096, &tmA2, &full[stage], 64 * p, t * kRows + 32 * rc);
-            tma_load_2d(dst + kPanelBytes + p * 4096, &tmC2, &full[stage], 64 * p, t * kRows + 32 * rc);
+            tma_load_2d(dst + p * 4096, &tmA2, &full[stage], 64 * p, sub * kSub + 32 * c);
+            tma_load_2d(dst + kPanelBytes + p * 4096, &tmC2, &full[stage], 64 * p, sub * kSub + 32 * c);
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
+      };
+      int prev = -1;
+      for (int sub = rb; sub < n_sub; sub += nRB) {
+        load_g1(sub);
+        if (prev >= 0) load_g2(prev);
+        prev = sub;
       }
+      if (prev >= 0) load_g2(prev);
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
-      // GEMM1: one MMA covers the A rows and the C rows of the tile (N = 256: the C panel follows the A panel in
-      // shared memory, so the stacked [A; C] tile is one K-major operand) -- U^T is read once per k-step, not twice
-      constexpr uint32_t idesc1 = make_idesc_f16(kNG, 2 * kRows, 0, 0);
-      constexpr uint32_t idesc2 = make_idesc_f16(kNG, D, 0, 1);       // P^T (TMEM)   x row chunk (MN-major, N = D)
-      const uint32_t tX = tmem_base, tHA = tmem_base + 256, tHC = tmem_base + 384;
+      constexpr uint32_t idesc1 = make_idesc_f16(kNG, 2 * kSub, 0, 0);  // U^T (K-major) x stacked [A;C] subtile (K-major)
+      constexpr uint32_t idesc2 = make_idesc_f16(kNG, D, 0, 1);         // P^T (TMEM)   x row chunk (MN-major, N = D)
+      const uint32_t tX = tmem_base;
       mbar_wait(u_full, 0);
       tc_fence_after();
-      int stage = 0; uint32_t phase = 0, tile_parity = 0; bool first = true;
-      long long pa = 0, pb = 0, pc = 0, t0 = 0, t1 = 0, t2 = 0;
-      for (int t = rb; t < num_tiles; t += nRB) {
-        if (prof) t0 = clock64();
-        // ---- GEMM1: HA^T, HC^T [128 cols of U x 128 rows], K = D
-        for (int p = 0; p < C::kPanels; ++p) {
+      int stage = 0; uint32_t phase = 0; bool first = true;
+      long long pa = 0, pb = 0, pc = 0;
+      // ---- GEMM1(i): [HA^T | HC^T] (128 columns of U x (64 + 64) rows) -> H[i & 1], K = D
+      auto gemm1 = [&](int i) {
+        const long long t0 = prof ? clock64() : 0;
+        const uint32_t tH = tmem_base + 256 + 128 * (i & 1);
+        for (int hs = 0; hs < C::kPanels / 2; ++hs) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          // descriptors: the high word is constant, the low word is (address >> 4) | LBO field; advancing
-          // along K inside the 128-byte swizzle atom adds 32 B (>> 4 = 2) to the low word
-          const uint32_t uh = kdesc_lo(smem_u32(sU_hi + p * kPanelBytes)), ul = kdesc_lo(smem_u32(sU_lo + p * kPanelBytes));
-          const uint32_t bA = smem_u32(sStage + stage * C::kStageBytes);
-          const uint32_t dAC = kdesc_lo(bA);
+          const uint32_t base = smem_u32(sStage + stage * C::kStageBytes);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint32_t acc = (p | kk) ? 1u : 0u;
-            const uint64_t d_ac = desc64(dAC + 2 * kk);
-            umma_ss_f16(tHA, desc64(uh + 2 * kk), d_ac, idesc1, acc);
-            umma_ss_f16(tHA, desc64(ul + 2 * kk), d_ac, idesc1, 1u);
+          for (int pp = 0; pp < 2; ++pp) {
+            const int p = 2 * hs + pp;
+            // descriptors: the high word is constant, the low word is (address >> 4) | LBO field; advancing
+            // along K inside the 128-byte swizzle atom adds 32 B (>> 4 = 2) to the low word
+            const uint32_t uh = kdesc_lo(smem_u32(sU_hi + p * kPanelBytes)), ul = kdesc_lo(smem_u32(sU_lo + p * kPanelBytes));
+            const uint32_t dAC = kdesc_lo(base + pp * kPanelBytes);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t d_ac = desc64(dAC + 2 * kk);
+              umma_ss_f16(tH, desc64(uh + 2 * kk), d_ac, idesc1, (p | kk) ? 1u : 0u);
+              if (kSplitU) umma_ss_f16(tH, desc64(ul + 2 * kk), d_ac, idesc1, 1u);
+            }
           }
           umma_commit(&empty[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(h_full);
-        if (prof) t1 = clock64();
-        if (prof) t2 = t1;
-        // ---- GEMM2: X^T[:, 0..D) += P^T rows_A + Q^T rows_C, K = 128 rows in 4 chunks of 32.  One MMA covers all D
-        //      channels (N = D) so the TMEM-resident operand P^T is read once per k-step, not once per panel.
-        for (int rq = 0; rq < 4; ++rq) {
-          const int rc = chunk_order(rq);
-          mbar_wait(&p_full[rc], tile_parity);      // P^T / Q^T of this chunk written by its 4 epilogue warps
-          if (prof && rq == 0) t2 = clock64();
+        umma_commit(&h_full[i & 1]);
+        if (prof) pa += clock64() - t0;
+      };
+      // ---- GEMM2(i): X^T[:, 0..D) += P^T rows_A + Q^T rows_C, K = 64 rows in 2 chunks of 32.  One MMA covers all D
+      //      channels (N = D) so the TMEM-resident operand P^T is read once per k-step.
+      auto gemm2 = [&](int i) {
+        const long long t0 = prof ? clock64() : 0;
+        long long t1 = t0;
+        const uint32_t tH = tmem_base + 256 + 128 * (i & 1);
+        const uint32_t par = (uint32_t)(i >> 1) & 1u;
+        for (int c = 0; c < 2; ++c) {
+          mbar_wait(&p_full[2 * (i & 1) + c], par);
+          if (prof && c == 0) t1 = clock64();
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t bA = smem_u32(sStage + stage * C::kStageBytes);
-          const uint32_t dA = mndesc_lo(bA), dC = mndesc_lo(bA + kPanelBytes);
+          const uint32_t base = smem_u32(sStage + stage * C::kStageBytes);
+          const uint32_t dA = mndesc_lo(base), dC = mndesc_lo(base + kPanelBytes);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             // 16 rows of K = two 8-row swizzle atoms = 2048 B (>> 4 = 128); P^T k-step = 8 TMEM columns
-            const uint32_t off = 32 * rc + 8 * h;
-            umma_ts_f16(tX, tHA + off, desc64(dA + 128 * h), idesc2, (first && rq == 0 && h == 0) ? 0u : 1u);
-            umma_ts_f16(tX, tHC + off, desc64(dC + 128 * h), idesc2, 1u);
+            const uint32_t off = 32 * c + 8 * h;
+            umma_ts_f16(tX, tH + off, desc64(dA + 128 * h), idesc2, first ? 0u : 1u);
+            umma_ts_f16(tX, tH + kSub + off, desc64(dC + 128 * h), idesc2, 1u);
+            first = false;
           }
           umma_commit(&empty[stage]);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        first = false;
-        tile_parity ^= 1;
-        if (prof) { const long long t3 = clock64(); pa += t1 - t0; pb += t2 - t1; pc += t3 - t2; }
+        if (prof) { pb += t1 - t0; pc += clock64() - t1; }
+      };
+      int i = 0;
+      for (int sub = rb; sub < n_sub; sub += nRB, ++i) {
+        gemm1(i);
+        if (i > 0) gemm2(i - 1);
       }
+      if (i > 0) gemm2(i - 1);
       umma_commit(x_full);
       if (prof && blockIdx.x == 0) { prof[0] = pa; prof[1] = pb; prof[2] = pc; }
     }
   } else {
     // ======================= epilogue warps =======================
     const int q = warp & 3;                     // TMEM lane quarter this warp may touch
-    const int half = (warp - 2) >> 2;           // two warps per quarter: each takes two of the four 32-row chunks
+    const int set = (warp - 2) >> 3;            // warps 2..9 take the even subtiles (H buffer 0), warps 10..17 the odd ones
+    const int c = ((warp - 2) >> 2) & 1;        // the 32-row chunk of those subtiles this warp works on
     const int j = 32 * q + lane;                // projected column within the group
     const int wpc = d_k >> 5;                   // warps per concept (d_k in {32, 64, 128})
     const int q0 = (q / wpc) * wpc;
     const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
-    const bool owner = (j % d_k) == 0;           // one thread per (concept, half) accumulates sum g^2
+    const bool owner = (j % d_k) == 0;           // one thread per (concept, chunk) accumulates sum g^2
     float ssq = 0.f;
-    uint32_t tile_parity = 0;
     long long ea = 0, eb = 0, e0 = 0, e1 = 0;
-    for (int t = rb; t < num_tiles; t += nRB) {
+    for (int i = set, sub = rb + set * nRB; sub < n_sub; sub += 2 * nRB, i += 2) {
+      const int buf = set;
       if (prof) e0 = clock64();
-      mbar_wait(h_full, tile_parity);
+      mbar_wait(&h_full[buf], (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
       if (prof) e1 = clock64();
-#pragma unroll 1
-      for (int c = 2 * half; c < 2 * half + 2; ++c) {
-        uint32_t ha[32], hc[32];
-        tmem_ld32(lane_base + 256 + 32 * c, ha);
-        tmem_ld32(lane_base + 384 + 32 * c, hc);
-        tmem_ld_wait();
-        float pr[32];
+      const uint32_t tHA = lane_base + 256 + 128 * buf + 32 * c, tHC = tHA + kSub;
+      float* redb = red + buf * (4 * kSub);
+      uint32_t ha[32], hc[32];
+      tmem_ld32(tHA, ha);
+      tmem_ld32(tHC, hc);
+      tmem_ld_wait();
+      float pr[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) pr[i] = __uint_as_float(ha[i]) * __uint_as_float(hc[i]);
-        // transpose-reduce: afterwards lane l holds sum over the warp's 32 lanes of column l
+      for (int e = 0; e < 32; ++e) pr[e] = __uint_as_float(ha[e]) * __uint_as_float(hc[e]);
+      // transpose-reduce: afterwards lane l holds sum over the warp's 32 lanes of column l
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-          const bool upper = (lane & off) != 0;
+      for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
 #pragma unroll
-          for (int i = 0; i < off; ++i) {
-            const float send = upper ? pr[i] : pr[i + off];
-            const float keep = upper ? pr[i + off] : pr[i];
-            pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-          }
+        for (int e = 0; e < off; ++e) {
+          const float send = upper ? pr[e] : pr[e + off];
+          const float keep = upper ? pr[e + off] : pr[e];
+          pr[e] = keep + __shfl_xor_sync(0xffffffffu, send, off);
         }
-        red[q * kRows + 32 * c + lane] = pr[0];
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");   // the 4 warps working on this chunk
-        uint32_t pk[16], qk[16];
-#pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {
-          float4 s4 = *reinterpret_cast<const float4*>(&red[q0 * kRows + 32 * c + 4 * i4]);
-#pragma unroll
-          for (int w = 1; w < 4; ++w) {
-            if (w < wpc) {
-              const float4 o = *reinterpret_cast<const float4*>(&red[(q0 + w) * kRows + 32 * c + 4 * i4]);
-              s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w;
-            }
-          }
-          // s is in packed scale (sA*sC*s_true): sums of squares are taken in true scale, the fp16
-          // operands P, Q of GEMM2 in packed scale times pq_scale (overflow-safe by construction)
-          float g0 = fmaxf(s4.x, 0.f), g1 = fmaxf(s4.y, 0.f), g2 = fmaxf(s4.z, 0.f), g3 = fmaxf(s4.w, 0.f);
-          if (owner) {
-            const float t0 = g0 * inv_scale, t1 = g1 * inv_scale, t2 = g2 * inv_scale, t3 = g3 * inv_scale;
-            ssq += t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3;
-          }
-          g0 *= pq_scale; g1 *= pq_scale; g2 *= pq_scale; g3 *= pq_scale;
-          const int i = 4 * i4;
-          pk[2 * i4] = pack_h2_sat(g0 * __uint_as_float(hc[i]), g1 * __uint_as_float(hc[i + 1]));
-          pk[2 * i4 + 1] = pack_h2_sat(g2 * __uint_as_float(hc[i + 2]), g3 * __uint_as_float(hc[i + 3]));
-          qk[2 * i4] = pack_h2_sat(g0 * __uint_as_float(ha[i]), g1 * __uint_as_float(ha[i + 1]));
-          qk[2 * i4 + 1] = pack_h2_sat(g2 * __uint_as_float(ha[i + 2]), g3 * __uint_as_float(ha[i + 3]));
-        }
-        tmem_st16(lane_base + 256 + 32 * c, pk);   // P^T = g * HC^T (pairs with A rows)
-        tmem_st16(lane_base + 384 + 32 * c, qk);   // Q^T = g * HA^T (pairs with C rows)
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_full[c]);
       }
-      tile_parity ^= 1;
+      redb[q * kSub + 32 * c + lane] = pr[0];
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + 2 * set + c) : "memory");   // the 4 warps working on this chunk
+      uint32_t pk[16], qk[16];
+#pragma unroll
+      for (int i4 = 0; i4 < 8; ++i4) {
+        float4 s4 = *reinterpret_cast<const float4*>(&redb[q0 * kSub + 32 * c + 4 * i4]);
+#pragma unroll
+        for (int w = 1; w < 4; ++w) {
+          if (w < wpc) {
+            const float4 o = *reinterpret_cast<const float4*>(&redb[(q0 + w) * kSub + 32 * c + 4 * i4]);
+            s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w;
+          }
+        }
+        // s is in packed scale (sA*sC*s_true): sums of squares are taken in true scale, the fp16
+        // operands P, Q of GEMM2 in packed scale times pq_scale (overflow-safe by construction)
+        float g0 = fmaxf(s4.x, 0.f), g1 = fmaxf(s4.y, 0.f), g2 = fmaxf(s4.z, 0.f), g3 = fmaxf(s4.w, 0.f);
+        if (owner) {
+          const float t0 = g0 * inv_scale, t1 = g1 * inv_scale, t2 = g2 * inv_scale, t3 = g3 * inv_scale;
+          ssq += t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3;
+        }
+        g0 *= pq_scale; g1 *= pq_scale; g2 *= pq_scale; g3 *= pq_scale;
+        const int e = 4 * i4;
+        pk[2 * i4] = pack_h2_sat(g0 * __uint_as_float(hc[e]), g1 * __uint_as_float(hc[e + 1]));
+        pk[2 * i4 + 1] = pack_h2_sat(g2 * __uint_as_float(hc[e + 2]), g3 * __uint_as_float(hc[e + 3]));
+        qk[2 * i4] = pack_h2_sat(g0 * __uint_as_float(ha[e]), g1 * __uint_as_float(ha[e + 1]));
+        qk[2 * i4 + 1] = pack_h2_sat(g2 * __uint_as_float(ha[e + 2]), g3 * __uint_as_float(ha[e + 3]));
+      }
+      tmem_st16(tHA, pk);   // P^T = g * HC^T (pairs with A rows)
+      tmem_st16(tHC, qk);   // Q^T = g * HA^T (pairs with C rows)
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[2 * buf + c]);
       if (prof) { ea += e1 - e0; eb += clock64() - e1; }
     }
     if (prof && blockIdx.x == 0 && warp == 2 && lane == 0) { prof[3] = ea; prof[4] = eb; }
@@ -320,17 +342,18 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     float* dst = part + ((int64_t)blockIdx.x * kNG + j) * D;
 #pragma unroll 1
-    for (int cc = half; cc < D / 32; cc += 2) {
+    for (int cc = (warp - 2) >> 2; cc < D / 32; cc += 4) {
       uint32_t v[32];
       tmem_ld32(lane_base + 32 * cc, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        *reinterpret_cast<float4*>(dst + 32 * cc + 4 * i) =
-            make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                        __uint_as_float(v[4 * i + 3]));
+      for (int e = 0; e < 8; ++e)
+        *reinterpret_cast<float4*>(dst + 32 * cc + 4 * e) =
+            make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
+                        __uint_as_float(v[4 * e + 3]));
     }
-    if (owner) atomicAdd(&ss_part[(int64_t)rb * (G * (kNG / d_k)) + g * (kNG / d_k) + j / d_k], ssq);   // 2 adds: order-independent
+    // one slot per (row block, concept, warp group): summed in a fixed order by tc_reduce_kernel (deterministic)
+    if (owner) ss_part[((int64_t)rb * (G * (kNG / d_k)) + g * (kNG / d_k) + j / d_k) * 4 + 2 * set + c] = ssq;
     tc_fence_before();
   }
   __syncthreads();
@@ -368,7 +391,10 @@ __global__ void __launch_bounds__(1024) tc_reduce_kernel(const float* __restrict
   sums[(int64_t)(i0 + ty) * m + c0 + tx] = tile[tx][ty] * x_scale;
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < K) {
     float s = 0.f;
-    for (int r = 0; r < nRB; ++r) s += ss_part[(int64_t)r * K + threadIdx.x];
+    for (int r = 0; r < nRB; ++r) {
+      const float4 v = *reinterpret_cast<const float4*>(ss_part + ((int64_t)r * K + threadIdx.x) * 4);
+      s += (v.x + v.y) + (v.z + v.w);
+    }
     sums[(int64_t)d * m + threadIdx.x] = s;
   }
 }
@@ -423,13 +449,13 @@ struct TcPlan { int G, nRB, num_tiles; int64_t part_bytes, ss_bytes; };
 TcPlan plan_for(int64_t M, int d, int m, int K) {
   TcPlan p;
   p.G = m / kNG;
-  p.num_tiles = (int)((M + kRows - 1) / kRows);
+  p.num_tiles = (int)((M + kSub - 1) / kSub);      // 64-row subtiles
   int nrb = sm_count() / p.G;
   if (nrb < 1) nrb = 1;
   if (nrb > p.num_tiles) nrb = p.num_tiles;
   p.nRB = nrb;
   p.part_bytes = align_up((int64_t)p.nRB * p.G * kNG * d * 4, 256);
-  p.ss_bytes = align_up((int64_t)p.nRB * K * 4, 256);
+  p.ss_bytes = align_up((int64_t)p.nRB * K * 4 * 4, 256);
   return p;
 }
 }  // namespace
@@ -445,9 +471,25 @@ int64_t step_tc_workspace_bytes(int64_t M, int d, int m, int K) {
   return p.part_bytes + p.ss_bytes + 256;
 }
 
+template <int D, bool kSplitU, typename... Args>
+int launch_step(int grid, cudaStream_t stream, Args... args) {
+  static bool attr_set = false;      // one process per GPU: a per-process flag is enough
+  if (!attr_set) {
+    DRSA_CUDA(cudaFuncSetAttribute(drsa_tc_step_kernel<D, kSplitU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg<D, kSplitU>::kSmemBytes));
+    attr_set = true;
+  }
+  drsa_tc_step_kernel<D, kSplitU><<<grid, kThreads, Cfg<D, kSplitU>::kSmemBytes, stream>>>(args...);
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+// split_u = true: U^T = hi + lo, two MMAs per product (DRSA_PREC_TC_F16X2); false: U^T = fp16(U) only (DRSA_PREC_TC_F16)
 int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_lo, int64_t M, int d, int m, int K,
-            float scaleA, float scaleC, float pq_scale, float* sums, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+            float scaleA, float scaleC, float pq_scale, bool split_u, float* sums, void* workspace, int64_t workspace_bytes,
+            cudaStream_t stream) {
   if (!tc_shape_supported(d, m, K)) return DRSA_ERR_SHAPE;
+  if (!split_u) Ut_lo = Ut_hi;       // never read; keeps the tensor map valid
   if (!aligned16(A16) || !aligned16(C16) || !aligned16(Ut_hi) || !aligned16(Ut_lo)) return DRSA_ERR_ALIGN;
   if (M >= ((int64_t)1 << 31)) return DRSA_ERR_SHAPE;
   TcPlan p = plan_for(M, d, m, K);
@@ -458,8 +500,8 @@ int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_
   int* err = reinterpret_cast<int*>(w);
 
   CUtensorMap tmA, tmC, tmA2, tmC2, tmUh, tmUl;
-  DRSA_TRY(make_tmap_f16_sw128(&tmA, A16, (uint64_t)M, (uint64_t)d, kRows));
-  DRSA_TRY(make_tmap_f16_sw128(&tmC, C16, (uint64_t)M, (uint64_t)d, kRows));
+  DRSA_TRY(make_tmap_f16_sw128(&tmA, A16, (uint64_t)M, (uint64_t)d, kSub));
+  DRSA_TRY(make_tmap_f16_sw128(&tmC, C16, (uint64_t)M, (uint64_t)d, kSub));
   DRSA_TRY(make_tmap_f16_sw128(&tmA2, A16, (uint64_t)M, (uint64_t)d, 32));
   DRSA_TRY(make_tmap_f16_sw128(&tmC2, C16, (uint64_t)M, (uint64_t)d, 32));
   DRSA_TRY(make_tmap_f16_sw128(&tmUh, Ut_hi, (uint64_t)m, (uint64_t)d, kNG));
@@ -468,27 +510,18 @@ int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_
   const float inv_scale = 1.0f / (scaleA * scaleC);
   const int d_k = m / K;
   const int grid = p.nRB * p.G;
-  DRSA_CUDA(cudaMemsetAsync(ss_part, 0, (size_t)p.nRB * K * 4, stream));
-  if (d == 256) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      DRSA_CUDA(cudaFuncSetAttribute(drsa_tc_step_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg<256>::kSmemBytes));
-      attr_set = true;
-    }
-    drsa_tc_step_kernel<256><<<grid, kThreads, Cfg<256>::kSmemBytes, stream>>>(
-        tmA, tmC, tmA2, tmC2, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale, pq_scale, part, ss_part, err, g_tc_prof);
-  } else {
-    static bool attr_set = false;
-    if (!attr_set) {
-      DRSA_CUDA(cudaFuncSetAttribute(drsa_tc_step_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     Cfg<128>::kSmemBytes));
-      attr_set = true;
-    }
-    drsa_tc_step_kernel<128><<<grid, kThreads, Cfg<128>::kSmemBytes, stream>>>(
-        tmA, tmC, tmA2, tmC2, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale, pq_scale, part, ss_part, err, g_tc_prof);
-  }
-  DRSA_LAUNCH_CHECK();
+  int st;
+  if (d == 256)
+    st = split_u ? launch_step<256, true>(grid, stream, tmA, tmC, tmA2, tmC2, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale,
+                                          pq_scale, part, ss_part, err, g_tc_prof)
+                 : launch_step<256, false>(grid, stream, tmA, tmC, tmA2, tmC2, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale,
+                                           pq_scale, part, ss_part, err, g_tc_prof);
+  else
+    st = split_u ? launch_step<128, true>(grid, stream, tmA, tmC, tmA2, tmC2, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale,
+                                          pq_scale, part, ss_part, err, g_tc_prof)
+                 : launch_step<128, false>(grid, stream, tmA, tmC, tmA2, tmC2, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale,
+                                           pq_scale, part, ss_part, err, g_tc_prof);
+  DRSA_TRY(st);
   dim3 rgrid(m / 32, d / 32);
   // X' = pq_scale * (sA sC)^2 * X
   tc_reduce_kernel<<<rgrid, 1024, 0, stream>>>(part, ss_part, p.nRB, p.G, d, m, K, inv_scale * inv_scale / pq_scale, sums);
@@ -524,6 +557,17 @@ int absmax(const float* in, int64_t count, float* out, cudaStream_t stream) {
 }
 
 void set_tc_profile(long long* p) { g_tc_prof = p; }
+
+// numRegs, maxThreadsPerBlock, static shared bytes, local bytes, max dynamic shared bytes of the row-pass kernel
+int tc_kernel_attrs(int d, int split, int* out5) {
+  cudaFuncAttributes a;
+  const void* fn = d == 256 ? (split ? (const void*)drsa_tc_step_kernel<256, true> : (const void*)drsa_tc_step_kernel<256, false>)
+                            : (split ? (const void*)drsa_tc_step_kernel<128, true> : (const void*)drsa_tc_step_kernel<128, false>);
+  DRSA_CUDA(cudaFuncGetAttributes(&a, fn));
+  out5[0] = a.numRegs; out5[1] = a.maxThreadsPerBlock; out5[2] = (int)a.sharedSizeBytes; out5[3] = (int)a.localSizeBytes;
+  out5[4] = a.maxDynamicSharedSizeBytes;
+  return DRSA_OK;
+}
 
 int rownorm_max(const float* in, int64_t rows, int d, float* out, cudaStream_t stream) {
   DRSA_CUDA(cudaMemsetAsync(out, 0, sizeof(float), stream));

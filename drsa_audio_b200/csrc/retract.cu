@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) select_kernel(const float* __restrict__ X
       const int r = (int)(i / m), c = (int)(i % m);
       const __half hi = __float2half_rn(v);
       Ut_hi[(int64_t)c * d + r] = hi;
-      Ut_lo[(int64_t)c * d + r] = __float2half_rn(v - __half2float(hi));
+      if (Ut_lo != nullptr) Ut_lo[(int64_t)c * d + r] = __float2half_rn(v - __half2float(hi));
     }
   }
 }
@@ -177,7 +177,7 @@ __global__ void split_u_kernel(const float* __restrict__ U, int d, int m, __half
     const float v = U[i];
     const __half hi = __float2half_rn(v);
     Ut_hi[(int64_t)c * d + r] = hi;
-    Ut_lo[(int64_t)c * d + r] = __float2half_rn(v - __half2float(hi));
+    if (Ut_lo != nullptr) Ut_lo[(int64_t)c * d + r] = __float2half_rn(v - __half2float(hi));
   }
 }
 
@@ -218,8 +218,8 @@ int polar_from_Y(const PolarWs& p, int d, int m, float* U_out, void* Ut_hi, void
 bool finish_fused_supported(int d, int m, int K);
 int64_t finish_fused_workspace_bytes(int d, int m);
 int finish_fused(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out, void* Ut_hi,
-                 void* Ut_lo, float* obj_log, int64_t log_index, int max_iters, float tol, int* status, void* workspace,
-                 int64_t workspace_bytes, const float* Y_in, cudaStream_t stream);
+                 void* Ut_lo, float* obj_log, int64_t log_index, int max_iters, float tol, int u_rounded, int* status,
+                 void* workspace, int64_t workspace_bytes, const float* Y_in, cudaStream_t stream);
 
 int64_t finish_workspace_bytes(int d, int m) {
   const int64_t a = polar_ws_bytes(d, m), b = finish_fused_workspace_bytes(d, m);
@@ -228,10 +228,11 @@ int64_t finish_workspace_bytes(int d, int m) {
 
 int finish_step(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out,
                 void* Ut_hi, void* Ut_lo, float* obj_log, int64_t log_index, int max_iters, float tol,
-                int* status, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+                int u_rounded, int* status, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
   if (finish_fused_supported(d, m, K))       // one cooperative kernel instead of ~30 dependent launches
-    return finish_fused(sums, M_global, U, d, m, K, U_out, Ut_hi, Ut_lo, obj_log, log_index, max_iters, tol, status,
-                        workspace, workspace_bytes, nullptr, stream);
+    return finish_fused(sums, M_global, U, d, m, K, U_out, Ut_hi, Ut_lo, obj_log, log_index, max_iters, tol, u_rounded,
+                        status, workspace, workspace_bytes, nullptr, stream);
+  if (u_rounded) return DRSA_ERR_SHAPE;      // the tensor-core modes only exist for shapes the fused kernel covers
   if (workspace_bytes < polar_ws_bytes(d, m)) return DRSA_ERR_WORKSPACE;
   PolarWs p = carve(workspace, d, m);
   const int64_t n = (int64_t)d * m;
@@ -247,7 +248,7 @@ int finish_step(const float* sums, int64_t M_global, const float* U, int d, int 
 int polar_retract(const float* Y, int d, int m, float* U_out, int max_iters, float tol, int* status,
                   void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
   if (finish_fused_supported(d, m, 1))
-    return finish_fused(nullptr, 1, nullptr, d, m, 1, U_out, nullptr, nullptr, nullptr, 0, max_iters, tol, status,
+    return finish_fused(nullptr, 1, nullptr, d, m, 1, U_out, nullptr, nullptr, nullptr, 0, max_iters, tol, 0, status,
                         workspace, workspace_bytes, Y, stream);
   if (workspace_bytes < polar_ws_bytes(d, m)) return DRSA_ERR_WORKSPACE;
   PolarWs p = carve(workspace, d, m);

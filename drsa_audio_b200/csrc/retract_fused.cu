@@ -24,6 +24,8 @@ struct FusedParams {
   float* rowsum;   // [m/32][m] per-tile-column partial row sums of |G| (summed in fixed order: deterministic)
   float* resid;    // [max_iters + 2][gridDim.x] per-CTA partial residuals (summed in fixed order)
   int have_sums;   // 0: Y already holds the matrix to retract (drsa_polar_retract)
+  int u_rounded;   // sums were evaluated at fp16(U): log f(fp16 U) + <grad, U - fp16 U> (first-order exact in the rounding)
+  float* corr;     // [gridDim.x] per-CTA partials of that inner product
 };
 
 // C[32x32] (+)= sum_k A_k(i) B_k(j) with both operands given as "row k, column contiguous" views:
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
   const int64_t n = (int64_t)d * m;
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + tid, gthreads = (int64_t)gridDim.x * blockDim.x;
 
-  // ---------------- phase 0: pooling scalars, objective log, Y = U + coef_k X_k
+  // ---------------- phase 0: pooling scalars, Y = U + coef_k X_k, objective log
   if (p.have_sums) {
     const int K = p.K, d_k = m / K;
     if (tid == 0) {
@@ -117,38 +119,55 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
         if (q == 0.f) ++degenerate;
         acc += sqrtf(q);
       }
-      const float root = acc / (float)K;
-      bc[0] = root;
-      if (blockIdx.x == 0) {
-        if (p.obj_log != nullptr) {
-          long long idx = p.log_index;
-          if (idx < 0) { idx = p.status[3]; p.status[3] = (int)idx + 1; }
-          p.obj_log[idx] = root * root;
-        }
-        if (p.status != nullptr) p.status[2] = degenerate;
-      }
+      bc[0] = acc / (float)K;
+      if (blockIdx.x == 0 && p.status != nullptr) p.status[2] = degenerate;
     }
     __syncthreads();
-    if (p.U_out == nullptr) return;             // objective only (uniform across the grid)
     const float root = bc[0];
-    for (int k = tid; k < K; k += blockDim.x) {
-      const float q = sqrtf((float)((double)p.sums[n + k] * p.inv_M));
-      // K > 64 is exotic: the factor is then recomputed on the fly below
-      if (K <= 64) coef[k] = (float)((double)root * p.inv_M / ((double)K * (double)q * sqrt((double)q)));
-    }
-    __syncthreads();
-    for (int64_t i = gtid; i < n; i += gthreads) {
-      const int k = (int)(i % m) / d_k;
-      float c;
-      if (K <= 64) c = coef[k];
-      else {
+    const bool need_grad = p.U_out != nullptr || p.u_rounded;
+    float corr = 0.f;
+    if (need_grad) {
+      for (int k = tid; k < K; k += blockDim.x) {
         const float q = sqrtf((float)((double)p.sums[n + k] * p.inv_M));
-        c = (float)((double)root * p.inv_M / ((double)K * (double)q * sqrt((double)q)));
+        // K > 64 is exotic: the factor is then recomputed on the fly below
+        if (K <= 64) coef[k] = (float)((double)root * p.inv_M / ((double)K * (double)q * sqrt((double)q)));
       }
-      p.Y[i] = p.U[i] + c * p.sums[i];
+      __syncthreads();
+      for (int64_t i = gtid; i < n; i += gthreads) {
+        const int k = (int)(i % m) / d_k;
+        float c;
+        if (K <= 64) c = coef[k];
+        else {
+          const float q = sqrtf((float)((double)p.sums[n + k] * p.inv_M));
+          c = (float)((double)root * p.inv_M / ((double)K * (double)q * sqrt((double)q)));
+        }
+        const float u = p.U[i], gr = c * p.sums[i];
+        if (p.U_out != nullptr) p.Y[i] = u + gr;
+        if (p.u_rounded) corr = fmaf(gr, u - __half2float(__float2half_rn(u)), corr);
+      }
+    }
+    if (p.u_rounded) {
+      const float tot = block_sum(corr, red);
+      if (tid == 0) p.corr[blockIdx.x] = tot;
+    }
+    if (p.U_out == nullptr) {                   // objective only: a single CTA (uniform across the grid)
+      if (tid == 0 && p.obj_log != nullptr) {
+        long long idx = p.log_index;
+        if (idx < 0) { idx = p.status[3]; p.status[3] = (int)idx + 1; }
+        p.obj_log[idx] = root * root + (p.u_rounded ? p.corr[0] : 0.f);
+      }
+      return;
     }
   }
   grid.sync();
+  if (p.have_sums && blockIdx.x == 0 && tid == 0 && p.obj_log != nullptr) {
+    float extra = 0.f;
+    if (p.u_rounded)
+      for (int b = 0; b < (int)gridDim.x; ++b) extra += __ldcg(p.corr + b);      // fixed order: bit-identical replicas
+    long long idx = p.log_index;
+    if (idx < 0) { idx = p.status[3]; p.status[3] = (int)idx + 1; }
+    p.obj_log[idx] = bc[0] * bc[0] + extra;
+  }
 
   const int tm = m / TS, td = d / TS;
   // ---------------- phase 1: G = Y^T Y, row sums of |G|
@@ -256,7 +275,7 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
       const int r = (int)(i / m), cc = (int)(i % m);
       const __half hi = __float2half_rn(v);
       p.Ut_hi[(int64_t)cc * d + r] = hi;
-      p.Ut_lo[(int64_t)cc * d + r] = __float2half_rn(v - __half2float(hi));
+      if (p.Ut_lo != nullptr) p.Ut_lo[(int64_t)cc * d + r] = __float2half_rn(v - __half2float(hi));
     }
   }
 }
@@ -273,8 +292,8 @@ int64_t finish_fused_workspace_bytes(int d, int m) { return fused_ws_bytes(d, m,
 
 // have_sums = 1: full finish step; have_sums = 0: retract the matrix already stored in Y_in (copied by the caller).
 int finish_fused(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out, void* Ut_hi,
-                 void* Ut_lo, float* obj_log, int64_t log_index, int max_iters, float tol, int* status, void* workspace,
-                 int64_t workspace_bytes, const float* Y_in, cudaStream_t stream) {
+                 void* Ut_lo, float* obj_log, int64_t log_index, int max_iters, float tol, int u_rounded, int* status,
+                 void* workspace, int64_t workspace_bytes, const float* Y_in, cudaStream_t stream) {
   if (max_iters > 64) max_iters = 64;
   if (workspace_bytes < fused_ws_bytes(d, m, 64)) return DRSA_ERR_WORKSPACE;
   char* w = static_cast<char*>(workspace);
@@ -290,6 +309,8 @@ int finish_fused(const float* sums, int64_t M_global, const float* U, int d, int
   p.U_out = U_out; p.Ut_hi = static_cast<__half*>(Ut_hi); p.Ut_lo = static_cast<__half*>(Ut_lo);
   p.obj_log = obj_log; p.log_index = log_index; p.max_iters = max_iters; p.tol2_m = tol * tol * (float)m;
   p.status = status; p.have_sums = (Y_in == nullptr) ? 1 : 0;
+  p.u_rounded = (u_rounded && Y_in == nullptr) ? 1 : 0;
+  p.corr = p.resid + (int64_t)(max_iters + 1) * 1024;       // the row after the last sweep's residual partials
   if (Y_in != nullptr) DRSA_CUDA(cudaMemcpyAsync(p.Y, Y_in, (int64_t)d * m * 4, cudaMemcpyDeviceToDevice, stream));
   int tiles = (d / TS) * (m / TS);
   const int t2 = (m / TS) * (m / TS);

@@ -47,8 +47,13 @@ typedef enum drsa_status {
  * autograd backward of them, drsa.py:100). */
 typedef enum drsa_precision {
   DRSA_PREC_FP32 = 0,       /* CUDA-core FFMA, fp32 throughout                        */
-  DRSA_PREC_TC_F16X2 = 1    /* tcgen05 kind::f16, fp32 accumulate in TMEM; A and C are
+  DRSA_PREC_TC_F16X2 = 1,   /* tcgen05 kind::f16, fp32 accumulate in TMEM; A and C are
                                stored once as scaled fp16, U is split hi+lo every step */
+  DRSA_PREC_TC_F16 = 2      /* as above with U rounded to fp16 once per step (one MMA per
+                               product): the sums are exact for fp16(U); drsa_finish_step
+                               (u_rounded = 1) adds the first-order term <grad, U - fp16(U)>
+                               to the logged objective, so the objective stays second-order
+                               accurate in the rounding                  */
 } drsa_precision;
 
 const char* drsa_status_string(int status);
@@ -96,7 +101,7 @@ int64_t drsa_step_workspace_bytes(int64_t M, int d, int m, int K, int precision)
  *   A, C      [M, d]   fp32 (DRSA_PREC_FP32) or scaled fp16 from drsa_pack_f16 (TC mode)
  *   U         [d, m]   fp32, m = K*d_k <= d               (FP32 mode; may be NULL in TC mode)
  *   Ut_hi/lo  [m, d]   fp16 split of U^T written by drsa_finish_step / drsa_split_u
- *                      (TC mode; may be NULL in FP32 mode)
+ *                      (TC modes; may be NULL in FP32 mode; Ut_lo is not read by DRSA_PREC_TC_F16)
  *   scaleA, scaleC      the pack scales of A and C (powers of two; 1 in FP32 mode)
  *   pq_scale            power of two applied to g before P = g*HC, Q = g*HA are rounded to
  *                       fp16 for the gradient GEMM (TC mode; undone exactly in the output)
@@ -105,7 +110,7 @@ int drsa_step(const void* A, const void* C, const float* U, const void* Ut_hi, c
               int64_t M, int d, int m, int K, int precision, float scaleA, float scaleC,
               float pq_scale, float* sums, void* workspace, int64_t workspace_bytes, void* stream);
 
-/* U [d,m] fp32 -> Ut_hi, Ut_lo [m,d] fp16 with U^T = hi + lo (+ O(2^-22)). */
+/* U [d,m] fp32 -> Ut_hi, Ut_lo [m,d] fp16 with U^T = hi + lo (+ O(2^-22)); Ut_lo may be NULL. */
 int drsa_split_u(const float* U, int d, int m, void* Ut_hi, void* Ut_lo, void* stream);
 
 int64_t drsa_finish_workspace_bytes(int d, int m);
@@ -117,7 +122,9 @@ int64_t drsa_finish_workspace_bytes(int d, int m);
  *   if U_out != NULL:
  *     Y = U + sqrt(obj) / (K M q_k^1.5) * X_k      (ascent, unit step)  drsa.py:102
  *     U_out = Y (Y^T Y)^(-1/2)                      (polar retraction)   drsa.py:201-221
- *     Ut_hi/Ut_lo (optional) = fp16 split of U_out^T for the next TC step
+ *     Ut_hi/Ut_lo (optional, Ut_lo alone may be NULL) = fp16 split of U_out^T for the next TC step
+ *   u_rounded != 0: `sums` came from DRSA_PREC_TC_F16, i.e. were evaluated at fp16(U); the logged objective is
+ *     f(fp16 U) + <grad f(fp16 U), U - fp16 U>, which equals f(U) up to second order in the rounding.
  * The polar factor is computed on the device by a scaled Newton-Schulz iteration in
  * fp32 (at most `max_iters` sweeps, stops when ||Y^T Y - I||_F < tol*sqrt(m)); the
  * reference uses an fp64 eigendecomposition on the host, both converge to the same
@@ -128,7 +135,7 @@ int64_t drsa_finish_workspace_bytes(int d, int m);
  */
 int drsa_finish_step(const float* sums, int64_t M_global, const float* U, int d, int m, int K,
                      float* U_out, void* Ut_hi, void* Ut_lo, float* obj_log, int64_t log_index,
-                     int max_iters, float tol, int* status, void* workspace,
+                     int max_iters, float tol, int u_rounded, int* status, void* workspace,
                      int64_t workspace_bytes, void* stream);
 
 /* orthogonalize(U) of drsa.py:201-221 on its own: U_out = Y (Y^T Y)^(-1/2). */
@@ -283,10 +290,13 @@ int lrp_tc_split_f16(const float* in, int64_t count, void* hi, void* lo, void* s
  * ---------------------------------------------------------------------------------- */
 int drsa_selftest_umma(int variant, float* max_err_host);
 
-/* Diagnostics: when set to a device buffer of 6 int64, CTA 0 of the tensor-core row pass stores the SM
+/* Diagnostics: when set to a device buffer of 16 int64 (zeroed by the caller), CTA 0 of the tensor-core row pass stores the SM
  * cycles its MMA thread spent issuing GEMM1 [0], waiting for the epilogue [1], issuing GEMM2 [2] and its
  * first epilogue warp spent waiting for GEMM1 [3] and working [4].  NULL switches it off (default). */
 int drsa_debug_set_tc_profile(void* device_buf6);
+/* Diagnostics: registers per thread, max threads per block, static shared bytes, local bytes and the configured
+ * dynamic shared-memory limit of the tensor-core row-pass kernel for d in {128, 256} (host ints). */
+int drsa_debug_tc_kernel_attrs(int d, int split_u, int* out5);
 
 #ifdef __cplusplus
 }

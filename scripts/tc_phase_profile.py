@@ -8,16 +8,16 @@ M, d, K = 640000, 256, 4
 dev = torch.device("cuda")
 A, C = synth_rows_cuda(M, d, 1, dev)
 U0 = torch.linalg.qr(torch.randn(d, d))[0]
-opt = SubspaceOptimizer(U0, A, C, None, num_concepts=K, precision="tc", use_cuda_graph=False)
+opt = SubspaceOptimizer(U0, A, C, None, num_concepts=K, precision=(sys.argv[1] if len(sys.argv) > 1 else "tc"), use_cuda_graph=False)
 opt._rows.split_u(opt.U)
 for _ in range(3): opt._rows.step(opt.U)
-buf = torch.zeros(6, dtype=torch.int64, device=dev)
+buf = torch.zeros(16, dtype=torch.int64, device=dev)
 L.lib().drsa_debug_set_tc_profile(buf.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); opt._rows.step(opt.U); e1.record(); torch.cuda.synchronize()
 L.lib().drsa_debug_set_tc_profile(None)
-tiles = -(-M // 128); nrb = 148 // 2; per = -(-tiles // nrb)
+tiles = -(-M // 64); nrb = 148 // 2; per = -(-tiles // nrb)      # 64-row subtiles
 v = buf.cpu().tolist()
-print(f"row pass {e0.elapsed_time(e1):.3f} ms, tiles per CTA ~{per}")
-for name, x in zip(["mma: GEMM1 issue", "mma: wait epilogue (incl. GEMM1 drain)", "mma: GEMM2 issue", "epi: wait GEMM1", "epi: work"], v):
-    print(f"  {name:42s} {x:10d} cycles total, {x/per:9.0f} per tile")
+print(f"row pass {e0.elapsed_time(e1):.3f} ms, 64-row subtiles per CTA ~{per}")
+for name, x in zip(["mma: GEMM1 issue", "mma: GEMM2 wait for first P chunk", "mma: GEMM2 issue", "epi: wait GEMM1", "epi: work"], v):
+    print(f"  {name:42s} {x:10d} cycles total, {x/per:9.0f} per subtile")
