@@ -103,6 +103,11 @@ def run_ours(args):
     M, d, K = CFG2["samples"] * CFG2["positions"], CFG2["d"], CFG2["K"]
     if args.rows:
         M = args.rows
+    if args.d:
+        d = args.d
+    if args.K:
+        K = args.K
+    custom = bool(args.rows or args.d or args.K)
     m = d
     A, C = synth_rows_cuda(M, d, 20262 + rank, dev)
     U0 = drsa_ref.synth_U0(d, seed=5)
@@ -120,7 +125,8 @@ def run_ours(args):
                             use_cuda_graph=not args.no_graph)
     opt._rows.split_u(opt.U)
     opt.reset_log(args.warmup + args.steps + 8)
-    opt.enqueue_steps(max(args.warmup, 3))          # warm-up (also captures the CUDA graph)
+    warm = max(args.warmup, 4 if not args.no_graph else 3)      # >= 4 so that the CUDA graph of one step is captured here,
+    opt.enqueue_steps(warm)                                     # not inside the timed region
     barrier()
     if rank == 0:
         t_wait = time.time() + 5.0
@@ -184,7 +190,7 @@ def run_ours(args):
 
     if rank == 0:
         ms_per_step = ms_total / args.steps
-        scale = (M * world) / float(CFG2["samples"] * CFG2["positions"])
+        scale = world if custom else (M * world) / float(CFG2["samples"] * CFG2["positions"])
         value = scale * 1000.0 / ms_per_step
         flops = 8.0 * M * d * m
         achieved = flops / (ms_kernel * 1e-3) / 1e12
@@ -193,21 +199,21 @@ def run_ours(args):
         elem = 2 if is_tc else 4
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"tc": "f16 operands / f32 accumulate", "tc_split": "f16 operands (U split hi+lo) / f32 accumulate"}.get(opt2.precision, "f32"),
             "data": "synthetic",
-            "config": {"workload": "cfg2" if not args.rows else f"custom rows={M}", "rows_per_gpu": M, "d": d, "m": m, "K": K,
-                       "d_k": m // K, "precision": opt2.precision, "cuda_graph": bool(opt2.use_cuda_graph),
+            "config": {"workload": "cfg2" if not custom else f"custom rows={M} d={d} K={K} (steps/s of THIS shape per GPU x GPUs)",
+                       "rows_per_gpu": M, "d": d, "m": m, "K": K, "d_k": m // K, "precision": opt2.precision, "cuda_graph": bool(opt2.use_cuda_graph),
                        "l2_policy": f"inputs larger than L2 ({2 * M * d * elem / 1e6:.0f} MB of rows per step vs 126 MB L2)",
                        "retraction_sweeps_last_step": status[0], "retraction_not_converged": status[1]},
             "rows_per_s": M * world * 1000.0 / ms_per_step,
             "gpu_launches": int(args.steps * launches_per_step(opt2)),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tf_sustained"], "traffic": TRAFFIC_BYTES_PER_LAUNCH if (is_tc and not args.rows) else None,
+                         "frac": achieved / peaks["tf_sustained"], "traffic": TRAFFIC_BYTES_PER_LAUNCH if (is_tc and not custom) else None,
                          "kernel": "drsa_tc_step_kernel (+ tc_reduce_kernel)" if is_tc else "sgemm_kernel chain",
                          "kernel_ms": ms_kernel, "algorithmic_flop_per_launch": flops,
                          "algorithmic_bytes_per_launch": 2.0 * M * d * elem,
-                         "executed_mma_flop_per_launch": flops * mma_factor,
+                         "executed_mma_flop_per_launch": flops * mma_factor * (1.5 if (is_tc and d > 256) else 1.0),
                          "hbm_frac": (2.0 * M * d * elem / (ms_kernel * 1e-3) / 1e9) / peaks["hbm"],
                          "peak_source": peaks["source"] + "; sustained bf16 figure (kernel timed in a loop)",
                          "share_of_step": ms_kernel / ms_per_step},
@@ -337,6 +343,10 @@ def run_reference(args):
     M, d, K = CFG2["samples"] * CFG2["positions"], CFG2["d"], CFG2["K"]
     if args.rows:
         M = args.rows
+    if args.d:
+        d = args.d
+    if args.K:
+        K = args.K
     world = int(os.environ.get("WORLD_SIZE", "1"))
     threads = os.cpu_count() or 1
     M_sample = min(M, 64_000)
@@ -374,6 +384,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="tc", choices=["tc", "tc_split", "fp32", "auto"])
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (default: cfg2 = 640000)")
+    ap.add_argument("--d", type=int, default=0, help="override the split-layer width (default: cfg2 = 256); cfg4 uses 512")
+    ap.add_argument("--K", type=int, default=0, help="override the number of concepts (default: cfg2 = 4); cfg4 uses 8")
     ap.add_argument("--e2e-steps", type=int, default=500)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -151,7 +151,7 @@ int64_t drsa_step_workspace_bytes(int64_t M, int d, int m, int K, int precision)
   if (!shape_ok(M, d, m, K)) return DRSA_ERR_ARG;
   if (precision == DRSA_PREC_FP32) return step_fp32_workspace_bytes(M, d, m, K);
   if (precision == DRSA_PREC_TC_F16X2 || precision == DRSA_PREC_TC_F16) {
-    if (!tc_shape_supported(d, m, K)) return DRSA_ERR_SHAPE;
+    if (!tc_shape_supported(d, m, K) || (d == 512 && precision == DRSA_PREC_TC_F16X2)) return DRSA_ERR_SHAPE;
     return step_tc_workspace_bytes(M, d, m, K);
   }
   return DRSA_ERR_ARG;
@@ -424,7 +424,7 @@ int lrp_tc_split_f16(const float* in, int64_t count, void* hi, void* lo, void* s
 }
 
 int drsa_debug_tc_kernel_attrs(int d, int split, int* out5) {
-  if (out5 == nullptr || (d != 128 && d != 256)) return DRSA_ERR_ARG;
+  if (out5 == nullptr || (d != 128 && d != 256 && d != 512)) return DRSA_ERR_ARG;
   return tc_kernel_attrs(d, split, out5);
 }
 

@@ -77,10 +77,15 @@ constexpr int kBarBytes = 256;
 
 template <int D, bool kSplitU>
 struct Cfg {
-  static constexpr int kPanels = D / 64;
+  static constexpr int kPanels = D / 64;                      // 64-channel panels of the GEMM1 contraction (K = D)
+  // channels of X^T a CTA accumulates (GEMM2 N): at most 256 TMEM columns.  d = 512 is split over kHalves CTAs per
+  // column group, each of which repeats GEMM1 for the full K = 512 (executed MMA work 1.5x the algorithmic).
+  static constexpr int kDN = D > 256 ? 256 : D;
+  static constexpr int kHalves = D / kDN;
+  static constexpr int kNPanels = kDN / 64;
   static constexpr int kUBytes = (kSplitU ? 2 : 1) * kPanels * kPanelBytes;   // U^T (hi, or hi + lo) of this column group
   static constexpr int kStageBytes = 2 * kPanelBytes;         // GEMM1: two [A64;C64] panels, GEMM2: 32 rows of A and of C
-  static constexpr int kStages = (D >= 256) ? (kSplitU ? 3 : 5) : (kSplitU ? 5 : 6);
+  static constexpr int kStages = (D >= 512) ? 3 : (D >= 256) ? (kSplitU ? 3 : 5) : (kSplitU ? 5 : 6);
   static constexpr int kDataBytes = kUBytes + kStages * kStageBytes;
   static constexpr int kSmemBytes = kDataBytes + kRedBytes + kBarBytes;
 };
@@ -126,7 +131,7 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x % G, rb = blockIdx.x / G;
+  const int g = blockIdx.x % G, ih = (blockIdx.x / G) % C::kHalves, rb = blockIdx.x / (G * C::kHalves);
 
   if ((smem_u32(smem) & 1023u) != 0) {   // 128-byte swizzle needs 1024-byte aligned panels
     if (threadIdx.x == 0) atomicExch(err_flag, 1);
@@ -173,11 +178,11 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       auto load_g2 = [&](int sub) {
         for (int c = 0; c < 2; ++c) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], 2 * C::kPanels * 4096);
+          mbar_expect_tx(&full[stage], 2 * C::kNPanels * 4096);
           uint8_t* dst = sStage + stage * C::kStageBytes;
-          for (int p = 0; p < C::kPanels; ++p) {
-            tma_load_2d(dst + p * 4096, &tmA2, &full[stage], 64 * p, sub * kSub + 32 * c);
-            tma_load_2d(dst + kPanelBytes + p * 4096, &tmC2, &full[stage], 64 * p, sub * kSub + 32 * c);
+          for (int p = 0; p < C::kNPanels; ++p) {
+            tma_load_2d(dst + p * 4096, &tmA2, &full[stage], C::kDN * ih + 64 * p, sub * kSub + 32 * c);
+            tma_load_2d(dst + kPanelBytes + p * 4096, &tmC2, &full[stage], C::kDN * ih + 64 * p, sub * kSub + 32 * c);
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
@@ -194,7 +199,7 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ======================= MMA issuer =======================
     if (lane == 0) {
       constexpr uint32_t idesc1 = make_idesc_f16(kNG, 2 * kSub, 0, 0);  // U^T (K-major) x stacked [A;C] subtile (K-major)
-      constexpr uint32_t idesc2 = make_idesc_f16(kNG, D, 0, 1);         // P^T (TMEM)   x row chunk (MN-major, N = D)
+      constexpr uint32_t idesc2 = make_idesc_f16(kNG, C::kDN, 0, 1);    // P^T (TMEM)   x row chunk (MN-major, N = kDN)
       const uint32_t tX = tmem_base;
       mbar_wait(u_full, 0);
       tc_fence_after();
@@ -340,9 +345,9 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ---- final: X^T of this CTA -> partial buffer [cta][j][D]
     mbar_wait(x_full, 0);
     tc_fence_after();
-    float* dst = part + ((int64_t)blockIdx.x * kNG + j) * D;
+    float* dst = part + (((int64_t)rb * G + g) * kNG + j) * D + C::kDN * ih;
 #pragma unroll 1
-    for (int cc = (warp - 2) >> 2; cc < D / 32; cc += 4) {
+    for (int cc = (warp - 2) >> 2; cc < C::kDN / 32; cc += 4) {
       uint32_t v[32];
       tmem_ld32(lane_base + 32 * cc, v);
       tmem_ld_wait();
@@ -353,7 +358,7 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         __uint_as_float(v[4 * e + 3]));
     }
     // one slot per (row block, concept, warp group): summed in a fixed order by tc_reduce_kernel (deterministic)
-    if (owner) ss_part[((int64_t)rb * (G * (kNG / d_k)) + g * (kNG / d_k) + j / d_k) * 4 + 2 * set + c] = ssq;
+    if (owner && ih == 0) ss_part[((int64_t)rb * (G * (kNG / d_k)) + g * (kNG / d_k) + j / d_k) * 4 + 2 * set + c] = ssq;
     tc_fence_before();
   }
   __syncthreads();
@@ -450,7 +455,7 @@ TcPlan plan_for(int64_t M, int d, int m, int K) {
   TcPlan p;
   p.G = m / kNG;
   p.num_tiles = (int)((M + kSub - 1) / kSub);      // 64-row subtiles
-  int nrb = sm_count() / p.G;
+  int nrb = sm_count() / (p.G * (d > 256 ? d / 256 : 1));
   if (nrb < 1) nrb = 1;
   if (nrb > p.num_tiles) nrb = p.num_tiles;
   p.nRB = nrb;
@@ -463,7 +468,7 @@ TcPlan plan_for(int64_t M, int d, int m, int K) {
 bool tc_shape_supported(int d, int m, int K) {
   if (K <= 0 || m % K != 0) return false;
   const int d_k = m / K;
-  return (d == 128 || d == 256) && m % kNG == 0 && m <= d && (d_k == 32 || d_k == 64 || d_k == 128);
+  return (d == 128 || d == 256 || d == 512) && m % kNG == 0 && m <= d && (d_k == 32 || d_k == 64 || d_k == 128);
 }
 
 int64_t step_tc_workspace_bytes(int64_t M, int d, int m, int K) {
@@ -509,9 +514,13 @@ int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_
 
   const float inv_scale = 1.0f / (scaleA * scaleC);
   const int d_k = m / K;
-  const int grid = p.nRB * p.G;
+  const int grid = p.nRB * p.G * (d > 256 ? d / 256 : 1);
+  if (d == 512 && split_u) return DRSA_ERR_SHAPE;      // U^T hi + lo of a column group (256 KB) does not fit in shared memory
   int st;
-  if (d == 256)
+  if (d == 512)
+    st = launch_step<512, false>(grid, stream, tmA, tmC, tmA2, tmC2, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale,
+                                 pq_scale, part, ss_part, err, g_tc_prof);
+  else if (d == 256)
     st = split_u ? launch_step<256, true>(grid, stream, tmA, tmC, tmA2, tmC2, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale,
                                           pq_scale, part, ss_part, err, g_tc_prof)
                  : launch_step<256, false>(grid, stream, tmA, tmC, tmA2, tmC2, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale,
@@ -561,7 +570,7 @@ void set_tc_profile(long long* p) { g_tc_prof = p; }
 // numRegs, maxThreadsPerBlock, static shared bytes, local bytes, max dynamic shared bytes of the row-pass kernel
 int tc_kernel_attrs(int d, int split, int* out5) {
   cudaFuncAttributes a;
-  const void* fn = d == 256 ? (split ? (const void*)drsa_tc_step_kernel<256, true> : (const void*)drsa_tc_step_kernel<256, false>)
+  const void* fn = d == 512 ? (const void*)drsa_tc_step_kernel<512, false> : d == 256 ? (split ? (const void*)drsa_tc_step_kernel<256, true> : (const void*)drsa_tc_step_kernel<256, false>)
                             : (split ? (const void*)drsa_tc_step_kernel<128, true> : (const void*)drsa_tc_step_kernel<128, false>);
   DRSA_CUDA(cudaFuncGetAttributes(&a, fn));
   out5[0] = a.numRegs; out5[1] = a.maxThreadsPerBlock; out5[2] = (int)a.sharedSizeBytes; out5[3] = (int)a.localSizeBytes;

@@ -19,7 +19,7 @@ from oracle.ref_import import load_reference_drsa
 GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
-def _case(ref, name, M, d, m, K, steps, seed, store_inputs):
+def _case(ref, name, M, d, m, K, steps, seed, store_inputs, light=False):
     torch.manual_seed(0)
     A, C = drsa_ref.synth_pairs(M, d, seed)
     U0 = drsa_ref.synth_U0(d, m, seed + 1)
@@ -27,7 +27,8 @@ def _case(ref, name, M, d, m, K, steps, seed, store_inputs):
     out = {"M": M, "d": d, "m": m, "K": K, "steps": steps, "seed": seed}
     if store_inputs:
         out.update(A=A.numpy(), C=C.numpy())
-    out["U0"] = U0.numpy()
+    if not light:       # light fixtures regenerate U0 from the seed (drsa_ref.synth_U0(d, m, seed + 1)) as well
+        out["U0"] = U0.numpy()
     out["in_checksum"] = np.array([A.double().sum().item(), C.double().sum().item(),
                                    (A.double() * C.double()).sum().item()])
     # objective + autograd gradient at U0 (drsa.py:91-100)
@@ -35,9 +36,10 @@ def _case(ref, name, M, d, m, K, steps, seed, store_inputs):
     obj = ref.SubspaceOptimizer.obj_val(A, C, U, ref.objective_fn, K, d_k)
     obj.backward()
     out["obj0"] = obj.detach().numpy()
-    out["grad0"] = U.grad.numpy()
-    # retraction (drsa.py:201-221)
-    out["U1"] = ref.orthogonalize(U0 + U.grad).numpy()
+    if not light:
+        out["grad0"] = U.grad.numpy()
+        # retraction (drsa.py:201-221)
+        out["U1"] = ref.orthogonalize(U0 + U.grad).numpy()
     if m == d:
         # full loop through the reference class (drsa.py:76-120) incl. its file outputs
         with tempfile.TemporaryDirectory() as tmp:
@@ -66,10 +68,13 @@ def _case(ref, name, M, d, m, K, steps, seed, store_inputs):
           os.path.getsize(os.path.join(GOLD, f"drsa_{name}.npz")))
 
 
-def main():
+def main(only=None):
     os.makedirs(GOLD, exist_ok=True)
     ref = load_reference_drsa()
     torch.set_num_threads(1)   # deterministic summation order for the fixtures
+    if only == "d512":         # cfg-4 width (added later; the other fixtures are left untouched)
+        _case(ref, "d512", M=8192, d=512, m=512, K=8, steps=8, seed=17, store_inputs=False, light=True)
+        return
     _case(ref, "tiny", M=384, d=32, m=32, K=4, steps=20, seed=11, store_inputs=True)
     _case(ref, "ragged", M=333, d=32, m=32, K=2, steps=10, seed=12, store_inputs=True)
     _case(ref, "toy64", M=4000, d=64, m=64, K=4, steps=60, seed=13, store_inputs=False)
@@ -86,4 +91,5 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    main(sys.argv[1] if len(sys.argv) > 1 else None)
