@@ -286,12 +286,80 @@ def lrp_throughput(args, dev, rank, world, barrier):
     t_e2e = time.perf_counter() - t0
     P = act.shape[0] // n
     flops = 2 * 1775.5e6 * n           # 2 x MACs of the widened arch A forward per sample
-    return {"metric": "LRP context vecs/s", "value": n * P * world / (ms * 1e-3), "unit": "vectors/s",
-            "samples_per_gpu": n, "positions": P, "d": int(act.shape[1]), "ms": ms,
-            "e2e_value": n * P * world / t_e2e, "h2d_bytes": int(xh.numel() * 4),
-            "forward_tflops": flops / (ms * 1e-3) / 1e12,
-            "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM, TMA im2col, fp16 hi/lo operands) + NHWC pooling; "
-                      "dense head and pool routing on CUDA cores"}
+    out = {"metric": "LRP context vecs/s", "value": n * P * world / (ms * 1e-3), "unit": "vectors/s",
+           "samples_per_gpu": n, "positions": P, "d": int(act.shape[1]), "ms": ms,
+           "e2e_value": n * P * world / t_e2e, "h2d_bytes": int(xh.numel() * 4),
+           "forward_tflops": flops / (ms * 1e-3) / 1e12,
+           "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM, TMA im2col, fp16 hi/lo operands) + NHWC pooling; "
+                     "dense head and pool routing on CUDA cores"}
+    if rank == 0:
+        out["roofline"] = lrp_conv_roofline(dev, ms / max(1, -(-n // 64)))
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = lrp_cpu_baseline(P)
+    return out
+
+
+def lrp_conv_roofline(dev, stage_ms_per_minibatch):
+    """The dominant kernel of stage 1 alone: conv3x3_tc_kernel<2, resident weights> on the 64 -> 64 layer at 128 x 256
+    (68 % of the forward MACs), one minibatch of 64 samples as the engine launches it, CUDA events on its stream."""
+    import torch
+    from drsa_audio_b200 import _lib as L
+    lib = L.lib()
+    B, H, W, Cc = 64, 128, 256, 64
+    g = torch.Generator(device=dev).manual_seed(1)
+    xh = torch.rand(B, H, W, Cc, generator=g, device=dev).half()
+    xl = (torch.rand(B, H, W, Cc, generator=g, device=dev) * 1e-4).half()
+    wt = torch.randn(9, Cc, Cc, generator=g, device=dev) / 24.0
+    wh = torch.empty(9, Cc, Cc, dtype=torch.float16, device=dev); wl = torch.empty_like(wh)
+    s = torch.cuda.current_stream().cuda_stream
+    L.check(lib.lrp_tc_split_f16(wt.data_ptr(), wt.numel(), wh.data_ptr(), wl.data_ptr(), s))
+    bias = torch.zeros(Cc, device=dev)
+    yh = torch.empty(B, H, W, Cc, dtype=torch.float16, device=dev); yl = torch.empty_like(yh)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def run():
+        L.check(lib.lrp_tc_conv3x3_forward(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), bias.data_ptr(), B, H, W,
+                                           Cc, Cc, Cc, 1, yh.data_ptr(), yl.data_ptr(), None, err.data_ptr(), s))
+    for _ in range(3):
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    kms = e0.elapsed_time(e1) / 10
+    flops = 2.0 * 9 * Cc * Cc * H * W * B
+    peaks = _peaks()
+    ach = flops / (kms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
+            "traffic": None, "kernel": "conv3x3_tc_kernel<2, resident weights> (64->64 @128x256, 64 samples)", "kernel_ms": kms,
+            "algorithmic_flop_per_launch": flops, "executed_mma_flop_per_launch": 3 * flops,
+            "algorithmic_bytes_per_launch": 4.0 * B * H * W * Cc * 2,
+            "share_of_stage": kms / stage_ms_per_minibatch,
+            "l2_policy": "inputs larger than L2 (537 MB of activation planes per launch)",
+            "peak_source": peaks["source"] + "; sustained bf16 figure"}
+
+
+def lrp_cpu_baseline(P: int, n: int = 4):
+    """The reference's stage 1 on the host cores: get_intermediate over the oracle's restatement of zennit's rules (general
+    multi-pass Gamma, backward continued to the input as zennit does), fp32, cfg-2 CNN, n samples."""
+    import torch
+    from oracle import lrp_ref
+    from cxai.utils.constants import lrp_name_map_6s
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    net = lrp_ref.genre_model(seed=0, last=256, input_size=(128, 256))
+    x = lrp_ref.synth_logmel(n, 128, 256, 20262)
+    nm = lrp_name_map_6s()
+    lrp_ref.get_intermediate(net, x[:1], nm, net.features[33], 0, dtype=torch.float32)       # warm-up
+    t0 = time.perf_counter()
+    lrp_ref.get_intermediate(net, x, nm, net.features[33], 0, dtype=torch.float32)
+    t = time.perf_counter() - t0
+    return {"value": n * P / t, "unit": "vectors/s", "cores": threads, "kind": "port",
+            "sample": f"{n} samples of 128x256 through oracle/lrp_ref.get_intermediate (torch {torch.__version__} CPU, fp32, "
+                      f"{threads} threads), {P} positions each", "sample_s": t}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one drsa_tc_step_kernel launch at cfg2 from the committed

@@ -118,7 +118,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
   uint64_t* w_full = bars + 20;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int acc_stages = (2 * g.Cout_p <= 512) ? 2 : 1;
+  // merged: one MMA of N = 2*Cout_p against the stacked [w_hi; w_lo] rows (they are adjacent in shared memory) gives
+  // x_hi*w_hi in accumulator columns [0, Cout_p) and x_hi*w_lo in [Cout_p, 2*Cout_p); a second MMA of N = Cout_p adds
+  // x_lo*w_hi.  Two MMAs instead of three per k-step and 14 KB instead of 18 KB of operand reads (Cout_p = 64): SS-mode
+  // MMAs at N = 64 are bound by shared-memory bandwidth, not by the tensor pipe.  The epilogue adds the two halves.
+  const bool merged = 2 * g.Cout_p <= 256;
+  const int acc_cols = merged ? 2 * g.Cout_p : g.Cout_p;
+  const int acc_stages = (2 * acc_cols <= 512) ? 2 : 1;
 
   if ((smem_u32(smem) & 1023u) != 0) {
     if (threadIdx.x == 0) atomicExch(err_flag, 1);
@@ -171,13 +177,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(kTilePix, g.Cout_p, 0, 0);
+      const uint32_t idesc2 = make_idesc_f16(kTilePix, 2 * g.Cout_p, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       if (kResW) { mbar_wait(w_full, 0); tc_fence_after(); }
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
         mbar_wait(&acc_empty[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + as * g.Cout_p;
+        const uint32_t tacc = tmem_base + as * acc_cols;
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -187,9 +194,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
           for (int kk = 0; kk < 4; ++kk) {
             const uint64_t dah = kdesc(a_hi + 32 * kk), dal = kdesc(a_lo + 32 * kk);
             const uint64_t dwh = kdesc(w_hi + 32 * kk), dwl = kdesc(w_lo + 32 * kk);
-            umma_ss_f16(tacc, dah, dwh, idesc, (it | kk) ? 1u : 0u);
-            umma_ss_f16(tacc, dal, dwh, idesc, 1u);
-            umma_ss_f16(tacc, dah, dwl, idesc, 1u);
+            if (merged) {
+              umma_ss_f16(tacc, dah, dwh, idesc2, (it | kk) ? 1u : 0u);      // [x_hi*w_hi | x_hi*w_lo]
+              umma_ss_f16(tacc, dal, dwh, idesc, 1u);                        // + x_lo*w_hi
+            } else {
+              umma_ss_f16(tacc, dah, dwh, idesc, (it | kk) ? 1u : 0u);
+              umma_ss_f16(tacc, dal, dwh, idesc, 1u);
+              umma_ss_f16(tacc, dah, dwl, idesc, 1u);
+            }
           }
           umma_commit(&empty[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -219,13 +231,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
 #pragma unroll 1
       for (int cc = 0; cc < g.Cout_p / 32; ++cc) {
         uint32_t v[32];
-        tmem_ld32(lane_base + as * g.Cout_p + 32 * cc, v);
+        float a[32];
+        tmem_ld32(lane_base + as * acc_cols + 32 * cc, v);
         tmem_ld_wait();
-        if (valid) {
-          float a[32];
-          const int64_t o = pbase + 32 * cc;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(v[i]);
+        for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(v[i]);
+        if (merged) {
+          tmem_ld32(lane_base + as * acc_cols + g.Cout_p + 32 * cc, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] += __uint_as_float(v[i]);
+        }
+        if (valid) {
+          const int64_t o = pbase + 32 * cc;
           if (g.epi != 2) {
 #pragma unroll
             for (int i4 = 0; i4 < 8; ++i4) {
@@ -324,8 +342,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
 }
 
 // First layer (Cin = 1): bandwidth-bound, CUDA cores.  x [B,1,H,W] fp32 -> y NHWC hi/lo [B,H,W,Cout_p].
-// One thread per pixel and 32 output channels: the 9 taps sit in registers, the weights are read as float4
-// broadcasts from shared memory ([tap][channel]), each thread writes 64 contiguous bytes per plane.
+// One thread per (pixel, 8 output channels), the channel group being the fast index: the Cout_p/8 threads of a pixel
+// write its whole channel row (16 B each, 128 B at Cout_p = 64), so a warp stores 512 contiguous bytes per plane.  The
+// 9 taps sit in registers (the threads of a pixel read the same addresses: broadcast), weights [tap][channel] in
+// shared memory.
 __global__ void __launch_bounds__(256) conv3x3_first_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                  const float* __restrict__ b, int64_t B, int H, int W,
                                                                  int Cout, int Cout_p, int relu, __half* __restrict__ y_hi,
@@ -338,12 +358,11 @@ __global__ void __launch_bounds__(256) conv3x3_first_nhwc_kernel(const float* __
   }
   for (int i = threadIdx.x; i < Cout_p; i += blockDim.x) sb[i] = i < Cout ? __ldg(b + i) : 0.f;
   __syncthreads();
-  const int groups = Cout_p / 32;
+  const int groups = Cout_p / 8;
   const int64_t total = B * H * W * groups;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    // consecutive threads take consecutive pixels (coalesced input reads); the channel group is the slow index
-    const int64_t p = i % (B * H * W);
-    const int gq = (int)(i / (B * H * W));
+    const int gq = (int)(i % groups);
+    const int64_t p = i / groups;
     const int xx = (int)(p % W), yy = (int)((p / W) % H);
     const int64_t n = p / ((int64_t)W * H);
     float v[9];
@@ -354,26 +373,23 @@ __global__ void __launch_bounds__(256) conv3x3_first_nhwc_kernel(const float* __
         const int gy = yy + ky - 1, gx = xx + kx - 1;
         v[ky * 3 + kx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(x + (n * H + gy) * W + gx) : 0.f;
       }
-    float acc[32];
-#pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) {
-      const float4 bb = *reinterpret_cast<const float4*>(&sb[gq * 32 + 4 * c4]);
-      acc[4 * c4] = bb.x; acc[4 * c4 + 1] = bb.y; acc[4 * c4 + 2] = bb.z; acc[4 * c4 + 3] = bb.w;
+    float acc[8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(&sb[gq * 8]), b1 = *reinterpret_cast<const float4*>(&sb[gq * 8 + 4]);
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
     }
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-#pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 ww = *reinterpret_cast<const float4*>(&sw[t * Cout_p + gq * 32 + 4 * c4]);
-        acc[4 * c4] = fmaf(v[t], ww.x, acc[4 * c4]);
-        acc[4 * c4 + 1] = fmaf(v[t], ww.y, acc[4 * c4 + 1]);
-        acc[4 * c4 + 2] = fmaf(v[t], ww.z, acc[4 * c4 + 2]);
-        acc[4 * c4 + 3] = fmaf(v[t], ww.w, acc[4 * c4 + 3]);
-      }
+      const float4 w0 = *reinterpret_cast<const float4*>(&sw[t * Cout_p + gq * 8]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&sw[t * Cout_p + gq * 8 + 4]);
+      acc[0] = fmaf(v[t], w0.x, acc[0]); acc[1] = fmaf(v[t], w0.y, acc[1]);
+      acc[2] = fmaf(v[t], w0.z, acc[2]); acc[3] = fmaf(v[t], w0.w, acc[3]);
+      acc[4] = fmaf(v[t], w1.x, acc[4]); acc[5] = fmaf(v[t], w1.y, acc[5]);
+      acc[6] = fmaf(v[t], w1.z, acc[6]); acc[7] = fmaf(v[t], w1.w, acc[7]);
     }
-    uint32_t hi[16], lo[16];
+    uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < 4; ++j) {
       float a = acc[2 * j], c = acc[2 * j + 1];
       if (relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
       const __half2 h = __floats2half2_rn(a, c);
@@ -382,14 +398,9 @@ __global__ void __launch_bounds__(256) conv3x3_first_nhwc_kernel(const float* __
       hi[j] = *reinterpret_cast<const uint32_t*>(&h);
       lo[j] = *reinterpret_cast<const uint32_t*>(&l);
     }
-    const int64_t o = p * Cout_p + gq * 32;
-    uint4* ph = reinterpret_cast<uint4*>(y_hi + o);
-    uint4* pl = reinterpret_cast<uint4*>(y_lo + o);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      ph[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-      pl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-    }
+    const int64_t o = p * Cout_p + gq * 8;
+    *reinterpret_cast<uint4*>(y_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(y_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -639,7 +650,7 @@ int conv_tc_forward(const void* x_hi, const void* x_lo, const void* w_hi, const 
 
 int conv_first_nhwc(const float* x, const float* w, const float* b, int64_t B, int H, int W, int Cout, int Cout_p,
                     int relu, void* y_hi, void* y_lo, cudaStream_t stream) {
-  conv3x3_first_nhwc_kernel<<<eblocks(B * H * W * (Cout_p / 32)), 256, (size_t)10 * Cout_p * sizeof(float), stream>>>(
+  conv3x3_first_nhwc_kernel<<<eblocks(B * H * W * (Cout_p / 8)), 256, (size_t)10 * Cout_p * sizeof(float), stream>>>(
       x, w, b, B, H, W, Cout, Cout_p, relu, static_cast<__half*>(y_hi), static_cast<__half*>(y_lo));
   DRSA_LAUNCH_CHECK();
   return DRSA_OK;
