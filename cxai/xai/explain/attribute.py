@@ -1,11 +1,25 @@
 """Attribution entry points -- mirror of the reference's cxai/xai/explain/attribute.py
-(``compute_relevances`` :70-108, ``lrp_output_modifier`` :111-160).  ``SubspaceHook`` (:12-67) belongs to
-the concept-heatmap consumer, a "next" row of SURVEY section 8(f)."""
+(``SubspaceHook`` :12-67, ``compute_relevances`` :70-108, ``lrp_output_modifier`` :111-160)."""
 from __future__ import annotations
 
 import torch
 
-__all__ = ["compute_relevances", "lrp_output_modifier"]
+__all__ = ["compute_relevances", "lrp_output_modifier", "SubspaceHook"]
+
+
+class SubspaceHook:
+    """Descriptor of the reference's backward hook on ``features.subspacefilter`` (attribute.py:12-67): the batch is
+    read as groups of ``num_concepts + 1`` clones of one sample; clone 0 keeps all relevance, clone k only the
+    relevance of concept block k of h.  The masking itself happens in ``lrp_subspace_filter`` (libdrsa_b200.so)."""
+    kind = "subspace_hook"
+
+    def __init__(self, num_concepts: int = 4, stabilizer: float = 1e-7, device=None) -> None:
+        self.num_concepts = num_concepts
+        self.stabilizer = stabilizer
+        self.device = device
+
+    def copy(self):
+        return self.__class__(num_concepts=self.num_concepts, stabilizer=self.stabilizer, device=self.device)
 
 
 def compute_relevances(model, input_batch: torch.Tensor, composite, num_classes: int = None, class_idx: int = None,
@@ -29,6 +43,7 @@ def lrp_output_modifier(class_idx: int = None, num_classes: int = None, one_hot_
             mask = torch.zeros_like(output)
             mask[..., class_idx] = 1
             return mask if one_hot_encoded else output * mask
+        extract_output_class.rowwise = True         # the seed of a row does not depend on the rest of the batch
         return extract_output_class
 
     def attribute_all_classes(output):

@@ -19,6 +19,7 @@ import torch.nn as nn
 
 from drsa_audio_b200 import _lib as _L
 from cxai.xai.explain import rules as R
+from cxai.model import modify_model as _MM
 
 __all__ = ["LRPPlan", "lrp_intermediate", "lrp_input_relevance", "forward_logits"]
 
@@ -56,6 +57,7 @@ class LRPPlan:
         self._tc_ok_cache = {}
         self.ops: List[_Op] = []
         self.module_to_op = {}
+        self.filter_index = None          # index of the Projection op of a ProjectionModel
         mods = [(f"features.{n}", m) for n, m in model.features.named_children()]
         mods.append(("flatten", None))
         mods += [(f"classifier.{n}", m) for n, m in model.classifier.named_children()]
@@ -98,12 +100,33 @@ class LRPPlan:
                 op.kh, op.kw = int(ks[0]), int(ks[1])
             elif isinstance(m, nn.Dropout):
                 op = _Op("identity", name, m, len(self.ops))
+            elif isinstance(m, (_MM.Projection, _MM.SubspaceFilter, _MM.InvProjection)):
+                # ProjectionModel (modify_model.py:4-59): h = a U -> SubspaceHook -> a' = h U^T
+                kind = {"Projection": "proj", "SubspaceFilter": "sfilter", "InvProjection": "invproj"}[type(m).__name__]
+                op = _Op(kind, name, m, len(self.ops))
+                op.rule = composite.rule_for(name)
+                if kind == "sfilter":
+                    if getattr(op.rule, "kind", None) != "subspace_hook":
+                        raise _L.DRSAError(f"{name}: expects a SubspaceHook (see explainer.get_class_composite)")
+                elif op.rule is None or op.rule.kind != "epsilon":
+                    raise _L.DRSAError(f"{name}: expects the Epsilon rule (see explainer.get_class_composite)")
+                if kind == "proj":
+                    op.w = m.U.detach().to(device, torch.float32).contiguous()          # U [d, m]
+                    self.filter_index = len(self.ops)
             else:
                 raise _L.DRSAError(f"{name}: layer type {type(m).__name__} is not on this path")
             self.ops.append(op)
             if m is not None:
                 self.module_to_op[m] = op
             i += 1
+        if self.filter_index is not None:
+            f = self.filter_index
+            kinds = [o.kind for o in self.ops[f:f + 3]]
+            if kinds != ["proj", "sfilter", "invproj"]:
+                raise _L.DRSAError("Projection, SubspaceFilter and InvProjection must be consecutive layers")
+            self.filter_K = self.ops[f + 1].rule.num_concepts
+            if self.ops[f].w.shape[1] % self.filter_K != 0:
+                raise _L.DRSAError("num_concepts must divide the number of columns of U")
         # fuse ReLU into the producing conv/dense: the pre-activation is never needed (rules recompute z')
         for k, op in enumerate(self.ops):
             if op.kind in ("conv", "dense"):
@@ -174,7 +197,7 @@ class LRPPlan:
             elif op.kind == "pool":
                 ok = H % op.kh == 0 and W % op.kw == 0 and op.kh * op.kw <= 255
                 H, W = H // max(op.kh, 1), W // max(op.kw, 1)
-            elif op.kind not in ("identity", "relu"):
+            elif op.kind not in ("identity", "relu", "proj", "sfilter", "invproj"):
                 ok = False
             if not ok:
                 break
@@ -219,6 +242,15 @@ class LRPPlan:
             tt[:, : op.cin, : op.cout] = op.w_mod.permute(2, 3, 1, 0).reshape(9, op.cin, op.cout).flip(0)
             th, tl = self._split_planes(tt)
             op.tc.update({"m_hi": mh, "m_lo": ml, "m_b": padded_bias(op.b_mod), "t_hi": th, "t_lo": tl})
+
+    def _project_rows(self, op: _Op, a_rows: torch.Tensor, P: int, d: int, ld: int):
+        """h = a U and a' = h U^T for position vectors stored as rows [P, ld] (lrp_subspace_project)."""
+        U = op.w
+        m = U.shape[1]
+        h = torch.empty(P, m, device=a_rows.device)
+        a_rec = torch.empty(P, ld, device=a_rows.device)
+        _L.check(_L.lib().lrp_subspace_project(_ptr(a_rows), _ptr(U), P, d, m, ld, _ptr(h), _ptr(a_rec), _stream()), op.name)
+        return h, a_rec
 
     def _nhwc_to_nchw(self, t):
         """(hi, lo, C, Cp, H, W) NHWC planes -> NCHW fp32 [B, C, H, W]."""
@@ -274,6 +306,17 @@ class LRPPlan:
             elif op.kind == "relu":
                 if keep:
                     saved[k] = ("tc_relu", cur)          # ReLU is fused into the producer: output == input
+            elif op.kind == "proj":
+                C, Cp = cur[2], cur[3]
+                P = B * H * W
+                a_rows = torch.empty(P, Cp, device=dev)
+                _L.check(lib.lrp_tc_planes_to_f32(_ptr(cur[0]), _ptr(cur[1]), a_rows.numel(), _ptr(a_rows), _stream()), op.name)
+                h, a_rec = self._project_rows(op, a_rows, P, C, Cp)
+                saved[k] = ("tc_filter", a_rows, h, a_rec, (B, H, W, C, Cp))
+                yh = torch.empty(B, H, W, Cp, dtype=torch.float16, device=dev)
+                yl = torch.empty_like(yh)
+                _L.check(lib.lrp_tc_split_f16(_ptr(a_rec), a_rec.numel(), _ptr(yh), _ptr(yl), _stream()), op.name)
+                cur = (yh, yl, C, Cp, H, W)
             outs[k] = ("nhwc", cur) if k >= keep_from - 1 else None
         return self._nhwc_to_nchw(cur)
 
@@ -326,21 +369,45 @@ class LRPPlan:
             elif op.kind == "relu":
                 if keep:
                     saved[k] = cur            # ReLU already applied by the producer: output == input here
+            elif op.kind == "proj":
+                N, Cc, H, W = cur.shape
+                P = N * H * W
+                a_rows = torch.empty(P, Cc, device=cur.device)
+                _L.check(lib.lrp_tc_nchw_to_nhwc_f32(_ptr(cur.contiguous()), N, H, W, Cc, Cc, _ptr(a_rows), _stream()), op.name)
+                h, a_rec = self._project_rows(op, a_rows, P, Cc, Cc)
+                saved[k] = ("filter", a_rows, h, a_rec, (N, H, W, Cc, Cc))
+                y = torch.empty(N, Cc, H, W, device=cur.device)
+                _L.check(lib.lrp_tc_nhwc_f32_to_nchw(_ptr(a_rec), N, H, W, Cc, Cc, _ptr(y), _stream()), op.name)
+                cur = y
             outs[k] = cur
         return cur, saved, outs
 
     # ------------------------------------------------------------------ backward
-    def backward(self, Rel: torch.Tensor, saved, stop_after: int = -1) -> torch.Tensor:
-        """Propagates relevance from the logits down to the OUTPUT of op `stop_after` (-1: to the input).  Inside the
-        tensor-core conv stack the relevance travels as NHWC fp32 with padded channels."""
+    def backward(self, Rel: torch.Tensor, saved, stop_after: int = -1, start: Optional[int] = None, nhwc=None,
+                 bound_feat: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Propagates relevance from the logits (or, with ``start``, from the output of op ``start``) down to the OUTPUT
+        of op ``stop_after`` (-1: to the input).  Inside the tensor-core conv stack the relevance travels as NHWC fp32
+        with padded channels (``nhwc`` = (C, Cp, H, W) when ``Rel`` already is).  ``bound_feat``: activation with the
+        layout of ``Rel`` such that Rel = bound_feat * c; max |c| per sample bounds the quotients of the layer below.
+        A ProjectionModel's filter turns the batch of B samples into B*(K+1) relevance maps (clone order of the
+        reference: sample-major)."""
         lib = _L.lib()
-        nhwc = None            # (C, Cp, H, W) while Rel is NHWC fp32
         feat = None            # output of model.features (NCHW fp32), set when the flatten op is crossed
         bound = None           # per-sample bound on |s| of the next tensor-core layer (device, [B])
         cmax = None
-        for k in range(len(self.ops) - 1, stop_after, -1):
+        if nhwc is not None:
+            cmax = torch.zeros(len(self.ops) + 1, Rel.size(0), device=Rel.device)
+            if bound_feat is not None:
+                bound = cmax[len(self.ops)]
+                _L.check(lib.lrp_tc_sample_absmax_ratio(_ptr(Rel), _ptr(bound_feat), Rel.size(0), Rel[0].numel(), _ptr(bound),
+                                                        _stream()), "absmax_ratio")
+        for k in range(len(self.ops) - 1 if start is None else start, stop_after, -1):
             op = self.ops[k]
             sv = saved[k]
+            if op.kind in ("sfilter", "proj"):
+                continue
+            if op.kind == "invproj":
+                return self._filter_backward(Rel, saved, stop_after, nhwc)
             is_tc = isinstance(sv, tuple) and len(sv) > 0 and isinstance(sv[0], str) and sv[0].startswith("tc_")
             if is_tc and nhwc is None and sv[0] != "tc_first":
                 # entering the NHWC stack from the dense head: Rel is NCHW fp32 [B, C, H, W]
@@ -436,6 +503,44 @@ class LRPPlan:
             Rel = self._rel_to_nchw(Rel, nhwc)
         return Rel
 
+    def _filter_backward(self, Rel: torch.Tensor, saved, stop_after: int, nhwc) -> torch.Tensor:
+        """InvProjection (Epsilon) -> SubspaceHook -> Projection (Epsilon) for all K+1 clones at once, then the layers
+        below once per clone on the shared forward state.  Returns [B*(K+1), ...] in the reference's clone order."""
+        lib = _L.lib()
+        f = self.filter_index
+        if stop_after >= f - 1:
+            raise _L.DRSAError("relevance can only be read out below the projection layers of a ProjectionModel")
+        mode, a_rows, h, a_rec, (B, H, W, C, ld) = saved[f]
+        K, U = self.filter_K, self.ops[f].w
+        m = U.shape[1]
+        P = B * H * W
+        if mode == "tc_filter":
+            if nhwc is None:                       # relevance arrives NCHW (no conv layer above the split)
+                t = torch.empty(B, H, W, ld, device=Rel.device)
+                _L.check(lib.lrp_tc_nchw_to_nhwc_f32(_ptr(Rel.contiguous()), B, H, W, C, ld, _ptr(t), _stream()), "to_nhwc")
+                Rel = t
+        else:
+            if nhwc is not None:
+                Rel = self._rel_to_nchw(Rel, nhwc)
+            t = torch.empty(B, H, W, ld, device=Rel.device)
+            _L.check(lib.lrp_tc_nchw_to_nhwc_f32(_ptr(Rel.contiguous()), B, H, W, C, ld, _ptr(t), _stream()), "to_nhwc")
+            Rel = t
+        out = torch.empty(K + 1, B, H, W, ld, device=Rel.device)
+        ws = torch.empty(int(_L.check(lib.lrp_subspace_filter_workspace_bytes(P, C, m))), dtype=torch.uint8, device=Rel.device)
+        _L.check(lib.lrp_subspace_filter(_ptr(a_rows), _ptr(h), _ptr(a_rec), _ptr(Rel.contiguous()), _ptr(U), P, C, m, K, ld,
+                                         self.ops[f + 2].rule.stabilizer, self.ops[f].rule.stabilizer, _ptr(out), _ptr(ws),
+                                         ws.numel(), _stream()), "lrp_subspace_filter")
+        res = []
+        for kk in range(K + 1):
+            if mode == "tc_filter":
+                res.append(self.backward(out[kk], saved, stop_after, start=f - 1, nhwc=(C, ld, H, W),
+                                         bound_feat=a_rows))
+            else:
+                Rk = torch.empty(B, C, H, W, device=Rel.device)
+                _L.check(lib.lrp_tc_nhwc_f32_to_nchw(_ptr(out[kk]), B, H, W, ld, C, _ptr(Rk), _stream()), "to_nchw")
+                res.append(self.backward(Rk, saved, stop_after, start=f - 1))
+        return torch.stack(res, dim=1).flatten(0, 1)
+
     def _rel_to_nchw(self, Rel: torch.Tensor, nhwc) -> torch.Tensor:
         C, Cp, H, W = nhwc
         B = Rel.size(0)
@@ -451,6 +556,8 @@ class LRPPlan:
             o = self.ops[j]
             if o.kind in ("identity", "pool", "flatten", "relu"):
                 continue
+            if o.kind == "proj":
+                return False          # Epsilon on the projection: R = a * (...)
             if o.kind in ("conv", "dense"):
                 return not (o.rule is not None and o.rule.kind in ("epsilon", "gamma", "zplus"))
             return True
@@ -562,16 +669,72 @@ def lrp_intermediate(model, input_batch, composite, layer, class_idx, attr_batch
     return torch.cat(a_maps, 0), torch.cat(r_maps, 0)
 
 
+def _seed_is_rowwise(fn) -> bool:
+    return bool(getattr(fn, "rowwise", False))
+
+
+def _run_relevance(plan, x, fn, batch_size, seed_rows=None):
+    out = []
+    for i in range(0, x.size(0), batch_size):
+        logits, saved, _ = plan.forward(x[i:i + batch_size], keep_from=0)
+        seed = fn(logits) if seed_rows is None else seed_rows(logits, i)
+        out.append(plan.backward(seed.contiguous(), saved, stop_after=-1))
+    return torch.cat(out, 0)
+
+
 def lrp_input_relevance(model, input_batch, composite, attr_output_fn: Callable, batch_size: int = 64) -> torch.Tensor:
-    """Relevance at the input (compute_relevances, attribute.py:70-108)."""
+    """Relevance at the input (compute_relevances, attribute.py:70-108).  The reference attributes the whole batch in
+    one pass; here it is cut into minibatches, so a seed function that looks at the batch as a whole (the balanced
+    all-classes mask of attribute.py:148-158) is evaluated on the logits of the full batch first.  For a
+    ProjectionModel the batch is read as groups of K+1 clones (explainer.py:90-99): identical clones share one forward
+    pass and the backward pass above the filter."""
     x = _prep_input(input_batch)
     with torch.cuda.device(x.device):
         plan = _plan(model, composite, x.device)
         while True:
-            out = []
-            for i in range(0, x.size(0), batch_size):
-                logits, saved, _ = plan.forward(x[i:i + batch_size], keep_from=0)
-                out.append(plan.backward(attr_output_fn(logits).contiguous(), saved, stop_after=-1))
+            if plan.filter_index is None:
+                if _seed_is_rowwise(attr_output_fn) or x.size(0) <= batch_size:
+                    res = _run_relevance(plan, x, attr_output_fn, batch_size)
+                else:
+                    logits = torch.cat([plan.forward(x[i:i + batch_size], keep_from=len(plan.ops))[0]
+                                        for i in range(0, x.size(0), batch_size)], 0)
+                    seed_full = attr_output_fn(logits)
+                    res = _run_relevance(plan, x, None, batch_size, lambda lg, i: seed_full[i:i + lg.size(0)])
+            else:
+                res = _clone_relevance(plan, x, attr_output_fn, batch_size)
             if not plan.tc_failed():
                 break
-    return torch.cat(out, 0)
+    return res
+
+
+def _clone_relevance(plan, x, fn, batch_size):
+    Kp1 = plan.filter_K + 1
+    N = x.size(0)
+    if N % Kp1 != 0:
+        raise _L.DRSAError(f"a ProjectionModel attributes groups of num_concepts + 1 = {Kp1} clones; got a batch of {N}")
+    B = N // Kp1
+    xg = x.view(B, Kp1, *x.shape[1:])
+    xu = xg[:, 0].contiguous()
+    if bool((xg == xg[:, :1]).all()):
+        # the reference's use: every sample repeated K+1 times -> one forward per sample
+        bs = max(1, batch_size // Kp1)
+        logits = torch.cat([plan.forward(xu[i:i + bs], keep_from=len(plan.ops))[0] for i in range(0, B, bs)], 0) \
+            if not _seed_is_rowwise(fn) else None
+        seed_full = None
+        if logits is not None:
+            seed_full = fn(logits.repeat_interleave(Kp1, dim=0)).view(B, Kp1, -1)
+            if not bool((seed_full == seed_full[:, :1]).all()):
+                seed_full = False               # clones of one sample are seeded differently: general path below
+        if seed_full is not False:
+            if seed_full is None:
+                return _run_relevance(plan, xu, fn, bs)
+            return _run_relevance(plan, xu, None, bs, lambda lg, i: seed_full[i:i + lg.size(0), 0])
+    # general case (clones differ): clone index k of every group is attributed on its own and keeps slot k
+    logits = torch.cat([plan.forward(x[i:i + batch_size], keep_from=len(plan.ops))[0] for i in range(0, N, batch_size)], 0)
+    seed_all = fn(logits).view(B, Kp1, -1)
+    res = torch.empty(B, Kp1, *x.shape[1:], device=x.device)
+    for kk in range(Kp1):
+        xk = xg[:, kk].contiguous()
+        r = _run_relevance(plan, xk, None, max(1, batch_size // Kp1), lambda lg, i: seed_all[i:i + lg.size(0), kk])
+        res[:, kk] = r.view(B, Kp1, *x.shape[1:])[:, kk]
+    return res.flatten(0, 1)

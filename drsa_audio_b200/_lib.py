@@ -80,6 +80,10 @@ SIGNATURES = {
                                        _vp]),
     "lrp_tc_sample_absmax_ratio": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "lrp_tc_relu_mask": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "lrp_tc_planes_to_f32": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "lrp_subspace_filter_workspace_bytes": (_i64, [_i64, _i32, _i32]),
+    "lrp_subspace_project": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "lrp_subspace_filter": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _i64, _vp]),
     "lrp_tc_nhwc_f32_to_nchw": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "lrp_tc_nchw_to_nhwc_f32": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "lrp_tc_nhwc_to_nchw": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),

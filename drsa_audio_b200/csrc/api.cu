@@ -65,6 +65,12 @@ int conv_tc_run(const void* x_hi, const void* x_lo, const void* w_hi, const void
                 int H, int W, int Cin_p, int Cout_p, int Cout, int relu, int epi, float eps, const float* aux_f32,
                 const void* aux_hi, const void* aux_lo, void* y_hi, void* y_lo, float* y_f32, float* y_nchw,
                 const float* scale_ref, float* cmax_out, int* err_flag, cudaStream_t stream);
+int64_t subspace_filter_workspace_bytes(int64_t P, int d, int m);
+int subspace_project(const float* a, const float* U, int64_t P, int d, int m, int ld, float* h, float* a2, cudaStream_t s);
+int subspace_filter_backward(const float* a, const float* h, const float* a2, const float* R, const float* U, int64_t P, int d,
+                             int m, int K, int ld, float eps_inv, float eps_proj, float* out, void* workspace,
+                             int64_t workspace_bytes, cudaStream_t s);
+int planes_to_f32(const void* hi, const void* lo, int64_t count, float* out, cudaStream_t s);
 int sample_absmax_ratio(const float* R, const float* x, int64_t B, int64_t per, float* out, cudaStream_t stream);
 int maxpool_nhwc(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int kh, int kw, void* y_hi,
                  void* y_lo, void* argmax_u8, cudaStream_t stream);
@@ -390,6 +396,35 @@ int lrp_tc_sample_absmax_ratio(const float* R, const float* x, int64_t B, int64_
   if (R == nullptr || x == nullptr || out == nullptr || B <= 0 || per_sample <= 0) return DRSA_ERR_ARG;
   DRSA_TRY(require_sm100());
   return sample_absmax_ratio(R, x, B, per_sample, out, static_cast<cudaStream_t>(stream));
+}
+
+int64_t lrp_subspace_filter_workspace_bytes(int64_t P, int d, int m) {
+  if (P <= 0 || d <= 0 || m <= 0) return DRSA_ERR_ARG;
+  return subspace_filter_workspace_bytes(P, d, m);
+}
+
+int lrp_subspace_project(const float* a, const float* U, int64_t P, int d, int m, int ld, float* h, float* a_rec,
+                         void* stream) {
+  if (a == nullptr || U == nullptr || h == nullptr || P <= 0 || d <= 0 || m <= 0 || ld < d) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return subspace_project(a, U, P, d, m, ld, h, a_rec, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_subspace_filter(const float* a, const float* h, const float* a_rec, const float* R, const float* U, int64_t P,
+                        int d, int m, int K, int ld, float eps_invprojection, float eps_projection, float* out,
+                        void* workspace, int64_t workspace_bytes, void* stream) {
+  if (a == nullptr || h == nullptr || a_rec == nullptr || R == nullptr || U == nullptr || out == nullptr ||
+      workspace == nullptr || P <= 0 || d <= 0 || m <= 0 || K <= 0 || m % K != 0 || ld < d)
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return subspace_filter_backward(a, h, a_rec, R, U, P, d, m, K, ld, eps_invprojection, eps_projection, out, workspace,
+                                  workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int lrp_tc_planes_to_f32(const void* x_hi, const void* x_lo, int64_t count, float* out, void* stream) {
+  if (x_hi == nullptr || x_lo == nullptr || out == nullptr || count <= 0) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return planes_to_f32(x_hi, x_lo, count, out, static_cast<cudaStream_t>(stream));
 }
 
 int lrp_tc_relu_mask(float* R, const void* a_hi, const void* a_lo, int64_t count, void* stream) {

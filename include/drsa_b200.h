@@ -280,6 +280,26 @@ int lrp_tc_nchw_to_nhwc_f32(const float* x, int64_t B, int H, int W, int C, int 
 int lrp_tc_nhwc_to_nchw(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int C, float* y,
                         void* stream);
 
+/* hi + lo -> fp32 over `count` elements (hand-over from the NHWC planes to the fp32 projection kernels). */
+int lrp_tc_planes_to_f32(const void* x_hi, const void* x_lo, int64_t count, float* out, void* stream);
+
+/* ---- concept-conditional relevance at the split layer -----------------------------------------------------
+ * The reference inserts Projection (h = a U), SubspaceFilter (+ SubspaceHook) and InvProjection (a' = h U^T)
+ * after the layer where U was optimised (cxai/model/modify_model.py:4-123, cxai/xai/explain/attribute.py:12-67)
+ * and attributes every sample K+1 times (explainer.py:68-123).  Position vectors are rows [P, ld] (NHWC view,
+ * ld >= d, padded columns zero), U is [d, m] row-major.
+ *   lrp_subspace_project: h [P, m] = a U and (optional) a_rec [P, ld] = h U^T, the activation the rest of the
+ *     network sees.
+ *   lrp_subspace_filter: Epsilon rule on InvProjection (R_h = h * ((R / stab(a_rec)) U)), the SubspaceHook mask,
+ *     Epsilon rule on Projection (R_a = a * ((R_h / stab(h)) U^T)) for all K+1 clones at once:
+ *     out [(K+1), P, ld], slot 0 = unmasked (standard) relevance, slot k = relevance through concept k only. */
+int64_t lrp_subspace_filter_workspace_bytes(int64_t P, int d, int m);
+int lrp_subspace_project(const float* a, const float* U, int64_t P, int d, int m, int ld, float* h, float* a_rec,
+                         void* stream);
+int lrp_subspace_filter(const float* a, const float* h, const float* a_rec, const float* R, const float* U,
+                        int64_t P, int d, int m, int K, int ld, float eps_invprojection, float eps_projection,
+                        float* out, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* hi = fp16(in), lo = fp16(in - hi) over `count` floats. */
 int lrp_tc_split_f16(const float* in, int64_t count, void* hi, void* lo, void* stream);
 

@@ -149,6 +149,8 @@ def lrp_pass(model: nn.Module, x: torch.Tensor, name_map, seed_fn: Callable, spl
             cur = F.max_pool2d(cur, m.kernel_size, m.stride, m.padding)
         elif isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d)):
             cur = F.batch_norm(cur, cast(m.running_mean), cast(m.running_var), cast(m.weight), cast(m.bias), False, 0.0, m.eps)
+        elif type(m).__name__ in ("Projection", "SubspaceFilter", "InvProjection"):
+            cur = m(cur)            # modify_model.py:62-123 (U follows the dtype of the activations)
         else:
             raise TypeError(type(m))
         acts.append(cur)
@@ -183,6 +185,22 @@ def lrp_pass(model: nn.Module, x: torch.Tensor, name_map, seed_fn: Callable, spl
         elif isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d)):
             scale = cast(m.weight) / torch.sqrt(cast(m.running_var) + m.eps)
             R = R * scale.view(1, -1, *([1] * (R.dim() - 2)))
+        elif type(m).__name__ in ("Projection", "InvProjection"):
+            # zennit Epsilon (BasicHook) on a parameter-free module: R_in = x * d/dx [module(x)] . (R_out / stabilize(module(x)))
+            rule = rules[name]
+            assert rule.kind == "epsilon"
+            with torch.enable_grad():
+                xi = xin.detach().requires_grad_(True)
+                yo = m(xi)
+                grad, = torch.autograd.grad(yo, xi, R / stabilize(yo.detach(), rule.stabilizer))
+            R = xi.detach() * grad
+        elif type(m).__name__ == "SubspaceFilter":
+            # SubspaceHook.backward, attribute.py:42-60, verbatim
+            K = rules[name].num_concepts
+            batch, num_vecs, c, d_c = R.size()
+            R = R.clone().view(-1, K + 1, num_vecs, c, d_c)
+            R[:, 1:] *= torch.eye(K, dtype=R.dtype)[None, :, None, :, None]
+            R = R.view(batch, num_vecs, c, d_c)
     out["R_input"] = R
     return out
 

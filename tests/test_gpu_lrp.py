@@ -372,3 +372,113 @@ def test_tc_prefix_equals_fp32_path_full_resolution():
     assert res[True][0].shape == (3, 256, 8, 8)
     assert _rel_per_sample(res[True][0], res[False][0]) < 1e-5
     _assert_relevance_close_up_to_pool_ties(res[True][0], res[True][1], res[False][1], (2, 2))
+
+
+def test_subspace_filter_kernels_match_fp64():
+    """lrp_subspace_project / lrp_subspace_filter (Epsilon on both projections + SubspaceHook mask) vs fp64 torch on
+    the SAME inputs, padded leading dimension included."""
+    L = _L(); lib = L.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(5)
+    for (P, d, m, K, ld) in ((300, 16, 16, 4, 64), (1000, 128, 128, 4, 128), (257, 100, 100, 5, 128), (64, 64, 32, 2, 64)):
+        a = torch.relu(torch.randn(P, d, generator=g))
+        U = drsa_ref.synth_U0(d, m, seed=d + m)
+        ap = torch.zeros(P, ld); ap[:, :d] = a
+        ad, Ud = ap.cuda(), U.cuda().contiguous()
+        h = torch.empty(P, m, device="cuda"); arec = torch.full((P, ld), float("nan"), device="cuda")
+        L.check(lib.lrp_subspace_project(ad.data_ptr(), Ud.data_ptr(), P, d, m, ld, h.data_ptr(), arec.data_ptr(), s))
+        # the relevance that reaches InvProjection has the form a' * c (the rule of the layer above multiplies by its input)
+        R = torch.randn(P, d, generator=g) * arec.cpu()[:, :d]
+        Rp = torch.zeros(P, ld); Rp[:, :d] = R
+        Rd = Rp.cuda()
+        hw = a.double() @ U.double()
+        np.testing.assert_allclose(h.cpu().numpy(), hw.numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(arec.cpu()[:, :d].numpy(), (hw @ U.double().T).numpy(), rtol=1e-5, atol=1e-6)
+        assert float(arec[:, d:].abs().max()) == 0.0 if ld > d else True
+        out = torch.full((K + 1, P, ld), float("nan"), device="cuda")
+        ws = torch.empty(int(L.check(lib.lrp_subspace_filter_workspace_bytes(P, d, m))), dtype=torch.uint8, device="cuda")
+        L.check(lib.lrp_subspace_filter(ad.data_ptr(), h.data_ptr(), arec.data_ptr(), Rd.data_ptr(), Ud.data_ptr(), P, d, m, K, ld,
+                                        1e-6, 1e-6, out.data_ptr(), ws.data_ptr(), ws.numel(), s))
+        # fp64 on the kernel's own h and a_rec (the quotients amplify any difference in them, see the test below)
+        h64, ar64, U64 = h.cpu().double(), arec.cpu()[:, :d].double(), U.double()
+        sref = R.double() / lrp_ref.stabilize(ar64, 1e-6)
+        v = h64 * (sref @ U64) / lrp_ref.stabilize(h64, 1e-6)
+        d_k = m // K
+        got = out.cpu().double()
+        tot = torch.zeros(P, d, dtype=torch.float64)
+        for k in range(1, K + 1):
+            wk = a.double() * (v[:, (k - 1) * d_k:k * d_k] @ U64[:, (k - 1) * d_k:k * d_k].T)
+            tot += wk
+            assert float((got[k, :, :d] - wk).norm() / wk.norm()) < 2e-5, (P, d, k)
+        assert float((got[0, :, :d] - tot).norm() / tot.norm()) < 2e-5
+        assert float(got[:, :, d:].abs().max()) == 0.0 if ld > d else True
+
+
+@pytest.mark.parametrize("case", ["toy", "genre_bn"])
+@pytest.mark.parametrize("umode", ["signed_permutation", "orthogonal"])
+def test_heatmap_generator_matches_oracle(case, umode):
+    """Concept-conditional heatmaps (explainer.py:68-123): HeatmapGenerator on the CUDA engine vs the oracle pushing the
+    K+1 clones of every sample through the ProjectionModel like the reference does.
+
+    With a signed permutation U the projections are exact and every map must agree to the LRP tolerance.  With a
+    general orthogonal U the concept maps are only defined up to ~1e-2 -- in the reference as well: where a ReLU
+    output is exactly 0, a' = (a U) U^T is rounding noise (~1e-8), the relevance arriving there is a' * c, and the
+    Epsilon quotient a' c / (a' +- 1e-6) lets ~1 % of c through with the sign of the noise.  The standard map
+    (U U^T = I removes it again) and the sum of the concept maps are not affected and are held to the tolerance."""
+    from cxai.utils.constants import LRP_NAME_MAP_TOY, lrp_name_map_6s
+    from cxai.xai.explain.explainer import HeatmapGenerator, get_class_composite
+    from cxai.xai.explain.rules import SequentialMergeBatchNorm
+    from cxai.xai.explain.attribute import compute_relevances
+    from cxai.model.modify_model import ProjectionModel
+    K = 4
+    if case == "toy":
+        net = lrp_ref.toy_model(seed=0, last=64)
+        x = lrp_ref.synth_logmel(5, 64, 64, 11)
+        nm, layer_idx, d, cls, canon, shape = LRP_NAME_MAP_TOY, 10, 16, "class2", (), (64, 64)
+    else:
+        net = lrp_ref.genre_model(seed=0, last=64, input_size=(32, 64))
+        x = lrp_ref.synth_logmel(6, 32, 64, 20262)      # the inputs of test_compute_relevances_...: no max-pool near-ties
+        nm, layer_idx, d, cls, canon, shape = lrp_name_map_6s(), 26, 128, "blues", [SequentialMergeBatchNorm()], (32, 64)
+    if umode == "orthogonal":
+        U = drsa_ref.synth_U0(d, seed=40)
+    else:
+        gperm = torch.Generator().manual_seed(41)
+        U = torch.zeros(d, d)
+        U[torch.arange(d), torch.randperm(d, generator=gperm)] = torch.where(torch.rand(d, generator=gperm) < 0.5, -1.0, 1.0)
+    strict = umode == "signed_permutation"
+    gen = HeatmapGenerator(net, U, nm, cls, num_concepts=K, layer_idx=layer_idx, device="cuda", canonizers=canon)
+    gen.generate_subspace_heatmaps(x)
+    pm = ProjectionModel(net, layer_idx, U.double(), K, case="toy" if case == "toy" else "gtzan")
+    comp = get_class_composite(nm, K)
+    want = lrp_ref.lrp_pass(pm, x.repeat_interleave(K + 1, dim=0), comp.name_map, lrp_ref.output_modifier(gen.class_idx))
+    Hw = want["R_input"].view(x.size(0), K + 1, *shape)
+    std = torch.from_numpy(gen.info["standard_heatmaps"])
+    assert std.shape == (x.size(0), 1, *shape)
+    assert _rel_per_sample(std[:, 0], Hw[:, 0]) < TOL
+    # concept heatmaps arrive sorted by descending relevance; undo with the returned mask
+    sub = torch.from_numpy(gen.info["subspace_heatmaps"].copy())
+    mask = torch.from_numpy(gen.info["mask"].copy())
+    rel_w = Hw[:, 1:].sum(dim=(-2, -1))
+    if strict:
+        np.testing.assert_array_equal(mask.numpy(), torch.argsort(rel_w, dim=-1, descending=True).numpy())
+    for b in range(x.size(0)):
+        assert sorted(mask[b].tolist()) == list(range(K))
+        for j in range(K):
+            w = Hw[b, 1 + int(mask[b, j])]
+            assert float((sub[b, j].double() - w).norm() / w.norm()) < (TOL if strict else 0.1)
+    np.testing.assert_allclose(gen.info["subspace_relevances"], np.take_along_axis(rel_w.numpy(), mask.numpy(), 1),
+                               rtol=2e-3 if strict else 0.1, atol=(1e-4 if strict else 2e-2) * float(rel_w.abs().max()))
+    assert np.all(np.diff(gen.info["subspace_relevances"], axis=1) <= 0)          # sorted, descending
+    # concept maps add up to the standard map (size-independent property)
+    assert float((sub.sum(1) - std[:, 0]).abs().max() / std.abs().max()) < 1e-4
+    assert gen.info["standard_relevance"].shape == (x.size(0),)
+    if not strict:
+        return
+    # clones that differ (not the reference's use, but defined by the hook): every row keeps the slot of its position
+    xr = x.repeat_interleave(K + 1, dim=0).clone()
+    xr[1::K + 1] += 0.25
+    got = compute_relevances(gen.projectionmodel, xr, gen.composite, class_idx=gen.class_idx)
+    wantg = lrp_ref.lrp_pass(pm, xr, comp.name_map, lrp_ref.output_modifier(gen.class_idx))["R_input"]
+    ref_scale = wantg.double().flatten(1).norm(dim=1).view(-1, K + 1).max(dim=1).values.repeat_interleave(K + 1)
+    err = (got.double().cpu() - wantg).flatten(1).norm(dim=1) / ref_scale
+    assert float(err.max()) < TOL

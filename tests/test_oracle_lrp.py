@@ -92,3 +92,31 @@ def test_batchnorm_merge_matches_eval_forward():
         ref_logits = net.double()(x.double())
     np.testing.assert_allclose(o["logits"].numpy(), ref_logits.numpy(), rtol=1e-4, atol=1e-7)
     assert o["a_split"].shape == (2, 32, 2, 2)
+
+
+def test_projection_model_oracle_invariants():
+    """ProjectionModel + SubspaceHook (modify_model.py:4-123, attribute.py:12-67, explainer.py:186-203) in the oracle:
+    the concept heatmaps add up to the standard heatmap (every layer below the filter is linear in the relevance),
+    clone 0 equals the plain LRP pass up to the stabilisers of the two projection layers, and the projections do not
+    change the logits for an orthogonal U."""
+    import torch
+    from oracle import drsa_ref
+    from cxai.utils.constants import LRP_NAME_MAP_TOY
+    from cxai.model.modify_model import ProjectionModel
+    from cxai.xai.explain.explainer import get_class_composite
+    net = lrp_ref.toy_model(seed=0, last=64)
+    x = lrp_ref.synth_logmel(3, 64, 64, 5)
+    K = 4
+    U = torch.linalg.qr(torch.randn(16, 16, dtype=torch.float64, generator=torch.Generator().manual_seed(3)))[0]
+    pm = ProjectionModel(net, 10, U, K, case="toy")
+    comp = get_class_composite(LRP_NAME_MAP_TOY, K)
+    o = lrp_ref.lrp_pass(pm, x.repeat_interleave(K + 1, dim=0), comp.name_map, lrp_ref.output_modifier(1))
+    Hm = o["R_input"].view(3, K + 1, 64, 64)
+    plain = lrp_ref.lrp_pass(net, x, LRP_NAME_MAP_TOY, lrp_ref.output_modifier(1))
+    assert float((Hm[:, 1:].sum(1) - Hm[:, 0]).abs().max() / Hm[:, 0].abs().max()) < 1e-12
+    assert float((Hm[:, 0] - plain["R_input"].view(3, 64, 64)).abs().max() / plain["R_input"].abs().max()) < 1e-3
+    assert float((o["logits"][::K + 1] - plain["logits"]).abs().max()) < 1e-12
+    # the torch forward of the ProjectionModel itself agrees as well (InvProjection handles non-square maps)
+    with torch.no_grad():
+        assert float((pm.double()(x.double()) - net.double()(x.double())).abs().max()) < 1e-10
+    net.float()
