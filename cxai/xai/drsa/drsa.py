@@ -157,13 +157,15 @@ class SubspaceOptimizer:
         process_group: torch.distributed group over which the rows are sharded; ``activation_vecs``
             / ``context_vecs`` are then this rank's slice.  Defaults to the world group if
             torch.distributed is initialised.
-        retraction_iters / retraction_tol: bounds of the on-device Newton-Schulz polar iteration.
+        retraction_iters / retraction_tol: bounds of the on-device Newton-Schulz polar iteration (it stops as soon
+            as it has converged: 4-5 sweeps in a normal step; the first steps of a tiny problem, where the
+            gradient dwarfs U, need 15-25).
         use_cuda_graph: capture one step and replay it (single process only).
     """
 
     def __init__(self, U: torch.Tensor, activation_vecs: torch.Tensor, context_vecs: torch.Tensor,
                  path_to_model: Optional[str], num_concepts: int = 4, device=_DEFAULT_DEVICE, *,
-                 precision: str = "auto", process_group=None, retraction_iters: int = 8,
+                 precision: str = "auto", process_group=None, retraction_iters: int = 40,
                  retraction_tol: float = 1e-6, use_cuda_graph: bool = True) -> None:
         assert num_concepts > 0, "num_concepts must be a positive number"
         assert U.size(1) % num_concepts == 0, "num_concepts must be a divisor of the number of columns of U"
@@ -210,6 +212,10 @@ class SubspaceOptimizer:
             hist = self._obj_log[: steps + 1].cpu().numpy()   # the only device->host copy of the loop
             self.last_status = self._rows.status.cpu().numpy()
         self.obj_history = hist
+        if int(self.last_status[1]) != 0:
+            import warnings
+            warnings.warn(f"DRSA: the polar retraction did not converge within {self.retraction_iters} sweeps in "
+                          f"{int(self.last_status[1])} step(s); raise retraction_iters")
         if save and self.path_to_model is not None:
             self.save_model()
             self.save_train_stats([np.asarray(v) for v in hist])

@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
     ++it;
   }
   // ---------------- output
-  if (blockIdx.x == 0 && tid == 0 && p.status != nullptr) { p.status[0] = it; p.status[1] = converged ? 0 : 1; }
+  if (blockIdx.x == 0 && tid == 0 && p.status != nullptr) { p.status[0] = it; if (!converged) p.status[1] += 1; }   // [1]: sticky count
   for (int64_t i = gtid; i < n; i += gthreads) {
     const float v = cur[i];
     p.U_out[i] = v;

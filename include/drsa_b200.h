@@ -128,8 +128,9 @@ int64_t drsa_finish_workspace_bytes(int d, int m);
  * The polar factor is computed on the device by a scaled Newton-Schulz iteration in
  * fp32 (at most `max_iters` sweeps, stops when ||Y^T Y - I||_F < tol*sqrt(m)); the
  * reference uses an fp64 eigendecomposition on the host, both converge to the same
- * (unique) polar factor.  status (4 ints, device): [0] = sweeps used, [1] = 1 if not
- * converged, [2] = number of concepts with q_k == 0 (the reference yields NaN there),
+ * (unique) polar factor.  status (4 ints, device): [0] = sweeps used, [1] = number of calls
+ * since the caller last zeroed it whose iteration did not converge within max_iters,
+ * [2] = number of concepts with q_k == 0 (the reference yields NaN there),
  * [3] = append cursor: when log_index < 0 the objective is stored at obj_log[status[3]++]
  * so that a captured CUDA graph of one step can be replayed without changing arguments.
  */

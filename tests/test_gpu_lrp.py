@@ -482,3 +482,51 @@ def test_heatmap_generator_matches_oracle(case, umode):
     ref_scale = wantg.double().flatten(1).norm(dim=1).view(-1, K + 1).max(dim=1).values.repeat_interleave(K + 1)
     err = (got.double().cpu() - wantg).flatten(1).norm(dim=1) / ref_scale
     assert float(err.max()) < TOL
+
+
+def test_end_to_end_cfg5_small(tmp_path):
+    """BASELINE cfg 5 at reduced size: for each class, synthetic log-mel batch -> BatchNorm CNN forward -> LRP to the
+    last conv -> (a, c) pairs at all positions -> normalise -> DRSA, against the same pipeline on the CPU oracle;
+    also the reference's on-disk formats of the data sets and of the optimiser outputs."""
+    import pickle
+    from scipy.stats import ortho_group
+    from cxai.utils.constants import lrp_name_map_6s
+    from cxai.xai.explain.rules import NameMapComposite, SequentialMergeBatchNorm
+    from cxai.xai.drsa.cluster import optsubspaces, getdrsadata
+    net = lrp_ref.genre_model(seed=0, last=64, input_size=(32, 64))
+    nm = lrp_name_map_6s()
+    comp = NameMapComposite(nm, canonizers=[SequentialMergeBatchNorm()])
+    K, steps, layer_idx = 4, 25, 33
+    data = {c: lrp_ref.synth_logmel(10, 32, 64, 700 + c) for c in (2, 7)}
+    res = optsubspaces.all_classes_pipeline(net, data, comp, layer_idx, str(tmp_path), num_concepts=K, steps=steps, runs=2,
+                                            seed=42)
+    for c, x in data.items():
+        aw, Rw = lrp_ref.get_intermediate(net, x, nm, net.features[layer_idx], c)
+        av = drsa_ref.vectors_from_maps_all(aw.float()); rv = drsa_ref.vectors_from_maps_all(Rw.float())
+        A = drsa_ref.normalize_vectors(av); C = drsa_ref.normalize_vectors(drsa_ref.compute_context_vectors(av, rv))
+        np.random.seed(42)
+        U = ortho_group.rvs(A.size(1))
+        for run in (1, 2):
+            U = U[:, np.random.permutation(A.size(1))]
+            objs_ref, U_ref = drsa_ref.run_autograd(A, C, torch.tensor(U, dtype=torch.float32), K, steps)
+            root = tmp_path / f"class{c}" / f"layer{layer_idx}" / f"run{run}"
+            with open(root / "projection_matrix.pkl", "rb") as f:
+                Ug = pickle.load(f)
+            lines = open(root / "train_stats.csv").read().splitlines()
+            objs = np.array([float(l.split(",")[1]) for l in lines[1:]])
+            assert lines[0] == ",loss" and len(objs) == steps + 1
+            assert np.max(np.abs(objs - objs_ref) / np.abs(objs_ref)) < 1e-4
+            assert drsa_ref.principal_angle(torch.from_numpy(Ug), U_ref, K) < 1e-3
+        Ul, hist, rows = res[c]
+        assert rows == 10 * 4 and np.allclose(hist, objs)        # 2 x 2 positions at layer 33 of a 32 x 64 input
+    # data-set files of getdrsadata.py:26-59 round-trip through the reference's format
+    act, ctx = getdrsadata.preprocess_data(net, data[2], comp, layer_idx, class_idx=2, num_locations=None)
+    fp = getdrsadata.save_data(act.cpu().numpy(), ctx.cpu().numpy(), layer=layer_idx, sample_class="disco", model="t",
+                               output_path=str(tmp_path))
+    assert fp.endswith("gtzan/t/disco/dataset_layer33.pkl")
+    with open(fp, "rb") as f:
+        ds = pickle.load(f)
+    assert isinstance(ds, list) and len(ds) == act.size(0) and ds[0][0].shape == (act.size(1),)
+    an, cn = getdrsadata.load_and_normalize_data(fp, device="cuda")
+    np.testing.assert_allclose(an.cpu().numpy(), drsa_ref.normalize_vectors(act.cpu()).numpy(), rtol=3e-6, atol=1e-8)
+    np.testing.assert_allclose(cn.cpu().numpy(), drsa_ref.normalize_vectors(ctx.cpu()).numpy(), rtol=3e-6, atol=1e-7)
