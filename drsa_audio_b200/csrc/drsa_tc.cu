@@ -565,7 +565,8 @@ int absmax(const float* in, int64_t count, float* out, cudaStream_t stream) {
   return DRSA_OK;
 }
 
-void set_tc_profile(long long* p) { g_tc_prof = p; }
+extern long long* g_fused_prof;
+void set_tc_profile(long long* p) { g_tc_prof = p; g_fused_prof = p; }
 
 // numRegs, maxThreadsPerBlock, static shared bytes, local bytes, max dynamic shared bytes of the row-pass kernel
 int tc_kernel_attrs(int d, int split, int* out5) {

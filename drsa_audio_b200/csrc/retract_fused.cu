@@ -12,9 +12,10 @@ namespace cg = cooperative_groups;
 
 namespace drsa {
 
+long long* g_fused_prof = nullptr;     // debug: see drsa_debug_set_tc_profile
+
 namespace {
 constexpr int TS = 32;
-constexpr int LDS = 34;   // padded leading dimension (even: float2 reads stay 8-byte aligned)
 
 struct FusedParams {
   const float* sums; double inv_M; const float* U; int d, m, K;
@@ -26,51 +27,124 @@ struct FusedParams {
   int have_sums;   // 0: Y already holds the matrix to retract (drsa_polar_retract)
   int u_rounded;   // sums were evaluated at fp16(U): log f(fp16 U) + <grad, U - fp16 U> (first-order exact in the rounding)
   float* corr;     // [gridDim.x] per-CTA partials of that inner product
+  long long* prof; // debug: %globaltimer stamps of CTA 0 at the phase boundaries (drsa_debug_set_tc_profile), or NULL
 };
 
-// C[32x32] (+)= sum_k A_k(i) B_k(j) with both operands given as "row k, column contiguous" views:
-//   MODE 0 (gram): A_k(i) = X[k*ld + i0 + i],  B_k(j) = X[k*ld + j0 + j]
-//   MODE 1 (mul) : A_k(i) = X[(i0 + i)*ldx + k], B_k(j) = T[k*ldt + j0 + j]
+__device__ __forceinline__ void stamp(const FusedParams& p, int& slot) {
+  if (p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && slot < 40) {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.prof[16 + slot] = t;
+  }
+  ++slot;
+}
+
+// C[32x32] = sum_k A_k(i) B_k(j) over the FULL contraction length, both operand panels staged in shared memory by
+// cp.async (all loads of a tile are in flight at once; the panels land in up to four groups and the FMA loop starts
+// on the first while the rest is still arriving -- the previous version streamed 32-wide chunks with one chunk of
+// prefetch and was bound by eight dependent L2 round trips per tile):
+//   MODE 0 (gram): A_k(i) = X[k*ld + i0 + i],  B_k(j) = X[k*ld + j0 + j]      panels k-major  [K][LDT]
+//   MODE 1 (mul) : A_k(i) = X[(i0 + i)*ldx + k] (panel [32][K + 4]),  B_k(j) = T[k*ldt + j0 + j]
+constexpr int LDT = 36;   // padded row stride (floats) of a k-major panel: 16-byte aligned rows, conflict-free float2 reads
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int n) {      // wait until at most n groups are pending
+  if (n <= 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+  else if (n == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+  else if (n == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+  else asm volatile("cp.async.wait_group 3;" ::: "memory");
+}
+
 template <int MODE>
 __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, int i0, const float* __restrict__ B,
-                                          int ldb, int j0, int Kdim, float (&acc)[2][2], float (*As)[LDS],
-                                          float (*Bs)[LDS]) {
+                                          int ldb, int j0, int Kdim, float (&acc)[2][2], float* sm) {
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int lc = tid & 31, lr = tid >> 5;     // loader: column lc, rows lr + 8q
-  float ra[4], rb[4];
-  auto load = [&](int k0) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int rr = lr + 8 * q;
-      if (MODE == 0) ra[q] = A[(int64_t)(k0 + rr) * lda + i0 + lc];          // As[k = rr][i = lc]
-      else           ra[q] = A[(int64_t)(i0 + rr) * lda + k0 + lc];          // As[k = lc][i = rr]
-      rb[q] = B[(int64_t)(k0 + rr) * ldb + j0 + lc];                          // Bs[k = rr][j = lc]
+  const int lda_s = MODE == 0 ? LDT : Kdim + 4;
+  float* As = sm;
+  float* Bs = sm + (MODE == 0 ? Kdim * LDT : 32 * (Kdim + 4));
+  const int groups = (Kdim % 128 == 0) ? 4 : ((Kdim % 64 == 0) ? 2 : 1);
+  const int Kg = Kdim / groups;               // multiple of 32
+  __syncthreads();                            // the previous tile's panels are no longer read
+  for (int g = 0; g < groups; ++g) {
+    const int k0 = g * Kg;
+    for (int p = 0; p < Kg / 32; ++p) {
+      const int idx = tid + 256 * p;
+      {   // B panel (and the A panel of MODE 0): 8 segments of 16 bytes per k row
+        const int k = k0 + (idx >> 3), seg = idx & 7;
+        cp_async16(Bs + k * LDT + 4 * seg, B + (int64_t)k * ldb + j0 + 4 * seg);
+        if (MODE == 0) cp_async16(As + k * LDT + 4 * seg, A + (int64_t)k * lda + i0 + 4 * seg);
+      }
+      if (MODE == 1) {   // A panel: 32 rows, Kg/4 segments of this group per row
+        const int spr = Kg >> 2;
+        const int row = idx / spr, seg = idx % spr;
+        cp_async16(As + row * lda_s + k0 + 4 * seg, A + (int64_t)(i0 + row) * lda + k0 + 4 * seg);
+      }
     }
-  };
-  auto store = [&]() {
+    cp_async_commit();
+  }
+  // Each warp takes 4 consecutive k of every 32 and accumulates a full 32 x 32 partial tile in registers (4 x 8 per
+  // lane: 3 LDS.128 per 32 FMA); the eight partials are summed through shared memory at the end.
+  const int warp = tid >> 5, lane = tid & 31;
+  const int ri = lane >> 2, ci = lane & 3;
+  float part[4][8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int rr = lr + 8 * q;
-      if (MODE == 0) As[rr][lc] = ra[q]; else As[lc][rr] = ra[q];
-      Bs[rr][lc] = rb[q];
-    }
-  };
-  acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = 0.f;
-  load(0);
-  for (int k0 = 0; k0 < Kdim; k0 += TS) {
-    __syncthreads();          // previous chunk fully consumed
-    store();
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) part[r][c] = 0.f;
+  for (int g = 0; g < groups; ++g) {
+    cp_async_wait_pending(groups - 1 - g);
     __syncthreads();
-    if (k0 + TS < Kdim) load(k0 + TS);
+    for (int kb = g * Kg; kb < (g + 1) * Kg; kb += 32) {
+      const int k4 = kb + 4 * warp;
+      float av[4][4];                         // [u = k offset][r = row of this lane]
+      if (MODE == 0) {                        // rows 4*ri .. 4*ri+3, contiguous in the k-major panel
 #pragma unroll
-    for (int kk = 0; kk < TS; ++kk) {
-      const float2 a = *reinterpret_cast<const float2*>(&As[kk][2 * ty]);
-      const float2 b = *reinterpret_cast<const float2*>(&Bs[kk][2 * tx]);
-      acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
-      acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+        for (int u = 0; u < 4; ++u) {
+          const float4 a = *reinterpret_cast<const float4*>(&As[(k4 + u) * LDT + 4 * ri]);
+          av[u][0] = a.x; av[u][1] = a.y; av[u][2] = a.z; av[u][3] = a.w;
+        }
+      } else {                                // rows ri, ri+8, ri+16, ri+24 (conflict-free with the K+4 row stride)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float4 a = *reinterpret_cast<const float4*>(&As[(ri + 8 * r) * lda_s + k4]);
+          av[0][r] = a.x; av[1][r] = a.y; av[2][r] = a.z; av[3][r] = a.w;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[(k4 + u) * LDT + 8 * ci]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[(k4 + u) * LDT + 8 * ci + 4]);
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) part[r][c] = fmaf(av[u][r], bv[c], part[r][c]);
+      }
     }
   }
+  __syncthreads();                            // every warp is done reading the panels: reuse them for the partial tiles
+  float* red_t = sm + warp * (32 * 33);       // [32][33] per warp
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int row = MODE == 0 ? 4 * ri + r : ri + 8 * r;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) red_t[row * 33 + 8 * ci + c] = part[r][c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += sm[w * (32 * 33) + (2 * ty + aa) * 33 + 2 * tx + bb];     // fixed order
+      acc[aa][bb] = v;
+    }
 }
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
@@ -99,8 +173,7 @@ __device__ __forceinline__ float grid_total(const float* part, float* red) {
 
 __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ __align__(16) float As[TS][LDS];
-  __shared__ __align__(16) float Bs[TS][LDS];
+  extern __shared__ __align__(16) float panels[];      // operand panels of tile_gemm (fused_smem_bytes)
   __shared__ float red[8];
   __shared__ float coef[64];
   __shared__ float bc[2];
@@ -108,6 +181,8 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
   const int d = p.d, m = p.m;
   const int64_t n = (int64_t)d * m;
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + tid, gthreads = (int64_t)gridDim.x * blockDim.x;
+  int slot = 0;
+  stamp(p, slot);
 
   // ---------------- phase 0: pooling scalars, Y = U + coef_k X_k, objective log
   if (p.have_sums) {
@@ -159,7 +234,9 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
       return;
     }
   }
+  stamp(p, slot);
   grid.sync();
+  stamp(p, slot);
   if (p.have_sums && blockIdx.x == 0 && tid == 0 && p.obj_log != nullptr) {
     float extra = 0.f;
     if (p.u_rounded)
@@ -174,7 +251,7 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
   for (int t = blockIdx.x; t < tm * tm; t += gridDim.x) {
     const int ti = t / tm, tj = t % tm;
     float acc[2][2];
-    tile_gemm<0>(p.Y, m, ti * TS, p.Y, m, tj * TS, d, acc, As, Bs);
+    tile_gemm<0>(p.Y, m, ti * TS, p.Y, m, tj * TS, d, acc, panels);
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
       const int gi = ti * TS + 2 * ty + a;
@@ -186,7 +263,9 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
       if (tx == 0) p.rowsum[(int64_t)tj * m + gi] = rs;     // every (tj, gi) is written by exactly one tile
     }
   }
+  stamp(p, slot);
   grid.sync();
+  stamp(p, slot);
   // ---------------- phase 2: c = ||G||_inf, X0 = Y / sqrt(c), G <- T_0 = 1.5 I - 0.5 G / c, resid[0]
   {
     float best = 0.f;
@@ -217,7 +296,9 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
     const float tot = block_sum(r, red);
     if (tid == 0) p.resid[blockIdx.x] = tot;
   }
+  stamp(p, slot);
   grid.sync();
+  stamp(p, slot);
 
   // ---------------- Newton-Schulz sweeps
   int it = 0, converged = 0;
@@ -231,20 +312,22 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
     for (int t = blockIdx.x; t < td * tm; t += gridDim.x) {
       const int tr = t / tm, tj = t % tm;
       float acc[2][2];
-      tile_gemm<1>(cur, m, tr * TS, p.G, m, tj * TS, m, acc, As, Bs);
+      tile_gemm<1>(cur, m, tr * TS, p.G, m, tj * TS, m, acc, panels);
 #pragma unroll
       for (int a = 0; a < 2; ++a) {
         const int gi = tr * TS + 2 * ty + a;
         *reinterpret_cast<float2*>(&nxt[(int64_t)gi * m + tj * TS + 2 * tx]) = make_float2(acc[a][0], acc[a][1]);
       }
     }
+    stamp(p, slot);
     grid.sync();
+    stamp(p, slot);
     // G = nxt^T nxt -> residual, T
     float r = 0.f;
     for (int t = blockIdx.x; t < tm * tm; t += gridDim.x) {
       const int ti = t / tm, tj = t % tm;
       float acc[2][2];
-      tile_gemm<0>(nxt, m, ti * TS, nxt, m, tj * TS, d, acc, As, Bs);
+      tile_gemm<0>(nxt, m, ti * TS, nxt, m, tj * TS, d, acc, panels);
 #pragma unroll
       for (int a = 0; a < 2; ++a) {
         const int gi = ti * TS + 2 * ty + a;
@@ -262,11 +345,14 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
       const float tot = block_sum(r, red);
       if (tid == 0) p.resid[(int64_t)(it + 1) * gridDim.x + blockIdx.x] = tot;
     }
+    stamp(p, slot);
     grid.sync();
+    stamp(p, slot);
     float* tmp = cur; cur = nxt; nxt = tmp;
     ++it;
   }
   // ---------------- output
+  stamp(p, slot);
   if (blockIdx.x == 0 && tid == 0 && p.status != nullptr) { p.status[0] = it; if (!converged) p.status[1] += 1; }   // [1]: sticky count
   for (int64_t i = gtid; i < n; i += gthreads) {
     const float v = cur[i];
@@ -278,6 +364,14 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
       if (p.Ut_lo != nullptr) p.Ut_lo[(int64_t)cc * d + r] = __float2half_rn(v - __half2float(hi));
     }
   }
+  stamp(p, slot);
+  if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) p.prof[15] = slot;
+}
+
+int fused_smem_bytes(int d, int m) {
+  const int gram = 2 * d * LDT, mul = 32 * (m + 4) + m * LDT, red = 8 * 32 * 33;      // floats
+  const int mx = gram > mul ? (gram > red ? gram : red) : (mul > red ? mul : red);
+  return mx * 4;
 }
 
 int64_t fused_ws_bytes(int d, int m, int max_iters) {
@@ -286,7 +380,9 @@ int64_t fused_ws_bytes(int d, int m, int max_iters) {
 }
 }  // namespace
 
-bool finish_fused_supported(int d, int m, int K) { return d % TS == 0 && m % TS == 0 && d >= TS && m >= TS && K >= 1; }
+bool finish_fused_supported(int d, int m, int K) {
+  return d % TS == 0 && m % TS == 0 && d >= TS && m >= TS && K >= 1 && fused_smem_bytes(d, m) <= 200 * 1024;
+}
 
 int64_t finish_fused_workspace_bytes(int d, int m) { return fused_ws_bytes(d, m, 64); }
 
@@ -308,6 +404,7 @@ int finish_fused(const float* sums, int64_t M_global, const float* U, int d, int
   p.sums = sums; p.inv_M = M_global > 0 ? 1.0 / (double)M_global : 0.0; p.U = U; p.d = d; p.m = m; p.K = K;
   p.U_out = U_out; p.Ut_hi = static_cast<__half*>(Ut_hi); p.Ut_lo = static_cast<__half*>(Ut_lo);
   p.obj_log = obj_log; p.log_index = log_index; p.max_iters = max_iters; p.tol2_m = tol * tol * (float)m;
+  p.prof = g_fused_prof;
   p.status = status; p.have_sums = (Y_in == nullptr) ? 1 : 0;
   p.u_rounded = (u_rounded && Y_in == nullptr) ? 1 : 0;
   p.corr = p.resid + (int64_t)(max_iters + 1) * 1024;       // the row after the last sweep's residual partials
@@ -316,18 +413,25 @@ int finish_fused(const float* sums, int64_t M_global, const float* U, int d, int
   const int t2 = (m / TS) * (m / TS);
   if (t2 > tiles) tiles = t2;
   int grid = tiles;
-  static int max_coresident = 0;
-  if (max_coresident == 0) {
-    int per_sm = 0;
-    DRSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, finish_fused_kernel, 256, 0));
-    max_coresident = per_sm * sm_count();
-    if (max_coresident < 1) return DRSA_ERR_CUDA;
+  const int smem = fused_smem_bytes(d, m);
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    DRSA_CUDA(cudaFuncSetAttribute(finish_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
   }
+  static int occ_smem = -1, occ_blocks = 0;          // one process per GPU: per-process cache of the occupancy query
+  if (occ_smem != smem) {
+    int per_sm = 0;
+    DRSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, finish_fused_kernel, 256, smem));
+    occ_smem = smem; occ_blocks = per_sm * sm_count();
+  }
+  const int max_coresident = occ_blocks;
+  if (max_coresident < 1) return DRSA_ERR_CUDA;
   if (grid > max_coresident) grid = max_coresident;
   if (grid > 1024) grid = 1024;            // resid partials are sized for <= 1024 CTAs
   if (U_out == nullptr) grid = 1;
   void* args[] = {&p};
-  DRSA_CUDA(cudaLaunchCooperativeKernel((const void*)finish_fused_kernel, dim3(grid), dim3(256), args, 0, stream));
+  DRSA_CUDA(cudaLaunchCooperativeKernel((const void*)finish_fused_kernel, dim3(grid), dim3(256), args, smem, stream));
   return DRSA_OK;
 }
 

@@ -311,7 +311,8 @@ int lrp_tc_split_f16(const float* in, int64_t count, void* hi, void* lo, void* s
  * ---------------------------------------------------------------------------------- */
 int drsa_selftest_umma(int variant, float* max_err_host);
 
-/* Diagnostics: when set to a device buffer of 16 int64 (zeroed by the caller), CTA 0 of the tensor-core row pass stores the SM
+/* Diagnostics: when set to a device buffer of 64 int64 (zeroed by the caller; [15] and [16..55] receive the number of and
+ * the %globaltimer stamps at the phase boundaries of the fused finish kernel), CTA 0 of the tensor-core row pass stores the SM
  * cycles its MMA thread spent issuing GEMM1 [0], waiting for the epilogue [1], issuing GEMM2 [2] and its
  * first epilogue warp spent waiting for GEMM1 [3] and working [4].  NULL switches it off (default). */
 int drsa_debug_set_tc_profile(void* device_buf6);
