@@ -14,7 +14,7 @@
 // memory as 128 rows of 128 bytes with the 128-byte swizzle, i.e. directly in the K-major operand layout
 // of tcgen05.mma.  Accumulators live in TMEM (double buffered when 2*Cout <= 512 columns); the epilogue
 // (4 warps, one pixel per thread) adds the bias, applies ReLU and writes the next layer's hi/lo planes.
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue; persistent over tiles.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue (two per TMEM lane quarter, alternating 32-channel chunks); persistent over tiles.
 #include <cuda.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -59,7 +59,7 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, u
 
 constexpr int kTilePix = 128;
 constexpr int kABytes = kTilePix * 128;        // one [128 pixels x 64 ch] fp16 box
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;      // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 constexpr uint32_t kDescHiK = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
 __device__ __forceinline__ uint64_t kdesc(uint32_t smem_addr) {
   return ((uint64_t)kDescHiK << 32) | ((smem_addr >> 4) | (1u << 16));
@@ -87,6 +87,13 @@ __device__ __forceinline__ float pow2_scale(float bound) {
   return __uint_as_float((uint32_t)(k + 127) << 23);
 }
 
+// TMA prefetch of a box into L2 (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 struct ConvGeom {
   int B, H, W, Cin_p, Cout_p, Cout;      // padded channel counts (multiples of 64) and the real Cout
   int nb, th, tw;                        // tile = nb images x th rows x tw columns = 128 pixels
@@ -96,7 +103,16 @@ struct ConvGeom {
   float eps;
 };
 
-template <int kStages, bool kResW>
+// kHalo (with resident weights, tiles of th = 8 rows x tw = 16 columns of one image): instead of one TMA box per tap
+// (9 boxes of 128 pixels per tile and channel chunk, i.e. every activation is fetched from L2 nine times -- the
+// kernel was bound by L2 -> SM bandwidth, not by the tensor pipe) a stage holds, for one kx, the box of (th + 2) x tw
+// pixels starting one row above the tile.  The three taps (ky, kx) of that stage read it through descriptors whose
+// start address is advanced by ky * tw rows = ky * 1024 B, a whole number of 128-byte-swizzle atoms, so the swizzle
+// phase of the operand rows is unchanged.  L2 traffic per tile drops from 9 x 32 KB to 3 x 36 KB.
+constexpr int kHaloTw = 16, kHaloTh = 8;
+constexpr int kHaloBytes = (kHaloTh + 2) * kHaloTw * 128;      // 18 KB: one plane of one kx box
+
+template <int kStages, bool kResW, bool kHalo>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                   const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, ConvGeom g,
@@ -108,7 +124,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
   const int wbytes = g.Cout_p * 128;                 // one [Cout_p x 64] weight box
   // kResW (Cin_p = Cout_p = 64): all 9 taps of the hi/lo weights (144 KB) stay resident in shared memory and the
   // ring only carries the activation boxes; otherwise the weight boxes travel with the activations.
-  const int stage_bytes = kResW ? 2 * kABytes : 2 * kABytes + 2 * wbytes;
+  const int stage_bytes = kHalo ? 2 * kHaloBytes : (kResW ? 2 * kABytes : 2 * kABytes + 2 * wbytes);
   uint8_t* sW = smem + kStages * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (kResW ? 18 * wbytes : 0));
   uint64_t* full = bars;                // [kStages]
@@ -132,7 +148,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
   }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 256); }
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
@@ -158,6 +174,26 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
         const int txi = tile % g.tiles_x, tyi = (tile / g.tiles_x) % g.tiles_y, tbi = tile / (g.tiles_x * g.tiles_y);
         const int x0 = txi * g.tw, y0 = tyi * g.th, n0 = tbi * g.nb;
+        if (kHalo) {
+          {   // pull the next tile's rows into L2 while this tile is computed: with two stages of 36 KB the ring cannot
+              // hide an HBM round trip, an L2 hit it can (the kx = 1 box covers all but two pixel columns of the three)
+            const int nt = tile + gridDim.x;
+            if (nt < g.num_tiles) {
+              const int ntx = nt % g.tiles_x, nty = (nt / g.tiles_x) % g.tiles_y, ntb = nt / (g.tiles_x * g.tiles_y);
+              tma_prefetch_l2_4d(&tmXh, 0, ntx * g.tw, nty * g.th - 1, ntb * g.nb);
+              tma_prefetch_l2_4d(&tmXl, 0, ntx * g.tw, nty * g.th - 1, ntb * g.nb);
+            }
+          }
+          for (int kx = 0; kx < 3; ++kx) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], stage_bytes);
+            uint8_t* dst = smem + stage * stage_bytes;
+            tma_load_4d(dst, &tmXh, &full[stage], 0, x0 + kx - 1, y0 - 1, n0);
+            tma_load_4d(dst + kHaloBytes, &tmXl, &full[stage], 0, x0 + kx - 1, y0 - 1, n0);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         for (int it = 0; it < kiters; ++it) {
           const int tap = it / kchunks, kc = it % kchunks;
           const int ky = tap / 3, kx = tap % 3;
@@ -185,6 +221,29 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
         mbar_wait(&acc_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * acc_cols;
+        if (kHalo) {
+          for (int kx = 0; kx < 3; ++kx) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t box_hi = smem_u32(smem + stage * stage_bytes), box_lo = box_hi + kHaloBytes;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const uint32_t a_hi = box_hi + ky * (kHaloTw * 128), a_lo = box_lo + ky * (kHaloTw * 128);
+              const uint32_t w_hi = smem_u32(sW + 2 * (ky * 3 + kx) * wbytes);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t dwh = kdesc(w_hi + 32 * kk);
+                umma_ss_f16(tacc, kdesc(a_hi + 32 * kk), dwh, idesc2, (kx | ky | kk) ? 1u : 0u);   // [x_hi*w_hi | x_hi*w_lo]
+                umma_ss_f16(tacc, kdesc(a_lo + 32 * kk), dwh, idesc, 1u);                         // + x_lo*w_hi
+              }
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&acc_full[as]);
+          if (++as == acc_stages) { as = 0; aphase ^= 1; }
+          continue;
+        }
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -212,6 +271,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;                     // the two warps of a lane quarter split the channel chunks
     const int pix = 32 * q + lane;                        // pixel of the tile = TMEM lane
     const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
     int as = 0; uint32_t aphase = 0;
@@ -229,7 +289,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
       tc_fence_after();
       const int64_t pbase = (((int64_t)n * g.H + y) * g.W + x) * g.Cout_p;
 #pragma unroll 1
-      for (int cc = 0; cc < g.Cout_p / 32; ++cc) {
+      for (int cc = half; cc < g.Cout_p / 32; cc += 2) {
         uint32_t v[32];
         float a[32];
         tmem_ld32(lane_base + as * acc_cols + 32 * cc, v);
@@ -615,17 +675,19 @@ int conv_tc_run(const void* x_hi, const void* x_lo, const void* w_hi, const void
   if (!conv_tc_supported(B, Cin_p, Cout_p, H, W) || B > 2147483647LL / ((int64_t)H * W)) return DRSA_ERR_SHAPE;
   g.B = (int)B; g.H = H; g.W = W; g.Cin_p = Cin_p; g.Cout_p = Cout_p; g.Cout = Cout; g.relu = relu; g.epi = epi; g.eps = eps;
   pick_tile(g.B, H, W, &g.nb, &g.th, &g.tw);
+  const bool halo = Cout_p == 64 && Cin_p == 64 && W % kHaloTw == 0 && H % kHaloTh == 0;
+  if (halo) { g.nb = 1; g.th = kHaloTh; g.tw = kHaloTw; }
   g.tiles_x = W / g.tw; g.tiles_y = H / g.th; g.tiles_b = (g.B + g.nb - 1) / g.nb;
   g.num_tiles = g.tiles_x * g.tiles_y * g.tiles_b;
   CUtensorMap tmXh, tmXl, tmWh, tmWl;
-  DRSA_TRY(make_tmap_nhwc(&tmXh, x_hi, (uint64_t)B, H, W, Cin_p, g.nb, g.th, g.tw));
-  DRSA_TRY(make_tmap_nhwc(&tmXl, x_lo, (uint64_t)B, H, W, Cin_p, g.nb, g.th, g.tw));
+  DRSA_TRY(make_tmap_nhwc(&tmXh, x_hi, (uint64_t)B, H, W, Cin_p, g.nb, halo ? g.th + 2 : g.th, g.tw));
+  DRSA_TRY(make_tmap_nhwc(&tmXl, x_lo, (uint64_t)B, H, W, Cin_p, g.nb, halo ? g.th + 2 : g.th, g.tw));
   DRSA_TRY(make_tmap_f16_sw128(&tmWh, w_hi, (uint64_t)9 * Cout_p, (uint64_t)Cin_p, (uint32_t)Cout_p));
   DRSA_TRY(make_tmap_f16_sw128(&tmWl, w_lo, (uint64_t)9 * Cout_p, (uint64_t)Cin_p, (uint32_t)Cout_p));
   int grid = sm_count();
   if (grid > g.num_tiles) grid = g.num_tiles;
   auto launch = [&](auto kernel, int stages, bool resw) -> int {
-    const int stage_bytes = resw ? 2 * kABytes : 2 * kABytes + 2 * Cout_p * 128;
+    const int stage_bytes = halo ? 2 * kHaloBytes : (resw ? 2 * kABytes : 2 * kABytes + 2 * Cout_p * 128);
     const int smem_bytes = stages * stage_bytes + (resw ? 18 * Cout_p * 128 : 0) + 256;
     DRSA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmXh, tmXl, tmWh, tmWl, g, bias, aux_f32,
@@ -635,10 +697,11 @@ int conv_tc_run(const void* x_hi, const void* x_lo, const void* w_hi, const void
     DRSA_LAUNCH_CHECK();
     return DRSA_OK;
   };
-  if (Cout_p == 64 && Cin_p == 64) return launch(conv3x3_tc_kernel<2, true>, 2, true);
-  if (Cout_p <= 64) return launch(conv3x3_tc_kernel<4, false>, 4, false);
-  if (Cout_p <= 128) return launch(conv3x3_tc_kernel<3, false>, 3, false);
-  return launch(conv3x3_tc_kernel<2, false>, 2, false);
+  if (halo) return launch(conv3x3_tc_kernel<2, true, true>, 2, true);
+  if (Cout_p == 64 && Cin_p == 64) return launch(conv3x3_tc_kernel<2, true, false>, 2, true);
+  if (Cout_p <= 64) return launch(conv3x3_tc_kernel<4, false, false>, 4, false);
+  if (Cout_p <= 128) return launch(conv3x3_tc_kernel<3, false, false>, 3, false);
+  return launch(conv3x3_tc_kernel<2, false, false>, 2, false);
 }
 
 int conv_tc_forward(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int64_t B,
