@@ -91,6 +91,7 @@ SIGNATURES = {
     "drsa_selftest_umma": (_i32, [_i32, _vp]),
     "drsa_debug_set_tc_profile": (_i32, [_vp]),
     "drsa_debug_tc_kernel_attrs": (_i32, [_i32, _i32, _vp]),
+    "drsa_debug_set_tc_variant": (_i32, [_i32]),
 }
 
 _lock = threading.Lock()

@@ -94,6 +94,7 @@ int split_u(const float* U, int d, int m, void* Ut_hi, void* Ut_lo, cudaStream_t
 int selftest_umma(int variant, float* max_err_host);
 void set_tc_profile(long long* p);
 int tc_kernel_attrs(int d, int split, int* out5);
+void set_tc_variant(int v);
 int64_t subspace_relevances_workspace_bytes(int64_t B, int64_t P, int d, int m);
 int subspace_relevances(const float* act, const float* ctx, const float* U, int64_t B, int64_t P, int d, int m, int K,
                         float* out, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
@@ -457,6 +458,8 @@ int lrp_tc_split_f16(const float* in, int64_t count, void* hi, void* lo, void* s
   DRSA_TRY(require_sm100());
   return split_f16(in, count, hi, lo, static_cast<cudaStream_t>(stream));
 }
+
+int drsa_debug_set_tc_variant(int variant) { set_tc_variant(variant); return DRSA_OK; }
 
 int drsa_debug_tc_kernel_attrs(int d, int split, int* out5) {
   if (out5 == nullptr || (d != 128 && d != 256 && d != 512)) return DRSA_ERR_ARG;

@@ -368,6 +368,268 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Single-pass variant for d <= 256 (DRSA_PREC_TC_F16): U^T lives in TENSOR MEMORY.
+//
+// What bounds the kernel above is shared-memory operand bandwidth, not the tensor pipe: an SS-mode MMA reads both
+// operands from shared memory (GEMM1 at M = N = 128: 8 KB per 64-cycle MMA = the full 128 B/clk, ~80 B/clk are
+// sustained next to the TMA writes), and every row is staged twice (GEMM1 and GEMM2 views).  Here
+//   * U^T (fp16, 128 x D) is written once into 128 x D/2 TMEM columns and GEMM1 runs in TS mode (A from TMEM): per
+//     MMA only the 2 KB row operand comes from shared memory;
+//   * subtiles have 32 rows, so two H buffers need 2 x 64 columns: X^T 256 + U^T 128 + H 128 = 512 columns;
+//   * a stage holds, per 64-channel panel, [A rows | C rows] of the subtile (K-major operand of GEMM1 with N = 64)
+//     and GEMM2 reads THE SAME bytes as its MN-major operand (N-block stride 8 KB): every row is staged once.
+// Per 32-row subtile: GEMM1 16 MMAs (M128 N64 K16), GEMM2 4 MMAs (M128 N256 K16, 128 cycles) for 64 KB of operand reads
+// and 32 KB of TMA writes.  Schedule, barriers and epilogue arithmetic as above.  EXPERIMENTAL: see g_tc_variant below
+// for the measured outcome (the N = 64 MMAs do not run at 32 cycles).
+constexpr int kSub32 = 32;
+__device__ __forceinline__ uint32_t mndesc8k_lo(uint32_t smem_addr) { return (smem_addr >> 4) | ((8192u >> 4) << 16); }   // LBO 8 KB
+
+template <int D>
+struct Cfg32 {
+  static constexpr int kPanels = D / 64;
+  static constexpr int kStageBytes = kPanels * 8192;              // per panel: A rows (4 KB) | C rows (4 KB)
+  static constexpr int kStages = (D >= 256) ? 6 : 8;
+  static constexpr int kRedBytes = 2 * 4 * kSub32 * 4;
+  static constexpr int kDataBytes = kStages * kStageBytes;
+  static constexpr int kSmemBytes = kDataBytes + kRedBytes + kBarBytes;
+  static constexpr int kUCols = D / 2;                            // TMEM columns of U^T (fp16 pairs)
+  static constexpr uint32_t tX = 0, tU = D, tH = D + D / 2;       // column offsets: X^T [0,D) | U^T | H0 (64) | H1 (64)
+};
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 1)
+drsa_tc_step32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC,
+                      const __half* __restrict__ Ut_hi, int n_sub, int G, int nRB, int d_k, float inv_scale, float pq_scale,
+                      float* __restrict__ part, float* __restrict__ ss_part, int* __restrict__ err_flag,
+                      long long* __restrict__ prof) {
+  using C = Cfg32<D>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sStage = smem;
+  float* red = reinterpret_cast<float*>(smem + C::kDataBytes);      // [2 buffers][4 lane quarters][32 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kDataBytes + C::kRedBytes);
+  uint64_t* full = bars;            // [kStages]
+  uint64_t* empty = bars + 8;       // [kStages]
+  uint64_t* u_full = bars + 16;
+  uint64_t* x_full = bars + 17;
+  uint64_t* h_full = bars + 18;     // [2]
+  uint64_t* p_full = bars + 20;     // [2 buffers][2 half-chunks of 16 rows]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x % G, rb = blockIdx.x / G;
+
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) atomicExch(err_flag, 1);
+    return;
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(u_full, 512); mbar_init(x_full, 1); mbar_init(&h_full[0], 1); mbar_init(&h_full[1], 1);
+    for (int c = 0; c < 4; ++c) mbar_init(&p_full[c], 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ======================= TMA producer: one stage per subtile =======================
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmC);
+      int stage = 0; uint32_t phase = 0;
+      for (int sub = rb; sub < n_sub; sub += nRB) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], C::kStageBytes);
+        uint8_t* dst = sStage + stage * C::kStageBytes;
+#pragma unroll
+        for (int p = 0; p < C::kPanels; ++p) {
+          tma_load_2d(dst + p * 8192, &tmA, &full[stage], 64 * p, sub * kSub32);
+          tma_load_2d(dst + p * 8192 + 4096, &tmC, &full[stage], 64 * p, sub * kSub32);
+        }
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_idesc_f16(kNG, 2 * kSub32, 0, 0);   // U^T (TMEM) x stacked [A;C] subtile (K-major, N = 64)
+      constexpr uint32_t idesc2 = make_idesc_f16(kNG, D, 0, 1);            // P^T (TMEM) x the same rows (MN-major, N = D)
+      const uint32_t tX = tmem_base + C::tX, tU = tmem_base + C::tU;
+      mbar_wait(u_full, 0);                                                // U^T has been written to tensor memory
+      tc_fence_after();
+      bool first = true;
+      long long pa = 0, pb = 0, pc = 0;
+      auto gemm1 = [&](int i) {
+        const long long t0 = prof ? clock64() : 0;
+        const int stage = i % C::kStages;
+        const uint32_t tH = tmem_base + C::tH + 64 * (i & 1);
+        mbar_wait(&full[stage], (uint32_t)(i / C::kStages) & 1u);
+        tc_fence_after();
+        const uint32_t base = smem_u32(sStage + stage * C::kStageBytes);
+#pragma unroll
+        for (int p = 0; p < C::kPanels; ++p) {
+          const uint32_t dAC = kdesc_lo(base + p * 8192);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_ts_f16(tH, tU + 8 * (4 * p + kk), desc64(dAC + 2 * kk), idesc1, (p | kk) ? 1u : 0u);
+        }
+        umma_commit(&h_full[i & 1]);
+        if (prof) pa += clock64() - t0;
+      };
+      auto gemm2 = [&](int i) {
+        const long long t0 = prof ? clock64() : 0;
+        long long t1 = t0;
+        const int stage = i % C::kStages;
+        const uint32_t tH = tmem_base + C::tH + 64 * (i & 1);
+        const uint32_t par = (uint32_t)(i >> 1) & 1u;
+        const uint32_t base = smem_u32(sStage + stage * C::kStageBytes);
+        const uint32_t dA = mndesc8k_lo(base), dC = mndesc8k_lo(base + 4096);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&p_full[2 * (i & 1) + h], par);       // P^T / Q^T of rows 16h .. 16h+15
+          if (prof && h == 0) t1 = clock64();
+          tc_fence_after();
+          umma_ts_f16(tX, tH + 16 * h, desc64(dA + 128 * h), idesc2, first ? 0u : 1u);
+          umma_ts_f16(tX, tH + kSub32 + 16 * h, desc64(dC + 128 * h), idesc2, 1u);
+          first = false;
+        }
+        umma_commit(&empty[stage]);                       // the stage served GEMM1 and GEMM2 of this subtile
+        if (prof) { pb += t1 - t0; pc += clock64() - t1; }
+      };
+      int i = 0;
+      for (int sub = rb; sub < n_sub; sub += nRB, ++i) {
+        gemm1(i);
+        if (i > 0) gemm2(i - 1);
+      }
+      if (i > 0) gemm2(i - 1);
+      umma_commit(x_full);
+      if (prof && blockIdx.x == 0) { prof[0] = pa; prof[1] = pb; prof[2] = pc; }
+    }
+  } else {
+    // ======================= epilogue warps =======================
+    const int q = warp & 3;                     // TMEM lane quarter this warp may touch
+    const int e = warp - 2;                     // 0 .. 15
+    const int set = e >> 3;                     // even / odd subtiles
+    const int ch = (e >> 2) & 1;                // rows 16*ch .. 16*ch+15 of those subtiles
+    const int j = 32 * q + lane;                // projected column within the group
+    const int wpc = d_k >> 5;
+    const int q0 = (q / wpc) * wpc;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
+    const bool owner = (j % d_k) == 0;
+    // ---- U^T of this column group -> tensor memory: lane j holds U^T[g*128 + j][0 .. D) as fp16 pairs; the four
+    //      warps of a lane quarter write D/8 columns each
+    {
+      const int part_cols = C::kUCols / 4;                                // 32 (D = 256) or 16 (D = 128)
+      const int c0 = (e >> 2) * part_cols;
+      const uint4* src = reinterpret_cast<const uint4*>(Ut_hi + ((int64_t)g * kNG + j) * D + 2 * c0);
+#pragma unroll
+      for (int b = 0; b < part_cols / 16; ++b) {
+        uint32_t v[16];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint4 w = __ldg(src + 4 * b + t);
+          v[4 * t] = w.x; v[4 * t + 1] = w.y; v[4 * t + 2] = w.z; v[4 * t + 3] = w.w;
+        }
+        tmem_st16(lane_base + C::tU + c0 + 16 * b, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(u_full);
+    }
+    float ssq = 0.f;
+    long long ea = 0, eb = 0, e0 = 0, e1 = 0;
+    // column of the 16-wide chunk whose sum this lane holds after the transpose-reduce (bit 0 of the lane is a duplicate)
+    const int mycol = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    for (int i = set, sub = rb + set * nRB; sub < n_sub; sub += 2 * nRB, i += 2) {
+      const int buf = set;
+      if (prof) e0 = clock64();
+      mbar_wait(&h_full[buf], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      if (prof) e1 = clock64();
+      const uint32_t tHA = lane_base + C::tH + 64 * buf + 16 * ch, tHC = tHA + kSub32;
+      float* redb = red + buf * (4 * kSub32);
+      uint32_t ha[16], hc[16];
+      tmem_ld16(tHA, ha);
+      tmem_ld16(tHC, hc);
+      tmem_ld_wait();
+      float pr[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) pr[t] = __uint_as_float(ha[t]) * __uint_as_float(hc[t]);
+      // transpose-reduce over the 32 lanes: 8 + 4 + 2 + 1 exchanges, then one add between the duplicate lanes
+#pragma unroll
+      for (int off = 16, n = 8; n >= 1; off >>= 1, n >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int t = 0; t < n; ++t) {
+          const float send = upper ? pr[t] : pr[t + n];
+          const float keep = upper ? pr[t + n] : pr[t];
+          pr[t] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      pr[0] += __shfl_xor_sync(0xffffffffu, pr[0], 1);
+      if ((lane & 1) == 0) redb[q * kSub32 + 16 * ch + mycol] = pr[0];
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + 2 * set + ch) : "memory");   // the 4 warps working on these 16 rows
+      uint32_t pk[8], qk[8];
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4) {
+        float4 s4 = *reinterpret_cast<const float4*>(&redb[q0 * kSub32 + 16 * ch + 4 * i4]);
+#pragma unroll
+        for (int w = 1; w < 4; ++w) {
+          if (w < wpc) {
+            const float4 o = *reinterpret_cast<const float4*>(&redb[(q0 + w) * kSub32 + 16 * ch + 4 * i4]);
+            s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w;
+          }
+        }
+        float g0 = fmaxf(s4.x, 0.f), g1 = fmaxf(s4.y, 0.f), g2 = fmaxf(s4.z, 0.f), g3 = fmaxf(s4.w, 0.f);
+        if (owner) {
+          const float t0 = g0 * inv_scale, t1 = g1 * inv_scale, t2 = g2 * inv_scale, t3 = g3 * inv_scale;
+          ssq += t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3;
+        }
+        g0 *= pq_scale; g1 *= pq_scale; g2 *= pq_scale; g3 *= pq_scale;
+        const int t = 4 * i4;
+        pk[2 * i4] = pack_h2_sat(g0 * __uint_as_float(hc[t]), g1 * __uint_as_float(hc[t + 1]));
+        pk[2 * i4 + 1] = pack_h2_sat(g2 * __uint_as_float(hc[t + 2]), g3 * __uint_as_float(hc[t + 3]));
+        qk[2 * i4] = pack_h2_sat(g0 * __uint_as_float(ha[t]), g1 * __uint_as_float(ha[t + 1]));
+        qk[2 * i4 + 1] = pack_h2_sat(g2 * __uint_as_float(ha[t + 2]), g3 * __uint_as_float(ha[t + 3]));
+      }
+      // packed fp16 pairs of rows 16*ch .. 16*ch+15 go to the first 8 of this half-chunk's OWN 16 columns (the other
+      // half-chunk's warps may still be reading theirs)
+      tmem_st8(tHA, pk);
+      tmem_st8(tHC, qk);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[2 * buf + ch]);
+      if (prof) { ea += e1 - e0; eb += clock64() - e1; }
+    }
+    if (prof && blockIdx.x == 0 && warp == 2 && lane == 0) { prof[3] = ea; prof[4] = eb; }
+    // ---- final: X^T of this CTA -> partial buffer [rb][g][j][D]
+    mbar_wait(x_full, 0);
+    tc_fence_after();
+    float* dst = part + (((int64_t)rb * G + g) * kNG + j) * D;
+#pragma unroll 1
+    for (int cc = e >> 2; cc < D / 32; cc += 4) {
+      uint32_t v[32];
+      tmem_ld32(lane_base + C::tX + 32 * cc, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        *reinterpret_cast<float4*>(dst + 32 * cc + 4 * t) =
+            make_float4(__uint_as_float(v[4 * t]), __uint_as_float(v[4 * t + 1]), __uint_as_float(v[4 * t + 2]),
+                        __uint_as_float(v[4 * t + 3]));
+    }
+    if (owner) ss_part[((int64_t)rb * (G * (kNG / d_k)) + g * (kNG / d_k) + j / d_k) * 4 + 2 * set + ch] = ssq;
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // sums[i*m + col] = x_scale * sum_rb part[(rb*G + col/128)*128 + col%128][i] ; sums[d*m + k] = sum_rb ss_part.
 // One thread per output element (32 x 32 tile per CTA), the row-block loop unrolled so that many independent
 // L2 reads are in flight; fixed summation order (deterministic).
@@ -451,10 +713,10 @@ __global__ void __launch_bounds__(256) rownorm_max_kernel(const float* __restric
 long long* g_tc_prof = nullptr;   // debug: per-phase cycle counters of CTA 0 (drsa_debug_set_tc_profile)
 
 struct TcPlan { int G, nRB, num_tiles; int64_t part_bytes, ss_bytes; };
-TcPlan plan_for(int64_t M, int d, int m, int K) {
+TcPlan plan_for(int64_t M, int d, int m, int K, int sub_rows = kSub) {
   TcPlan p;
   p.G = m / kNG;
-  p.num_tiles = (int)((M + kSub - 1) / kSub);      // 64-row subtiles
+  p.num_tiles = (int)((M + sub_rows - 1) / sub_rows);      // 64-row (or 32-row) subtiles
   int nrb = sm_count() / (p.G * (d > 256 ? d / 256 : 1));
   if (nrb < 1) nrb = 1;
   if (nrb > p.num_tiles) nrb = p.num_tiles;
@@ -472,8 +734,31 @@ bool tc_shape_supported(int d, int m, int K) {
 }
 
 int64_t step_tc_workspace_bytes(int64_t M, int d, int m, int K) {
-  TcPlan p = plan_for(M, d, m, K);
+  TcPlan p = plan_for(M, d, m, K, kSub32);       // the 32-row variant never has fewer row blocks: upper bound for both
   return p.part_bytes + p.ss_bytes + 256;
+}
+
+// 0 (default): the shared-memory-operand kernel above; 1: U^T in tensor memory for d <= 256 in the single-pass mode.
+// Measured at cfg 2: variant 1 is correct but slower (0.368 vs 0.333 ms): its GEMM1 MMAs have N = 64 and take ~76
+// cycles each instead of the 32 the M*N/256 rule promises -- tcgen05.mma has a floor of roughly 64 cycles per
+// instruction at M = 128, so only N = 256 shapes run at the full rate (GEMM1 at N = 256 in the first version of this
+// kernel, GEMM2 everywhere).  Kept selectable for A/B runs (drsa_debug_set_tc_variant).
+int g_tc_variant = 0;
+void set_tc_variant(int v) { g_tc_variant = v; }
+
+template <int D>
+int launch_step32(int grid, cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmC, const void* Ut_hi, int n_sub,
+                  int G, int nRB, int d_k, float inv_scale, float pq_scale, float* part, float* ss_part, int* err) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    DRSA_CUDA(cudaFuncSetAttribute(drsa_tc_step32_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg32<D>::kSmemBytes));
+    attr_set = true;
+  }
+  drsa_tc_step32_kernel<D><<<grid, kThreads, Cfg32<D>::kSmemBytes, stream>>>(
+      tmA, tmC, static_cast<const __half*>(Ut_hi), n_sub, G, nRB, d_k, inv_scale, pq_scale, part, ss_part, err, g_tc_prof);
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
 }
 
 template <int D, bool kSplitU, typename... Args>
@@ -497,13 +782,29 @@ int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_
   if (!split_u) Ut_lo = Ut_hi;       // never read; keeps the tensor map valid
   if (!aligned16(A16) || !aligned16(C16) || !aligned16(Ut_hi) || !aligned16(Ut_lo)) return DRSA_ERR_ALIGN;
   if (M >= ((int64_t)1 << 31)) return DRSA_ERR_SHAPE;
-  TcPlan p = plan_for(M, d, m, K);
+  const bool tmem_u = !split_u && d <= 256 && g_tc_variant == 1;
+  TcPlan p = plan_for(M, d, m, K, tmem_u ? kSub32 : kSub);
   if (workspace_bytes < p.part_bytes + p.ss_bytes + 256) return DRSA_ERR_WORKSPACE;
   char* w = static_cast<char*>(workspace);
   float* part = reinterpret_cast<float*>(w); w += p.part_bytes;
   float* ss_part = reinterpret_cast<float*>(w); w += p.ss_bytes;
   int* err = reinterpret_cast<int*>(w);
 
+  if (tmem_u) {
+    CUtensorMap tA, tC;
+    DRSA_TRY(make_tmap_f16_sw128(&tA, A16, (uint64_t)M, (uint64_t)d, kSub32));
+    DRSA_TRY(make_tmap_f16_sw128(&tC, C16, (uint64_t)M, (uint64_t)d, kSub32));
+    const float inv_s = 1.0f / (scaleA * scaleC);
+    const int grid32 = p.nRB * p.G;
+    DRSA_TRY(d == 256 ? launch_step32<256>(grid32, stream, tA, tC, Ut_hi, p.num_tiles, p.G, p.nRB, m / K, inv_s, pq_scale, part,
+                                           ss_part, err)
+                      : launch_step32<128>(grid32, stream, tA, tC, Ut_hi, p.num_tiles, p.G, p.nRB, m / K, inv_s, pq_scale, part,
+                                           ss_part, err));
+    dim3 rg(m / 32, d / 32);
+    tc_reduce_kernel<<<rg, 1024, 0, stream>>>(part, ss_part, p.nRB, p.G, d, m, K, inv_s * inv_s / pq_scale, sums);
+    DRSA_LAUNCH_CHECK();
+    return DRSA_OK;
+  }
   CUtensorMap tmA, tmC, tmA2, tmC2, tmUh, tmUl;
   DRSA_TRY(make_tmap_f16_sw128(&tmA, A16, (uint64_t)M, (uint64_t)d, kSub));
   DRSA_TRY(make_tmap_f16_sw128(&tmC, C16, (uint64_t)M, (uint64_t)d, kSub));

@@ -319,6 +319,9 @@ int drsa_debug_set_tc_profile(void* device_buf6);
 /* Diagnostics: registers per thread, max threads per block, static shared bytes, local bytes and the configured
  * dynamic shared-memory limit of the tensor-core row-pass kernel for d in {128, 256} (host ints). */
 int drsa_debug_tc_kernel_attrs(int d, int split_u, int* out5);
+/* Diagnostics: 0 (default) = the shared-memory-operand row-pass kernel, 1 = DRSA_PREC_TC_F16 with d <= 256 runs the
+ * experimental kernel that keeps U^T in tensor memory (correct, measured slower; for A/B comparisons). */
+int drsa_debug_set_tc_variant(int variant);
 
 #ifdef __cplusplus
 }

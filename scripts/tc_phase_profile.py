@@ -16,8 +16,8 @@ L.lib().drsa_debug_set_tc_profile(buf.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); opt._rows.step(opt.U); e1.record(); torch.cuda.synchronize()
 L.lib().drsa_debug_set_tc_profile(None)
-tiles = -(-M // 64); nrb = 148 // 2; per = -(-tiles // nrb)      # 64-row subtiles
+sub = 32 if (len(sys.argv) <= 1 or sys.argv[1] == "tc") else 64; tiles = -(-M // sub); nrb = 148 // 2; per = -(-tiles // nrb)
 v = buf.cpu().tolist()
-print(f"row pass {e0.elapsed_time(e1):.3f} ms, 64-row subtiles per CTA ~{per}")
+print(f"row pass {e0.elapsed_time(e1):.3f} ms, {sub}-row subtiles per CTA ~{per}")
 for name, x in zip(["mma: GEMM1 issue", "mma: GEMM2 wait for first P chunk", "mma: GEMM2 issue", "epi: wait GEMM1", "epi: work"], v):
     print(f"  {name:42s} {x:10d} cycles total, {x/per:9.0f} per subtile")

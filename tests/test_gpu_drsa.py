@@ -114,6 +114,23 @@ def test_row_sums_tensor_core_match_oracle(L, M, d, m, K, prec):
                                atol=(1e-2 if M < 64 else 0.0) * float(ssr.max()))
 
 
+@pytest.mark.parametrize("M,d,m,K", [(31, 128, 128, 4), (5000, 128, 128, 2), (20011, 256, 256, 8), (3000, 256, 128, 2)])
+def test_row_sums_tmem_resident_u_variant(L, M, d, m, K):
+    """The experimental row-pass variant with U^T in tensor memory (drsa_debug_set_tc_variant(1)) computes the same sums."""
+    A, C = drsa_ref.synth_pairs(M, d, 300 + d + K)
+    U = drsa_ref.synth_U0(d, m, 9)
+    L.lib().drsa_debug_set_tc_variant(1)
+    try:
+        X, ss = _sums_gpu(L, A, C, U, K, "tc")
+    finally:
+        L.lib().drsa_debug_set_tc_variant(0)
+    X0, ss0 = _sums_gpu(L, A, C, U, K, "tc")
+    Xq, ssq = drsa_ref.step_sums(A.half().double(), C.half().double(), U.half().double(), K)
+    assert float(torch.linalg.norm(X - Xq) / torch.linalg.norm(Xq)) < (4e-4 if M < 4096 else 1.5e-4)
+    np.testing.assert_allclose(ss.numpy(), ssq.numpy(), rtol=2e-5, atol=(1e-3 if M < 64 else 0.0) * float(ssq.max()))
+    assert float(torch.linalg.norm(X - X0) / torch.linalg.norm(X0)) < 3e-4
+
+
 def test_tensor_core_scale_invariance(L):
     """power-of-two pre-scaling of the fp16 rows is undone exactly: unnormalised inputs 1000x larger
     give row sums 1e6x / 1e12x larger."""
