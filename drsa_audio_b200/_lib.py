@@ -88,6 +88,9 @@ SIGNATURES = {
     "lrp_tc_nchw_to_nhwc_f32": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "lrp_tc_nhwc_to_nchw": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "lrp_tc_split_f16": (_i32, [_vp, _i64, _vp, _vp, _vp]),
+    "logmel_transform_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),
+    "logmel_transform_wav": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _i64,
+                                    _vp]),
     "drsa_selftest_umma": (_i32, [_i32, _vp]),
     "drsa_debug_set_tc_profile": (_i32, [_vp]),
     "drsa_debug_tc_kernel_attrs": (_i32, [_i32, _i32, _vp]),

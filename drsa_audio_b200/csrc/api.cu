@@ -71,6 +71,10 @@ int subspace_filter_backward(const float* a, const float* h, const float* a2, co
                              int m, int K, int ld, float eps_inv, float eps_proj, float* out, void* workspace,
                              int64_t workspace_bytes, cudaStream_t s);
 int planes_to_f32(const void* hi, const void* lo, int64_t count, float* out, cudaStream_t s);
+int64_t logmel_workspace_bytes(int64_t B, int n_fft, int n_mels, int width);
+int logmel_transform(const float* wav, const float* window, const float* basis, const float* fb, int64_t B, int64_t n_samples,
+                     int n_fft, int hop, int n_mels, int first_frame, int width, int do_clamp, float clamp_min, float* out,
+                     void* workspace, int64_t workspace_bytes, cudaStream_t s);
 int sample_absmax_ratio(const float* R, const float* x, int64_t B, int64_t per, float* out, cudaStream_t stream);
 int maxpool_nhwc(const void* x_hi, const void* x_lo, int64_t B, int H, int W, int Cp, int kh, int kw, void* y_hi,
                  void* y_lo, void* argmax_u8, cudaStream_t stream);
@@ -457,6 +461,23 @@ int lrp_tc_split_f16(const float* in, int64_t count, void* hi, void* lo, void* s
   if (in == nullptr || hi == nullptr || lo == nullptr || count <= 0) return DRSA_ERR_ARG;
   DRSA_TRY(require_sm100());
   return split_f16(in, count, hi, lo, static_cast<cudaStream_t>(stream));
+}
+
+int64_t logmel_transform_workspace_bytes(int64_t B, int n_fft, int n_mels, int width) {
+  if (B <= 0 || n_fft < 2 || n_mels <= 0 || width <= 0) return DRSA_ERR_ARG;
+  return logmel_workspace_bytes(B, n_fft, n_mels, width);
+}
+
+int logmel_transform_wav(const float* wav, const float* window, const float* dft_basis, const float* mel_fb, int64_t B,
+                         int64_t n_samples, int n_fft, int hop_length, int n_mels, int first_frame, int width, int clamp,
+                         float clamp_min, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (wav == nullptr || window == nullptr || dft_basis == nullptr || mel_fb == nullptr || out == nullptr ||
+      workspace == nullptr || B <= 0 || n_samples <= 0 || n_fft < 2 || hop_length <= 0 || n_mels <= 0 || first_frame < 0 ||
+      width <= 0)
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return logmel_transform(wav, window, dft_basis, mel_fb, B, n_samples, n_fft, hop_length, n_mels, first_frame, width, clamp,
+                          clamp_min, out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int drsa_debug_set_tc_variant(int variant) { set_tc_variant(variant); return DRSA_OK; }

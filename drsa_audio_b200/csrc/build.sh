@@ -4,7 +4,7 @@ set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 OUT="$HERE/../libdrsa_b200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-SRCS=(api.cu sgemm.cu drsa_fp32.cu drsa_tc.cu retract.cu retract_fused.cu misc.cu lrp.cu conv_tc.cu subspace_filter.cu)
+SRCS=(api.cu sgemm.cu drsa_fp32.cu drsa_tc.cu retract.cu retract_fused.cu misc.cu lrp.cu conv_tc.cu subspace_filter.cu logmel.cu)
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
        --expt-relaxed-constexpr -Xptxas -v)
 OBJS=()

@@ -304,6 +304,20 @@ int lrp_subspace_filter(const float* a, const float* h, const float* a_rec, cons
 /* hi = fp16(in), lo = fp16(in - hi) over `count` floats. */
 int lrp_tc_split_f16(const float* in, int64_t count, void* hi, void* lo, void* stream);
 
+/* ---- log-mel frontend (Loader.transform_wav, cxai/utils/dataloading.py:138-176) -------------------------------
+ * wav [B, n_samples] fp32 (peak-normalised by the caller) -> out [B, 1, n_mels, width] fp32:
+ *   torchaudio Spectrogram(n_fft, hop_length, power=None) (periodic hann window of n_fft, centred frames, reflect
+ *   padding) -> |.| -> MelScale -> log10(. + 1e-7) -> clamp(min = clamp_min) if `clamp` -> frames first_frame ..
+ *   first_frame + width - 1 (the reference keeps frames 1 .. width).
+ *   window [n_fft]; dft_basis [n_fft, 2F] row-major with F = n_fft/2 + 1, column f = cos(2 pi f n / n_fft), column
+ *   F + f = -sin(...); mel_fb [F, n_mels] (torchaudio.functional.melscale_fbanks).  All three are built once by the
+ *   host (cxai.utils.dataloading.Loader). */
+int64_t logmel_transform_workspace_bytes(int64_t B, int n_fft, int n_mels, int width);
+int logmel_transform_wav(const float* wav, const float* window, const float* dft_basis, const float* mel_fb, int64_t B,
+                         int64_t n_samples, int n_fft, int hop_length, int n_mels, int first_frame, int width,
+                         int clamp, float clamp_min, float* out, void* workspace, int64_t workspace_bytes,
+                         void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Self tests of the tcgen05 / TMA building blocks (used by tests/ on the GPU box).
  * Each returns DRSA_OK and writes max |error| against a CUDA-core computation of the

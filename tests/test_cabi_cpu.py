@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared():
     src = open(os.path.join(ROOT, "include", "drsa_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:drsa|lrp)_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b((?:drsa|lrp|logmel)_[a-z0-9_]+)\s*\(", src)))
 
 
 @pytest.fixture(scope="module")
