@@ -402,65 +402,65 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
 }
 
 // First layer (Cin = 1): bandwidth-bound, CUDA cores.  x [B,1,H,W] fp32 -> y NHWC hi/lo [B,H,W,Cout_p].
-// One thread per (pixel, 8 output channels), the channel group being the fast index: the Cout_p/8 threads of a pixel
-// write its whole channel row (16 B each, 128 B at Cout_p = 64), so a warp stores 512 contiguous bytes per plane.  The
-// 9 taps sit in registers (the threads of a pixel read the same addresses: broadcast), weights [tap][channel] in
-// shared memory.
+// A thread owns one group of 8 output channels for the whole launch (its 72 weights and 8 biases live in registers)
+// and walks over pixels; the Cout_p/8 threads of a pixel are adjacent, so a warp stores 512 contiguous bytes per
+// plane (Cout_p = 64).  A CTA takes one image row at a time: all index arithmetic inside the loops is 32-bit and
+// division-free (the first version of this kernel spent most of its instructions on 64-bit div/mod).
 __global__ void __launch_bounds__(256) conv3x3_first_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                  const float* __restrict__ b, int64_t B, int H, int W,
                                                                  int Cout, int Cout_p, int relu, __half* __restrict__ y_hi,
                                                                  __half* __restrict__ y_lo) {
-  extern __shared__ __align__(16) float sw[];      // [9][Cout_p] weights, then [Cout_p] bias
-  float* sb = sw + 9 * Cout_p;
-  for (int i = threadIdx.x; i < 9 * Cout_p; i += blockDim.x) {
-    const int t = i / Cout_p, c = i % Cout_p;
-    sw[i] = c < Cout ? __ldg(w + c * 9 + t) : 0.f;
-  }
-  for (int i = threadIdx.x; i < Cout_p; i += blockDim.x) sb[i] = i < Cout ? __ldg(b + i) : 0.f;
-  __syncthreads();
-  const int groups = Cout_p / 8;
-  const int64_t total = B * H * W * groups;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int gq = (int)(i % groups);
-    const int64_t p = i / groups;
-    const int xx = (int)(p % W), yy = (int)((p / W) % H);
-    const int64_t n = p / ((int64_t)W * H);
-    float v[9];
+  const int groups = Cout_p / 8;                       // host guarantees groups <= 256 and 256 % groups == 0
+  const int gq = threadIdx.x % groups, px = threadIdx.x / groups, ppi = 256 / groups;   // pixels per iteration
+  float wr[9][8], br[8];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+  for (int c = 0; c < 8; ++c) {
+    const int ch = gq * 8 + c;
+    br[c] = ch < Cout ? __ldg(b + ch) : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[t][c] = ch < Cout ? __ldg(w + ch * 9 + t) : 0.f;
+  }
+  const int64_t rows = B * H;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int yy = (int)(row % H);
+    const float* xr = x + row * W;                     // row yy of image n; rows above / below are +-W away
+    const bool up = yy > 0, down = yy + 1 < H;
+    __half* oh = y_hi + row * W * (int64_t)Cout_p;
+    __half* ol = y_lo + row * W * (int64_t)Cout_p;
+    for (int x0 = 0; x0 < W; x0 += ppi) {
+      const int xx = x0 + px;
+      if (xx >= W) continue;
+      float v[9];
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int gy = yy + ky - 1, gx = xx + kx - 1;
-        v[ky * 3 + kx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(x + (n * H + gy) * W + gx) : 0.f;
+        const int gx = xx + kx - 1;
+        const bool in = gx >= 0 && gx < W;
+        v[kx] = (in && up) ? __ldg(xr - W + gx) : 0.f;
+        v[3 + kx] = in ? __ldg(xr + gx) : 0.f;
+        v[6 + kx] = (in && down) ? __ldg(xr + W + gx) : 0.f;
       }
-    float acc[8];
-    {
-      const float4 b0 = *reinterpret_cast<const float4*>(&sb[gq * 8]), b1 = *reinterpret_cast<const float4*>(&sb[gq * 8 + 4]);
-      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
-    }
+      float acc[8];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const float4 w0 = *reinterpret_cast<const float4*>(&sw[t * Cout_p + gq * 8]);
-      const float4 w1 = *reinterpret_cast<const float4*>(&sw[t * Cout_p + gq * 8 + 4]);
-      acc[0] = fmaf(v[t], w0.x, acc[0]); acc[1] = fmaf(v[t], w0.y, acc[1]);
-      acc[2] = fmaf(v[t], w0.z, acc[2]); acc[3] = fmaf(v[t], w0.w, acc[3]);
-      acc[4] = fmaf(v[t], w1.x, acc[4]); acc[5] = fmaf(v[t], w1.y, acc[5]);
-      acc[6] = fmaf(v[t], w1.z, acc[6]); acc[7] = fmaf(v[t], w1.w, acc[7]);
-    }
-    uint32_t hi[4], lo[4];
+      for (int c = 0; c < 8; ++c) acc[c] = br[c];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a = acc[2 * j], c = acc[2 * j + 1];
-      if (relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
-      const __half2 h = __floats2half2_rn(a, c);
-      const float2 hf = __half22float2(h);
-      const __half2 l = __floats2half2_rn(a - hf.x, c - hf.y);
-      hi[j] = *reinterpret_cast<const uint32_t*>(&h);
-      lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = fmaf(v[t], wr[t][c], acc[c]);
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = acc[2 * j], c = acc[2 * j + 1];
+        if (relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+        const __half2 h = __floats2half2_rn(a, c);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(a - hf.x, c - hf.y);
+        hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+      }
+      const int o = xx * Cout_p + gq * 8;
+      *reinterpret_cast<uint4*>(oh + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(ol + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
-    const int64_t o = p * Cout_p + gq * 8;
-    *reinterpret_cast<uint4*>(y_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(y_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -713,7 +713,10 @@ int conv_tc_forward(const void* x_hi, const void* x_lo, const void* w_hi, const 
 
 int conv_first_nhwc(const float* x, const float* w, const float* b, int64_t B, int H, int W, int Cout, int Cout_p,
                     int relu, void* y_hi, void* y_lo, cudaStream_t stream) {
-  conv3x3_first_nhwc_kernel<<<eblocks(B * H * W * (Cout_p / 8)), 256, (size_t)10 * Cout_p * sizeof(float), stream>>>(
+  const int groups = Cout_p / 8;
+  if (groups > 256 || 256 % groups != 0) return DRSA_ERR_SHAPE;
+  const int64_t rows = B * H;
+  conv3x3_first_nhwc_kernel<<<(int)(rows < 148 * 8 ? rows : 148 * 8), 256, 0, stream>>>(
       x, w, b, B, H, W, Cout, Cout_p, relu, static_cast<__half*>(y_hi), static_cast<__half*>(y_lo));
   DRSA_LAUNCH_CHECK();
   return DRSA_OK;
