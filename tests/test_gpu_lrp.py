@@ -530,3 +530,32 @@ def test_end_to_end_cfg5_small(tmp_path):
     an, cn = getdrsadata.load_and_normalize_data(fp, device="cuda")
     np.testing.assert_allclose(an.cpu().numpy(), drsa_ref.normalize_vectors(act.cpu()).numpy(), rtol=3e-6, atol=1e-8)
     np.testing.assert_allclose(cn.cpu().numpy(), drsa_ref.normalize_vectors(ctx.cpu()).numpy(), rtol=3e-6, atol=1e-7)
+
+
+def test_prototypes_and_best_run(tmp_path):
+    """get_prototypes (prototypes.py:59-130 on an in-memory batch) picks the subset with the highest objective; the
+    result-tree reader get_best_run (evaluation.py:107-141) finds the run with the highest final objective."""
+    from cxai.utils.constants import LRP_NAME_MAP_TOY
+    from cxai.xai.explain.rules import NameMapComposite
+    from cxai.xai.drsa.prototypes import get_prototypes
+    from cxai.xai.drsa import drsa
+    from cxai.utils.evaluation import get_best_run
+    net = lrp_ref.toy_model(seed=0, last=64)
+    x = lrp_ref.synth_logmel(12, 64, 64, 77)
+    U = drsa_ref.synth_U0(64, seed=3)
+    K, n = 4, 3
+    a, c, idx, objs, _ = get_prototypes(net, 13, U, NameMapComposite(LRP_NAME_MAP_TOY), x, 1, num_concepts=K, n=n, seed=5)
+    perm = torch.randperm(12, generator=torch.Generator().manual_seed(5))
+    aw, Rw = lrp_ref.get_intermediate(net, x[perm], LRP_NAME_MAP_TOY, net.features[13], 1)
+    av = drsa_ref.vectors_from_maps_all(aw.float()); cv = drsa_ref.compute_context_vectors(av, drsa_ref.vectors_from_maps_all(Rw.float()))
+    want = [float(drsa_ref.obj_val(av[i * n * 16:(i + 1) * n * 16], cv[i * n * 16:(i + 1) * n * 16], U, K, 16)) for i in range(4)]
+    np.testing.assert_allclose(objs, want, rtol=2e-4)
+    best = int(np.argmax(want))
+    assert idx.tolist() == perm[best * n:(best + 1) * n].tolist()
+    assert a.shape == (n * 16, 64) and _rel_per_sample(a, av[best * n * 16:(best + 1) * n * 16]) < 1e-5
+    # result tree of drsa.main -> get_best_run
+    A, C = drsa_ref.synth_pairs(600, 32, 9)
+    drsa.main(A, C, str(tmp_path), num_concepts=2, steps=5, runs=3, seed=1)
+    run, loss, _, path, losses = get_best_run(str(tmp_path))
+    finals = {r: float(open(tmp_path / f"run{r}" / "train_stats.csv").read().splitlines()[-1].split(",")[1]) for r in (1, 2, 3)}
+    assert run == max(finals, key=finals.get) and abs(loss - finals[run]) < 1e-12 and path.endswith(f"run{run}") and len(losses) == 6
