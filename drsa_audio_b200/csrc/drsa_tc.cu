@@ -1,27 +1,29 @@
-// DRSA row pass on the 5th-generation tensor cores (DRSA_PREC_TC_F16X2).
+// DRSA row pass on the 5th-generation tensor cores (DRSA_PREC_TC_F16 / DRSA_PREC_TC_F16X2).
 //
-// One kernel does, per tile of 128 (activation, context) rows and per group of 128 projected
+// One kernel does, per subtile of 64 (activation, context) rows and per group of 128 projected
 // columns (= 128/d_k whole concepts), everything drsa.py:148-155 and the backward of drsa.py:100
 // do, without the projected activations ever leaving the SM:
 //
 //   GEMM1 (tcgen05.mma SS, fp16 x fp16 -> fp32 in TMEM), transposed so that a TMEM lane is a
-//          projected column j and a TMEM column is a row r of the tile:
-//              HA^T[j][r] = sum_i U^T[j][i] A[r][i]        (U^T = hi + lo, two MMAs)
-//              HC^T[j][r] = sum_i U^T[j][i] C[r][i]
-//   epilogue (4 warps, tcgen05.ld): s_rk = sum_{j in k} HA^T[j][r] HC^T[j][r] is a reduction across
-//          TMEM lanes -> warp transpose-reduce (31 shuffles per 32 rows) + a 2 KB smem exchange;
+//          projected column j and a TMEM column is a row r of the subtile; the C rows are stacked
+//          under the A rows, so one MMA of N = 128 gives both projections:
+//              [HA^T | HC^T][j][r] = sum_i U^T[j][i] [A; C][r][i]      (U^T = fp16(U), or hi + lo: two MMAs)
+//   epilogue (8 warps per subtile, tcgen05.ld): s_rk = sum_{j in k} HA^T[j][r] HC^T[j][r] is a reduction
+//          across TMEM lanes -> warp transpose-reduce (31 shuffles per 32 rows) + a 2 KB smem exchange;
 //          g = relu(s) ; sumsq_k += g^2 ; P^T = g * HC^T and Q^T = g * HA^T are written back over
 //          HA^T / HC^T in TMEM as packed fp16 (tcgen05.st) -- the A operand of GEMM2.
-//   GEMM2 (tcgen05.mma TS, A operand from TMEM, B operand = the same row tile read MN-major):
+//   GEMM2 (tcgen05.mma TS, A operand from TMEM, B operand = the same rows read MN-major, N = D):
 //              X^T[j][i] += sum_r P^T[j][r] A[r][i] + Q^T[j][r] C[r][i]
-//          accumulated in TMEM over ALL row tiles of the CTA and written out once.
+//          accumulated in TMEM over ALL subtiles of the CTA and written out once.
 //
-// A and C are stored once as scaled fp16 (drsa_pack_f16), U^T is split into fp16 hi + lo every
-// step (its rounding is systematic, that of the rows averages out over M).
-// Operand staging: TMA (cp.async.bulk.tensor, 128-byte swizzle) into an mbarrier ring;
-// U^T of the CTA's column group stays resident in shared memory.
+// TMEM: X^T 256 columns + two H buffers of 128 columns, so the epilogue of subtile i runs under GEMM1 of
+// subtile i+1 (issue order G1(0) G1(1) G2(0) G1(2) G2(1) ...).  A and C are stored once as scaled fp16
+// (drsa_pack_f16); U is rounded to fp16 once per step (or split hi + lo).
+// Operand staging: TMA (cp.async.bulk.tensor, 128-byte swizzle) into an mbarrier ring; U^T of the CTA's
+// column group stays resident in shared memory.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) + TMEM owner,
-// warps 2..9 = epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter split the 4 row chunks).
+// warps 2..17 = epilogue (TMEM lane quarter = warp % 4; warps 2..9 take the even subtiles, 10..17 the odd ones).
+// d = 512 splits X^T over two CTAs per column group.
 #include <cuda.h>
 #include <vector>
 #include <cmath>
