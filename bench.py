@@ -172,6 +172,13 @@ def run_ours(args):
     Ah, Ch = A.cpu().pin_memory(), C.cpu().pin_memory()
     del opt
     torch.cuda.synchronize()
+    # one untimed call first (like the warm-up steps above): the stage-1 benchmark left the caching allocator fragmented
+    # and the first construction after it pays for cudaFree/cudaMalloc round trips that are not part of the path
+    optw = SubspaceOptimizer(U0, Ah, Ch, None, num_concepts=K, device=dev, precision=args.precision,
+                             use_cuda_graph=not args.no_graph)
+    optw.run(steps=8, save=False)
+    del optw
+    torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     opt2 = SubspaceOptimizer(U0, Ah, Ch, None, num_concepts=K, device=dev, precision=args.precision,
@@ -454,7 +461,8 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (default: cfg2 = 640000)")
     ap.add_argument("--d", type=int, default=0, help="override the split-layer width (default: cfg2 = 256); cfg4 uses 512")
     ap.add_argument("--K", type=int, default=0, help="override the number of concepts (default: cfg2 = 4); cfg4 uses 8")
-    ap.add_argument("--e2e-steps", type=int, default=500)
+    ap.add_argument("--e2e-steps", type=int, default=2000,
+                    help="steps of the end-to-end call (default: the reference's run(steps=2000), drsa.py:76)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lrp", action="store_true")

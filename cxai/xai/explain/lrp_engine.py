@@ -598,6 +598,18 @@ class LRPPlan:
 
 _PLAN_CACHE = {}
 
+# Samples per engine pass.  The reference cuts the batch into minibatches of ``attr_batch_size`` = 64 to bound autograd
+# memory (preprocessing.py:150-167); every kernel here treats samples independently (per-sample scales, eval-mode
+# BatchNorm folded), so the result does not depend on the cut and the engine is free to take more samples per pass:
+# the last conv layers and the dense head only fill the 148 SMs from ~256 samples on.  ``attr_batch_size`` is honoured
+# as a lower bound; the upper bound keeps the activation planes of one pass below ~12 GB.
+ENGINE_CHUNK = 256
+
+
+def _engine_chunk(x: torch.Tensor, requested: int) -> int:
+    per_sample = max(1, x[0].numel()) * 1400          # bytes: hi/lo planes + fp32 relevance of the widest layers
+    return max(int(requested), min(ENGINE_CHUNK, max(1, (12 << 30) // per_sample)))
+
 
 def _plan(model, composite, device) -> LRPPlan:
     key = (id(model), id(composite), str(device))
@@ -621,6 +633,7 @@ def _prep_input(input_batch: torch.Tensor) -> torch.Tensor:
 
 def forward_logits(model, input_batch, composite=None, batch_size: int = 64) -> torch.Tensor:
     x = _prep_input(input_batch)
+    batch_size = _engine_chunk(x, batch_size)
     with torch.cuda.device(x.device):
         plan = _plan(model, composite or R.NameMapComposite([], canonizers=[R.SequentialMergeBatchNorm()]), x.device)
         while True:
@@ -637,6 +650,8 @@ def lrp_intermediate(model, input_batch, composite, layer, class_idx, attr_batch
     from cxai.xai.explain.attribute import lrp_output_modifier
     x = _prep_input(input_batch)
     fn = attr_output_fn or lrp_output_modifier(class_idx, one_hot_encoded=one_hot_encoded)
+    if _seed_is_rowwise(fn):          # a seed that looks at the minibatch as a whole keeps the reference's cut
+        attr_batch_size = _engine_chunk(x, attr_batch_size)
     with torch.cuda.device(x.device):
         plan = _plan(model, composite, x.device)
         op = plan.module_to_op.get(layer)
@@ -689,6 +704,7 @@ def lrp_input_relevance(model, input_batch, composite, attr_output_fn: Callable,
     ProjectionModel the batch is read as groups of K+1 clones (explainer.py:90-99): identical clones share one forward
     pass and the backward pass above the filter."""
     x = _prep_input(input_batch)
+    batch_size = _engine_chunk(x, batch_size)
     with torch.cuda.device(x.device):
         plan = _plan(model, composite, x.device)
         while True:

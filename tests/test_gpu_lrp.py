@@ -374,6 +374,30 @@ def test_tc_prefix_equals_fp32_path_full_resolution():
     _assert_relevance_close_up_to_pool_ties(res[True][0], res[True][1], res[False][1], (2, 2))
 
 
+def test_engine_chunk_does_not_change_results(monkeypatch):
+    """The engine takes up to ENGINE_CHUNK samples per pass instead of the reference's minibatches of 64
+    (preprocessing.py:150-167); samples are independent, so the maps must not depend on the cut."""
+    from cxai.utils.constants import lrp_name_map_6s
+    from cxai.xai.explain.rules import NameMapComposite, SequentialMergeBatchNorm
+    from cxai.xai.explain import lrp_engine
+    from cxai.xai.explain.attribute import compute_relevances
+    from cxai.xai.drsa.preprocessing import get_intermediate
+    net = lrp_ref.genre_model(seed=0, last=64, input_size=(32, 64))
+    x = lrp_ref.synth_logmel(7, 32, 64, 20263).cuda()
+    comp = NameMapComposite(lrp_name_map_6s(), canonizers=[SequentialMergeBatchNorm()])
+    assert lrp_engine._engine_chunk(x, 2) >= 7
+    whole = get_intermediate(net, x, comp, net.features[26], 1, attr_batch_size=2)
+    Rw = compute_relevances(net, x, comp, class_idx=1)
+    monkeypatch.setattr(lrp_engine, "ENGINE_CHUNK", 1)
+    assert lrp_engine._engine_chunk(x, 2) == 2
+    cut = get_intermediate(net, x, comp, net.features[26], 1, attr_batch_size=2)
+    monkeypatch.setattr(lrp_engine, "ENGINE_CHUNK", 3)
+    Rc = compute_relevances(net, x, comp, class_idx=1)
+    # (kernel selection in the dense head may depend on the row count: summation order, not arithmetic, differs)
+    assert _rel_per_sample(whole[0], cut[0]) < 1e-6 and _rel_per_sample(whole[1], cut[1]) < 1e-5
+    assert _rel_per_sample(Rw, Rc) < 1e-5
+
+
 def test_subspace_filter_kernels_match_fp64():
     """lrp_subspace_project / lrp_subspace_filter (Epsilon on both projections + SubspaceHook mask) vs fp64 torch on
     the SAME inputs, padded leading dimension included."""
