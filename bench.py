@@ -122,7 +122,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()                             # started early: nvidia-smi start-up must not land in the timed region
     opt = SubspaceOptimizer(U0, A, C, None, num_concepts=K, device=dev, precision=args.precision,
-                            use_cuda_graph=not args.no_graph)
+                            use_cuda_graph=not args.no_graph, exchange=args.exchange)
     opt._rows.split_u(opt.U)
     opt.reset_log(args.warmup + args.steps + 8)
     warm = max(args.warmup, 4 if not args.no_graph else 3)      # >= 4 so that the CUDA graph of one step is captured here,
@@ -175,14 +175,14 @@ def run_ours(args):
     # one untimed call first (like the warm-up steps above): the stage-1 benchmark left the caching allocator fragmented
     # and the first construction after it pays for cudaFree/cudaMalloc round trips that are not part of the path
     optw = SubspaceOptimizer(U0, Ah, Ch, None, num_concepts=K, device=dev, precision=args.precision,
-                             use_cuda_graph=not args.no_graph)
+                             use_cuda_graph=not args.no_graph, exchange=args.exchange)
     optw.run(steps=8, save=False)
     del optw
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     opt2 = SubspaceOptimizer(U0, Ah, Ch, None, num_concepts=K, device=dev, precision=args.precision,
-                             use_cuda_graph=not args.no_graph)
+                             use_cuda_graph=not args.no_graph, exchange=args.exchange)
     opt2.run(steps=e2e_steps, save=False)
     U_host = opt2.U.cpu()
     barrier()
@@ -211,6 +211,9 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "cfg2" if not custom else f"custom rows={M} d={d} K={K} (steps/s of THIS shape per GPU x GPUs)",
                        "rows_per_gpu": M, "d": d, "m": m, "K": K, "d_k": m // K, "precision": opt2.precision, "cuda_graph": bool(opt2.use_cuda_graph),
+                       "exchange": {"none": "single rank", "nccl": "NCCL all-reduce of d*m+K floats per step",
+                                    "p2p": "all-reduce fused into the finish kernel over NVLink peer memory (cudaIpc buffers)",
+                                    "p2p_symm": "all-reduce fused into the finish kernel over NVLink peer memory (torch symmetric memory)"}[opt2.exchange],
                        "l2_policy": f"inputs larger than L2 ({2 * M * d * elem / 1e6:.0f} MB of rows per step vs 126 MB L2)",
                        "retraction_sweeps_last_step": status[0], "retraction_not_converged": status[1]},
             "rows_per_s": M * world * 1000.0 / ms_per_step,
@@ -466,6 +469,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lrp", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "p2p_symm", "nccl"],
+                    help="how the row sums are joined across ranks (see SubspaceOptimizer)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly (used for the ncu captures)")
     ap.add_argument("--lrp-samples", type=int, default=256)
     args = ap.parse_args()

@@ -134,13 +134,85 @@ class _RowPass:
                  "drsa_step")
 
     def finish(self, U: torch.Tensor, M_global: int, obj_log: Optional[torch.Tensor], log_index: int, update: bool,
-               max_iters: int, tol: float):
+               max_iters: int, tol: float, px: "Optional[_PeerExchange]" = None):
+        if px is not None:          # all-reduce of self.sums over the ranks inside the kernel (peer memory)
+            import ctypes as C
+            _L.check(self.lib.drsa_finish_step_p2p(C.byref(px.desc), _ptr(self.sums), M_global, _ptr(U), self.d, self.m,
+                                                   self.K, _ptr(U) if update else None,
+                                                   _ptr(self.Ut_hi) if update else None,
+                                                   _ptr(self.Ut_lo) if update else None, _ptr(obj_log), log_index,
+                                                   max_iters, tol, self.u_rounded, _ptr(self.status), _ptr(self.ws_fin),
+                                                   self.ws_fin.numel(), _stream()), "drsa_finish_step_p2p")
+            return
         _L.check(self.lib.drsa_finish_step(_ptr(self.sums), M_global, _ptr(U), self.d, self.m, self.K,
                                            _ptr(U) if update else None,
                                            _ptr(self.Ut_hi) if update else None, _ptr(self.Ut_lo) if update else None,
                                            _ptr(obj_log), log_index, max_iters, tol, self.u_rounded, _ptr(self.status),
                                            _ptr(self.ws_fin), self.ws_fin.numel(), _stream()),
                  "drsa_finish_step")
+
+
+class _PeerExchange:
+    """Exchange buffers for the all-reduce that is fused into the finish kernel (drsa_finish_step_p2p): one buffer per
+    rank, every rank maps all of them (NVLink / NVSwitch peer memory).  Buffers are shared through cudaIpc handles sent
+    over the process group ('ipc'), or come from torch's symmetric memory ('symm').  They are cached per
+    (group, device, size) and live until the process exits: the protocol state inside them (exchange counter, parity)
+    stays consistent as long as every rank makes the same sequence of calls, so optimisers can share them."""
+
+    _cache = {}
+
+    def __init__(self, group, world: int, rank: int, nbytes: int, dev: torch.device, how: str):
+        import ctypes as C
+        lib = _L.lib()
+        self.world, self.rank, self.nbytes = world, rank, nbytes
+        self.desc = _L.PeerExchange()
+        self.desc.world, self.desc.rank = world, rank
+        if how == "symm":
+            import torch.distributed._symmetric_memory as symm
+            self._t = symm.empty(nbytes // 4, dtype=torch.float32, device=dev)
+            self._t.zero_()
+            self._hdl = symm.rendezvous(self._t, group if group is not None else torch.distributed.group.WORLD)
+            ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+        else:
+            own = C.c_void_p()
+            handle = C.create_string_buffer(64)
+            _L.check(lib.drsa_ipc_alloc(nbytes, C.byref(own), handle), "drsa_ipc_alloc")
+            handles = [None] * world
+            torch.distributed.all_gather_object(handles, bytes(handle.raw), group=group)
+            ptrs = []
+            for r in range(world):
+                if r == rank:
+                    ptrs.append(own.value)
+                else:
+                    q = C.c_void_p()
+                    _L.check(lib.drsa_ipc_open(handles[r], C.byref(q)), "drsa_ipc_open")
+                    ptrs.append(q.value)
+        for r in range(world):
+            self.desc.buffers[r] = ptrs[r]
+        torch.cuda.synchronize(dev)
+
+    @classmethod
+    def get(cls, group, nbytes: int, dev: torch.device, how: str):
+        """Collective over ``group``: returns the shared exchange (or None on every rank if any rank failed)."""
+        dist = torch.distributed
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        key = (id(group) if group is not None else 0, str(dev), nbytes, how)
+        px = cls._cache.get(key)
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        if px is None:
+            try:
+                px = cls(group, world, rank, nbytes, dev, how)
+            except Exception as e:          # noqa: BLE001 -- any failure means "keep NCCL", decided jointly below
+                import warnings
+                warnings.warn(f"DRSA: peer-memory exchange unavailable ({e}); using the NCCL all-reduce")
+                px = None
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                return None
+            cls._cache[key] = px
+            dist.barrier(group=group)       # every buffer is zero-filled and mapped before anyone pushes into it
+        return px
 
 
 class SubspaceOptimizer:
@@ -160,13 +232,17 @@ class SubspaceOptimizer:
         retraction_iters / retraction_tol: bounds of the on-device Newton-Schulz polar iteration (it stops as soon
             as it has converged: 4-5 sweeps in a normal step; the first steps of a tiny problem, where the
             gradient dwarfs U, need 15-25).
-        use_cuda_graph: capture one step and replay it (single process only).
+        use_cuda_graph: capture one step and replay it (single process, or several ranks with the peer exchange).
+        exchange: how the ``d*m + K`` row sums are joined across ranks: 'p2p' = inside the finish kernel over
+            NVLink peer memory (drsa_finish_step_p2p; buffers shared through cudaIpc), 'p2p_symm' = the same with
+            torch symmetric memory, 'nccl' = ``all_reduce`` between the two kernels, 'auto' = 'p2p' when the process
+            group runs on NCCL with at most 8 ranks and the shape is supported, else 'nccl'.
     """
 
     def __init__(self, U: torch.Tensor, activation_vecs: torch.Tensor, context_vecs: torch.Tensor,
                  path_to_model: Optional[str], num_concepts: int = 4, device=_DEFAULT_DEVICE, *,
                  precision: str = "auto", process_group=None, retraction_iters: int = 40,
-                 retraction_tol: float = 1e-6, use_cuda_graph: bool = True) -> None:
+                 retraction_tol: float = 1e-6, use_cuda_graph: bool = True, exchange: str = "auto") -> None:
         assert num_concepts > 0, "num_concepts must be a positive number"
         assert U.size(1) % num_concepts == 0, "num_concepts must be a divisor of the number of columns of U"
         assert activation_vecs.shape == context_vecs.shape and activation_vecs.dim() == 2
@@ -185,7 +261,11 @@ class SubspaceOptimizer:
             self._rows = _RowPass(self.act_vecs, self.ctx_vecs, U.size(0), U.size(1), num_concepts, precision)
         self.precision = self._rows.precision
         self.retraction_iters, self.retraction_tol = retraction_iters, retraction_tol
-        self.use_cuda_graph = use_cuda_graph and not self._dist
+        self._px = None
+        self.exchange = "none"
+        if self._dist:
+            self.exchange = self._setup_exchange(exchange, U.size(0), U.size(1), num_concepts)
+        self.use_cuda_graph = use_cuda_graph and (not self._dist or self._px is not None)
         M_local = torch.tensor([self.act_vecs.size(0)], dtype=torch.int64, device=self.device)
         if self._dist:
             torch.distributed.all_reduce(M_local, group=self._group)
@@ -193,13 +273,36 @@ class SubspaceOptimizer:
         self.obj_history: Optional[np.ndarray] = None
         self.last_status: Optional[np.ndarray] = None
 
+    def _setup_exchange(self, exchange: str, d: int, m: int, K: int) -> str:
+        dist = torch.distributed
+        if exchange not in ("auto", "p2p", "p2p_symm", "nccl"):
+            raise ValueError("exchange must be 'auto', 'p2p', 'p2p_symm' or 'nccl'")
+        exchange = os.environ.get("DRSA_EXCHANGE", exchange)
+        world = dist.get_world_size(self._group)
+        if exchange == "nccl" or world < 2:
+            return "nccl"
+        nbytes = int(_L.lib().drsa_exchange_bytes(d, m, K, world))
+        on_nccl = dist.get_backend(self._group) == "nccl"
+        if nbytes < 0 or not on_nccl:
+            if exchange != "auto":
+                raise _L.DRSAError(f"exchange='{exchange}' needs an NCCL group of at most {_L.MAX_PEERS} ranks and d, m "
+                                   "multiples of 32")
+            return "nccl"
+        with torch.cuda.device(self.device):
+            self._px = _PeerExchange.get(self._group, nbytes, self.device, "symm" if exchange == "p2p_symm" else "ipc")
+        if self._px is None:
+            if exchange != "auto":
+                raise _L.DRSAError(f"exchange='{exchange}': the peer buffers could not be set up on every rank")
+            return "nccl"
+        return "p2p_symm" if exchange == "p2p_symm" else "p2p"
+
     # ------------------------------------------------------------------ one step
     def _step(self, obj_log: torch.Tensor, log_index: int, update: bool) -> None:
         self._rows.step(self.U)
-        if self._dist:
+        if self._dist and self._px is None:
             torch.distributed.all_reduce(self._rows.sums, group=self._group)   # d*m + K floats over NVLink
         self._rows.finish(self.U, self.M_global, obj_log, log_index, update, self.retraction_iters,
-                          self.retraction_tol)
+                          self.retraction_tol, self._px)
 
     def run(self, steps: int = 2000, save: bool = True) -> None:
         """``steps`` ascent steps; the objective is logged before every update plus once at the end

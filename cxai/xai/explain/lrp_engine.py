@@ -53,6 +53,7 @@ class LRPPlan:
             raise _L.DRSAError("LRP needs model.eval() (BatchNorm running statistics are folded)")
         self.device = device
         self.use_tc = True          # run model.features on the tcgen05 NHWC pipeline when the shapes allow it
+        self.fuse_pool = True       # max-pooling in the epilogue of the convolution before it, where nothing reads the un-pooled map
         self._tc_err = None
         self._tc_ok_cache = {}
         self.ops: List[_Op] = []
@@ -260,9 +261,30 @@ class LRPPlan:
         _L.check(_L.lib().lrp_tc_nhwc_to_nchw(_ptr(hi), _ptr(lo), B, H, W, Cp, C, _ptr(out), _stream()), "nhwc_to_nchw")
         return out
 
-    def _forward_tc_stack(self, x: torch.Tensor, keep_from: int, saved, outs):
+    def _fusable_pool(self, k: int, keep_from: int, out_index, B: int, H: int, W: int):
+        """Index of the MaxPool2d that can be fused into the epilogue of conv op k, or None.  Conditions: only ReLU /
+        folded BatchNorm / Dropout between them, nobody reads the un-pooled activation (it is not the requested output,
+        and no ReLU in between needs its mask in the backward), and the kernel covers the shape."""
+        if out_index is None or k == 0 or not self.fuse_pool:
+            return None
+        op = self.ops[k]
+        j = k + 1
+        end = self._stack_end()
+        while j < end and self.ops[j].kind in ("identity", "relu"):
+            if self.ops[j].kind == "relu" and j >= keep_from and self._relu_needs_mask(j):
+                return None
+            j += 1
+        if j >= end or self.ops[j].kind != "pool" or k <= out_index < j:
+            return None
+        pool = self.ops[j]
+        if _L.lib().lrp_tc_conv3x3_pool_supported(B, self._pad64(op.cin), self._pad64(op.cout), H, W, pool.kh, pool.kw) != 0:
+            return None
+        return j
+
+    def _forward_tc_stack(self, x: torch.Tensor, keep_from: int, saved, outs, out_index=None):
         """model.features on the tensor cores.  Keeps, for ops >= keep_from, the NHWC input planes of every conv and
-        the arg-max of every pool; returns the features as NCHW fp32 for the dense head."""
+        the arg-max of every pool; returns the features as NCHW fp32 for the dense head.  ``out_index``: the only op
+        whose output the caller reads from ``outs`` (-1: none; None: any, which disables the conv + pool fusion)."""
         lib = _L.lib()
         B, _, H, W = x.shape
         dev = x.device
@@ -270,9 +292,37 @@ class LRPPlan:
             self._tc_err = torch.zeros(1, dtype=torch.int32, device=dev)
         end = self._stack_end()
         cur = None                                   # (hi, lo, C, Cp, H, W)
+        skip_until = -1
         for k in range(end):
             op = self.ops[k]
             keep = k >= keep_from
+            if k <= skip_until:                      # ReLU / pool already done by the fused conv + pool kernel
+                if op.kind == "relu" and keep:
+                    saved[k] = ("tc_relu", None)     # never dereferenced: _fusable_pool checked that no mask is needed
+                outs[k] = ("nhwc", cur) if (k == skip_until and k >= keep_from - 1) else None
+                continue
+            kp = self._fusable_pool(k, keep_from, out_index, B, H, W) if op.kind == "conv" else None
+            if kp is not None:
+                pool = self.ops[kp]
+                self._prepare_tc(op, first=False)
+                cout_p = op.tc["cout_p"]
+                Ho, Wo = H // pool.kh, W // pool.kw
+                yh = torch.empty(B, Ho, Wo, cout_p, dtype=torch.float16, device=dev)
+                yl = torch.empty_like(yh)
+                am = torch.empty(B, Ho, Wo, cout_p, dtype=torch.uint8, device=dev) if kp >= keep_from else None
+                _L.check(lib.lrp_tc_conv3x3_forward_pool(_ptr(cur[0]), _ptr(cur[1]), _ptr(op.tc["hi"]), _ptr(op.tc["lo"]),
+                                                         _ptr(op.tc["b"]), B, H, W, op.tc["cin_p"], cout_p, op.cout,
+                                                         int(op.relu), pool.kh, pool.kw, _ptr(yh), _ptr(yl), _ptr(am),
+                                                         _ptr(self._tc_err), _stream()), op.name)
+                if keep:
+                    saved[k] = ("tc_conv", cur)
+                if kp >= keep_from:
+                    saved[kp] = ("tc_pool", am, (H, W, cout_p))
+                H, W = Ho, Wo
+                cur = (yh, yl, op.cout, cout_p, H, W)
+                skip_until = kp
+                outs[k] = None
+                continue
             if op.kind == "conv":
                 self._prepare_tc(op, first=(k == 0))
                 cout_p = op.tc["cout_p"]
@@ -321,9 +371,10 @@ class LRPPlan:
         return self._nhwc_to_nchw(cur)
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x: torch.Tensor, keep_from: int = 0):
-        """Runs the network; returns (logits, saved) where saved[k] holds what op k needs in the backward
-        (its input, and the arg-max for pooling).  Only ops with index >= keep_from are kept."""
+    def forward(self, x: torch.Tensor, keep_from: int = 0, out_index=None):
+        """Runs the network; returns (logits, saved, outs) where saved[k] holds what op k needs in the backward
+        (its input, and the arg-max for pooling).  Only ops with index >= keep_from are kept.  ``out_index``: see
+        _forward_tc_stack."""
         lib = _L.lib()
         saved = [None] * len(self.ops)
         outs = [None] * len(self.ops)
@@ -331,7 +382,7 @@ class LRPPlan:
         n_tc = 0
         if self._tc_stack_ok(x):
             n_tc = self._stack_end()
-            cur = self._forward_tc_stack(x, keep_from, saved, outs)
+            cur = self._forward_tc_stack(x, keep_from, saved, outs, out_index)
         for k, op in enumerate(self.ops):
             if k < n_tc:
                 continue
@@ -637,7 +688,8 @@ def forward_logits(model, input_batch, composite=None, batch_size: int = 64) -> 
     with torch.cuda.device(x.device):
         plan = _plan(model, composite or R.NameMapComposite([], canonizers=[R.SequentialMergeBatchNorm()]), x.device)
         while True:
-            outs = [plan.forward(x[i:i + batch_size], keep_from=len(plan.ops))[0] for i in range(0, x.size(0), batch_size)]
+            outs = [plan.forward(x[i:i + batch_size], keep_from=len(plan.ops), out_index=-1)[0]
+                    for i in range(0, x.size(0), batch_size)]
             if not plan.tc_failed():
                 break
     return torch.cat(outs, 0)
@@ -674,7 +726,7 @@ def lrp_intermediate(model, input_batch, composite, layer, class_idx, attr_batch
         while True:
             a_maps, r_maps = [], []
             for i in range(0, x.size(0), attr_batch_size):
-                logits, saved, outs = plan.forward(x[i:i + attr_batch_size], keep_from=split + 1)
+                logits, saved, outs = plan.forward(x[i:i + attr_batch_size], keep_from=split + 1, out_index=split)
                 seed = fn(logits).contiguous()
                 r_maps.append(plan.backward(seed, saved, stop_after=split))
                 o = outs[split]
@@ -691,7 +743,7 @@ def _seed_is_rowwise(fn) -> bool:
 def _run_relevance(plan, x, fn, batch_size, seed_rows=None):
     out = []
     for i in range(0, x.size(0), batch_size):
-        logits, saved, _ = plan.forward(x[i:i + batch_size], keep_from=0)
+        logits, saved, _ = plan.forward(x[i:i + batch_size], keep_from=0, out_index=-1)
         seed = fn(logits) if seed_rows is None else seed_rows(logits, i)
         out.append(plan.backward(seed.contiguous(), saved, stop_after=-1))
     return torch.cat(out, 0)
@@ -712,7 +764,7 @@ def lrp_input_relevance(model, input_batch, composite, attr_output_fn: Callable,
                 if _seed_is_rowwise(attr_output_fn) or x.size(0) <= batch_size:
                     res = _run_relevance(plan, x, attr_output_fn, batch_size)
                 else:
-                    logits = torch.cat([plan.forward(x[i:i + batch_size], keep_from=len(plan.ops))[0]
+                    logits = torch.cat([plan.forward(x[i:i + batch_size], keep_from=len(plan.ops), out_index=-1)[0]
                                         for i in range(0, x.size(0), batch_size)], 0)
                     seed_full = attr_output_fn(logits)
                     res = _run_relevance(plan, x, None, batch_size, lambda lg, i: seed_full[i:i + lg.size(0)])
@@ -734,7 +786,7 @@ def _clone_relevance(plan, x, fn, batch_size):
     if bool((xg == xg[:, :1]).all()):
         # the reference's use: every sample repeated K+1 times -> one forward per sample
         bs = max(1, batch_size // Kp1)
-        logits = torch.cat([plan.forward(xu[i:i + bs], keep_from=len(plan.ops))[0] for i in range(0, B, bs)], 0) \
+        logits = torch.cat([plan.forward(xu[i:i + bs], keep_from=len(plan.ops), out_index=-1)[0] for i in range(0, B, bs)], 0) \
             if not _seed_is_rowwise(fn) else None
         seed_full = None
         if logits is not None:
@@ -746,7 +798,8 @@ def _clone_relevance(plan, x, fn, batch_size):
                 return _run_relevance(plan, xu, fn, bs)
             return _run_relevance(plan, xu, None, bs, lambda lg, i: seed_full[i:i + lg.size(0), 0])
     # general case (clones differ): clone index k of every group is attributed on its own and keeps slot k
-    logits = torch.cat([plan.forward(x[i:i + batch_size], keep_from=len(plan.ops))[0] for i in range(0, N, batch_size)], 0)
+    logits = torch.cat([plan.forward(x[i:i + batch_size], keep_from=len(plan.ops), out_index=-1)[0]
+                        for i in range(0, N, batch_size)], 0)
     seed_all = fn(logits).view(B, Kp1, -1)
     res = torch.empty(B, Kp1, *x.shape[1:], device=x.device)
     for kk in range(Kp1):

@@ -97,6 +97,27 @@ SIGNATURES = {
     "drsa_debug_set_tc_variant": (_i32, [_i32]),
 }
 
+MAX_PEERS = 8
+
+
+class PeerExchange(C.Structure):
+    """drsa_peer_exchange of include/drsa_b200.h."""
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("buffers", C.c_void_p * MAX_PEERS)]
+
+
+SIGNATURES.update({
+    "drsa_exchange_bytes": (_i64, [_i32, _i32, _i32, _i32]),
+    "drsa_finish_step_p2p": (_i32, [C.POINTER(PeerExchange), _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64,
+                                    _i32, _f32, _i32, _vp, _vp, _i64, _vp]),
+    "lrp_tc_conv3x3_pool_supported": (_i32, [_i64, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "lrp_tc_conv3x3_forward_pool": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
+                                           _vp, _vp, _vp, _vp, _vp]),
+    "drsa_ipc_alloc": (_i32, [_i64, C.POINTER(C.c_void_p), C.c_char_p]),
+    "drsa_ipc_open": (_i32, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "drsa_ipc_close": (_i32, [_vp]),
+    "drsa_ipc_free": (_i32, [_vp]),
+})
+
 _lock = threading.Lock()
 _lib = None
 

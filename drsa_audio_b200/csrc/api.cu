@@ -1,5 +1,6 @@
 // extern "C" surface of libdrsa_b200.so (see include/drsa_b200.h).  Argument checking lives
 // here; the kernels live in the other translation units.
+#include <string.h>
 #include "common.cuh"
 
 namespace drsa {
@@ -64,7 +65,12 @@ int conv_first_nhwc(const float* x, const float* w, const float* b, int64_t B, i
 int conv_tc_run(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int64_t B,
                 int H, int W, int Cin_p, int Cout_p, int Cout, int relu, int epi, float eps, const float* aux_f32,
                 const void* aux_hi, const void* aux_lo, void* y_hi, void* y_lo, float* y_f32, float* y_nchw,
-                const float* scale_ref, float* cmax_out, int* err_flag, cudaStream_t stream);
+                const float* scale_ref, float* cmax_out, int* err_flag, cudaStream_t stream, int pkh, int pkw,
+                void* amax_out);
+bool conv_tc_pool_supported(int64_t B, int Cin_p, int Cout_p, int H, int W, int kh, int kw);
+int conv_tc_forward_pool(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int64_t B,
+                         int H, int W, int Cin_p, int Cout_p, int Cout, int relu, int kh, int kw, void* y_hi, void* y_lo,
+                         void* argmax_u8, int* err_flag, cudaStream_t stream);
 int64_t subspace_filter_workspace_bytes(int64_t P, int d, int m);
 int subspace_project(const float* a, const float* U, int64_t P, int d, int m, int ld, float* h, float* a2, cudaStream_t s);
 int subspace_filter_backward(const float* a, const float* h, const float* a2, const float* R, const float* U, int64_t P, int d,
@@ -91,7 +97,9 @@ int absmax(const float* in, int64_t count, float* out, cudaStream_t stream);
 int64_t finish_workspace_bytes(int d, int m);
 int finish_step(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out, void* Ut_hi,
                 void* Ut_lo, float* obj_log, int64_t log_index, int max_iters, float tol, int u_rounded, int* status,
-                void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+                void* workspace, int64_t workspace_bytes, const drsa_peer_exchange* px, cudaStream_t stream);
+bool finish_fused_supported(int d, int m, int K);
+int64_t exchange_bytes(int d, int m, int K, int world);
 int polar_retract(const float* Y, int d, int m, float* U_out, int max_iters, float tol, int* status, void* workspace,
                   int64_t workspace_bytes, cudaStream_t stream);
 int split_u(const float* U, int d, int m, void* Ut_hi, void* Ut_lo, cudaStream_t stream);
@@ -211,7 +219,66 @@ int drsa_finish_step(const float* sums, int64_t M_global, const float* U, int d,
   if (obj_log != nullptr && log_index < 0 && status == nullptr) return DRSA_ERR_ARG;
   DRSA_TRY(require_sm100());
   return finish_step(sums, M_global, U, d, m, K, U_out, Ut_hi, Ut_lo, obj_log, log_index, max_iters, tol, u_rounded,
-                     status, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+                     status, workspace, workspace_bytes, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int64_t drsa_exchange_bytes(int d, int m, int K, int world) {
+  if (d <= 0 || m <= 0 || m > d || K <= 0 || m % K != 0 || world < 2) return DRSA_ERR_ARG;
+  if (world > DRSA_MAX_PEERS || !finish_fused_supported(d, m, K)) return DRSA_ERR_SHAPE;
+  return exchange_bytes(d, m, K, world);
+}
+
+int drsa_finish_step_p2p(const drsa_peer_exchange* px, const float* sums, int64_t M_global, const float* U, int d,
+                         int m, int K, float* U_out, void* Ut_hi, void* Ut_lo, float* obj_log, int64_t log_index,
+                         int max_iters, float tol, int u_rounded, int* status, void* workspace,
+                         int64_t workspace_bytes, void* stream) {
+  if (px == nullptr || px->world < 2 || px->world > DRSA_MAX_PEERS || px->rank < 0 || px->rank >= px->world)
+    return DRSA_ERR_ARG;
+  if (sums == nullptr || !shape_ok(M_global, d, m, K) || workspace == nullptr) return DRSA_ERR_ARG;
+  if (U_out != nullptr && (U == nullptr || max_iters < 1 || !(tol > 0.f))) return DRSA_ERR_ARG;
+  if (Ut_lo != nullptr && Ut_hi == nullptr) return DRSA_ERR_ARG;
+  if (u_rounded && U == nullptr) return DRSA_ERR_ARG;
+  if (K > 1024 || !finish_fused_supported(d, m, K)) return DRSA_ERR_SHAPE;
+  if (obj_log != nullptr && log_index < 0 && status == nullptr) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return finish_step(sums, M_global, U, d, m, K, U_out, Ut_hi, Ut_lo, obj_log, log_index, max_iters, tol, u_rounded,
+                     status, workspace, workspace_bytes, px, static_cast<cudaStream_t>(stream));
+}
+
+/* cudaIpc plumbing for the exchange buffers (used when torch's symmetric memory is not available) */
+int drsa_ipc_alloc(int64_t bytes, void** ptr, unsigned char* handle64) {
+  if (bytes <= 0 || ptr == nullptr || handle64 == nullptr) return DRSA_ERR_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  void* p = nullptr;
+  DRSA_CUDA(cudaMalloc(&p, (size_t)bytes));
+  cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e); }
+  memcpy(handle64, &h, 64);
+  *ptr = p;
+  return DRSA_OK;
+}
+
+int drsa_ipc_open(const unsigned char* handle64, void** ptr) {
+  if (handle64 == nullptr || ptr == nullptr) return DRSA_ERR_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  DRSA_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return DRSA_OK;
+}
+
+int drsa_ipc_close(void* ptr) {
+  if (ptr == nullptr) return DRSA_ERR_ARG;
+  DRSA_CUDA(cudaIpcCloseMemHandle(ptr));
+  return DRSA_OK;
+}
+
+int drsa_ipc_free(void* ptr) {
+  if (ptr == nullptr) return DRSA_ERR_ARG;
+  DRSA_CUDA(cudaFree(ptr));
+  return DRSA_OK;
 }
 
 int drsa_polar_retract(const float* Y, int d, int m, float* U_out, int max_iters, float tol, int* status,
@@ -348,6 +415,21 @@ int lrp_tc_conv3x3_forward(const void* x_hi, const void* x_lo, const void* w_hi,
                          static_cast<cudaStream_t>(stream));
 }
 
+int lrp_tc_conv3x3_pool_supported(int64_t B, int Cin_p, int Cout_p, int H, int W, int kh, int kw) {
+  return conv_tc_pool_supported(B, Cin_p, Cout_p, H, W, kh, kw) ? DRSA_OK : DRSA_ERR_SHAPE;
+}
+
+int lrp_tc_conv3x3_forward_pool(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                                int64_t B, int H, int W, int Cin_p, int Cout_p, int Cout, int relu, int kh, int kw,
+                                void* y_hi, void* y_lo, void* argmax_u8, int* err_flag, void* stream) {
+  if (x_hi == nullptr || x_lo == nullptr || w_hi == nullptr || w_lo == nullptr || bias == nullptr || err_flag == nullptr ||
+      y_hi == nullptr || y_lo == nullptr || Cout <= 0 || Cout > Cout_p || kh <= 0 || kw <= 0)
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return conv_tc_forward_pool(x_hi, x_lo, w_hi, w_lo, bias, B, H, W, Cin_p, Cout_p, Cout, relu, kh, kw, y_hi, y_lo, argmax_u8,
+                              err_flag, static_cast<cudaStream_t>(stream));
+}
+
 int lrp_tc_conv3x3_first(const float* x, const float* w, const float* b, int64_t B, int H, int W, int Cout, int Cout_p,
                          int relu, void* y_hi, void* y_lo, void* stream) {
   if (x == nullptr || w == nullptr || b == nullptr || y_hi == nullptr || y_lo == nullptr || B <= 0 || H <= 0 || W <= 0 ||
@@ -383,7 +465,7 @@ int lrp_tc_conv3x3_ratio(const void* x_hi, const void* x_lo, const void* w_hi, c
     return DRSA_ERR_ARG;
   DRSA_TRY(require_sm100());
   return conv_tc_run(x_hi, x_lo, w_hi, w_lo, bias, B, H, W, Cin_p, Cout_p, Cout_p, 0, 1, eps, R_out, nullptr, nullptr, s_hi,
-                     s_lo, nullptr, nullptr, scale_ref, nullptr, err_flag, static_cast<cudaStream_t>(stream));
+                     s_lo, nullptr, nullptr, scale_ref, nullptr, err_flag, static_cast<cudaStream_t>(stream), 0, 0, nullptr);
 }
 
 int lrp_tc_conv3x3_inputmul(const void* s_hi, const void* s_lo, const void* wt_hi, const void* wt_lo, const void* x_hi,
@@ -394,7 +476,7 @@ int lrp_tc_conv3x3_inputmul(const void* s_hi, const void* s_lo, const void* wt_h
     return DRSA_ERR_ARG;
   DRSA_TRY(require_sm100());
   return conv_tc_run(s_hi, s_lo, wt_hi, wt_lo, nullptr, B, H, W, Cout_p, Cin_p, Cin_p, 0, 2, 0.f, nullptr, x_hi, x_lo, nullptr,
-                     nullptr, R_in, nullptr, scale_ref, cmax_out, err_flag, static_cast<cudaStream_t>(stream));
+                     nullptr, R_in, nullptr, scale_ref, cmax_out, err_flag, static_cast<cudaStream_t>(stream), 0, 0, nullptr);
 }
 
 int lrp_tc_sample_absmax_ratio(const float* R, const float* x, int64_t B, int64_t per_sample, float* out, void* stream) {

@@ -101,6 +101,7 @@ struct ConvGeom {
   int relu;
   int epi;      // 0: y = relu?(acc + b); 1: y = aux_f32 / stabilize(acc + b, eps); 2: y = (aux_hi + aux_lo) * acc
   float eps;
+  int pkh, pkw;   // > 0: MaxPool2d(pkh, pkw) fused into the epi == 0 epilogue (y planes and arg-max are the POOLED maps)
 };
 
 // kHalo (with resident weights, tiles of th = 8 rows x tw = 16 columns of one image): instead of one TMA box per tap
@@ -119,7 +120,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
                   const float* __restrict__ bias, const float* __restrict__ aux_f32, const __half* __restrict__ aux_hi,
                   const __half* __restrict__ aux_lo, __half* __restrict__ y_hi, __half* __restrict__ y_lo,
                   float* __restrict__ y_f32, float* __restrict__ y_nchw, const float* __restrict__ scale_ref,
-                  float* __restrict__ cmax_out, int* __restrict__ err_flag) {
+                  float* __restrict__ cmax_out, int* __restrict__ err_flag, uint8_t* __restrict__ amax_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int wbytes = g.Cout_p * 128;                 // one [Cout_p x 64] weight box
   // kResW (Cin_p = Cout_p = 64): all 9 taps of the hi/lo weights (144 KB) stay resident in shared memory and the
@@ -302,7 +303,81 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; ++i) a[i] += __uint_as_float(v[i]);
         }
-        if (valid) {
+        if (g.pkh > 0) {
+          // Fused MaxPool2d(pkh, pkw), stride = kernel (create_model.py:120): the window of a pooled pixel lies inside
+          // this warp's 32 pixels (host picks tw <= 16, so a warp holds 32 / tw >= pkh rows of the tile), i.e. the
+          // maximum is a butterfly over the lane bits of x (masks 1 .. pkw/2) and y (masks tw .. tw*pkh/2).  Ties keep
+          // the first element in row-major window order like PyTorch.  The full-resolution map is never written.
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + 32 * cc) + i4);
+            a[4 * i4] += bb.x; a[4 * i4 + 1] += bb.y; a[4 * i4 + 2] += bb.z; a[4 * i4 + 3] += bb.w;
+          }
+          if (g.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = fmaxf(a[i], 0.f);
+          }
+          // Two passes, both with the channel loop innermost so that the 32 shuffles / votes of a stage are independent
+          // (a per-channel butterfly that carries the arg-max along serialises 3 dependent shuffles per channel and made
+          // the epilogue, not the tensor pipe, the bottleneck): (1) max over the window, (2) arg-max = first lane of the
+          // window, in lane order = row-major window order, whose value equals the maximum.
+          const int widx = (yy % g.pkh) * g.pkw + (xx % g.pkw);
+          const int tw_shift = g.tw == 16 ? 4 : 3;
+          const int base = lane - (((lane >> tw_shift) % g.pkh) << tw_shift) - ((lane & (g.tw - 1)) % g.pkw);
+          uint32_t wmask = 0u;
+          for (int dy = 0; dy < g.pkh; ++dy)
+            for (int dx = 0; dx < g.pkw; ++dx) wmask |= 1u << (base + (dy << tw_shift) + dx);
+          float vmax[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) vmax[i] = a[i];
+          for (int mk = 1; mk < g.pkw; mk <<= 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) vmax[i] = fmaxf(vmax[i], __shfl_xor_sync(0xffffffffu, vmax[i], mk));
+          }
+          for (int mk = g.tw; mk < g.tw * g.pkh; mk <<= 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) vmax[i] = fmaxf(vmax[i], __shfl_xor_sync(0xffffffffu, vmax[i], mk));
+          }
+          uint32_t packed_idx[8];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const uint32_t hit = __ballot_sync(0xffffffffu, a[i] == vmax[i]) & wmask;
+            const int rel = hit ? (__ffs(hit) - 1 - base) : 0;
+            const uint32_t idx = (uint32_t)((rel >> tw_shift) * g.pkw + (rel & (g.tw - 1)));
+            if ((i & 3) == 0) packed_idx[i >> 2] = 0u;
+            packed_idx[i >> 2] |= idx << (8 * (i & 3));
+            a[i] = vmax[i];
+          }
+          if (valid && widx == 0) {
+            const int Ho = g.H / g.pkh, Wo = g.W / g.pkw;
+            const int64_t po = (((int64_t)n * Ho + y / g.pkh) * Wo + x / g.pkw) * g.Cout_p + 32 * cc;
+            uint32_t hi[16], lo[16];
+            float am = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) am = fmaxf(am, fabsf(a[i]));
+            ovf = ovf || !(am < 60000.f);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const __half2 h = __floats2half2_rn(a[2 * i], a[2 * i + 1]);
+              const float2 hf = __half22float2(h);
+              const __half2 l = __floats2half2_rn(a[2 * i] - hf.x, a[2 * i + 1] - hf.y);
+              hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+              lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            uint4* ph = reinterpret_cast<uint4*>(y_hi + po);
+            uint4* pl = reinterpret_cast<uint4*>(y_lo + po);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              ph[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+              pl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            }
+            if (amax_out != nullptr) {
+              uint4* pa = reinterpret_cast<uint4*>(amax_out + po);
+              pa[0] = make_uint4(packed_idx[0], packed_idx[1], packed_idx[2], packed_idx[3]);
+              pa[1] = make_uint4(packed_idx[4], packed_idx[5], packed_idx[6], packed_idx[7]);
+            }
+          }
+        } else if (valid) {
           const int64_t o = pbase + 32 * cc;
           if (g.epi != 2) {
 #pragma unroll
@@ -659,7 +734,16 @@ bool pick_tile(int B, int H, int W, int* nb, int* th, int* tw) {
   *nb = n; *th = h; *tw = w;
   return true;
 }
+// Tile for a conv with the max-pool fused into its epilogue: at most 16 pixels per tile row so that a warp (32 TMEM
+// lanes) holds at least two rows of the tile.
+bool pool_tile(int H, int W, int* nb, int* th, int* tw) {
+  if (W % 16 == 0 && H % 8 == 0) { *nb = 1; *th = 8; *tw = 16; return true; }
+  if (W == 8 && H == 8) { *nb = 2; *th = 8; *tw = 8; return true; }
+  return false;
+}
 }  // namespace
+
+bool conv_tc_pool_supported(int64_t B, int Cin_p, int Cout_p, int H, int W, int kh, int kw);
 
 bool conv_tc_supported(int64_t B, int Cin_p, int Cout_p, int H, int W) {
   int nb, th, tw;
@@ -667,16 +751,31 @@ bool conv_tc_supported(int64_t B, int Cin_p, int Cout_p, int H, int W) {
   return pick_tile((int)B, H, W, &nb, &th, &tw);
 }
 
+bool conv_tc_pool_supported(int64_t B, int Cin_p, int Cout_p, int H, int W, int kh, int kw) {
+  int nb, th, tw;
+  if (!conv_tc_supported(B, Cin_p, Cout_p, H, W) || !pool_tile(H, W, &nb, &th, &tw)) return false;
+  const bool pow2 = kh > 0 && kw > 0 && (kh & (kh - 1)) == 0 && (kw & (kw - 1)) == 0;
+  return pow2 && kw <= tw && kh <= 32 / tw && kh * kw <= 255 && H % kh == 0 && W % kw == 0;
+}
+
 int conv_tc_run(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int64_t B,
                 int H, int W, int Cin_p, int Cout_p, int Cout, int relu, int epi, float eps, const float* aux_f32,
                 const void* aux_hi, const void* aux_lo, void* y_hi, void* y_lo, float* y_f32, float* y_nchw,
-                const float* scale_ref, float* cmax_out, int* err_flag, cudaStream_t stream) {
+                const float* scale_ref, float* cmax_out, int* err_flag, cudaStream_t stream, int pkh, int pkw,
+                void* amax_out) {
   ConvGeom g{};
   if (!conv_tc_supported(B, Cin_p, Cout_p, H, W) || B > 2147483647LL / ((int64_t)H * W)) return DRSA_ERR_SHAPE;
   g.B = (int)B; g.H = H; g.W = W; g.Cin_p = Cin_p; g.Cout_p = Cout_p; g.Cout = Cout; g.relu = relu; g.epi = epi; g.eps = eps;
   pick_tile(g.B, H, W, &g.nb, &g.th, &g.tw);
   const bool halo = Cout_p == 64 && Cin_p == 64 && W % kHaloTw == 0 && H % kHaloTh == 0;
   if (halo) { g.nb = 1; g.th = kHaloTh; g.tw = kHaloTw; }
+  g.pkh = g.pkw = 0;
+  if (pkh > 0 || pkw > 0) {
+    if (epi != 0 || y_f32 != nullptr || y_nchw != nullptr || y_hi == nullptr || !conv_tc_pool_supported(B, Cin_p, Cout_p, H, W, pkh, pkw))
+      return DRSA_ERR_SHAPE;
+    pool_tile(H, W, &g.nb, &g.th, &g.tw);
+    g.pkh = pkh; g.pkw = pkw;
+  }
   g.tiles_x = W / g.tw; g.tiles_y = H / g.th; g.tiles_b = (g.B + g.nb - 1) / g.nb;
   g.num_tiles = g.tiles_x * g.tiles_y * g.tiles_b;
   CUtensorMap tmXh, tmXl, tmWh, tmWl;
@@ -693,7 +792,7 @@ int conv_tc_run(const void* x_hi, const void* x_lo, const void* w_hi, const void
     kernel<<<grid, kConvThreads, smem_bytes, stream>>>(tmXh, tmXl, tmWh, tmWl, g, bias, aux_f32,
                                                         static_cast<const __half*>(aux_hi), static_cast<const __half*>(aux_lo),
                                                         static_cast<__half*>(y_hi), static_cast<__half*>(y_lo), y_f32, y_nchw,
-                                                        scale_ref, cmax_out, err_flag);
+                                                        scale_ref, cmax_out, err_flag, static_cast<uint8_t*>(amax_out));
     DRSA_LAUNCH_CHECK();
     return DRSA_OK;
   };
@@ -708,7 +807,15 @@ int conv_tc_forward(const void* x_hi, const void* x_lo, const void* w_hi, const 
                     int H, int W, int Cin_p, int Cout_p, int Cout, int relu, void* y_hi, void* y_lo, float* y_nchw,
                     int* err_flag, cudaStream_t stream) {
   return conv_tc_run(x_hi, x_lo, w_hi, w_lo, bias, B, H, W, Cin_p, Cout_p, Cout, relu, 0, 0.f, nullptr, nullptr, nullptr, y_hi,
-                     y_lo, nullptr, y_nchw, nullptr, nullptr, err_flag, stream);
+                     y_lo, nullptr, y_nchw, nullptr, nullptr, err_flag, stream, 0, 0, nullptr);
+}
+
+// conv + bias (+ ReLU) + MaxPool2d(kh, kw): y planes [B, H/kh, W/kw, Cout_p], argmax_u8 (optional) the window index
+int conv_tc_forward_pool(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int64_t B,
+                         int H, int W, int Cin_p, int Cout_p, int Cout, int relu, int kh, int kw, void* y_hi, void* y_lo,
+                         void* argmax_u8, int* err_flag, cudaStream_t stream) {
+  return conv_tc_run(x_hi, x_lo, w_hi, w_lo, bias, B, H, W, Cin_p, Cout_p, Cout, relu, 0, 0.f, nullptr, nullptr, nullptr, y_hi,
+                     y_lo, nullptr, nullptr, nullptr, nullptr, err_flag, stream, kh, kw, argmax_u8);
 }
 
 int conv_first_nhwc(const float* x, const float* w, const float* b, int64_t B, int H, int W, int Cout, int Cout_p,

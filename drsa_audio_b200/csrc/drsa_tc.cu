@@ -633,38 +633,55 @@ drsa_tc_step32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }
 
 // sums[i*m + col] = x_scale * sum_rb part[(rb*G + col/128)*128 + col%128][i] ; sums[d*m + k] = sum_rb ss_part.
-// One thread per output element (32 x 32 tile per CTA), the row-block loop unrolled so that many independent
-// L2 reads are in flight; fixed summation order (deterministic).
-__global__ void __launch_bounds__(1024) tc_reduce_kernel(const float* __restrict__ part, const float* __restrict__ ss_part,
-                                                         int nRB, int G, int d, int m, int K, float x_scale,
-                                                         float* __restrict__ sums) {
-  __shared__ float tile[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 32
-  const int i0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  const int col = c0 + ty;
+// A CTA reduces a tile of 16 columns x 32 channels with 512 threads: 128 float4 lanes x 4 groups that take the row
+// blocks rb = grp, grp + 4, ... (m/16 x d/32 CTAs = 128 at cfg 2).  The kernel is bound by the latency of its dependent
+// load rounds, not by bandwidth (19 MB of partials): with eight independent 16-byte reads per thread and four groups
+// a thread needs ceil(nRB / 32) rounds (3 at cfg 2; the first version, one scalar lane per element, needed 10).  The
+// groups are combined through shared memory in a fixed order (deterministic; replicas stay bit-identical).
+constexpr int kRedGroups = 4;
+__global__ void __launch_bounds__(128 * kRedGroups) tc_reduce_kernel(const float* __restrict__ part,
+                                                                    const float* __restrict__ ss_part, int nRB, int G, int d,
+                                                                    int m, int K, float x_scale, float* __restrict__ sums) {
+  __shared__ float tile[kRedGroups][16][33];
+  const int lane128 = threadIdx.x & 127, grp = threadIdx.x >> 7;
+  const int q = lane128 & 7, cl = lane128 >> 3;             // channels 4q..4q+3 of column cl
+  const int i0 = blockIdx.y * 32, c0 = blockIdx.x * 16;
+  const int col = c0 + cl;
   const int gg = col >> 7, jj = col & 127;
-  const float* src = part + ((int64_t)gg * 128 + jj) * d + i0 + tx;
-  const int64_t stride = (int64_t)G * 128 * d;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int rb = 0;
-  for (; rb + 8 <= nRB; rb += 8) {
-    float v[8];
+  const float4* src = reinterpret_cast<const float4*>(part + ((int64_t)gg * 128 + jj) * d + i0) + q;
+  const int64_t stride = (int64_t)G * 128 * d / 4;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+  auto add = [](float4& a, const float4& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; };
+  int rb = grp;
+  for (; rb + 7 * kRedGroups < nRB; rb += 8 * kRedGroups) {
+    float4 v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (rb + u) * stride);
-    a0 += v[0]; a1 += v[1]; a2 += v[2]; a3 += v[3];
-    a0 += v[4]; a1 += v[5]; a2 += v[6]; a3 += v[7];
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (rb + u * kRedGroups) * stride);
+    add(a0, v[0]); add(a1, v[1]); add(a0, v[2]); add(a1, v[3]);
+    add(a0, v[4]); add(a1, v[5]); add(a0, v[6]); add(a1, v[7]);
   }
-  for (; rb < nRB; ++rb) a0 += __ldg(src + rb * stride);
-  tile[ty][tx] = (a0 + a1) + (a2 + a3);      // tile[col_local][i_local]
+  for (; rb < nRB; rb += kRedGroups) add(a0, __ldg(src + rb * stride));
+  tile[grp][cl][4 * q] = a0.x + a1.x;
+  tile[grp][cl][4 * q + 1] = a0.y + a1.y;
+  tile[grp][cl][4 * q + 2] = a0.z + a1.z;
+  tile[grp][cl][4 * q + 3] = a0.w + a1.w;
   __syncthreads();
-  sums[(int64_t)(i0 + ty) * m + c0 + tx] = tile[tx][ty] * x_scale;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < K) {
-    float s = 0.f;
-    for (int r = 0; r < nRB; ++r) {
-      const float4 v = *reinterpret_cast<const float4*>(ss_part + ((int64_t)r * K + threadIdx.x) * 4);
-      s += (v.x + v.y) + (v.z + v.w);
+  {
+    const int oc = threadIdx.x & 15, oi = threadIdx.x >> 4;      // 16 consecutive columns of channel row oi (0..31)
+    float v = 0.f;
+#pragma unroll
+    for (int g2 = 0; g2 < kRedGroups; ++g2) v += tile[g2][oc][oi];
+    sums[(int64_t)(i0 + oi) * m + c0 + oc] = v * x_scale;
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      float s = 0.f;
+      for (int r = 0; r < nRB; ++r) {
+        const float4 v = *reinterpret_cast<const float4*>(ss_part + ((int64_t)r * K + k) * 4);
+        s += (v.x + v.y) + (v.z + v.w);
+      }
+      sums[(int64_t)d * m + k] = s;
     }
-    sums[(int64_t)d * m + threadIdx.x] = s;
   }
 }
 
@@ -802,8 +819,8 @@ int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_
                                            ss_part, err)
                       : launch_step32<128>(grid32, stream, tA, tC, Ut_hi, p.num_tiles, p.G, p.nRB, m / K, inv_s, pq_scale, part,
                                            ss_part, err));
-    dim3 rg(m / 32, d / 32);
-    tc_reduce_kernel<<<rg, 1024, 0, stream>>>(part, ss_part, p.nRB, p.G, d, m, K, inv_s * inv_s / pq_scale, sums);
+    dim3 rg(m / 16, d / 32);
+    tc_reduce_kernel<<<rg, 128 * kRedGroups, 0, stream>>>(part, ss_part, p.nRB, p.G, d, m, K, inv_s * inv_s / pq_scale, sums);
     DRSA_LAUNCH_CHECK();
     return DRSA_OK;
   }
@@ -834,9 +851,9 @@ int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_
                  : launch_step<128, false>(grid, stream, tmA, tmC, tmA2, tmC2, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale,
                                            pq_scale, part, ss_part, err, g_tc_prof);
   DRSA_TRY(st);
-  dim3 rgrid(m / 32, d / 32);
+  dim3 rgrid(m / 16, d / 32);
   // X' = pq_scale * (sA sC)^2 * X
-  tc_reduce_kernel<<<rgrid, 1024, 0, stream>>>(part, ss_part, p.nRB, p.G, d, m, K, inv_scale * inv_scale / pq_scale, sums);
+  tc_reduce_kernel<<<rgrid, 128 * kRedGroups, 0, stream>>>(part, ss_part, p.nRB, p.G, d, m, K, inv_scale * inv_scale / pq_scale, sums);
   DRSA_LAUNCH_CHECK();
   return DRSA_OK;
 }

@@ -219,7 +219,8 @@ bool finish_fused_supported(int d, int m, int K);
 int64_t finish_fused_workspace_bytes(int d, int m);
 int finish_fused(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out, void* Ut_hi,
                  void* Ut_lo, float* obj_log, int64_t log_index, int max_iters, float tol, int u_rounded, int* status,
-                 void* workspace, int64_t workspace_bytes, const float* Y_in, cudaStream_t stream);
+                 void* workspace, int64_t workspace_bytes, const float* Y_in, const drsa_peer_exchange* px,
+                 cudaStream_t stream);
 
 int64_t finish_workspace_bytes(int d, int m) {
   const int64_t a = polar_ws_bytes(d, m), b = finish_fused_workspace_bytes(d, m);
@@ -228,10 +229,12 @@ int64_t finish_workspace_bytes(int d, int m) {
 
 int finish_step(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out,
                 void* Ut_hi, void* Ut_lo, float* obj_log, int64_t log_index, int max_iters, float tol,
-                int u_rounded, int* status, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+                int u_rounded, int* status, void* workspace, int64_t workspace_bytes, const drsa_peer_exchange* px,
+                cudaStream_t stream) {
   if (finish_fused_supported(d, m, K))       // one cooperative kernel instead of ~30 dependent launches
     return finish_fused(sums, M_global, U, d, m, K, U_out, Ut_hi, Ut_lo, obj_log, log_index, max_iters, tol, u_rounded,
-                        status, workspace, workspace_bytes, nullptr, stream);
+                        status, workspace, workspace_bytes, nullptr, px, stream);
+  if (px != nullptr && px->world > 1) return DRSA_ERR_SHAPE;      // the peer exchange lives in the fused kernel
   if (u_rounded) return DRSA_ERR_SHAPE;      // the tensor-core modes only exist for shapes the fused kernel covers
   if (workspace_bytes < polar_ws_bytes(d, m)) return DRSA_ERR_WORKSPACE;
   PolarWs p = carve(workspace, d, m);
@@ -249,7 +252,7 @@ int polar_retract(const float* Y, int d, int m, float* U_out, int max_iters, flo
                   void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
   if (finish_fused_supported(d, m, 1))
     return finish_fused(nullptr, 1, nullptr, d, m, 1, U_out, nullptr, nullptr, nullptr, 0, max_iters, tol, 0, status,
-                        workspace, workspace_bytes, Y, stream);
+                        workspace, workspace_bytes, Y, nullptr, stream);
   if (workspace_bytes < polar_ws_bytes(d, m)) return DRSA_ERR_WORKSPACE;
   PolarWs p = carve(workspace, d, m);
   DRSA_CUDA(cudaMemcpyAsync(p.Y, Y, (int64_t)d * m * 4, cudaMemcpyDeviceToDevice, stream));

@@ -24,11 +24,83 @@ struct FusedParams {
   float* Y; float* X0; float* X1; float* G;
   float* rowsum;   // [m/32][m] per-tile-column partial row sums of |G| (summed in fixed order: deterministic)
   float* resid;    // [max_iters + 2][gridDim.x] per-CTA partial residuals (summed in fixed order)
+  float* fro;      // [(m/32)^2] per-tile partials of ||Y^T Y - I||_F^2 (decides whether the start needs scaling)
   int have_sums;   // 0: Y already holds the matrix to retract (drsa_polar_retract)
   int u_rounded;   // sums were evaluated at fp16(U): log f(fp16 U) + <grad, U - fp16 U> (first-order exact in the rounding)
   float* corr;     // [gridDim.x] per-CTA partials of that inner product
   long long* prof; // debug: %globaltimer stamps of CTA 0 at the phase boundaries (drsa_debug_set_tc_profile), or NULL
+  // peer exchange (world > 1): xbuf[r] = rank r's exchange buffer as mapped into this process (NVLink peer memory).
+  // Layout of a buffer: 64 x u32 header ([0] = exchange counter of the owner, [16] / [32] = arrival counters of the two
+  // parities), then floats data[parity][source rank][xstride].
+  int world, rank;
+  float* xbuf[DRSA_MAX_PEERS];
+  int64_t xstride;
 };
+
+constexpr int kXHeaderFloats = 64;
+__device__ __forceinline__ void red_release_sys_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// The all-reduce of the row sums, fused into the head of the finish kernel (push model over NVLink peer memory):
+// every CTA stores its grid-stride share of this rank's `sums` into slot [parity][rank] of EVERY peer's buffer,
+// fences, and bumps the peer's arrival counter once; then it waits until all (world - 1) * gridDim.x arrivals of the
+// peers have landed in its own buffer.  The reduced value of element i is the sum over ranks in rank order (own
+// share read from `sums`), so every rank adds the same floats in the same order: replicas of U stay bit-identical.
+// Two parities: a peer can run at most one exchange ahead (it needs this rank's arrivals of exchange s + 1 before it
+// can finish it), so slot [s & 1] is never overwritten while it is still being read.  Returns the parity.
+__device__ __forceinline__ int peer_exchange(const FusedParams& p, int64_t total) {
+  unsigned* hdr = reinterpret_cast<unsigned*>(p.xbuf[p.rank]);
+  const unsigned s = __ldcg(hdr);
+  const int par = (int)(s & 1u);
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t slot = ((int64_t)par * p.world + p.rank) * p.xstride + kXHeaderFloats;
+  // 16-byte stores (d*m is a multiple of 1024, the slot offsets of 64 floats; the K pooling scalars follow one by one)
+  const int64_t n4 = (total & ~(int64_t)3) >> 2;
+  for (int64_t i = gtid; i < n4; i += gthreads) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p.sums) + i);
+    for (int r = 0; r < p.world; ++r)
+      if (r != p.rank) reinterpret_cast<float4*>(p.xbuf[r] + slot)[i] = v;
+  }
+  for (int64_t i = 4 * n4 + gtid; i < total; i += gthreads) {
+    const float v = p.sums[i];
+    for (int r = 0; r < p.world; ++r)
+      if (r != p.rank) p.xbuf[r][slot + i] = v;
+  }
+  // The CTA barrier orders every thread's stores before thread 0's release (cumulativity), so ONE system-scope release
+  // per CTA and peer publishes the whole share; a __threadfence_system() in every thread (first version) cost ~20 us.
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int r = 0; r < p.world; ++r)
+      if (r != p.rank) red_release_sys_add(reinterpret_cast<unsigned*>(p.xbuf[r]) + 16 + 16 * par, 1u);
+    const unsigned expected = (unsigned)(p.world - 1) * gridDim.x;
+    const long long t0 = global_ns();
+    unsigned polls = 0;
+    while (ld_relaxed_sys(hdr + 16 + 16 * par) < expected) {
+      // a peer that never arrives (crashed rank, mismatched call sequence) must not hang the GPU: trap after 30 s
+      if ((++polls & 0xffffu) == 0 && global_ns() - t0 > 30000000000LL) __trap();
+    }
+    fence_acq_rel_sys();
+  }
+  __syncthreads();
+  return par;
+}
 
 __device__ __forceinline__ void stamp(const FusedParams& p, int& slot) {
   if (p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && slot < 40) {
@@ -171,6 +243,19 @@ __device__ __forceinline__ float grid_total(const float* part, float* red) {
   return t;       // identical in every thread
 }
 
+// Sum of `count` partials, same order in every CTA and on every rank.
+__device__ __forceinline__ float fixed_total(const float* part, int count, float* red) {
+  float v = 0.f;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) v += __ldcg(part + i);
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < 8; ++w) t += red[w];
+  return t;       // identical in every thread
+}
+
 __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) float panels[];      // operand panels of tile_gemm (fused_smem_bytes)
@@ -185,12 +270,21 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
   stamp(p, slot);
 
   // ---------------- phase 0: pooling scalars, Y = U + coef_k X_k, objective log
+  int xpar = 0;
   if (p.have_sums) {
     const int K = p.K, d_k = m / K;
+    if (p.world > 1) xpar = peer_exchange(p, n + K);
+    const float* inbox = p.world > 1 ? p.xbuf[p.rank] + kXHeaderFloats + (int64_t)xpar * p.world * p.xstride : nullptr;
+    auto S = [&](int64_t i) -> float {          // element i of the row sums reduced over the ranks, fixed order
+      if (p.world <= 1) return p.sums[i];
+      float v = 0.f;
+      for (int r = 0; r < p.world; ++r) v += (r == p.rank) ? p.sums[i] : __ldcg(inbox + (int64_t)r * p.xstride + i);
+      return v;
+    };
     if (tid == 0) {
       float acc = 0.f; int degenerate = 0;
       for (int k = 0; k < K; ++k) {
-        const float q = sqrtf((float)((double)p.sums[n + k] * p.inv_M));
+        const float q = sqrtf((float)((double)S(n + k) * p.inv_M));
         if (q == 0.f) ++degenerate;
         acc += sqrtf(q);
       }
@@ -203,7 +297,7 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
     float corr = 0.f;
     if (need_grad) {
       for (int k = tid; k < K; k += blockDim.x) {
-        const float q = sqrtf((float)((double)p.sums[n + k] * p.inv_M));
+        const float q = sqrtf((float)((double)S(n + k) * p.inv_M));
         // K > 64 is exotic: the factor is then recomputed on the fly below
         if (K <= 64) coef[k] = (float)((double)root * p.inv_M / ((double)K * (double)q * sqrt((double)q)));
       }
@@ -213,10 +307,10 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
         float c;
         if (K <= 64) c = coef[k];
         else {
-          const float q = sqrtf((float)((double)p.sums[n + k] * p.inv_M));
+          const float q = sqrtf((float)((double)S(n + k) * p.inv_M));
           c = (float)((double)root * p.inv_M / ((double)K * (double)q * sqrt((double)q)));
         }
-        const float u = p.U[i], gr = c * p.sums[i];
+        const float u = p.U[i], gr = c * S(i);
         if (p.U_out != nullptr) p.Y[i] = u + gr;
         if (p.u_rounded) corr = fmaf(gr, u - __half2float(__float2half_rn(u)), corr);
       }
@@ -231,12 +325,24 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
         if (idx < 0) { idx = p.status[3]; p.status[3] = (int)idx + 1; }
         p.obj_log[idx] = root * root + (p.u_rounded ? p.corr[0] : 0.f);
       }
+      if (p.world > 1 && tid == 0) {            // single CTA here: close this exchange (see below)
+        unsigned* hdr = reinterpret_cast<unsigned*>(p.xbuf[p.rank]);
+        hdr[16 + 16 * xpar] = 0u;
+        hdr[0] = __ldcg(hdr) + 1u;
+      }
       return;
     }
   }
   stamp(p, slot);
   grid.sync();
   stamp(p, slot);
+  if (p.have_sums && p.world > 1 && blockIdx.x == 0 && tid == 0) {
+    // every CTA has passed its wait and read its share: rewind this parity's arrival counter and advance the exchange
+    // counter (the peers' next arrivals on this parity come two exchanges later, after this kernel has ended)
+    unsigned* hdr = reinterpret_cast<unsigned*>(p.xbuf[p.rank]);
+    hdr[16 + 16 * xpar] = 0u;
+    hdr[0] = __ldcg(hdr) + 1u;
+  }
   if (p.have_sums && blockIdx.x == 0 && tid == 0 && p.obj_log != nullptr) {
     float extra = 0.f;
     if (p.u_rounded)
@@ -247,27 +353,41 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
   }
 
   const int tm = m / TS, td = d / TS;
-  // ---------------- phase 1: G = Y^T Y, row sums of |G|
+  // ---------------- phase 1: G = Y^T Y, row sums of |G|, ||G - I||_F^2
   for (int t = blockIdx.x; t < tm * tm; t += gridDim.x) {
     const int ti = t / tm, tj = t % tm;
     float acc[2][2];
     tile_gemm<0>(p.Y, m, ti * TS, p.Y, m, tj * TS, d, acc, panels);
+    float fr = 0.f;
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
       const int gi = ti * TS + 2 * ty + a;
       float rs = fabsf(acc[a][0]) + fabsf(acc[a][1]);
       p.G[(int64_t)gi * m + tj * TS + 2 * tx] = acc[a][0];
       p.G[(int64_t)gi * m + tj * TS + 2 * tx + 1] = acc[a][1];
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const float e = acc[a][b] - (gi == tj * TS + 2 * tx + b ? 1.f : 0.f);
+        fr = fmaf(e, e, fr);
+      }
       // the 16 threads of a half-warp share the row gi
       for (int o = 8; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
       if (tx == 0) p.rowsum[(int64_t)tj * m + gi] = rs;     // every (tj, gi) is written by exactly one tile
     }
+    const float tot = block_sum(fr, red);
+    if (tid == 0) p.fro[t] = tot;
   }
   stamp(p, slot);
   grid.sync();
   stamp(p, slot);
-  // ---------------- phase 2: c = ||G||_inf, X0 = Y / sqrt(c), G <- T_0 = 1.5 I - 0.5 G / c, resid[0]
+  // ---------------- phase 2: X0 = Y / sqrt(c), G <- T_0 = 1.5 I - 0.5 G / c, resid[0]
+  // Newton-Schulz converges for ||G||_2 < 3.  After an ascent step from an orthonormal U the Gram matrix is I + E with
+  // E small, and then the iteration is started from Y itself (c = 1): ||E||_2 <= ||E||_F < 1/2 guarantees convergence
+  // and the first residual is ||E|| instead of the ~0.2 per singular value that the safe scaling c = ||G||_inf (used
+  // otherwise) introduces -- two sweeps fewer in a normal step.  The decision is taken from the same partials by every
+  // CTA on every rank.
   {
+    const float fro2 = fixed_total(p.fro, tm * tm, red);
     float best = 0.f;
     for (int i = tid; i < m; i += blockDim.x) {
       float rs = 0.f;
@@ -278,7 +398,11 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
     __syncthreads();
     if ((tid & 31) == 0) red[tid >> 5] = best;
     __syncthreads();
-    if (tid == 0) { float v = 0.f; for (int w = 0; w < 8; ++w) v = fmaxf(v, red[w]); bc[1] = v; }
+    if (tid == 0) {
+      float v = 0.f;
+      for (int w = 0; w < 8; ++w) v = fmaxf(v, red[w]);
+      bc[1] = (fro2 < 0.25f) ? 1.f : v;
+    }
     __syncthreads();
   }
   const float c = bc[1];
@@ -308,6 +432,10 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
     const float res = grid_total(p.resid + (int64_t)it * gridDim.x, red);
     if (res < p.tol2_m) { converged = 1; break; }
     if (it >= p.max_iters) break;
+    // In the quadratic regime ||G' - I||_F <= 0.75 ||G - I||_F^2 (eigenvalues g -> -0.75 g^2 + O(g^3)).  If that bound
+    // is already below half the tolerance, this sweep is the last one and its Gram matrix (one GEMM phase and one grid
+    // barrier, only needed to confirm convergence) is not formed.  res = ||G - I||_F^2.
+    const bool last = 0.5625f * res * res < 0.25f * p.tol2_m;
     // nxt = cur * T
     for (int t = blockIdx.x; t < td * tm; t += gridDim.x) {
       const int tr = t / tm, tj = t % tm;
@@ -318,6 +446,13 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
         const int gi = tr * TS + 2 * ty + a;
         *reinterpret_cast<float2*>(&nxt[(int64_t)gi * m + tj * TS + 2 * tx]) = make_float2(acc[a][0], acc[a][1]);
       }
+    }
+    if (last) {
+      float* tmp = cur; cur = nxt; nxt = tmp;
+      ++it; converged = 1;
+      stamp(p, slot);
+      grid.sync();            // nxt is complete before the output phase reads it
+      break;
     }
     stamp(p, slot);
     grid.sync();
@@ -376,7 +511,7 @@ int fused_smem_bytes(int d, int m) {
 
 int64_t fused_ws_bytes(int d, int m, int max_iters) {
   return align_up((int64_t)d * m * 4, 256) * 3 + align_up((int64_t)m * m * 4, 256) +
-         align_up((int64_t)(m / TS) * m * 4, 256) + align_up((int64_t)(max_iters + 2) * 1024 * 4, 256);
+         align_up((int64_t)(m / TS) * m * 4, 256) + align_up((int64_t)(max_iters + 3) * 1024 * 4, 256);
 }
 }  // namespace
 
@@ -386,10 +521,17 @@ bool finish_fused_supported(int d, int m, int K) {
 
 int64_t finish_fused_workspace_bytes(int d, int m) { return fused_ws_bytes(d, m, 64); }
 
+// floats per (parity, source rank) slot of an exchange buffer, and the size of one rank's buffer
+int64_t exchange_stride(int d, int m, int K) { return align_up((int64_t)d * m + K, 64); }
+int64_t exchange_bytes(int d, int m, int K, int world) {
+  return (kXHeaderFloats + 2 * (int64_t)world * exchange_stride(d, m, K)) * 4;
+}
+
 // have_sums = 1: full finish step; have_sums = 0: retract the matrix already stored in Y_in (copied by the caller).
 int finish_fused(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out, void* Ut_hi,
                  void* Ut_lo, float* obj_log, int64_t log_index, int max_iters, float tol, int u_rounded, int* status,
-                 void* workspace, int64_t workspace_bytes, const float* Y_in, cudaStream_t stream) {
+                 void* workspace, int64_t workspace_bytes, const float* Y_in, const drsa_peer_exchange* px,
+                 cudaStream_t stream) {
   if (max_iters > 64) max_iters = 64;
   if (workspace_bytes < fused_ws_bytes(d, m, 64)) return DRSA_ERR_WORKSPACE;
   char* w = static_cast<char*>(workspace);
@@ -408,6 +550,17 @@ int finish_fused(const float* sums, int64_t M_global, const float* U, int d, int
   p.status = status; p.have_sums = (Y_in == nullptr) ? 1 : 0;
   p.u_rounded = (u_rounded && Y_in == nullptr) ? 1 : 0;
   p.corr = p.resid + (int64_t)(max_iters + 1) * 1024;       // the row after the last sweep's residual partials
+  p.fro = p.resid + (int64_t)(64 + 2) * 1024;                // last row of the 64 + 3 the workspace is sized for
+  p.world = 1; p.rank = 0;
+  if (px != nullptr && px->world > 1 && Y_in == nullptr) {
+    if (px->world > DRSA_MAX_PEERS || px->rank < 0 || px->rank >= px->world) return DRSA_ERR_ARG;
+    p.world = px->world; p.rank = px->rank;
+    p.xstride = exchange_stride(d, m, K);
+    for (int r = 0; r < px->world; ++r) {
+      if (px->buffers[r] == nullptr || !aligned16(px->buffers[r])) return DRSA_ERR_ARG;
+      p.xbuf[r] = static_cast<float*>(px->buffers[r]);
+    }
+  }
   if (Y_in != nullptr) DRSA_CUDA(cudaMemcpyAsync(p.Y, Y_in, (int64_t)d * m * 4, cudaMemcpyDeviceToDevice, stream));
   int tiles = (d / TS) * (m / TS);
   const int t2 = (m / TS) * (m / TS);

@@ -139,6 +139,45 @@ int drsa_finish_step(const float* sums, int64_t M_global, const float* U, int d,
                      int max_iters, float tol, int u_rounded, int* status, void* workspace,
                      int64_t workspace_bytes, void* stream);
 
+/*
+ * Data-parallel variant: the all-reduce of `sums` over the ranks (one process per GPU) fused into the head of the
+ * finish kernel over NVLink / NVSwitch peer memory, instead of an NCCL call between drsa_step and drsa_finish_step.
+ * (The reference is single-device, drsa.py:84-104; the sums are additive over row shards)
+ *
+ *   px->buffers[r]   rank r's exchange buffer of drsa_exchange_bytes(d, m, K, world) bytes as mapped into THIS
+ *                    process (buffers[px->rank] is this rank's own); zero-filled once, before the first call, with a
+ *                    host barrier between the fill and the first call.  Symmetric memory from
+ *                    torch.distributed._symmetric_memory or buffers shared with drsa_ipc_* both work.
+ *
+ * Every CTA pushes its share of this rank's sums into all peers' buffers, signals, waits for the peers' shares and adds
+ * the shares in rank order, so all ranks obtain bit-identical results.  All ranks must make the same sequence of
+ * calls (same shapes, same U_out == NULL pattern).  Asynchronous, capturable in a CUDA graph; a peer that does not
+ * arrive within 30 s makes the kernel trap (launch failure) rather than hang.  Shapes: d, m multiples of 32 (the
+ * fused finish kernel); drsa_exchange_bytes returns DRSA_ERR_SHAPE otherwise, and the caller keeps NCCL.
+ */
+#define DRSA_MAX_PEERS 8
+typedef struct drsa_peer_exchange {
+  int world;                       /* number of ranks, 2..DRSA_MAX_PEERS */
+  int rank;                        /* this process's rank */
+  void* buffers[DRSA_MAX_PEERS];   /* device addresses valid in this process */
+} drsa_peer_exchange;
+
+int64_t drsa_exchange_bytes(int d, int m, int K, int world);
+
+int drsa_finish_step_p2p(const drsa_peer_exchange* px, const float* sums, int64_t M_global, const float* U,
+                         int d, int m, int K, float* U_out, void* Ut_hi, void* Ut_lo, float* obj_log,
+                         int64_t log_index, int max_iters, float tol, int u_rounded, int* status,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/* cudaIpc plumbing for exchange buffers when torch's symmetric memory is unavailable.  These are the only entry
+ * points of the library that allocate: drsa_ipc_alloc returns a zero-filled cudaMalloc'ed buffer and its 64-byte
+ * cudaIpcMemHandle_t (to be sent to the peers through any host channel); drsa_ipc_open maps a peer's buffer;
+ * drsa_ipc_close / drsa_ipc_free undo them (close every mapping before the owner frees). */
+int drsa_ipc_alloc(int64_t bytes, void** ptr, unsigned char* handle64);
+int drsa_ipc_open(const unsigned char* handle64, void** ptr);
+int drsa_ipc_close(void* ptr);
+int drsa_ipc_free(void* ptr);
+
 /* orthogonalize(U) of drsa.py:201-221 on its own: U_out = Y (Y^T Y)^(-1/2). */
 int drsa_polar_retract(const float* Y, int d, int m, float* U_out, int max_iters, float tol,
                        int* status, void* workspace, int64_t workspace_bytes, void* stream);
@@ -237,6 +276,18 @@ int lrp_tc_conv3x3_supported(int64_t B, int Cin_p, int Cout_p, int H, int W);
 int lrp_tc_conv3x3_forward(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
                            const float* bias, int64_t B, int H, int W, int Cin_p, int Cout_p, int Cout,
                            int relu, void* y_hi, void* y_lo, float* y_nchw, int* err_flag, void* stream);
+
+/* The same convolution with the MaxPool2d(kh, kw) that follows it (stride = kernel, create_model.py:120-127) fused into
+ * the epilogue: y_hi / y_lo are the POOLED planes [B, H/kh, W/kw, Cout_p], argmax_u8 (optional) as in lrp_tc_maxpool.
+ * The full-resolution map is never written (for the first block of the genre CNN that is 8.4 MB per sample, written
+ * and read again by lrp_tc_maxpool).  kh, kw powers of two; tiles of 8 x 16 pixels (H % 8 == 0, W % 16 == 0) or whole
+ * 8 x 8 maps; lrp_tc_conv3x3_pool_supported returns DRSA_OK for shapes this covers.  Only valid when nothing needs
+ * the un-pooled activation (no split layer, no un-hooked ReLU mask between the convolution and the pooling). */
+int lrp_tc_conv3x3_pool_supported(int64_t B, int Cin_p, int Cout_p, int H, int W, int kh, int kw);
+int lrp_tc_conv3x3_forward_pool(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                                const float* bias, int64_t B, int H, int W, int Cin_p, int Cout_p, int Cout,
+                                int relu, int kh, int kw, void* y_hi, void* y_lo, void* argmax_u8,
+                                int* err_flag, void* stream);
 
 /* First layer (Cin = 1, bandwidth bound, CUDA cores): x [B,1,H,W] fp32, w [Cout,9] -> NHWC hi/lo planes. */
 int lrp_tc_conv3x3_first(const float* x, const float* w, const float* b, int64_t B, int H, int W, int Cout,

@@ -26,16 +26,27 @@ def _worker(rank, world, port, ret):
     U0 = drsa_ref.synth_U0(d, seed=78)
     lo, hi = (0, 9000) if rank == 0 else (9000, M)           # uneven shards
     out = {}
-    for prec in ("fp32", "tc"):
-        opt = SubspaceOptimizer(U0, A[lo:hi], C[lo:hi], None, num_concepts=K, device=f"cuda:{rank}", precision=prec)
+    # exchange: NCCL all-reduce between the kernels / fused into the finish kernel over peer memory (CUDA graph replay
+    # and direct launches)
+    for prec, exch, graph in (("fp32", "nccl", True), ("tc", "nccl", True), ("fp32", "p2p", True), ("tc", "p2p", True),
+                              ("tc", "p2p", False)):
+        opt = SubspaceOptimizer(U0, A[lo:hi], C[lo:hi], None, num_concepts=K, device=f"cuda:{rank}", precision=prec,
+                                exchange=exch, use_cuda_graph=graph)
+        assert opt.exchange == exch and opt.use_cuda_graph == (graph and exch == "p2p")
         opt.run(steps=steps, save=False)
         gathered = [torch.zeros_like(opt.U) for _ in range(world)]
         dist.all_gather(gathered, opt.U)
-        out[prec] = (opt.obj_history.copy(), opt.U.cpu(), float((gathered[0] - gathered[1]).abs().max()), opt.M_global)
+        out[(prec, exch, graph)] = (opt.obj_history.copy(), opt.U.cpu(), float((gathered[0] - gathered[1]).abs().max()),
+                                    opt.M_global)
     if rank == 0:
         objs_ref, U_ref = drsa_ref.run_autograd(A, C, U0, K, steps)
-        for prec, (objs, U, rep, Mg) in out.items():
-            ret[prec] = (float(np.max(np.abs(objs - objs_ref) / np.abs(objs_ref))), drsa_ref.principal_angle(U, U_ref, K), rep, Mg)
+        for key, (objs, U, rep, Mg) in out.items():
+            ret["/".join(map(str, key))] = (float(np.max(np.abs(objs - objs_ref) / np.abs(objs_ref))),
+                                            drsa_ref.principal_angle(U, U_ref, K), rep, Mg)
+        # two ranks: a + b is the same float whoever adds it, so both exchanges give the same bits
+        ret["same_bits"] = bool(torch.equal(out[("tc", "nccl", True)][1], out[("tc", "p2p", True)][1])
+                                and torch.equal(out[("tc", "p2p", True)][1], out[("tc", "p2p", False)][1])
+                                and torch.equal(out[("fp32", "nccl", True)][1], out[("fp32", "p2p", True)][1]))
     dist.destroy_process_group()
 
 
@@ -47,9 +58,13 @@ def test_two_rank_row_sharding_matches_reference():
     with mp.Manager() as mgr:
         ret = mgr.dict()
         mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
-        for prec in ("fp32", "tc"):
-            rel, ang, rep, Mg = ret[prec]
-            print(prec, rel, ang, rep)
+        assert len(ret) == 6
+        for key in ret.keys():
+            if key == "same_bits":
+                continue
+            rel, ang, rep, Mg = ret[key]
+            print(key, rel, ang, rep)
             assert Mg == 20000
             assert rel < 1e-4 and ang < 1e-3
             assert rep == 0.0
+        assert ret["same_bits"]

@@ -398,6 +398,49 @@ def test_engine_chunk_does_not_change_results(monkeypatch):
     assert _rel_per_sample(Rw, Rc) < 1e-5
 
 
+@pytest.mark.parametrize("case", ["genre_bn", "toy"])
+def test_fused_conv_pool_equals_separate_kernels(case):
+    """MaxPool2d fused into the epilogue of the convolution before it (lrp_tc_conv3x3_forward_pool) against the separate
+    pooling kernel: activations and relevance at a split layer (pools below the split are fused), and the full-depth
+    relevance (every pool fused, arg-max bytes written by the epilogue)."""
+    from cxai.utils.constants import lrp_name_map_6s, LRP_NAME_MAP_TOY
+    from cxai.xai.explain.rules import NameMapComposite, SequentialMergeBatchNorm
+    from cxai.xai.explain import lrp_engine
+    from cxai.xai.explain.attribute import compute_relevances
+    from cxai.xai.drsa.preprocessing import get_intermediate
+    if case == "genre_bn":
+        net = lrp_ref.genre_model(seed=0, last=256, input_size=(128, 256))
+        x = lrp_ref.synth_logmel(3, 128, 256, 20264).cuda()
+        comp = NameMapComposite(lrp_name_map_6s(), canonizers=[SequentialMergeBatchNorm()])
+        layer, n_fused = net.features[33], 4
+    else:
+        net = lrp_ref.toy_model(seed=0, last=64)
+        x = lrp_ref.synth_logmel(5, 64, 64, 20265).cuda()         # odd batch: the 8 x 8 layer packs two images per tile
+        comp = NameMapComposite(LRP_NAME_MAP_TOY)
+        layer, n_fused = net.features[13], 3
+    plan = lrp_engine._plan(net, comp, x.device)
+    assert plan._tc_stack_ok(x)
+    res = {}
+    for fuse in (True, False):
+        plan.fuse_pool = fuse
+        res[fuse] = (get_intermediate(net, x, comp, layer, 1), compute_relevances(net, x, comp, class_idx=1))
+    plan.fuse_pool = True
+    split = plan.module_to_op[layer].index
+    H, W = x.shape[2:]
+    fused = []
+    for k, op in enumerate(plan.ops):
+        if op.kind == "conv":
+            fused.append(plan._fusable_pool(k, split + 1, split, x.size(0), H, W) is not None)
+        elif op.kind == "pool":
+            H, W = H // op.kh, W // op.kw
+    assert sum(fused) == n_fused
+    (a1, R1), full1 = res[True]
+    (a0, R0), full0 = res[False]
+    assert _rel_per_sample(a1, a0) < 1e-6
+    assert _rel_per_sample(R1, R0) < 1e-5
+    assert _rel_per_sample(full1, full0) < 1e-5
+
+
 def test_subspace_filter_kernels_match_fp64():
     """lrp_subspace_project / lrp_subspace_filter (Epsilon on both projections + SubspaceHook mask) vs fp64 torch on
     the SAME inputs, padded leading dimension included."""
