@@ -164,6 +164,12 @@ def run_ours(args):
     torch.cuda.synchronize()
     ms_finish = f0.elapsed_time(f1) / args.steps
     status = opt._rows.status.cpu().numpy().tolist()
+    per_rank = None
+    if world > 1:          # the step is synchronous: the slowest rank's row pass sets the pace (power capping differs per GPU)
+        tk = torch.tensor([ms_kernel], dtype=torch.float64, device=dev)
+        allk = [torch.zeros_like(tk) for _ in range(world)]
+        dist.all_gather(allk, tk)
+        per_rank = [round(float(v.item()), 4) for v in allk]
     lrp = None if args.no_lrp else lrp_throughput(args, dev, rank, world, barrier)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -227,7 +233,8 @@ def run_ours(args):
                          "hbm_frac": (2.0 * M * d * elem / (ms_kernel * 1e-3) / 1e9) / peaks["hbm"],
                          "peak_source": peaks["source"] + "; sustained bf16 figure (kernel timed in a loop)",
                          "share_of_step": ms_kernel / ms_per_step},
-            "step_breakdown_ms": {"row_pass": ms_kernel, "ascent_and_retraction": ms_finish},
+            "step_breakdown_ms": {"row_pass": ms_kernel, "ascent_and_retraction": ms_finish,
+                                  **({"row_pass_per_rank": per_rank} if per_rank else {})},
             "lrp": lrp,
             "e2e": {"value": scale * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_steps,
                     "d2h_bytes_per_step": d2h / e2e_steps, "steps": e2e_steps,

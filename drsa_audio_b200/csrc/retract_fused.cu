@@ -30,8 +30,8 @@ struct FusedParams {
   float* corr;     // [gridDim.x] per-CTA partials of that inner product
   long long* prof; // debug: %globaltimer stamps of CTA 0 at the phase boundaries (drsa_debug_set_tc_profile), or NULL
   // peer exchange (world > 1): xbuf[r] = rank r's exchange buffer as mapped into this process (NVLink peer memory).
-  // Layout of a buffer: 64 x u32 header ([0] = exchange counter of the owner, [16] / [32] = arrival counters of the two
-  // parities), then floats data[parity][source rank][xstride].
+  // Layout of a buffer: 64 x u32 header ([0] = exchange counter of the owner, [8] / [9] = local CTA counters and
+  // [16] / [32] = arrival counters of the two parities), then floats data[parity][source rank][xstride].
   int world, rank;
   float* xbuf[DRSA_MAX_PEERS];
   int64_t xstride;
@@ -59,9 +59,9 @@ __device__ __forceinline__ long long global_ns() {
 }
 
 // The all-reduce of the row sums, fused into the head of the finish kernel (push model over NVLink peer memory):
-// every CTA stores its grid-stride share of this rank's `sums` into slot [parity][rank] of EVERY peer's buffer,
-// fences, and bumps the peer's arrival counter once; then it waits until all (world - 1) * gridDim.x arrivals of the
-// peers have landed in its own buffer.  The reduced value of element i is the sum over ranks in rank order (own
+// every CTA stores its grid-stride share of this rank's `sums` into slot [parity][rank] of EVERY peer's buffer and
+// fences; the last CTA to do so bumps every peer's arrival counter; then all CTAs wait until the world - 1 arrivals
+// of the peers have landed in their own buffer.  The reduced value of element i is the sum over ranks in rank order (own
 // share read from `sums`), so every rank adds the same floats in the same order: replicas of U stay bit-identical.
 // Two parities: a peer can run at most one exchange ahead (it needs this rank's arrivals of exchange s + 1 before it
 // can finish it), so slot [s & 1] is never overwritten while it is still being read.  Returns the parity.
@@ -83,13 +83,22 @@ __device__ __forceinline__ int peer_exchange(const FusedParams& p, int64_t total
     for (int r = 0; r < p.world; ++r)
       if (r != p.rank) p.xbuf[r][slot + i] = v;
   }
-  // The CTA barrier orders every thread's stores before thread 0's release (cumulativity), so ONE system-scope release
-  // per CTA and peer publishes the whole share; a __threadfence_system() in every thread (first version) cost ~20 us.
+  // Publication: the CTA barrier orders every thread's stores before thread 0, which makes them visible system-wide
+  // with ONE fence per CTA (a __threadfence_system() in every thread, the first version, cost ~20 us) and then counts
+  // itself on a local counter; the last CTA of the grid signals every peer once.  (One remote arrival per CTA and peer,
+  // the second version, serialises (world - 1) * gridDim.x atomics on one address of every receiver: fine for two
+  // ranks; at eight the step went from 0.433 to 0.409 ms with this version.)
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int r = 0; r < p.world; ++r)
-      if (r != p.rank) red_release_sys_add(reinterpret_cast<unsigned*>(p.xbuf[r]) + 16 + 16 * par, 1u);
-    const unsigned expected = (unsigned)(p.world - 1) * gridDim.x;
+    fence_acq_rel_sys();
+    unsigned* done = hdr + 8 + par;
+    if (atomicAdd(done, 1u) == gridDim.x - 1) {
+      *done = 0u;                                     // next used two exchanges later
+      __threadfence();
+      for (int r = 0; r < p.world; ++r)
+        if (r != p.rank) red_release_sys_add(reinterpret_cast<unsigned*>(p.xbuf[r]) + 16 + 16 * par, 1u);
+    }
+    const unsigned expected = (unsigned)(p.world - 1);
     const long long t0 = global_ns();
     unsigned polls = 0;
     while (ld_relaxed_sys(hdr + 16 + 16 * par) < expected) {
