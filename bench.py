@@ -307,18 +307,20 @@ def lrp_throughput(args, dev, rank, world, barrier):
            "samples_per_gpu": n, "positions": P, "d": int(act.shape[1]), "ms": ms,
            "e2e_value": n * P * world / t_e2e, "h2d_bytes": int(xh.numel() * 4),
            "forward_tflops": flops / (ms * 1e-3) / 1e12,
-           "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM, TMA im2col, fp16 hi/lo operands) + NHWC pooling; "
-                     "dense head and pool routing on CUDA cores"}
+           "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM, TMA im2col, fp16 hi/lo operands, max-pool fused into the "
+                     "epilogue below the split layer); first conv, dense head and pool routing on CUDA cores",
+           "samples_per_engine_pass": min(n, 256)}
     if rank == 0:
-        out["roofline"] = lrp_conv_roofline(dev, ms / max(1, -(-n // 64)))
+        out["roofline"] = lrp_conv_roofline(dev, ms / max(1, n / 64.0))
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = lrp_cpu_baseline(P)
     return out
 
 
 def lrp_conv_roofline(dev, stage_ms_per_minibatch):
-    """The dominant kernel of stage 1 alone: conv3x3_tc_kernel<2, resident weights> on the 64 -> 64 layer at 128 x 256
-    (68 % of the forward MACs), one minibatch of 64 samples as the engine launches it, CUDA events on its stream."""
+    """The dominant kernel of stage 1 alone: conv3x3_tc_kernel<2, resident weights, halo boxes> on the 64 -> 64 layer at
+    128 x 256 (68 % of the forward MACs) with the (2, 4) max-pool of create_model.py:120 fused into its epilogue, as the
+    engine launches it below the split layer; 64 samples per launch, CUDA events on its stream."""
     import torch
     from drsa_audio_b200 import _lib as L
     lib = L.lib()
@@ -331,12 +333,12 @@ def lrp_conv_roofline(dev, stage_ms_per_minibatch):
     s = torch.cuda.current_stream().cuda_stream
     L.check(lib.lrp_tc_split_f16(wt.data_ptr(), wt.numel(), wh.data_ptr(), wl.data_ptr(), s))
     bias = torch.zeros(Cc, device=dev)
-    yh = torch.empty(B, H, W, Cc, dtype=torch.float16, device=dev); yl = torch.empty_like(yh)
+    yh = torch.empty(B, H // 2, W // 4, Cc, dtype=torch.float16, device=dev); yl = torch.empty_like(yh)
     err = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def run():
-        L.check(lib.lrp_tc_conv3x3_forward(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), bias.data_ptr(), B, H, W,
-                                           Cc, Cc, Cc, 1, yh.data_ptr(), yl.data_ptr(), None, err.data_ptr(), s))
+        L.check(lib.lrp_tc_conv3x3_forward_pool(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), bias.data_ptr(), B, H,
+                                                W, Cc, Cc, Cc, 1, 2, 4, yh.data_ptr(), yl.data_ptr(), None, err.data_ptr(), s))
     for _ in range(3):
         run()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -350,13 +352,23 @@ def lrp_conv_roofline(dev, stage_ms_per_minibatch):
     flops = 2.0 * 9 * Cc * Cc * H * W * B
     peaks = _peaks()
     ach = flops / (kms * 1e-3) / 1e12
+    in_bytes, out_bytes = 2.0 * B * H * W * Cc * 2, 2.0 * B * (H // 2) * (W // 4) * Cc * 2
     return {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
-            "traffic": None, "kernel": "conv3x3_tc_kernel<2, resident weights> (64->64 @128x256, 64 samples)", "kernel_ms": kms,
-            "algorithmic_flop_per_launch": flops, "executed_mma_flop_per_launch": 3 * flops,
-            "algorithmic_bytes_per_launch": 4.0 * B * H * W * Cc * 2,
+            "traffic": LRP_CONV_TRAFFIC_BYTES_PER_LAUNCH,
+            "kernel": "conv3x3_tc_kernel<2, resident weights, halo boxes> + fused (2,4) max-pool (64->64 @128x256, 64 samples)",
+            "kernel_ms": kms, "algorithmic_flop_per_launch": flops, "executed_mma_flop_per_launch": 3 * flops,
+            "algorithmic_bytes_per_launch": in_bytes + out_bytes,
+            "hbm_frac": ((in_bytes + out_bytes) / (kms * 1e-3) / 1e9) / peaks["hbm"],
             "share_of_stage": kms / stage_ms_per_minibatch,
+            "note": "fp32-class accuracy needs three fp16 products per MAC (hi*hi + lo*hi + hi*lo, SURVEY H4), so the "
+                    "algorithmic fraction is bounded by 1/3; executed MMA flop / peak = 3 x frac",
             "l2_policy": "inputs larger than L2 (537 MB of activation planes per launch)",
             "peak_source": peaks["source"] + "; sustained bf16 figure"}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of that launch (profiles/r01_ncu_full_conv_first_fusedpool_v6.csv):
+# 537.1 MB read + 61.3 MB written vs 536.9 + 67.1 MB algorithmic
+LRP_CONV_TRAFFIC_BYTES_PER_LAUNCH = 598.4e6
 
 
 def lrp_cpu_baseline(P: int, n: int = 4):
