@@ -45,8 +45,18 @@ __global__ void __launch_bounds__(256) context_gather_kernel(const float* __rest
     }
   }
   if (sumsq != nullptr) {
-    double da = warp_sum((double)sa), dc = warp_sum((double)sc);
-    if (tx == 0) { atomicAdd(&sumsq[0], da); atomicAdd(&sumsq[1], dc); }
+    // one pair of atomics per CTA: one per warp (65 k double atomics on two addresses for 256 samples) serialised in
+    // L2 and made this kernel 7x slower than its memory traffic
+    __shared__ double red[2][8];
+    const double da = warp_sum((double)sa), dc = warp_sum((double)sc);
+    if (tx == 0) { red[0][ty] = da; red[1][ty] = dc; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+      atomicAdd(&sumsq[threadIdx.x], t);
+    }
   }
 }
 
