@@ -99,6 +99,15 @@ __device__ __forceinline__ uint32_t kdesc_lo(uint32_t smem_addr) { return (smem_
 __device__ __forceinline__ uint32_t mndesc_lo(uint32_t smem_addr) { return (smem_addr >> 4) | ((4096u >> 4) << 16); }            // LBO 4 KB: next 64-channel panel
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
 
+// TMA prefetch of a box into L2 (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+constexpr int kPrefetchAhead = 3;      // subtiles (pair kernel only; measured: no effect on either kernel -- the waits on the
+                                       // `full` barriers are not HBM latency)
+
 __device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // d = {hi : upper, lo : lower}
@@ -632,6 +641,370 @@ drsa_tc_step32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for d = 256, single-pass mode, an even number of column groups.
+//
+// The kernel above is bound by shared-memory bandwidth, not by the tensor pipe: per 64-row subtile a CTA moves 320 KB
+// through shared memory (GEMM1 operand reads 128 KB, GEMM2 operand reads 64 KB, TMA writes 128 KB) in ~3 350 cycles =
+// 96 B/clk of the 128 B/clk peak, while the MMAs need 2 048 cycles.  Here the two CTAs of a cluster (one TPC) take the
+// two column groups of the SAME row block and issue every MMA together (M = 256: lanes 0..127 of CTA r are the 128
+// projected columns of group 2*gp + r), so the row operand is shared:
+//   GEMM1  D[256][64 A rows | 64 C rows] : A operand = each CTA's resident U^T panel, B operand (N = 128) split by the
+//          hardware: CTA 0 stages the 64 A rows, CTA 1 the 64 C rows               (6 KB instead of 8 KB per MMA and CTA)
+//   GEMM2  D[256][256 channels]          : A operand = each CTA's P^T | Q^T in TMEM, B operand (N = 256) split:
+//          CTA r stages channels 128 r .. 128 r + 127 of the A and C rows          (4 KB instead of 8 KB per MMA and CTA)
+// and every CTA stages half of the bytes: 192 KB per subtile and CTA.  Only the leader (rank 0) issues MMAs; TMA loads of
+// both CTAs complete on the leader's `full` barriers; tcgen05.commit multicasts to the `empty` / `h_full` / `x_full`
+// barriers of both CTAs; the epilogue warps of both CTAs arrive on the leader's `p_full` barriers.  Epilogue arithmetic,
+// TMEM layout (X^T 256 | H0 128 | H1 128 columns) and the partial-sum layout are those of the kernel above.
+//
+// EXPERIMENTAL (drsa_debug_set_tc_variant(2)), parity-tested, NOT the default.  Measured at cfg 2: correct (sums agree to
+// 1e-8), shared-memory traffic falls as planned (ncu: tensor-core smem wavefronts 40 % -> 24 %, bank writes 15 % -> 7 %),
+// but the row pass is slower, 0.33-0.36 ms against 0.30-0.33 ms.  The MMA issue-rate probe (drsa_selftest_umma(10..15),
+// scripts/umma_rate.py; operands resident, nothing else running) explains why the premise was wrong: an SS-mode MMA
+// costs its compute time PLUS the 32 cycles it takes to fetch the 128 x 16 A-operand slice from shared memory
+// (M128 N128: 102 cycles, N256: 166), a TS-mode MMA only compute + 9 (N256: 137), and cta_group::2 changes neither
+// (M256 N128 SS: 104, M256 N256 TS: 137).  GEMM1 at N = 128 is therefore 16 x 102 = 1 632 cycles per subtile in either
+// kernel (measured 1 619 / 1 610), GEMM2 8 x 137 = 1 096: a practical floor of ~2 730 cycles per subtile where the
+// single-CTA kernel takes ~3 350, not the 2 048 the tensor pipe alone would need.  What the pair adds on top is
+// cross-CTA hand-over latency on the critical path E(i) -> GEMM2(i) (a .release.cluster arrive cost ~1 800 cycles; with
+// the default semantics ~300) and an epilogue whose ~1 800 issue cycles per subtile no longer hide under slower MMAs.
+constexpr int kPairStageBytes = 16384;
+constexpr int kPairStages = 9;
+constexpr int kPairBarBytes = 320;               // 32 mbarriers + the TMEM address slot
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;       // shared::cluster address of the same offset in the even CTA of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc512_pair(uint32_t* smem_result) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(smem_result)) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc512_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(taddr) : "memory");
+}
+// TMA load whose bytes are counted on the LEADER's mbarrier (address with the peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_ss_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// all MMAs issued so far arrive on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+// Arrive on a barrier of another CTA of the cluster.  Default semantics (release at CTA scope) as in CUTLASS's
+// ClusterBarrier::arrive: what the waiter consumes is tensor memory, made visible by tcgen05.wait::st + tcgen05.fence
+// before this; .release.cluster here cost ~1 800 cycles per arrival (measured), i.e. most of the epilogue latency.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+template <int D>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+drsa_tc_step_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC,
+                         const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmC2,
+                         const __grid_constant__ CUtensorMap tmUh, int n_sub, int G, int nRB, int d_k, float inv_scale,
+                         float pq_scale, float* __restrict__ part, float* __restrict__ ss_part, int* __restrict__ err_flag,
+                         long long* __restrict__ prof, int debug_no_pwait) {
+  static_assert(D == 256, "pair kernel: d = 256");
+  constexpr int kPanels = D / 64;
+  constexpr int kUBytes = kPanels * kPanelBytes;                 // this CTA's [128 x D] fp16 panel of U^T
+  constexpr int kDataBytes = kUBytes + kPairStages * kPairStageBytes;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sU = smem;
+  uint8_t* sStage = smem + kUBytes;
+  float* red = reinterpret_cast<float*>(smem + kDataBytes);      // [2 buffers][4 lane quarters][64 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDataBytes + kRedBytes);
+  uint64_t* full = bars;             // [kPairStages]   used in the leader only
+  uint64_t* empty = bars + 10;       // [kPairStages]
+  uint64_t* u_full = bars + 20;      // leader only
+  uint64_t* x_full = bars + 21;
+  uint64_t* h_full = bars + 22;      // [2]
+  uint64_t* p_full = bars + 24;      // [2 buffers][4 chunks of 16 rows], leader only: one arrival per epilogue warp of both CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, G2 = G >> 1;
+  const int g = 2 * (pair % G2) + (int)rank, rb = pair / G2;
+
+  if ((smem_u32(smem) & 1023u) != 0) {   // same in both CTAs of the pair
+    if (threadIdx.x == 0) atomicExch(err_flag, 1);
+    return;
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kPairStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(u_full, 1); mbar_init(x_full, 1); mbar_init(&h_full[0], 1); mbar_init(&h_full[1], 1);
+    for (int c = 0; c < 8; ++c) mbar_init(&p_full[c], 8);      // 4 warps of each CTA
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc512_pair(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ======================= TMA producer (both CTAs) =======================
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmC); tma_prefetch_desc(&tmUh);
+      tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmC2);
+      if (rank == 0) mbar_expect_tx(u_full, 2 * kUBytes);
+      const uint32_t u_full_l = smem_u32(u_full) & kPeerMask;
+      for (int p = 0; p < kPanels; ++p) tma_load_2d_pair(sU + p * kPanelBytes, &tmUh, u_full_l, 64 * p, g * kNG);
+      int stage = 0; uint32_t phase = 0;
+      long long pe = 0;
+      // GEMM1 operand of this CTA: 64 rows (A rows in CTA 0, C rows in CTA 1) x two 64-channel panels per stage
+      auto load_g1 = [&](int sub) {
+        for (int hs = 0; hs < kPanels / 2; ++hs) {
+          const long long w0 = prof ? clock64() : 0;
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (prof) pe += clock64() - w0;
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * kPairStageBytes);
+          const uint32_t full_l = smem_u32(&full[stage]) & kPeerMask;
+          uint8_t* dst = sStage + stage * kPairStageBytes;
+#pragma unroll
+          for (int pp = 0; pp < 2; ++pp)
+            tma_load_2d_pair(dst + pp * 8192, rank == 0 ? &tmA : &tmC, full_l, 64 * (2 * hs + pp), sub * kSub);
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+      };
+      // GEMM2 operand of this CTA: 32-row chunks of A and of C, channels 128 rank .. 128 rank + 127 (two 4 KB panels each)
+      auto load_g2 = [&](int sub) {
+        for (int c = 0; c < 2; ++c) {
+          const long long w0 = prof ? clock64() : 0;
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (prof) pe += clock64() - w0;
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * kPairStageBytes);
+          const uint32_t full_l = smem_u32(&full[stage]) & kPeerMask;
+          uint8_t* dst = sStage + stage * kPairStageBytes;
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            tma_load_2d_pair(dst + p * 4096, &tmA2, full_l, 128 * (int)rank + 64 * p, sub * kSub + 32 * c);
+            tma_load_2d_pair(dst + 8192 + p * 4096, &tmC2, full_l, 128 * (int)rank + 64 * p, sub * kSub + 32 * c);
+          }
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+      };
+      int prev = -1;
+      for (int sub = rb; sub < n_sub; sub += nRB) {
+        {   // this CTA's rows (A in the leader, C in the peer) of a later subtile into L2
+          const int ps = sub + kPrefetchAhead * nRB;
+          if (ps < n_sub)
+            for (int p = 0; p < kPanels; ++p) tma_prefetch_l2_2d(rank == 0 ? &tmA : &tmC, 64 * p, ps * kSub);
+        }
+        load_g1(sub);
+        if (prev >= 0) load_g2(prev);
+        prev = sub;
+      }
+      if (prev >= 0) load_g2(prev);
+      if (prof && blockIdx.x < 2) prof[15 - blockIdx.x] = pe;
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer (leader CTA only) =======================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc1 = make_idesc_f16(2 * kNG, 2 * kSub, 0, 0);   // [U^T_g0 ; U^T_g1] x [A rows | C rows]
+      constexpr uint32_t idesc2 = make_idesc_f16(2 * kNG, D, 0, 1);          // P^T / Q^T (TMEM) x rows (MN-major, N = D)
+      const uint32_t tX = tmem_base;
+      mbar_wait(u_full, 0);
+      tc_fence_after();
+      int stage = 0; uint32_t phase = 0; bool first = true;
+      long long pa = 0, pb = 0, pc = 0, pw = 0;
+      auto gemm1 = [&](int i) {
+        const long long t0 = prof ? clock64() : 0;
+        const uint32_t tH = tmem_base + 256 + 128 * (i & 1);
+        for (int hs = 0; hs < kPanels / 2; ++hs) {
+          const long long w0 = prof ? clock64() : 0;
+          mbar_wait(&full[stage], phase);
+          if (prof) pw += clock64() - w0;
+          tc_fence_after();
+          const uint32_t base = smem_u32(sStage + stage * kPairStageBytes);
+#pragma unroll
+          for (int pp = 0; pp < 2; ++pp) {
+            const int p = 2 * hs + pp;
+            const uint32_t uh = kdesc_lo(smem_u32(sU + p * kPanelBytes));
+            const uint32_t dR = kdesc_lo(base + pp * 8192);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma2_ss_f16(tH, desc64(uh + 2 * kk), desc64(dR + 2 * kk), idesc1, (p | kk) ? 1u : 0u);
+          }
+          umma2_commit_both(&empty[stage]);
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+        umma2_commit_both(&h_full[i & 1]);
+        if (prof) pa += clock64() - t0;
+      };
+      auto gemm2 = [&](int i) {
+        const long long t0 = prof ? clock64() : 0;
+        long long t1 = t0;
+        const uint32_t tH = tmem_base + 256 + 128 * (i & 1);
+        const uint32_t par = (uint32_t)(i >> 1) & 1u;
+        for (int c = 0; c < 2; ++c) {
+          const long long w0 = prof ? clock64() : 0;
+          mbar_wait(&full[stage], phase);
+          if (prof) pw += clock64() - w0;
+          const uint32_t base = smem_u32(sStage + stage * kPairStageBytes);
+          const uint32_t dA = mndesc_lo(base), dC = mndesc_lo(base + 8192);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const long long w1 = prof ? clock64() : 0;
+            if (!debug_no_pwait) mbar_wait(&p_full[4 * (i & 1) + 2 * c + h], par);      // P^T / Q^T of rows 32 c + 16 h .. + 15
+            if (prof) t1 += clock64() - w1;
+            tc_fence_after();
+            const uint32_t off = 32 * c + 16 * h;                   // fp16 pairs: 8 TMEM columns from the chunk's first column
+            umma2_ts_f16(tX, tH + off, desc64(dA + 128 * h), idesc2, first ? 0u : 1u);
+            umma2_ts_f16(tX, tH + kSub + off, desc64(dC + 128 * h), idesc2, 1u);
+            first = false;
+          }
+          umma2_commit_both(&empty[stage]);
+          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+        }
+        if (prof) { pb += t1 - t0; pc += clock64() - t1; }
+      };
+      int i = 0;
+      for (int sub = rb; sub < n_sub; sub += nRB, ++i) {
+        gemm1(i);
+        if (i > 0) gemm2(i - 1);
+      }
+      if (i > 0) gemm2(i - 1);
+      umma2_commit_both(x_full);
+      if (prof && blockIdx.x == 0) { prof[0] = pa; prof[1] = pb; prof[2] = pc; prof[5] = pw; }
+    }
+  } else {
+    // ======================= epilogue warps (both CTAs, each on its own TMEM lanes) =======================
+    // All 16 warps work on EVERY subtile: warp = (TMEM lane quarter q, 16-row chunk c).  What bounds the pair kernel is
+    // the latency of this epilogue (GEMM2(i) can only start when E(i) is done, and the tensor pipe has just one GEMM2 and
+    // one GEMM1 = 2 048 cycles of other work to do meanwhile); two alternating sets of 8 warps working on 32-row chunks
+    // (the single-CTA kernel's arrangement) took ~3 600 cycles per subtile, this one half the per-warp work.
+    const int q = warp & 3;
+    const int c = (warp - 2) >> 2;              // 16-row chunk 0..3
+    const int j = 32 * q + lane;
+    const int wpc = d_k >> 5;
+    const int q0 = (q / wpc) * wpc;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
+    const bool owner = (j % d_k) == 0;
+    float ssq = 0.f;
+    uint32_t p_full_l[2];                       // the leader's p_full barriers of this warp's chunk, per H buffer
+#pragma unroll
+    for (int bfi = 0; bfi < 2; ++bfi) {
+      uint32_t a = smem_u32(&p_full[4 * bfi + c]);
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(p_full_l[bfi]) : "r"(a), "r"(0));
+    }
+    long long ea = 0, eb = 0, e0 = 0, e1 = 0;
+    int i = 0;
+    for (int sub = rb; sub < n_sub; sub += nRB, ++i) {
+      const int buf = i & 1;
+      if (prof) e0 = clock64();
+      mbar_wait(&h_full[buf], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      if (prof) e1 = clock64();
+      const uint32_t tHA = lane_base + 256 + 128 * buf + 16 * c, tHC = tHA + kSub;
+      float* redb = red + buf * (4 * kSub);
+      uint32_t ha[16], hc[16];
+      tmem_ld16(tHA, ha);
+      tmem_ld16(tHC, hc);
+      tmem_ld_wait();
+      float pr[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) pr[e] = __uint_as_float(ha[e]) * __uint_as_float(hc[e]);
+      // transpose-reduce over the lane bits 3..0: afterwards lane l holds the sum over its 16-lane half of column l & 15
+#pragma unroll
+      for (int off = 8; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int e = 0; e < off; ++e) {
+          const float send = upper ? pr[e] : pr[e + off];
+          const float keep = upper ? pr[e + off] : pr[e];
+          pr[e] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      pr[0] += __shfl_xor_sync(0xffffffffu, pr[0], 16);
+      if (lane < 16) redb[q * kSub + 16 * c + lane] = pr[0];
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + c) : "memory");   // the 4 warps (lane quarters) of this chunk
+      uint32_t pk[8], qk[8];
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4) {
+        float4 s4 = *reinterpret_cast<const float4*>(&redb[q0 * kSub + 16 * c + 4 * i4]);
+#pragma unroll
+        for (int w = 1; w < 4; ++w) {
+          if (w < wpc) {
+            const float4 o = *reinterpret_cast<const float4*>(&redb[(q0 + w) * kSub + 16 * c + 4 * i4]);
+            s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w;
+          }
+        }
+        float g0 = fmaxf(s4.x, 0.f), g1 = fmaxf(s4.y, 0.f), g2 = fmaxf(s4.z, 0.f), g3 = fmaxf(s4.w, 0.f);
+        if (owner) {
+          const float t0 = g0 * inv_scale, t1 = g1 * inv_scale, t2 = g2 * inv_scale, t3 = g3 * inv_scale;
+          ssq += t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3;
+        }
+        g0 *= pq_scale; g1 *= pq_scale; g2 *= pq_scale; g3 *= pq_scale;
+        const int e = 4 * i4;
+        pk[2 * i4] = pack_h2_sat(g0 * __uint_as_float(hc[e]), g1 * __uint_as_float(hc[e + 1]));
+        pk[2 * i4 + 1] = pack_h2_sat(g2 * __uint_as_float(hc[e + 2]), g3 * __uint_as_float(hc[e + 3]));
+        qk[2 * i4] = pack_h2_sat(g0 * __uint_as_float(ha[e]), g1 * __uint_as_float(ha[e + 1]));
+        qk[2 * i4 + 1] = pack_h2_sat(g2 * __uint_as_float(ha[e + 2]), g3 * __uint_as_float(ha[e + 3]));
+      }
+      tmem_st8(tHA, pk);   // P^T = g * HC^T (pairs with A rows)
+      tmem_st8(tHC, qk);   // Q^T = g * HA^T (pairs with C rows)
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      // one arrival per warp on the leader's barrier (a cluster address also for the leader itself)
+      if (lane == 0) mbar_arrive_remote(p_full_l[buf]);
+      if (prof) { ea += e1 - e0; eb += clock64() - e1; }
+    }
+    if (prof && blockIdx.x < 2 && warp == 2 && lane == 0) { prof[3 + 3 * blockIdx.x] = ea; prof[4 + 3 * blockIdx.x] = eb; }
+    mbar_wait(x_full, 0);
+    tc_fence_after();
+    float* dst = part + (((int64_t)rb * G + g) * kNG + j) * D;
+#pragma unroll 1
+    for (int cc = (warp - 2) >> 2; cc < D / 32; cc += 4) {
+      uint32_t v[32];
+      tmem_ld32(lane_base + 32 * cc, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        *reinterpret_cast<float4*>(dst + 32 * cc + 4 * e) =
+            make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
+                        __uint_as_float(v[4 * e + 3]));
+    }
+    if (owner) ss_part[((int64_t)rb * (G * (kNG / d_k)) + g * (kNG / d_k) + j / d_k) * 4 + c] = ssq;
+    tc_fence_before();
+  }
+  tc_fence_before();
+  cluster_sync_all();                  // nobody frees TMEM or leaves while the peer's MMAs / barriers may still touch this CTA
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc512_pair(tmem_base);
+  }
+}
+
 // sums[i*m + col] = x_scale * sum_rb part[(rb*G + col/128)*128 + col%128][i] ; sums[d*m + k] = sum_rb ss_part.
 // A CTA reduces a tile of 16 columns x 32 channels with 512 threads: 128 float4 lanes x 4 groups that take the row
 // blocks rb = grp, grp + 4, ... (m/16 x d/32 CTAs = 128 at cfg 2).  The kernel is bound by the latency of its dependent
@@ -757,7 +1130,8 @@ int64_t step_tc_workspace_bytes(int64_t M, int d, int m, int K) {
   return p.part_bytes + p.ss_bytes + 256;
 }
 
-// 0 (default): the shared-memory-operand kernel above; 1: U^T in tensor memory for d <= 256 in the single-pass mode.
+// 0 (default): the shared-memory-operand kernel above; 1: U^T in tensor memory for d <= 256 in the single-pass mode;
+// 2: the CTA-pair kernel (cta_group::2) for d = 256 in the single-pass mode.
 // Measured at cfg 2: variant 1 is correct but slower (0.368 vs 0.333 ms): its GEMM1 MMAs have N = 64 and take ~76
 // cycles each instead of the 32 the M*N/256 rule promises -- tcgen05.mma has a floor of roughly 64 cycles per
 // instruction at M = 128, so only N = 256 shapes run at the full rate (GEMM1 at N = 256 in the first version of this
@@ -793,6 +1167,30 @@ int launch_step(int grid, cudaStream_t stream, Args... args) {
   return DRSA_OK;
 }
 
+// CTA-pair kernel: shared memory, and how many 2-CTA clusters the device can hold at once (TPCs with both SMs free);
+// -1 if the query fails.
+constexpr int kPairSmemBytes = (256 / 64) * kPanelBytes + kPairStages * kPairStageBytes + kRedBytes + kPairBarBytes;
+int pair_max_clusters() {
+  static int cached = -2;
+  if (cached != -2) return cached;
+  cached = -1;
+  if (cudaFuncSetAttribute(drsa_tc_step_pair_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes) !=
+      cudaSuccess)
+    return cached;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * sm_count());
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kPairSmemBytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, drsa_tc_step_pair_kernel<256>, &cfg) == cudaSuccess && n > 0) cached = n;
+  else (void)cudaGetLastError();
+  return cached;
+}
+
 // split_u = true: U^T = hi + lo, two MMAs per product (DRSA_PREC_TC_F16X2); false: U^T = fp16(U) only (DRSA_PREC_TC_F16)
 int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_lo, int64_t M, int d, int m, int K,
             float scaleA, float scaleC, float pq_scale, bool split_u, float* sums, void* workspace, int64_t workspace_bytes,
@@ -808,6 +1206,30 @@ int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_
   float* part = reinterpret_cast<float*>(w); w += p.part_bytes;
   float* ss_part = reinterpret_cast<float*>(w); w += p.ss_bytes;
   int* err = reinterpret_cast<int*>(w);
+
+  if ((g_tc_variant == 2 || g_tc_variant == 3) && !split_u && d == 256 && p.G % 2 == 0 && pair_max_clusters() > 0) {
+    // CTA pairs: one cluster per (row block, pair of column groups); never more row blocks than the plan sized the
+    // workspace for, never more clusters than fit the device at once (a second wave would double the time)
+    const int G2 = p.G / 2;
+    int nrb = pair_max_clusters() / G2;
+    if (nrb > p.nRB) nrb = p.nRB;
+    if (nrb >= 1) {
+      CUtensorMap tmA, tmC, tmA2, tmC2, tmUh;
+      DRSA_TRY(make_tmap_f16_sw128(&tmA, A16, (uint64_t)M, (uint64_t)d, kSub));
+      DRSA_TRY(make_tmap_f16_sw128(&tmC, C16, (uint64_t)M, (uint64_t)d, kSub));
+      DRSA_TRY(make_tmap_f16_sw128(&tmA2, A16, (uint64_t)M, (uint64_t)d, 32));
+      DRSA_TRY(make_tmap_f16_sw128(&tmC2, C16, (uint64_t)M, (uint64_t)d, 32));
+      DRSA_TRY(make_tmap_f16_sw128(&tmUh, Ut_hi, (uint64_t)m, (uint64_t)d, kNG));
+      const float inv_s = 1.0f / (scaleA * scaleC);
+      drsa_tc_step_pair_kernel<256><<<2 * nrb * G2, kThreads, kPairSmemBytes, stream>>>(
+          tmA, tmC, tmA2, tmC2, tmUh, p.num_tiles, p.G, nrb, m / K, inv_s, pq_scale, part, ss_part, err, g_tc_prof, g_tc_variant == 3 ? 1 : 0);
+      DRSA_LAUNCH_CHECK();
+      dim3 rg(m / 16, d / 32);
+      tc_reduce_kernel<<<rg, 128 * kRedGroups, 0, stream>>>(part, ss_part, nrb, p.G, d, m, K, inv_s * inv_s / pq_scale, sums);
+      DRSA_LAUNCH_CHECK();
+      return DRSA_OK;
+    }
+  }
 
   if (tmem_u) {
     CUtensorMap tA, tC;
@@ -891,6 +1313,12 @@ void set_tc_profile(long long* p) { g_tc_prof = p; g_fused_prof = p; }
 // numRegs, maxThreadsPerBlock, static shared bytes, local bytes, max dynamic shared bytes of the row-pass kernel
 int tc_kernel_attrs(int d, int split, int* out5) {
   cudaFuncAttributes a;
+  if (split == 2) {      // the CTA-pair kernel; out5[4] = number of 2-CTA clusters the device holds at once
+    DRSA_CUDA(cudaFuncGetAttributes(&a, (const void*)drsa_tc_step_pair_kernel<256>));
+    out5[0] = a.numRegs; out5[1] = a.maxThreadsPerBlock; out5[2] = (int)a.sharedSizeBytes; out5[3] = (int)a.localSizeBytes;
+    out5[4] = pair_max_clusters();
+    return DRSA_OK;
+  }
   const void* fn = d == 512 ? (const void*)drsa_tc_step_kernel<512, false> : d == 256 ? (split ? (const void*)drsa_tc_step_kernel<256, true> : (const void*)drsa_tc_step_kernel<256, false>)
                             : (split ? (const void*)drsa_tc_step_kernel<128, true> : (const void*)drsa_tc_step_kernel<128, false>);
   DRSA_CUDA(cudaFuncGetAttributes(&a, fn));
@@ -990,7 +1418,84 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 }  // namespace
 
+// Issue rate of tcgen05.mma for the shapes of the row pass, operands resident (no TMA, no epilogue): cycles per MMA.
+//   mode 0: cta_group::1 SS M128 N128   1: cta_group::1 TS M128 N256   2: cta_group::2 SS M256 N128
+//   mode 3: cta_group::2 TS M256 N256   4: cta_group::2 SS M256 N256   5: cta_group::1 SS M128 N256
+template <bool kPair>
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int mode, int rounds, float* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 65536);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem + 65536 + 64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 65536 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  fence_async_smem();
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0) { if (kPair) tmem_alloc512_pair(slot); else tmem_alloc<512>(slot); }
+  tc_fence_before();
+  if (kPair) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *slot;
+  const bool leader = !kPair || cluster_ctarank() == 0;
+  if (warp == 1 && lane == 0 && leader) {
+    const int N = (mode == 0 || mode == 2) ? 128 : 256;
+    const bool ts = mode == 1 || mode == 3;
+    const uint32_t idesc = make_idesc_f16(kPair ? 256 : 128, N, 0, ts ? 1 : 0);
+    const uint32_t a_lo = kdesc_lo(smem_u32(smem)), b_lo = kdesc_lo(smem_u32(smem + 16384)), bm_lo = mndesc_lo(smem_u32(smem + 16384));
+    const long long t0 = clock64();
+    for (int r = 0; r < rounds; ++r) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if (kPair) {
+          if (ts) umma2_ts_f16(tm, tm + 256 + 8 * kk, desc64(bm_lo + 128 * (kk & 1)), idesc, 1u);
+          else umma2_ss_f16(tm, desc64(a_lo + 2 * kk), desc64(b_lo + 2 * kk), idesc, 1u);
+        } else {
+          if (ts) umma_ts_f16(tm, tm + 256 + 8 * kk, desc64(bm_lo + 128 * (kk & 1)), idesc, 1u);
+          else umma_ss_f16(tm, desc64(a_lo + 2 * kk), desc64(b_lo + 2 * kk), idesc, 1u);
+        }
+      }
+    }
+    if (kPair) umma2_commit_both(bar); else umma_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    out[0] = (float)(t1 - t0) / (4.0f * rounds);
+  }
+  tc_fence_before();
+  if (kPair) cluster_sync_all(); else __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    if (kPair) tmem_dealloc512_pair(tm); else tmem_dealloc<512>(tm);
+  }
+}
+
+int umma_rate(int mode, float* out_host) {
+  if (mode < 0 || mode > 5 || out_host == nullptr) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  float* d = nullptr;
+  DRSA_CUDA(cudaMalloc(&d, 4));
+  const int smem_bytes = 65536 + 256;
+  const bool pair = mode >= 2 && mode <= 4;
+  if (pair) {
+    DRSA_CUDA(cudaFuncSetAttribute(umma_rate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DRSA_CUDA(cudaLaunchKernelEx(&cfg, umma_rate_kernel<true>, mode, 2000, d));
+  } else {
+    DRSA_CUDA(cudaFuncSetAttribute(umma_rate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    umma_rate_kernel<false><<<1, 128, smem_bytes>>>(mode, 2000, d);
+  }
+  DRSA_LAUNCH_CHECK();
+  DRSA_CUDA(cudaDeviceSynchronize());
+  DRSA_CUDA(cudaMemcpy(out_host, d, 4, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return DRSA_OK;
+}
+
 int selftest_umma(int variant, float* max_err_host) {
+  if (variant >= 10 && variant <= 15) return umma_rate(variant - 10, max_err_host);      // MMA issue-rate probes
   if (variant < 0 || variant > 1 || max_err_host == nullptr) return DRSA_ERR_ARG;
   DRSA_TRY(require_sm100());
   // host data: small integers / 8 so every product and partial sum is exact in fp32

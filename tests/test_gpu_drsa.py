@@ -131,6 +131,24 @@ def test_row_sums_tmem_resident_u_variant(L, M, d, m, K):
     assert float(torch.linalg.norm(X - X0) / torch.linalg.norm(X0)) < 3e-4
 
 
+@pytest.mark.parametrize("M,d,m,K", [(31, 256, 256, 4), (5000, 256, 256, 2), (20011, 256, 256, 8), (150000, 256, 256, 4)])
+def test_row_sums_cta_pair_variant(L, M, d, m, K):
+    """The CTA-pair row pass (cta_group::2: the two column groups of a row block share the staged rows,
+    drsa_debug_set_tc_variant(2)) computes the same sums as the single-CTA kernel."""
+    A, C = drsa_ref.synth_pairs(M, d, 400 + M % 97 + K)
+    U = drsa_ref.synth_U0(d, m, 9)
+    L.lib().drsa_debug_set_tc_variant(2)
+    try:
+        X, ss = _sums_gpu(L, A, C, U, K, "tc")
+    finally:
+        L.lib().drsa_debug_set_tc_variant(0)
+    X0, ss0 = _sums_gpu(L, A, C, U, K, "tc")
+    Xq, ssq = drsa_ref.step_sums(A.half().double(), C.half().double(), U.half().double(), K)
+    assert float(torch.linalg.norm(X - Xq) / torch.linalg.norm(Xq)) < (4e-4 if M < 4096 else 1.5e-4)
+    np.testing.assert_allclose(ss.numpy(), ssq.numpy(), rtol=2e-5, atol=(1e-3 if M < 64 else 0.0) * float(ssq.max()))
+    assert float(torch.linalg.norm(X - X0) / torch.linalg.norm(X0)) < 3e-4
+
+
 def test_tensor_core_scale_invariance(L):
     """power-of-two pre-scaling of the fp16 rows is undone exactly: unnormalised inputs 1000x larger
     give row sums 1e6x / 1e12x larger."""
