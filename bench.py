@@ -301,6 +301,21 @@ def lrp_throughput(args, dev, rank, world, barrier):
     _ = act[:1].cpu()
     barrier()
     t_e2e = time.perf_counter() - t0
+    # full-depth relevance maps (compute_relevances, attribute.py:70-108: the other output of the same pass)
+    from cxai.xai.explain.attribute import compute_relevances
+    nf = min(n, 128)
+    compute_relevances(net, x[:nf], comp, class_idx=0)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    Rin = compute_relevances(net, x[:nf], comp, class_idx=0)
+    f1.record()
+    barrier()
+    ms_full = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_full, op=dist.ReduceOp.MAX)
+    ms_full = float(ms_full.item())
+    del Rin
     P = act.shape[0] // n
     flops = 2 * 1775.5e6 * n           # 2 x MACs of the widened arch A forward per sample
     out = {"metric": "LRP context vecs/s", "value": n * P * world / (ms * 1e-3), "unit": "vectors/s",
@@ -309,7 +324,10 @@ def lrp_throughput(args, dev, rank, world, barrier):
            "forward_tflops": flops / (ms * 1e-3) / 1e12,
            "kernel": "conv3x3_tc_kernel (tcgen05 implicit GEMM, TMA im2col, fp16 hi/lo operands, max-pool fused into the "
                      "epilogue below the split layer); first conv, dense head and pool routing on CUDA cores",
-           "samples_per_engine_pass": min(n, 256)}
+           "samples_per_engine_pass": min(n, 256),
+           "relevance_maps": {"metric": "LRP relevance maps at the input (compute_relevances, full-depth backward)",
+                              "value": nf * world / (ms_full * 1e-3), "unit": "maps/s", "samples_per_gpu": nf, "ms": ms_full,
+                              "algorithmic_tflops": 3 * 2 * 1775.5e6 * nf / (ms_full * 1e-3) / 1e12}}
     if rank == 0:
         out["roofline"] = lrp_conv_roofline(dev, ms / max(1, n / 64.0))
         if world == 1 and not args.no_cpu_baseline:

@@ -505,6 +505,15 @@ class LRPPlan:
                                                      _ptr(self._tc_err), _stream()), op.name)
                 Rel, nhwc, bound = R_in, (op.cin, cin_p, H, W), nxt
                 continue
+            if is_tc and sv[0] == "tc_first" and nhwc is not None and op.ones and nhwc[1] == 64 and op.rule is not None \
+                    and op.rule.kind in ("wsquare", "flat"):
+                # WSquare / Flat on the first layer: one pass over the NHWC relevance (no layout conversion, no s buffer)
+                B, H, W = Rel.size(0), nhwc[2], nhwc[3]
+                R_in = torch.empty(B, 1, H, W, device=Rel.device)
+                _L.check(lib.lrp_tc_first_ones_backward(_ptr(Rel), _ptr(op.w_mod), _ptr(op.b_mod), B, H, W, op.cout, nhwc[1],
+                                                        op.eps, _ptr(R_in), _stream()), op.name)
+                Rel, nhwc = R_in, None
+                continue
             if is_tc and sv[0] == "tc_first":
                 # leave the NHWC stack: the first conv (Cin = 1) runs on the CUDA-core kernels in NCHW
                 if nhwc is not None:

@@ -109,6 +109,7 @@ SIGNATURES.update({
     "drsa_exchange_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "drsa_finish_step_p2p": (_i32, [C.POINTER(PeerExchange), _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64,
                                     _i32, _f32, _i32, _vp, _vp, _i64, _vp]),
+    "lrp_tc_first_ones_backward": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),
     "lrp_tc_conv3x3_pool_supported": (_i32, [_i64, _i32, _i32, _i32, _i32, _i32, _i32]),
     "lrp_tc_conv3x3_forward_pool": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
                                            _vp, _vp, _vp, _vp, _vp]),

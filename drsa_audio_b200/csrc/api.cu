@@ -71,6 +71,8 @@ bool conv_tc_pool_supported(int64_t B, int Cin_p, int Cout_p, int H, int W, int 
 int conv_tc_forward_pool(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int64_t B,
                          int H, int W, int Cin_p, int Cout_p, int Cout, int relu, int kh, int kw, void* y_hi, void* y_lo,
                          void* argmax_u8, int* err_flag, cudaStream_t stream);
+int first_layer_ones_backward(const float* R_out, const float* w_mod, const float* b_mod, int64_t B, int H, int W, int Cout,
+                              int Cp, float eps, float* R_in, cudaStream_t stream);
 int64_t subspace_filter_workspace_bytes(int64_t P, int d, int m);
 int subspace_project(const float* a, const float* U, int64_t P, int d, int m, int ld, float* h, float* a2, cudaStream_t s);
 int subspace_filter_backward(const float* a, const float* h, const float* a2, const float* R, const float* U, int64_t P, int d,
@@ -413,6 +415,15 @@ int lrp_tc_conv3x3_forward(const void* x_hi, const void* x_lo, const void* w_hi,
   DRSA_TRY(require_sm100());
   return conv_tc_forward(x_hi, x_lo, w_hi, w_lo, bias, B, H, W, Cin_p, Cout_p, Cout, relu, y_hi, y_lo, y_nchw, err_flag,
                          static_cast<cudaStream_t>(stream));
+}
+
+int lrp_tc_first_ones_backward(const float* R_out, const float* w_mod, const float* b_mod, int64_t B, int H, int W, int Cout,
+                               int Cp, float eps, float* R_in, void* stream) {
+  if (R_out == nullptr || w_mod == nullptr || b_mod == nullptr || R_in == nullptr || B <= 0 || H <= 0 || W <= 0 || Cout <= 0)
+    return DRSA_ERR_ARG;
+  if (!aligned16(R_out)) return DRSA_ERR_ALIGN;
+  DRSA_TRY(require_sm100());
+  return first_layer_ones_backward(R_out, w_mod, b_mod, B, H, W, Cout, Cp, eps, R_in, static_cast<cudaStream_t>(stream));
 }
 
 int lrp_tc_conv3x3_pool_supported(int64_t B, int Cin_p, int Cout_p, int H, int W, int kh, int kw) {

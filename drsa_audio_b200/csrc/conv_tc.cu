@@ -555,6 +555,94 @@ __global__ void __launch_bounds__(256) conv3x3_first_nhwc_kernel(const float* __
   }
 }
 
+// LRP backward of the first layer (Cin = 1) under WSquare / Flat (constants.py:27-51: the input is replaced by ones,
+// the parameters by w^2 / ones, and there is no input factor), for relevance arriving from the tensor-core stack as NHWC
+// fp32 [B,H,W,64]:
+//   z[co](y',x')  = b'[co] + sum of w'[co][tap] over the taps that do not fall into the zero padding
+//   s             = R_out / stabilize(z, eps)
+//   R_in(y,x)     = sum_tap c[tap](y - ky + 1, x - kx + 1),   c[tap](y',x') = sum_co w'[co][tap] s[co](y',x')
+// z only depends on the channel and on which of the four image borders the pixel touches (16 classes), so the whole
+// rule is ONE pass over R_out: a CTA takes an 8 x 32 tile of R_in, four threads share a source pixel of the
+// (8+2) x (32+2) halo (16 channels each: 4 coalesced 16-byte loads, 144 FMAs against weights read from shared memory as
+// float4), the nine tap sums go through shared memory and every output pixel gathers its nine neighbours.  Replaces
+// two generic NCHW fp32 convolutions (1 -> 64 and 64 -> 1 channels) and a layout conversion: 7.9 ms -> see DESIGN 3.2.
+constexpr int kFbTh = 8, kFbTw = 32, kFbSrc = (kFbTh + 2) * (kFbTw + 2);
+__global__ void __launch_bounds__(512) first_layer_ones_bwd_kernel(const float* __restrict__ R_out, const float* __restrict__ w_mod,
+                                                                   const float* __restrict__ b_mod, int H, int W, int Cout,
+                                                                   float eps, float* __restrict__ R_in) {
+  __shared__ __align__(16) float ws[9][64];
+  __shared__ __align__(16) float zt[16][64];
+  __shared__ float contrib[9][kFbSrc];
+  const int tid = threadIdx.x;
+  const int tiles_x = (W + kFbTw - 1) / kFbTw, tiles_y = (H + kFbTh - 1) / kFbTh;
+  const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y;
+  const int64_t n = blockIdx.x / (tiles_x * tiles_y);
+  const int x0 = tx * kFbTw, y0 = ty * kFbTh;
+  for (int i = tid; i < 9 * 64; i += blockDim.x) {
+    const int tap = i / 64, co = i % 64;
+    ws[tap][co] = co < Cout ? __ldg(w_mod + co * 9 + tap) : 0.f;
+  }
+  __syncthreads();
+  for (int i = tid; i < 16 * 64; i += blockDim.x) {
+    const int cls = i / 64, co = i % 64;
+    float z = co < Cout ? __ldg(b_mod + co) : 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap % 3;
+      const bool pad = (ky == 0 && (cls & 1)) || (ky == 2 && (cls & 2)) || (kx == 0 && (cls & 4)) || (kx == 2 && (cls & 8));
+      if (!pad) z += ws[tap][co];
+    }
+    zt[cls][co] = z;
+  }
+  __syncthreads();
+  const int q = tid & 3;                                   // channels 16 q .. 16 q + 15
+  for (int it = 0; it < (kFbSrc + 127) / 128; ++it) {      // same trip count for every thread: the shuffles below need full warps
+    const int sp = it * 128 + (tid >> 2);
+    const int sy = y0 - 1 + sp / (kFbTw + 2), sx = x0 - 1 + sp % (kFbTw + 2);
+    float c[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) c[t] = 0.f;
+    if (sp < kFbSrc && sy >= 0 && sy < H && sx >= 0 && sx < W) {
+      const int cls = (sy == 0 ? 1 : 0) | (sy == H - 1 ? 2 : 0) | (sx == 0 ? 4 : 0) | (sx == W - 1 ? 8 : 0);
+      const float4* src = reinterpret_cast<const float4*>(R_out + ((n * H + sy) * W + sx) * 64 + 16 * q);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 r = __ldg(src + i);
+        const float4 z = *reinterpret_cast<const float4*>(&zt[cls][16 * q + 4 * i]);
+        const float s0 = r.x / stabilize(z.x, eps), s1 = r.y / stabilize(z.y, eps), s2 = r.z / stabilize(z.z, eps),
+                    s3 = r.w / stabilize(z.w, eps);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float4 w4 = *reinterpret_cast<const float4*>(&ws[t][16 * q + 4 * i]);
+          c[t] = fmaf(w4.x, s0, fmaf(w4.y, s1, fmaf(w4.z, s2, fmaf(w4.w, s3, c[t]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      c[t] += __shfl_xor_sync(0xffffffffu, c[t], 1);
+      c[t] += __shfl_xor_sync(0xffffffffu, c[t], 2);
+    }
+    if (q == 0 && sp < kFbSrc) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) contrib[t][sp] = c[t];
+    }
+  }
+  __syncthreads();
+  for (int o = tid; o < kFbTh * kFbTw; o += blockDim.x) {
+    const int oy = o / kFbTw, ox = o % kFbTw;
+    const int y = y0 + oy, x = x0 + ox;
+    if (y >= H || x >= W) continue;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)          // source pixel (y - ky + 1, x - kx + 1) -> halo-tile index (oy - ky + 2, ox - kx + 2)
+        acc += contrib[ky * 3 + kx][(oy - ky + 2) * (kFbTw + 2) + (ox - kx + 2)];
+    R_in[(n * H + y) * W + x] = acc;
+  }
+}
+
 // MaxPool2d(kh, kw), stride = kernel, on NHWC hi/lo planes; one thread per (output pixel, 8 channels).
 __global__ void __launch_bounds__(256) maxpool_nhwc_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo,
                                                            int64_t B, int H, int W, int Cp, int kh, int kw,
@@ -841,6 +929,16 @@ int conv_first_nhwc(const float* x, const float* w, const float* b, int64_t B, i
   const int64_t rows = B * H;
   conv3x3_first_nhwc_kernel<<<(int)(rows < 148 * 8 ? rows : 148 * 8), 256, 0, stream>>>(
       x, w, b, B, H, W, Cout, Cout_p, relu, static_cast<__half*>(y_hi), static_cast<__half*>(y_lo));
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+int first_layer_ones_backward(const float* R_out, const float* w_mod, const float* b_mod, int64_t B, int H, int W, int Cout,
+                              int Cp, float eps, float* R_in, cudaStream_t stream) {
+  if (Cp != 64 || Cout > 64) return DRSA_ERR_SHAPE;
+  const int64_t tiles = B * ((H + kFbTh - 1) / kFbTh) * ((W + kFbTw - 1) / kFbTw);
+  if (tiles > 2147483647LL) return DRSA_ERR_SHAPE;
+  first_layer_ones_bwd_kernel<<<(unsigned)tiles, 512, 0, stream>>>(R_out, w_mod, b_mod, H, W, Cout, eps, R_in);
   DRSA_LAUNCH_CHECK();
   return DRSA_OK;
 }

@@ -289,6 +289,14 @@ int lrp_tc_conv3x3_forward_pool(const void* x_hi, const void* x_lo, const void* 
                                 int relu, int kh, int kw, void* y_hi, void* y_lo, void* argmax_u8,
                                 int* err_flag, void* stream);
 
+/* LRP backward of the first layer (Cin = 1) under WSquare / Flat (rule maps utils/constants.py:27-51; zennit: input
+ * replaced by ones, parameters by w^2 / ones, no input factor) in one pass over the relevance R_out, NHWC fp32
+ * [B,H,W,Cp] as it leaves the tensor-core stack:  z = b' + sum of w' over the taps inside the image,
+ * s = R_out / stabilize(z, eps), R_in [B,1,H,W] = conv_transpose(s, w').  w_mod [Cout,9], b_mod [Cout] are the
+ * rule-modified parameters.  Cp must be 64 (DRSA_ERR_SHAPE otherwise: the caller uses lrp_conv3x3_backward). */
+int lrp_tc_first_ones_backward(const float* R_out, const float* w_mod, const float* b_mod, int64_t B, int H, int W,
+                               int Cout, int Cp, float eps, float* R_in, void* stream);
+
 /* First layer (Cin = 1, bandwidth bound, CUDA cores): x [B,1,H,W] fp32, w [Cout,9] -> NHWC hi/lo planes. */
 int lrp_tc_conv3x3_first(const float* x, const float* w, const float* b, int64_t B, int H, int W, int Cout,
                          int Cout_p, int relu, void* y_hi, void* y_lo, void* stream);

@@ -49,6 +49,27 @@ def test_workspace_queries_need_no_gpu(lib):
     assert lib.drsa_finish_workspace_bytes(256, 256) > 0
 
 
+def test_peer_exchange_and_fused_pool_queries_need_no_gpu(lib):
+    """Shape / argument checks of the entry points added for the multi-GPU exchange and the fused conv + pool."""
+    n = lib.drsa_exchange_bytes(256, 256, 4, 8)
+    assert n == (64 + 2 * 8 * (256 * 256 + 64)) * 4                     # header + 2 parities x 8 ranks x padded d*m+K floats
+    assert lib.drsa_exchange_bytes(256, 256, 4, 1) == -1                # a single rank has nothing to exchange
+    assert lib.drsa_exchange_bytes(256, 256, 4, 9) == -2                # more than DRSA_MAX_PEERS
+    assert lib.drsa_exchange_bytes(48, 48, 4, 2) == -2                  # not a shape of the fused finish kernel
+    px = _lib.PeerExchange()
+    px.world, px.rank = 1, 0
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    st = lib.drsa_finish_step_p2p(ctypes.byref(px), p, 100, p, 64, 64, 4, None, None, None, None, 0, 8, 1e-6, 0, None, p, 64, None)
+    assert st == -1
+    # 8 x 16 tiles or whole 8 x 8 maps, power-of-two windows that fit a warp's rows
+    assert lib.lrp_tc_conv3x3_pool_supported(64, 64, 64, 128, 256, 2, 4) == 0
+    assert lib.lrp_tc_conv3x3_pool_supported(3, 128, 128, 8, 8, 2, 2) == 0
+    assert lib.lrp_tc_conv3x3_pool_supported(3, 64, 64, 4, 4, 2, 2) == -2
+    assert lib.lrp_tc_conv3x3_pool_supported(3, 64, 64, 32, 32, 3, 3) == -2
+    assert lib.lrp_tc_conv3x3_pool_supported(3, 64, 64, 32, 32, 4, 2) == -2         # 4 rows do not fit a warp of a 16-wide tile
+
+
 def test_compute_fails_loudly_without_sm100(lib):
     import torch
     if torch.cuda.is_available():

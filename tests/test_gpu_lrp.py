@@ -441,6 +441,40 @@ def test_fused_conv_pool_equals_separate_kernels(case):
     assert _rel_per_sample(full1, full0) < 1e-5
 
 
+@pytest.mark.parametrize("B,H,W,Cout", [(3, 13, 37, 64), (2, 8, 32, 40), (1, 1, 5, 8), (2, 64, 64, 64)])
+def test_first_layer_ones_backward_matches_generic_path(B, H, W, Cout):
+    """WSquare / Flat on the first layer in one pass over NHWC relevance (lrp_tc_first_ones_backward) against the generic
+    fp32 pair of convolutions (lrp_conv3x3_backward with x_is_ones) and against fp64 torch; ragged tiles, borders, Cout < 64."""
+    L = _L()
+    lib = L.lib()
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + W)
+    w = torch.randn(Cout, 1, 3, 3, generator=g) ** 2 + 0.01            # WSquare: w^2
+    b = torch.randn(Cout, generator=g) ** 2
+    R = torch.randn(B, Cout, H, W, generator=g) * (torch.rand(B, Cout, H, W, generator=g) < 0.7)
+    eps = 1e-7
+    z = F.conv2d(torch.ones(B, 1, H, W, dtype=torch.float64), w.double(), b.double(), padding=1)
+    s_ref = R.double() / (z + torch.where(z >= 0, eps, -eps))
+    want = F.conv_transpose2d(s_ref, w.double(), padding=1)
+    Rn = torch.zeros(B, H, W, 64)
+    Rn[..., :Cout] = R.permute(0, 2, 3, 1)
+    Rd, wd, bd = Rn.cuda().contiguous(), w.reshape(Cout, 9).cuda().contiguous(), b.cuda()
+    out = torch.empty(B, 1, H, W, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(lib.lrp_tc_first_ones_backward(Rd.data_ptr(), wd.data_ptr(), bd.data_ptr(), B, H, W, Cout, 64, eps, out.data_ptr(), st))
+    assert _rel_per_sample(out, want) < 1e-5
+    # the generic path
+    wt = torch.empty(1, Cout, 3, 3, device="cuda")
+    w4 = w.cuda().contiguous()
+    L.check(lib.lrp_conv3x3_flip_weights(w4.data_ptr(), Cout, 1, wt.data_ptr(), st))
+    sbuf = torch.empty(B, Cout, H, W, device="cuda")
+    out2 = torch.empty(B, 1, H, W, device="cuda")
+    Rc = R.cuda().contiguous()
+    L.check(lib.lrp_conv3x3_backward(None, w4.data_ptr(), wt.data_ptr(), bd.data_ptr(), Rc.data_ptr(), B, 1, Cout, H, W, eps, 1,
+                                     sbuf.data_ptr(), out2.data_ptr(), st))
+    assert _rel_per_sample(out, out2) < 1e-5
+    assert lib.lrp_tc_first_ones_backward(Rd.data_ptr(), wd.data_ptr(), bd.data_ptr(), B, H, W, Cout, 128, eps, out.data_ptr(), st) == -2
+
+
 def test_subspace_filter_kernels_match_fp64():
     """lrp_subspace_project / lrp_subspace_filter (Epsilon on both projections + SubspaceHook mask) vs fp64 torch on
     the SAME inputs, padded leading dimension included."""
