@@ -196,7 +196,8 @@ class _PeerExchange:
         """Collective over ``group``: returns the shared exchange (or None on every rank if any rank failed)."""
         dist = torch.distributed
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        key = (id(group) if group is not None else 0, str(dev), nbytes, how)
+        # one exchange per stream: the protocol state inside the buffers assumes stream-ordered calls
+        key = (id(group) if group is not None else 0, str(dev), nbytes, how, torch.cuda.current_stream(dev).cuda_stream)
         px = cls._cache.get(key)
         ok = torch.ones(1, dtype=torch.int32, device=dev)
         if px is None:
