@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(256) conv3x3_first_nhwc_kernel(const float* __
 // the parameters by w^2 / ones, and there is no input factor), for relevance arriving from the tensor-core stack as NHWC
 // fp32 [B,H,W,64]:
 //   z[co](y',x')  = b'[co] + sum of w'[co][tap] over the taps that do not fall into the zero padding
-//   s             = R_out / stabilize(z, eps)
+//   s             = R_out / stabilize(z, eps)            (as R_out * (1 / stabilize(z, eps)): z has 16 x 64 distinct values)
 //   R_in(y,x)     = sum_tap c[tap](y - ky + 1, x - kx + 1),   c[tap](y',x') = sum_co w'[co][tap] s[co](y',x')
 // z only depends on the channel and on which of the four image borders the pixel touches (16 classes), so the whole
 // rule is ONE pass over R_out: a CTA takes an 8 x 32 tile of R_in, four threads share a source pixel of the
@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(512) first_layer_ones_bwd_kernel(const float* 
       const bool pad = (ky == 0 && (cls & 1)) || (ky == 2 && (cls & 2)) || (kx == 0 && (cls & 4)) || (kx == 2 && (cls & 8));
       if (!pad) z += ws[tap][co];
     }
-    zt[cls][co] = z;
+    zt[cls][co] = 1.f / stabilize(z, eps);      // the reciprocal once per class: 16 divisions per source pixel were a third of the kernel
   }
   __syncthreads();
   const int q = tid & 3;                                   // channels 16 q .. 16 q + 15
@@ -609,8 +609,7 @@ __global__ void __launch_bounds__(512) first_layer_ones_bwd_kernel(const float* 
       for (int i = 0; i < 4; ++i) {
         const float4 r = __ldg(src + i);
         const float4 z = *reinterpret_cast<const float4*>(&zt[cls][16 * q + 4 * i]);
-        const float s0 = r.x / stabilize(z.x, eps), s1 = r.y / stabilize(z.y, eps), s2 = r.z / stabilize(z.z, eps),
-                    s3 = r.w / stabilize(z.w, eps);
+        const float s0 = r.x * z.x, s1 = r.y * z.y, s2 = r.z * z.z, s3 = r.w * z.w;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           const float4 w4 = *reinterpret_cast<const float4*>(&ws[t][16 * q + 4 * i]);
