@@ -216,6 +216,31 @@ class _PeerExchange:
         return px
 
 
+def _pad_plan(d: int, m: int, K: int, rows: int):
+    """Shape (d', m') of an equivalent zero-padded problem that the tensor-core row pass covers, or None.
+
+    The reference's production split layers are not all tensor-core shapes (arch A, getdrsadata.py:72-73: layer 19 has
+    d = 100, i.e. K = 4 concepts of d_k = 25).  Padding is exact: every concept block is widened to d_k' in {32, 64, 128}
+    columns, the m' - m new columns are unit vectors in d' - d new (all-zero) channels of A and C, so projections,
+    relevances, pooling sums and the gradient of the original entries are unchanged, the new entries have zero gradient,
+    and the polar factor of the block-diagonal matrix is block-diagonal."""
+    lib = _L.lib()
+    if m % K != 0:
+        return None
+    d_k = m // K
+    for dkp in (32, 64, 128):
+        if dkp < d_k:
+            continue
+        mp = K * dkp
+        if mp % 128 != 0:
+            continue
+        for dp in (128, 256, 512):
+            if dp >= mp and dp - d >= mp - m and dp >= d and \
+                    lib.drsa_step_workspace_bytes(max(rows, 1), dp, mp, K, _L.PREC_TC_F16) >= 0:
+                return dp, mp, dkp
+    return None
+
+
 class SubspaceOptimizer:
     """Gradient ascent on the DRSA objective with a polar retraction after every step.
 
@@ -253,19 +278,45 @@ class SubspaceOptimizer:
         self.num_concepts = num_concepts
         self.d_k = U.size(1) // num_concepts          # drsa.py:68 (U square there)
         self.obj_fn = objective_fn
+        d, m = int(U.size(0)), int(U.size(1))
+        self._pad = None
         with torch.cuda.device(self.device):
-            self.U = _f32c(U, self.device).clone()
+            self._Uw = _f32c(U, self.device).clone()          # the matrix the kernels work on (padded if self._pad)
             self.act_vecs = _f32c(activation_vecs, self.device)
             self.ctx_vecs = _f32c(context_vecs, self.device)
             self._dist = torch.distributed.is_available() and torch.distributed.is_initialized()
             self._group = process_group
-            self._rows = _RowPass(self.act_vecs, self.ctx_vecs, U.size(0), U.size(1), num_concepts, precision)
+            rows = int(self.act_vecs.size(0))
+            native_tc = _L.lib().drsa_step_workspace_bytes(max(rows, 1), d, m, num_concepts, _L.PREC_TC_F16) >= 0
+            plan = None
+            if not native_tc and m == d and (precision in ("tc", "tc_split") or (precision == "auto" and rows >= 65536)):
+                plan = _pad_plan(d, m, num_concepts, rows)
+            if plan is not None:
+                dp, mp, dkp = plan
+                cols = (torch.arange(m, device=self.device) // self.d_k) * dkp + torch.arange(m, device=self.device) % self.d_k
+                Up = torch.zeros(dp, mp, device=self.device)
+                Up[:d, cols] = self._Uw
+                free = torch.ones(mp, dtype=torch.bool, device=self.device)
+                free[cols] = False
+                extra = torch.nonzero(free).flatten()          # m' - m padding columns: unit vectors in the new channels
+                Up[d + torch.arange(extra.numel(), device=self.device), extra] = 1.0
+                self._pad = dict(d=d, m=m, dp=dp, mp=mp, cols=cols)
+                self._Uw = Up
+                act_p = torch.zeros(rows, dp, device=self.device)
+                act_p[:, :d] = self.act_vecs
+                ctx_p = torch.zeros(rows, dp, device=self.device)
+                ctx_p[:, :d] = self.ctx_vecs
+                self._rows = _RowPass(act_p, ctx_p, dp, mp, num_concepts, "tc" if precision == "auto" else precision)
+                del act_p, ctx_p
+                d, m = dp, mp
+            else:
+                self._rows = _RowPass(self.act_vecs, self.ctx_vecs, d, m, num_concepts, precision)
         self.precision = self._rows.precision
         self.retraction_iters, self.retraction_tol = retraction_iters, retraction_tol
         self._px = None
         self.exchange = "none"
         if self._dist:
-            self.exchange = self._setup_exchange(exchange, U.size(0), U.size(1), num_concepts)
+            self.exchange = self._setup_exchange(exchange, d, m, num_concepts)
         self.use_cuda_graph = use_cuda_graph and (not self._dist or self._px is not None)
         M_local = torch.tensor([self.act_vecs.size(0)], dtype=torch.int64, device=self.device)
         if self._dist:
@@ -273,6 +324,23 @@ class SubspaceOptimizer:
         self.M_global = int(M_local.item())
         self.obj_history: Optional[np.ndarray] = None
         self.last_status: Optional[np.ndarray] = None
+
+    @property
+    def U(self) -> torch.Tensor:
+        """The d x m projection matrix (drsa.py:66).  When the problem runs zero-padded on the tensor cores this is a copy
+        of the original block of the working matrix."""
+        if self._pad is None:
+            return self._Uw
+        return self._Uw[: self._pad["d"]][:, self._pad["cols"]].contiguous()
+
+    @U.setter
+    def U(self, value: torch.Tensor) -> None:
+        v = _f32c(value, self.device)
+        if self._pad is None:
+            self._Uw = v.clone()
+        else:
+            self._Uw[: self._pad["d"]][:, self._pad["cols"]] = v
+        self._graph = None
 
     def _setup_exchange(self, exchange: str, d: int, m: int, K: int) -> str:
         dist = torch.distributed
@@ -299,17 +367,17 @@ class SubspaceOptimizer:
 
     # ------------------------------------------------------------------ one step
     def _step(self, obj_log: torch.Tensor, log_index: int, update: bool) -> None:
-        self._rows.step(self.U)
+        self._rows.step(self._Uw)
         if self._dist and self._px is None:
             torch.distributed.all_reduce(self._rows.sums, group=self._group)   # d*m + K floats over NVLink
-        self._rows.finish(self.U, self.M_global, obj_log, log_index, update, self.retraction_iters,
+        self._rows.finish(self._Uw, self.M_global, obj_log, log_index, update, self.retraction_iters,
                           self.retraction_tol, self._px)
 
     def run(self, steps: int = 2000, save: bool = True) -> None:
         """``steps`` ascent steps; the objective is logged before every update plus once at the end
         (drsa.py:84-117), then U and the statistics are written (drsa.py:119-120)."""
         with torch.cuda.device(self.device):
-            self._rows.split_u(self.U)
+            self._rows.split_u(self._Uw)
             self.reset_log(steps + 1)
             self.enqueue_steps(steps)
             self._step(self._obj_log, -1, False)          # final evaluation, no update (drsa.py:109-117)

@@ -10,14 +10,14 @@ dev = torch.device("cuda")
 A, C = synth_rows_cuda(M, d, 1, dev)
 U0 = torch.linalg.qr(torch.randn(d, d))[0]
 opt = SubspaceOptimizer(U0, A, C, None, num_concepts=K, precision="tc", use_cuda_graph=False)
-opt._rows.split_u(opt.U)
+opt._rows.split_u(opt._Uw)
 opt.reset_log(64)
 for _ in range(3): opt._step(opt._obj_log, -1, True)
 buf = torch.zeros(64, dtype=torch.int64, device=dev)
 L.lib().drsa_debug_set_tc_profile(buf.data_ptr())
-opt._rows.step(opt.U)
+opt._rows.step(opt._Uw)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); opt._rows.finish(opt.U, opt.M_global, opt._obj_log, -1, True, opt.retraction_iters, opt.retraction_tol); e1.record()
+e0.record(); opt._rows.finish(opt._Uw, opt.M_global, opt._obj_log, -1, True, opt.retraction_iters, opt.retraction_tol); e1.record()
 torch.cuda.synchronize()
 L.lib().drsa_debug_set_tc_profile(None)
 v = buf.cpu().tolist(); n = v[15]; st = v[16:16 + n]

@@ -15,7 +15,7 @@ A, C = synth_rows_cuda(M, d, 1 + rank, dev)
 U0 = torch.linalg.qr(torch.randn(d, d, generator=torch.Generator().manual_seed(3)))[0]
 for exch in ("p2p", "nccl"):
     opt = SubspaceOptimizer(U0, A, C, None, num_concepts=K, precision="tc", use_cuda_graph=False, exchange=exch)
-    opt._rows.split_u(opt.U)
+    opt._rows.split_u(opt._Uw)
     opt.reset_log(256)
     for _ in range(5): opt._step(opt._obj_log, -1, True)
     buf = torch.zeros(64, dtype=torch.int64, device=dev)
@@ -25,11 +25,11 @@ for exch in ("p2p", "nccl"):
         dist.barrier(); torch.cuda.synchronize()
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
-        opt._rows.step(opt.U)
+        opt._rows.step(opt._Uw)
         e1.record()
         if opt._px is None:
             dist.all_reduce(opt._rows.sums)
-        opt._rows.finish(opt.U, opt.M_global, opt._obj_log, -1, True, opt.retraction_iters, opt.retraction_tol, opt._px)
+        opt._rows.finish(opt._Uw, opt.M_global, opt._obj_log, -1, True, opt.retraction_iters, opt.retraction_tol, opt._px)
         e2.record()
         torch.cuda.synchronize()
         v = buf.cpu().tolist(); n = v[15]; st = v[16:16 + n]

@@ -10,16 +10,16 @@ M, d, K = (int(sys.argv[1]) if len(sys.argv) > 1 else 640000), 256, 4
 A, C = synth_rows_cuda(M, d, 20262, dev)
 U0 = drsa_ref.synth_U0(d, seed=5)
 opt = SubspaceOptimizer(U0, A, C, None, num_concepts=K, device=dev, precision="tc", use_cuda_graph=False)
-opt._rows.split_u(opt.U)
+opt._rows.split_u(opt._Uw)
 res = {}
 for rep in range(2):
     for v in (0, 2, 3):
         L.lib().drsa_debug_set_tc_variant(v)
-        for _ in range(3): opt._rows.step(opt.U)
+        for _ in range(3): opt._rows.step(opt._Uw)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(100): opt._rows.step(opt.U)
+        for _ in range(100): opt._rows.step(opt._Uw)
         e1.record(); torch.cuda.synchronize()
         res[v] = opt._rows.sums.clone()
         print(f"variant {v}: row pass {e0.elapsed_time(e1) / 100:.4f} ms  ({8.0 * M * d * d / (e0.elapsed_time(e1) / 100 * 1e-3) / 1e12:.0f} TFLOP/s)", flush=True)

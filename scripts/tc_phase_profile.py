@@ -9,14 +9,14 @@ dev = torch.device("cuda")
 A, C = synth_rows_cuda(M, d, 1, dev)
 U0 = torch.linalg.qr(torch.randn(d, d))[0]
 opt = SubspaceOptimizer(U0, A, C, None, num_concepts=K, precision=(sys.argv[1] if len(sys.argv) > 1 else "tc"), use_cuda_graph=False)
-opt._rows.split_u(opt.U)
+opt._rows.split_u(opt._Uw)
 variant = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 L.lib().drsa_debug_set_tc_variant(variant)
-for _ in range(3): opt._rows.step(opt.U)
+for _ in range(3): opt._rows.step(opt._Uw)
 buf = torch.zeros(16, dtype=torch.int64, device=dev)
 L.lib().drsa_debug_set_tc_profile(buf.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); opt._rows.step(opt.U); e1.record(); torch.cuda.synchronize()
+e0.record(); opt._rows.step(opt._Uw); e1.record(); torch.cuda.synchronize()
 L.lib().drsa_debug_set_tc_profile(None)
 L.lib().drsa_debug_set_tc_variant(0)
 sub = 32 if variant == 1 else 64; tiles = -(-M // sub); nrb = 148 // 2; per = -(-tiles // nrb)

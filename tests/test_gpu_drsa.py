@@ -149,6 +149,30 @@ def test_row_sums_cta_pair_variant(L, M, d, m, K):
     assert float(torch.linalg.norm(X - X0) / torch.linalg.norm(X0)) < 3e-4
 
 
+@pytest.mark.parametrize("d,K,M", [(100, 4, 30000), (64, 4, 30000), (96, 2, 20000)])
+def test_zero_padded_problem_runs_on_tensor_cores_and_matches_reference(d, K, M):
+    """Split layers that are not tensor-core shapes (arch A layer 19: d = 100, K = 4 x 25) run zero-padded (every concept
+    block widened to 32 / 64 columns, unit columns in new all-zero channels): trajectory and final subspaces must match the
+    reference algorithm like any other tensor-core shape, and U comes back in the original d x d layout, orthonormal."""
+    from cxai.xai.drsa.drsa import SubspaceOptimizer
+    steps = 40
+    A, C = drsa_ref.synth_pairs(M, d, 900 + d)
+    U0 = drsa_ref.synth_U0(d, seed=901)
+    opt = SubspaceOptimizer(U0, A, C, None, num_concepts=K, device="cuda", precision="tc")
+    assert opt._pad is not None and opt.precision == "tc" and tuple(opt.U.shape) == (d, d)
+    assert torch.equal(opt.U.cpu(), U0)
+    opt.run(steps=steps, save=False)
+    objs_ref, U_ref = drsa_ref.run_autograd(A, C, U0, K, steps)
+    rel = float(np.max(np.abs(opt.obj_history - objs_ref) / np.abs(objs_ref)))
+    ang = drsa_ref.principal_angle(opt.U.cpu(), U_ref, K)
+    assert rel < 1e-4 and ang < 1e-3, (rel, ang)
+    U = opt.U
+    assert float((U.T @ U - torch.eye(d, device=U.device)).abs().max()) < 1e-5
+    # 'auto' keeps the exact fp32 path for small problems and pads large ones
+    small = SubspaceOptimizer(U0, A[:4096], C[:4096], None, num_concepts=K, device="cuda")
+    assert small._pad is None and small.precision == "fp32"
+
+
 def test_tensor_core_scale_invariance(L):
     """power-of-two pre-scaling of the fp16 rows is undone exactly: unnormalised inputs 1000x larger
     give row sums 1e6x / 1e12x larger."""
