@@ -288,9 +288,13 @@ class SubspaceOptimizer:
             self._group = process_group
             rows = int(self.act_vecs.size(0))
             native_tc = _L.lib().drsa_step_workspace_bytes(max(rows, 1), d, m, num_concepts, _L.PREC_TC_F16) >= 0
-            plan = None
+            plan, pad_prec = None, "tc" if precision == "auto" else precision
             if not native_tc and m == d and (precision in ("tc", "tc_split") or (precision == "auto" and rows >= 65536)):
                 plan = _pad_plan(d, m, num_concepts, rows)
+            elif not native_tc and m == d and d > 64 and d % 32 != 0 and precision in ("auto", "fp32"):
+                # exact fp32 arithmetic, padded only so that the fused finish kernel (d, m multiples of 32) applies:
+                # the un-fused retraction costs ~30 launches (0.5 ms at d = 100)
+                plan, pad_prec = _pad_plan(d, m, num_concepts, rows), "fp32"
             if plan is not None:
                 dp, mp, dkp = plan
                 cols = (torch.arange(m, device=self.device) // self.d_k) * dkp + torch.arange(m, device=self.device) % self.d_k
@@ -306,7 +310,7 @@ class SubspaceOptimizer:
                 act_p[:, :d] = self.act_vecs
                 ctx_p = torch.zeros(rows, dp, device=self.device)
                 ctx_p[:, :d] = self.ctx_vecs
-                self._rows = _RowPass(act_p, ctx_p, dp, mp, num_concepts, "tc" if precision == "auto" else precision)
+                self._rows = _RowPass(act_p, ctx_p, dp, mp, num_concepts, pad_prec)
                 del act_p, ctx_p
                 d, m = dp, mp
             else:
