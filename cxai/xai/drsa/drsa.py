@@ -287,14 +287,23 @@ class SubspaceOptimizer:
             self._dist = torch.distributed.is_available() and torch.distributed.is_initialized()
             self._group = process_group
             rows = int(self.act_vecs.size(0))
-            native_tc = _L.lib().drsa_step_workspace_bytes(max(rows, 1), d, m, num_concepts, _L.PREC_TC_F16) >= 0
+            M_local = torch.tensor([rows], dtype=torch.int64, device=self.device)
+            if self._dist:
+                torch.distributed.all_reduce(M_local, group=self._group)
+            self.M_global = int(M_local.item())
+            # every rank must take the same decisions (arithmetic, padded shapes of the exchange): they are derived from
+            # the average shard size, not from this rank's
+            avg_rows = self.M_global // (torch.distributed.get_world_size(self._group) if self._dist else 1)
+            native_tc = _L.lib().drsa_step_workspace_bytes(max(avg_rows, 1), d, m, num_concepts, _L.PREC_TC_F16) >= 0
+            if precision == "auto" and native_tc:
+                precision = "tc" if avg_rows >= 8192 else "fp32"
             plan, pad_prec = None, "tc" if precision == "auto" else precision
-            if not native_tc and m == d and (precision in ("tc", "tc_split") or (precision == "auto" and rows >= 65536)):
-                plan = _pad_plan(d, m, num_concepts, rows)
+            if not native_tc and m == d and (precision in ("tc", "tc_split") or (precision == "auto" and avg_rows >= 65536)):
+                plan = _pad_plan(d, m, num_concepts, avg_rows)
             elif not native_tc and m == d and d > 64 and d % 32 != 0 and precision in ("auto", "fp32"):
                 # exact fp32 arithmetic, padded only so that the fused finish kernel (d, m multiples of 32) applies:
                 # the un-fused retraction costs ~30 launches (0.5 ms at d = 100)
-                plan, pad_prec = _pad_plan(d, m, num_concepts, rows), "fp32"
+                plan, pad_prec = _pad_plan(d, m, num_concepts, avg_rows), "fp32"
             if plan is not None:
                 dp, mp, dkp = plan
                 cols = (torch.arange(m, device=self.device) // self.d_k) * dkp + torch.arange(m, device=self.device) % self.d_k
@@ -322,10 +331,6 @@ class SubspaceOptimizer:
         if self._dist:
             self.exchange = self._setup_exchange(exchange, d, m, num_concepts)
         self.use_cuda_graph = use_cuda_graph and (not self._dist or self._px is not None)
-        M_local = torch.tensor([self.act_vecs.size(0)], dtype=torch.int64, device=self.device)
-        if self._dist:
-            torch.distributed.all_reduce(M_local, group=self._group)
-        self.M_global = int(M_local.item())
         self.obj_history: Optional[np.ndarray] = None
         self.last_status: Optional[np.ndarray] = None
 
