@@ -93,6 +93,17 @@ def test_python_mirror_refuses_cpu():
         SubspaceOptimizer(torch.eye(8), torch.rand(16, 8), torch.rand(16, 8), None, num_concepts=2, device="cuda")
 
 
+def test_pad_plan_for_shapes_off_the_tensor_core_grid(lib):
+    """Zero-padding plans of cxai.xai.drsa.drsa._pad_plan (host logic, no GPU): (d', m', d_k')."""
+    from cxai.xai.drsa.drsa import _pad_plan
+    assert _pad_plan(100, 100, 4, 200000) == (128, 128, 32)        # arch A layer 19: 4 x 25 -> 4 x 32
+    assert _pad_plan(64, 64, 4, 200000) == (128, 128, 32)
+    assert _pad_plan(96, 96, 2, 20000) == (128, 128, 64)
+    assert _pad_plan(200, 200, 4, 100000) == (256, 256, 64)
+    assert _pad_plan(100, 100, 5, 100000) is None                  # 5 x 32 = 160 columns: not a multiple of 128
+    assert _pad_plan(100, 100, 3, 100000) is None                  # m % K != 0
+
+
 def test_pow2_scale():
     from cxai.xai.drsa.drsa import _pow2_scale
     for mx in (1e-6, 0.03, 0.25, 1.0, 77.0, 5e4, 3e9):
