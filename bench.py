@@ -85,13 +85,19 @@ def synth_rows_cuda(M: int, d: int, seed: int, device):
     return nv(A).contiguous(), nv(C).contiguous()
 
 
+def synth_U0(d: int, seed: int = 5):
+    """Random orthogonal start (Q of a seeded Gaussian matrix), generated on the CPU and shared by both arms."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return torch.linalg.qr(torch.randn(d, d, generator=g))[0].contiguous()
+
+
 # =========================================================================== this repo's arm
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
     from cxai.xai.drsa.drsa import SubspaceOptimizer
-    from oracle import drsa_ref                      # cpu_baseline leg only
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -110,7 +116,7 @@ def run_ours(args):
     custom = bool(args.rows or args.d or args.K)
     m = d
     A, C = synth_rows_cuda(M, d, 20262 + rank, dev)
-    U0 = drsa_ref.synth_U0(d, seed=5)
+    U0 = synth_U0(d, seed=5)
     peaks = _peaks()
 
     def barrier():

@@ -8,12 +8,12 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import synth_rows_cuda          # noqa: E402
 from cxai.xai.drsa.drsa import SubspaceOptimizer          # noqa: E402
-from oracle import drsa_ref          # noqa: E402
+from bench import synth_U0          # noqa: E402
 
 dev = torch.device("cuda", 0)
 M, d, K = 640_000, 256, 4
 A, C = synth_rows_cuda(M, d, 20262, dev)
-U0 = drsa_ref.synth_U0(d, seed=5)
+U0 = synth_U0(d, seed=5)
 Ah, Ch = A.cpu().pin_memory(), C.cpu().pin_memory()
 del A, C
 torch.cuda.synchronize()

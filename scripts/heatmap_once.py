@@ -6,11 +6,11 @@ from bench import build_cfg2_model
 from cxai.utils.constants import lrp_name_map_6s
 from cxai.xai.explain.rules import SequentialMergeBatchNorm
 from cxai.xai.explain.explainer import HeatmapGenerator
-from oracle import drsa_ref
+from bench import synth_U0
 dev = torch.device("cuda", 0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 net = build_cfg2_model(dev)
-U = drsa_ref.synth_U0(256, seed=5)
+U = synth_U0(256, seed=5)
 gen = HeatmapGenerator(net, U, lrp_name_map_6s(), "blues", num_concepts=4, layer_idx=33, device=dev,
                        canonizers=[SequentialMergeBatchNorm()])
 g = torch.Generator(device=dev).manual_seed(20262)

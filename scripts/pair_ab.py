@@ -4,11 +4,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from drsa_audio_b200 import _lib as L
 from cxai.xai.drsa.drsa import SubspaceOptimizer
 from bench import synth_rows_cuda
-from oracle import drsa_ref
+from bench import synth_U0
 dev = torch.device("cuda", 0)
 M, d, K = (int(sys.argv[1]) if len(sys.argv) > 1 else 640000), 256, 4
 A, C = synth_rows_cuda(M, d, 20262, dev)
-U0 = drsa_ref.synth_U0(d, seed=5)
+U0 = synth_U0(d, seed=5)
 opt = SubspaceOptimizer(U0, A, C, None, num_concepts=K, device=dev, precision="tc", use_cuda_graph=False)
 opt._rows.split_u(opt._Uw)
 res = {}
