@@ -17,6 +17,7 @@ layer = net.features[33]
 def once():
     a, R = pp.get_intermediate(net, x, comp, layer, 0)
     return pp.gather_context_pairs(a, R, None, normalize=True)
+lrp_engine.ENGINE_CHUNK = int(os.environ.get('CHUNK', lrp_engine.ENGINE_CHUNK))
 plan = lrp_engine._plan(net, comp, dev)
 if "--ncu" in sys.argv:
     once(); torch.cuda.synchronize(); once(); torch.cuda.synchronize(); sys.exit(0)
