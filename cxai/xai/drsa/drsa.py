@@ -63,26 +63,39 @@ def _pow2_scale(absmax: float) -> float:
     return float(2.0 ** (7 - math.floor(math.log2(absmax))))
 
 
-class _RowPass:
-    """Device state of one row shard: the (packed) rows, workspaces and the step/finish calls."""
+_PRECISIONS = {"fp32": _L.PREC_FP32, "tc": _L.PREC_TC_F16, "tc_split": _L.PREC_TC_F16X2, "tc_hilo": _L.PREC_TC_F16_AC2,
+               "tc32": _L.PREC_TC_F32C, "tc_dc": _L.PREC_TC_F16_AC2}
+DC_EVERY = 8                        # 'tc_dc': steps between two evaluations of the row-rounding correction
+_PACK_CHUNK_ROWS = 1 << 20          # rows per host->device chunk when the fp32 rows do not fit next to the packed copy
 
-    def __init__(self, act: torch.Tensor, ctx: torch.Tensor, d: int, m: int, K: int, precision: str):
+
+class _RowPass:
+    """Device state of one row shard: the (packed) rows, workspaces and the step/finish calls.
+
+    ``act`` / ``ctx`` may live on the host: the tensor-core modes only ever need the packed fp16 planes on the device, so
+    the fp32 rows are uploaded (whole if they fit, else in chunks of ``_PACK_CHUNK_ROWS`` rows), packed and released --
+    cfg 4 (12.8 M rows x 512 channels = 26 GB per fp32 matrix) packs to 13 GB per matrix ('tc')."""
+
+    def __init__(self, act: torch.Tensor, ctx: torch.Tensor, d: int, m: int, K: int, precision: str, dev: torch.device):
         lib = _L.lib()
         self.lib = lib
         self.M, self.d, self.m, self.K = int(act.shape[0]), d, m, K
-        dev = act.device
-        tc_ok = lib.drsa_step_workspace_bytes(max(self.M, 1), d, m, K, _L.PREC_TC_F16) >= 0
-        if precision == "auto":
-            precision = "tc" if (tc_ok and self.M >= 8192) else "fp32"
-        if precision in ("tc", "tc_split") and not tc_ok:
-            raise _L.DRSAError(f"precision='{precision}' does not support d={d}, m={m}, K={K}")
-        if precision not in ("tc", "tc_split", "fp32"):
-            raise ValueError("precision must be 'auto', 'tc', 'tc_split' or 'fp32'")
+        if precision not in _PRECISIONS:
+            raise ValueError("precision must be 'auto', 'fp32', 'tc', 'tc_split', 'tc_hilo', 'tc_dc' or 'tc32'")
         self.precision = precision
-        self.prec_code = {"tc": _L.PREC_TC_F16, "tc_split": _L.PREC_TC_F16X2, "fp32": _L.PREC_FP32}[precision]
+        self.prec_code = _PRECISIONS[precision]
+        if lib.drsa_step_workspace_bytes(max(self.M, 1), d, m, K, self.prec_code) < 0:
+            raise _L.DRSAError(f"precision='{precision}' does not support d={d}, m={m}, K={K}")
         self.is_tc = precision != "fp32"
-        self.u_rounded = 1 if precision == "tc" else 0
+        self.u_split = precision in ("tc_split", "tc32")
+        self.hilo = precision in ("tc_hilo", "tc32", "tc_dc")
+        # U rounded to fp16 once per step, with error feedback through the lo plane (drsa_finish_step, u_rounded = 2)
+        self.u_rounded = 2 if precision in ("tc", "tc_hilo", "tc_dc") else 0
+        self.dc = precision == "tc_dc"
         self.sums = torch.zeros(d * m + K, dtype=torch.float32, device=dev)
+        if self.dc:                 # single-plane sums of the current step, and the correction kept between evaluations
+            self.sums_raw = torch.zeros_like(self.sums)
+            self.delta = torch.zeros_like(self.sums)
         self.status = torch.zeros(4, dtype=torch.int32, device=dev)
         self.scaleA = self.scaleC = self.pq_scale = 1.0
         self.Ut_hi = self.Ut_lo = None
@@ -91,31 +104,52 @@ class _RowPass:
             self.ws_step = torch.empty(max(int(ws), 256), dtype=torch.uint8, device=dev)
         if self.is_tc:
             self.Ut_hi = torch.empty(m, d, dtype=torch.float16, device=dev)
-            if precision == "tc_split":
+            if self.u_split or self.u_rounded == 2:
                 self.Ut_lo = torch.empty(m, d, dtype=torch.float16, device=dev)
-            self.A, self.scaleA, rhoA = self._pack(act)
-            self.C, self.scaleC, rhoC = self._pack(ctx)
+            self.A, self.scaleA, rhoA = self._pack(act, dev)
+            self.C, self.scaleC, rhoC = self._pack(ctx, dev)
             # |g*HC| <= pq * rhoA * rhoC^2 and |g*HA| <= pq * rhoA^2 * rhoC (rho = largest packed row norm):
             # choose the power of two pq that keeps both below 2^15, so fp16 P/Q can never overflow
             bound = max(rhoA * rhoC * rhoC, rhoA * rhoA * rhoC, 1e-30)
             self.pq_scale = float(2.0 ** math.floor(math.log2(32768.0 / bound)))
         else:
-            self.A, self.C = act, ctx
+            self.A, self.C = _f32c(act, dev), _f32c(ctx, dev)
         wf = _L.check(lib.drsa_finish_workspace_bytes(d, m), "drsa_finish_workspace_bytes")
         self.ws_fin = torch.empty(int(wf), dtype=torch.uint8, device=dev)
 
-    def _pack(self, x: torch.Tensor):
-        """fp16 copy of the rows, its power-of-two scale and the largest packed row norm."""
-        if x.numel() == 0:
-            return torch.empty_like(x, dtype=torch.float16), 1.0, 0.0
-        stats = torch.zeros(2, dtype=torch.float32, device=x.device)
-        _L.check(self.lib.drsa_absmax(_ptr(x), x.numel(), _ptr(stats[0:]), _stream()), "drsa_absmax")
-        _L.check(self.lib.drsa_rownorm_max(_ptr(x), x.size(0), x.size(1), _ptr(stats[1:]), _stream()),
-                 "drsa_rownorm_max")
+    def _pack(self, x: torch.Tensor, dev: torch.device):
+        """fp16 copy of the rows (one plane, or hi + lo planes back to back), its power-of-two scale and the largest
+        packed row norm."""
+        M, d = int(x.shape[0]), int(x.shape[1])
+        out = torch.empty((2, M, d) if self.hilo else (M, d), dtype=torch.float16, device=dev)
+        if M == 0:
+            return out, 1.0, 0.0
+        x = x.detach()
+        if x.is_cuda or 2 * x.numel() * 4 < torch.cuda.mem_get_info(dev)[0]:
+            chunks = [(0, M)]
+            whole = _f32c(x, dev)
+            get = lambda r0, r1: whole
+        else:                                   # two passes over the host rows (statistics, then packing)
+            chunks = [(r0, min(r0 + _PACK_CHUNK_ROWS, M)) for r0 in range(0, M, _PACK_CHUNK_ROWS)]
+            get = lambda r0, r1: _f32c(x[r0:r1], dev)
+        stats = torch.zeros(2, dtype=torch.float32, device=dev)
+        tmp = torch.zeros(2, dtype=torch.float32, device=dev)
+        for r0, r1 in chunks:
+            xc = get(r0, r1)
+            _L.check(self.lib.drsa_absmax(_ptr(xc), xc.numel(), _ptr(tmp[0:]), _stream()), "drsa_absmax")
+            _L.check(self.lib.drsa_rownorm_max(_ptr(xc), xc.size(0), d, _ptr(tmp[1:]), _stream()), "drsa_rownorm_max")
+            torch.maximum(stats, tmp, out=stats)
         mx, rho = (float(v) for v in stats.cpu())          # one host sync, once per optimiser
         scale = _pow2_scale(mx)
-        out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
-        _L.check(self.lib.drsa_pack_f16(_ptr(x), x.numel(), scale, _ptr(out), _stream()), "drsa_pack_f16")
+        flat = out.view(2, -1) if self.hilo else out.view(1, -1)
+        for r0, r1 in chunks:
+            xc = get(r0, r1)
+            hi = flat[0, r0 * d:]
+            if self.hilo:
+                _L.check(self.lib.drsa_pack_f16_hilo(_ptr(xc), xc.numel(), scale, _ptr(hi), _ptr(flat[1, r0 * d:]),
+                                                     _stream()), "drsa_pack_f16_hilo")
+            else:
+                _L.check(self.lib.drsa_pack_f16(_ptr(xc), xc.numel(), scale, _ptr(hi), _stream()), "drsa_pack_f16")
         return out, scale, rho * scale
 
     def split_u(self, U: torch.Tensor):
@@ -123,33 +157,49 @@ class _RowPass:
             _L.check(self.lib.drsa_split_u(_ptr(U), self.d, self.m, _ptr(self.Ut_hi), _ptr(self.Ut_lo), _stream()),
                      "drsa_split_u")
 
-    def step(self, U: torch.Tensor):
-        """Row sums of this shard into self.sums (drsa.py:148-155 + backward of :100)."""
+    def _row_sums(self, U: torch.Tensor, code: int, out: torch.Tensor):
+        _L.check(self.lib.drsa_step(_ptr(self.A), _ptr(self.C), _ptr(U), _ptr(self.Ut_hi), _ptr(self.Ut_lo), self.M,
+                                    self.d, self.m, self.K, code, self.scaleA, self.scaleC, self.pq_scale,
+                                    _ptr(out), _ptr(self.ws_step), self.ws_step.numel(), _stream()), "drsa_step")
+
+    def step(self, U: torch.Tensor, correct: bool = True):
+        """Row sums of this shard into self.sums (drsa.py:148-155 + backward of :100).
+
+        'tc_dc' (deferred correction): a step with ``correct`` evaluates the sums twice at the same U -- on the hi planes of
+        the rows alone and on hi + lo -- uses the latter and keeps the difference; the other steps read only the hi planes
+        (the first M*d elements of the packed buffer are a valid single-plane matrix) and add the kept difference."""
         if self.M == 0:
             self.sums.zero_()
             return
-        _L.check(self.lib.drsa_step(_ptr(self.A), _ptr(self.C), _ptr(U), _ptr(self.Ut_hi), _ptr(self.Ut_lo), self.M,
-                                    self.d, self.m, self.K, self.prec_code, self.scaleA, self.scaleC, self.pq_scale,
-                                    _ptr(self.sums), _ptr(self.ws_step), self.ws_step.numel(), _stream()),
-                 "drsa_step")
+        if not self.dc:
+            self._row_sums(U, self.prec_code, self.sums)
+            return
+        n = self.sums.numel()
+        self._row_sums(U, _L.PREC_TC_F16, self.sums_raw)
+        if correct:
+            self._row_sums(U, _L.PREC_TC_F16_AC2, self.sums)
+            _L.check(self.lib.drsa_sums_combine(_ptr(self.sums), _ptr(self.sums_raw), -1.0, _ptr(self.delta), n, _stream()),
+                     "drsa_sums_combine")
+        else:
+            _L.check(self.lib.drsa_sums_combine(_ptr(self.sums_raw), _ptr(self.delta), 1.0, _ptr(self.sums), n, _stream()),
+                     "drsa_sums_combine")
 
     def finish(self, U: torch.Tensor, M_global: int, obj_log: Optional[torch.Tensor], log_index: int, update: bool,
                max_iters: int, tol: float, px: "Optional[_PeerExchange]" = None):
+        # with error feedback (u_rounded = 2) the stored fp16 matrix is an INPUT as well: it is what the row pass used
+        hi = _ptr(self.Ut_hi) if (update or self.u_rounded == 2) else None
+        lo = _ptr(self.Ut_lo) if update else None
         if px is not None:          # all-reduce of self.sums over the ranks inside the kernel (peer memory)
             import ctypes as C
             _L.check(self.lib.drsa_finish_step_p2p(C.byref(px.desc), _ptr(self.sums), M_global, _ptr(U), self.d, self.m,
-                                                   self.K, _ptr(U) if update else None,
-                                                   _ptr(self.Ut_hi) if update else None,
-                                                   _ptr(self.Ut_lo) if update else None, _ptr(obj_log), log_index,
+                                                   self.K, _ptr(U) if update else None, hi, lo, _ptr(obj_log), log_index,
                                                    max_iters, tol, self.u_rounded, _ptr(self.status), _ptr(self.ws_fin),
                                                    self.ws_fin.numel(), _stream()), "drsa_finish_step_p2p")
             return
         _L.check(self.lib.drsa_finish_step(_ptr(self.sums), M_global, _ptr(U), self.d, self.m, self.K,
-                                           _ptr(U) if update else None,
-                                           _ptr(self.Ut_hi) if update else None, _ptr(self.Ut_lo) if update else None,
-                                           _ptr(obj_log), log_index, max_iters, tol, self.u_rounded, _ptr(self.status),
-                                           _ptr(self.ws_fin), self.ws_fin.numel(), _stream()),
-                 "drsa_finish_step")
+                                           _ptr(U) if update else None, hi, lo, _ptr(obj_log), log_index, max_iters, tol,
+                                           self.u_rounded, _ptr(self.status), _ptr(self.ws_fin), self.ws_fin.numel(),
+                                           _stream()), "drsa_finish_step")
 
 
 class _PeerExchange:
@@ -216,6 +266,27 @@ class _PeerExchange:
         return px
 
 
+# Long-horizon accuracy of the arithmetic modes (tests/test_gpu_drsa_long.py, scripts/horizon_parity.py,
+# scripts/sim_feedback_gpu.py).  Over the reference's horizon of 2 000 steps (drsa.py:76) two roundings move the final
+# subspaces against the fp32 trajectory (tolerance 1e-3 rad):
+#   * the per-step rounding of U to fp16 (3.8e-4 .. 7e-3 rad, worst where the objective has flat directions) -- removed by
+#     the error feedback of drsa_finish_step (u_rounded = 2): 1e-5 .. 1.4e-4 rad, at no cost;
+#   * storing the rows once in fp16, a FIXED perturbation of the data set: 4.2e-4 rad at M = 640 000 (d = 256) but
+#     1e-3 .. 5.6e-3 rad at M = 8 192 .. 65 536 -- removed by hi + lo planes ('tc_hilo', 2x the MMA work) or, at (n+2)/n of
+#     the single-plane cost, by the deferred correction 'tc_dc' (2.7e-5 .. 5.1e-4 rad at n = 8).
+# 'auto': CUDA-core fp32 below 8 192 rows per rank (the tensor cores do not matter there), 'tc_hilo' for medium problems (the
+# step is latency-bound anyway), 'tc_dc' from 262 144 rows.  'tc' (single plane, no correction) is never chosen
+# automatically: it is the fastest mode and within tolerance at cfg 2, but with less than 2x margin.
+_AUTO_FP32_BELOW = 8192
+_AUTO_DC_FROM = 262_144
+
+
+def _auto_precision(M_global: int, avg_rows: int, d: int, m: int, K: int) -> str:
+    if avg_rows < _AUTO_FP32_BELOW:
+        return "fp32"
+    return "tc_dc" if M_global >= _AUTO_DC_FROM else "tc_hilo"
+
+
 def _pad_plan(d: int, m: int, K: int, rows: int):
     """Shape (d', m') of an equivalent zero-padded problem that the tensor-core row pass covers, or None.
 
@@ -249,9 +320,14 @@ class SubspaceOptimizer:
     ``obj_val``, ``save_model`` and ``save_train_stats``.
 
     Extra keyword arguments (all optional, defaults keep the reference behaviour):
-        precision: 'auto' | 'tc' | 'tc_split' | 'fp32' -- arithmetic of the row pass (see include/drsa_b200.h):
-            'tc' = tcgen05 with U rounded to fp16 once per step and a first-order corrected objective,
-            'tc_split' = tcgen05 with U split hi + lo (1.5x the MMA work), 'fp32' = CUDA cores.
+        precision: 'auto' | 'fp32' | 'tc' | 'tc_split' | 'tc_hilo' | 'tc32' -- arithmetic of the row pass (see
+            include/drsa_b200.h): 'fp32' = CUDA cores; 'tc' = tcgen05, rows stored once in fp16, U rounded to fp16 once
+            per step with a first-order corrected objective; 'tc_split' = 'tc' with U split hi + lo; 'tc_hilo' = 'tc' with
+            the rows stored as hi + lo fp16 planes (22 bits, 2x the MMA work); 'tc_dc' = 'tc' plus a deferred correction
+            of the row rounding evaluated every ``DC_EVERY`` steps ((n+2)/n of the cost of 'tc'); 'tc32' = rows AND U
+            hi + lo: fp32-class operands on the tensor cores (2.6x).  In 'tc', 'tc_hilo' and 'tc_dc' the per-step rounding
+            of U uses error feedback.  'auto' picks by row count so that the result stays within 1e-3 rad of the fp32
+            trajectory over the reference's 2 000 steps (see ``_auto_precision``).
         process_group: torch.distributed group over which the rows are sharded; ``activation_vecs``
             / ``context_vecs`` are then this rank's slice.  Defaults to the world group if
             torch.distributed is initialised.
@@ -282,28 +358,36 @@ class SubspaceOptimizer:
         self._pad = None
         with torch.cuda.device(self.device):
             self._Uw = _f32c(U, self.device).clone()          # the matrix the kernels work on (padded if self._pad)
-            self.act_vecs = _f32c(activation_vecs, self.device)
-            self.ctx_vecs = _f32c(context_vecs, self.device)
+            # the rows as the caller passed them (host or device); a device fp32 copy is only made where the arithmetic
+            # needs one ('fp32') or on access of .act_vecs / .ctx_vecs -- the tensor-core modes keep only the packed planes
+            self._act_src, self._ctx_src = activation_vecs.detach(), context_vecs.detach()
+            self._act_dev = self._ctx_dev = None
             self._dist = torch.distributed.is_available() and torch.distributed.is_initialized()
             self._group = process_group
-            rows = int(self.act_vecs.size(0))
+            rows = int(activation_vecs.size(0))
             M_local = torch.tensor([rows], dtype=torch.int64, device=self.device)
             if self._dist:
                 torch.distributed.all_reduce(M_local, group=self._group)
             self.M_global = int(M_local.item())
             # every rank must take the same decisions (arithmetic, padded shapes of the exchange): they are derived from
-            # the average shard size, not from this rank's
+            # the average shard size and the global row count, not from this rank's
             avg_rows = self.M_global // (torch.distributed.get_world_size(self._group) if self._dist else 1)
-            native_tc = _L.lib().drsa_step_workspace_bytes(max(avg_rows, 1), d, m, num_concepts, _L.PREC_TC_F16) >= 0
+            lib = _L.lib()
+            native_tc = lib.drsa_step_workspace_bytes(max(avg_rows, 1), d, m, num_concepts, _L.PREC_TC_F16) >= 0
             if precision == "auto" and native_tc:
-                precision = "tc" if avg_rows >= 8192 else "fp32"
-            plan, pad_prec = None, "tc" if precision == "auto" else precision
-            if not native_tc and m == d and (precision in ("tc", "tc_split") or (precision == "auto" and avg_rows >= 65536)):
+                precision = _auto_precision(self.M_global, avg_rows, d, m, num_concepts)
+            plan, pad_prec = None, precision
+            if not native_tc and m == d and (precision in ("tc", "tc_split", "tc_hilo", "tc32") or
+                                             (precision == "auto" and avg_rows >= 65536)):
                 plan = _pad_plan(d, m, num_concepts, avg_rows)
+                if plan is not None and precision == "auto":
+                    pad_prec = _auto_precision(self.M_global, avg_rows, plan[0], plan[1], num_concepts)
             elif not native_tc and m == d and d > 64 and d % 32 != 0 and precision in ("auto", "fp32"):
                 # exact fp32 arithmetic, padded only so that the fused finish kernel (d, m multiples of 32) applies:
                 # the un-fused retraction costs ~30 launches (0.5 ms at d = 100)
                 plan, pad_prec = _pad_plan(d, m, num_concepts, avg_rows), "fp32"
+            if plan is None and precision == "auto":
+                precision = "fp32"
             if plan is not None:
                 dp, mp, dkp = plan
                 cols = (torch.arange(m, device=self.device) // self.d_k) * dkp + torch.arange(m, device=self.device) % self.d_k
@@ -316,14 +400,16 @@ class SubspaceOptimizer:
                 self._pad = dict(d=d, m=m, dp=dp, mp=mp, cols=cols)
                 self._Uw = Up
                 act_p = torch.zeros(rows, dp, device=self.device)
-                act_p[:, :d] = self.act_vecs
+                act_p[:, :d] = _f32c(self._act_src, self.device)
                 ctx_p = torch.zeros(rows, dp, device=self.device)
-                ctx_p[:, :d] = self.ctx_vecs
-                self._rows = _RowPass(act_p, ctx_p, dp, mp, num_concepts, pad_prec)
+                ctx_p[:, :d] = _f32c(self._ctx_src, self.device)
+                self._rows = _RowPass(act_p, ctx_p, dp, mp, num_concepts, pad_prec, self.device)
                 del act_p, ctx_p
                 d, m = dp, mp
             else:
-                self._rows = _RowPass(self.act_vecs, self.ctx_vecs, d, m, num_concepts, precision)
+                self._rows = _RowPass(self._act_src, self._ctx_src, d, m, num_concepts, precision, self.device)
+                if not self._rows.is_tc:
+                    self._act_dev, self._ctx_dev = self._rows.A, self._rows.C
         self.precision = self._rows.precision
         self.retraction_iters, self.retraction_tol = retraction_iters, retraction_tol
         self._px = None
@@ -333,6 +419,20 @@ class SubspaceOptimizer:
         self.use_cuda_graph = use_cuda_graph and (not self._dist or self._px is not None)
         self.obj_history: Optional[np.ndarray] = None
         self.last_status: Optional[np.ndarray] = None
+
+    @property
+    def act_vecs(self) -> torch.Tensor:
+        """The activation rows on the device in fp32 (drsa.py:70); materialised on first access."""
+        if self._act_dev is None:
+            self._act_dev = _f32c(self._act_src, self.device)
+        return self._act_dev
+
+    @property
+    def ctx_vecs(self) -> torch.Tensor:
+        """The context rows on the device in fp32 (drsa.py:71); materialised on first access."""
+        if self._ctx_dev is None:
+            self._ctx_dev = _f32c(self._ctx_src, self.device)
+        return self._ctx_dev
 
     @property
     def U(self) -> torch.Tensor:
@@ -375,8 +475,8 @@ class SubspaceOptimizer:
         return "p2p_symm" if exchange == "p2p_symm" else "p2p"
 
     # ------------------------------------------------------------------ one step
-    def _step(self, obj_log: torch.Tensor, log_index: int, update: bool) -> None:
-        self._rows.step(self._Uw)
+    def _step(self, obj_log: torch.Tensor, log_index: int, update: bool, correct: bool = True) -> None:
+        self._rows.step(self._Uw, correct)
         if self._dist and self._px is None:
             torch.distributed.all_reduce(self._rows.sums, group=self._group)   # d*m + K floats over NVLink
         self._rows.finish(self._Uw, self.M_global, obj_log, log_index, update, self.retraction_iters,
@@ -389,7 +489,7 @@ class SubspaceOptimizer:
             self._rows.split_u(self._Uw)
             self.reset_log(steps + 1)
             self.enqueue_steps(steps)
-            self._step(self._obj_log, -1, False)          # final evaluation, no update (drsa.py:109-117)
+            self._step(self._obj_log, -1, False, False)   # final evaluation, no update (drsa.py:109-117)
             hist = self._obj_log[: steps + 1].cpu().numpy()   # the only device->host copy of the loop
             self.last_status = self._rows.status.cpu().numpy()
         self.obj_history = hist
@@ -411,27 +511,37 @@ class SubspaceOptimizer:
 
     def enqueue_steps(self, n: int) -> None:
         """Enqueue ``n`` ascent steps on the current stream without any host synchronisation.  Each
-        step appends its objective to the device log.  Single process: one step is captured in a CUDA
-        graph once and replayed."""
+        step appends its objective to the device log.  One step is captured in a CUDA graph once and replayed
+        ('tc_dc': two graphs, the step that re-evaluates the correction and the plain one)."""
         if n <= 0:
             return
+        every = DC_EVERY if self._rows.dc else 1
+        count = getattr(self, "_steps_done", 0)
         if not (self.use_cuda_graph and n >= 4):
             for _ in range(n):
-                self._step(self._obj_log, -1, True)
+                self._step(self._obj_log, -1, True, count % every == 0)
+                count += 1
+            self._steps_done = count
             return
         if getattr(self, "_graph", None) is None:
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self._step(self._obj_log, -1, True)       # warm-up outside the graph (lazy module init)
+                self._step(self._obj_log, -1, True, count % every == 0)   # warm-up outside the graph (lazy module init)
             torch.cuda.current_stream().wait_stream(side)
+            count += 1
             n -= 1
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                self._step(self._obj_log, -1, True)       # capture does not execute
-            self._graph = graph
+            graphs = {}
+            for correct in ((True, False) if self._rows.dc else (True,)):
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._step(self._obj_log, -1, True, correct)          # capture does not execute
+                graphs[correct] = graph
+            self._graph = graphs
         for _ in range(n):
-            self._graph.replay()
+            self._graph[count % every == 0].replay()
+            count += 1
+        self._steps_done = count
 
     # ------------------------------------------------------------------ objective (static, differentiable)
     @staticmethod
@@ -462,7 +572,7 @@ class _ObjVal(torch.autograd.Function):
         dev = _as_device(U.device if U.is_cuda else _DEFAULT_DEVICE)
         with torch.cuda.device(dev):
             A, Cv, Uc = _f32c(act, dev), _f32c(cvec, dev), _f32c(U, dev)
-            rows = _RowPass(A, Cv, Uc.size(0), Uc.size(1), K, "fp32")
+            rows = _RowPass(A, Cv, Uc.size(0), Uc.size(1), K, "fp32", dev)
             rows.step(Uc)
             obj = torch.zeros(1, dtype=torch.float32, device=dev)
             rows.finish(Uc, A.size(0), obj, 0, False, 1, 1e-6)

@@ -14,6 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PREC_FP32 = 0
 PREC_TC_F16X2 = 1
 PREC_TC_F16 = 2
+PREC_TC_F16_AC2 = 3
+PREC_TC_F32C = 4
 
 
 class DRSAError(RuntimeError):
@@ -45,11 +47,13 @@ SIGNATURES = {
     "drsa_last_cuda_error": (_i32, []),
     "drsa_check_device": (_i32, [_i32]),
     "drsa_pack_f16": (_i32, [_vp, _i64, _f32, _vp, _vp]),
+    "drsa_pack_f16_hilo": (_i32, [_vp, _i64, _f32, _vp, _vp, _vp]),
     "drsa_absmax": (_i32, [_vp, _i64, _vp, _vp]),
     "drsa_step_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32, _i32]),
     "drsa_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _vp, _i64, _vp]),
     "drsa_rownorm_max": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "drsa_split_u": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp]),
+    "drsa_sums_combine": (_i32, [_vp, _vp, _f32, _vp, _i64, _vp]),
     "drsa_finish_workspace_bytes": (_i64, [_i32, _i32]),
     "drsa_finish_step": (_i32, [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp,
                                 _i64, _vp]),

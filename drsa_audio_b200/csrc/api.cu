@@ -39,8 +39,8 @@ int step_fp32(const float* A, const float* C, const float* U, int64_t M, int d, 
 bool tc_shape_supported(int d, int m, int K);
 int64_t step_tc_workspace_bytes(int64_t M, int d, int m, int K);
 int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_lo, int64_t M, int d, int m, int K,
-            float scaleA, float scaleC, float pq_scale, bool split_u, float* sums, void* workspace, int64_t workspace_bytes,
-            cudaStream_t stream);
+            float scaleA, float scaleC, float pq_scale, bool split_u, bool split_ac, float* sums, void* workspace,
+            int64_t workspace_bytes, cudaStream_t stream);
 int rownorm_max(const float* in, int64_t rows, int d, float* out, cudaStream_t stream);
 int conv3x3_forward(const float* x, const float* w, const float* b, int64_t N, int Cin, int Cout, int H, int W, int relu,
                     float* y, cudaStream_t s);
@@ -95,6 +95,7 @@ int nhwc_to_nchw(const void* x_hi, const void* x_lo, int64_t B, int H, int W, in
 int split_f16(const float* in, int64_t count, void* hi, void* lo, cudaStream_t stream);
 int relu_mask_nhwc(float* R, const void* a_hi, const void* a_lo, int64_t count, cudaStream_t stream);
 int pack_f16(const float* in, int64_t count, float scale, void* out, cudaStream_t stream);
+int pack_f16_hilo(const float* in, int64_t count, float scale, void* out_hi, void* out_lo, cudaStream_t stream);
 int absmax(const float* in, int64_t count, float* out, cudaStream_t stream);
 int64_t finish_workspace_bytes(int d, int m);
 int finish_step(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out, void* Ut_hi,
@@ -117,6 +118,7 @@ int context_gather(const float* a_map, const float* R_map, int64_t N, int d, int
 int context_vectors(const float* a, const float* R, int64_t count, float* out, cudaStream_t stream);
 int sumsq(const float* v, int64_t count, double* out, cudaStream_t stream);
 int normalize(float* v, int64_t rows, int d, const double* sumsq, int64_t count_global, cudaStream_t stream);
+int sums_combine(const float* a, const float* b, float beta, float* out, int64_t n, cudaStream_t stream);
 
 static bool shape_ok(int64_t M, int d, int m, int K) {
   return M > 0 && d > 0 && m > 0 && K > 0 && m <= d && m % K == 0;
@@ -156,6 +158,12 @@ int drsa_pack_f16(const float* in, int64_t count, float scale, void* out_f16, vo
   return pack_f16(in, count, scale, out_f16, static_cast<cudaStream_t>(stream));
 }
 
+int drsa_pack_f16_hilo(const float* in, int64_t count, float scale, void* out_hi_f16, void* out_lo_f16, void* stream) {
+  if (in == nullptr || out_hi_f16 == nullptr || out_lo_f16 == nullptr || count <= 0 || !(scale > 0.f)) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return pack_f16_hilo(in, count, scale, out_hi_f16, out_lo_f16, static_cast<cudaStream_t>(stream));
+}
+
 int drsa_absmax(const float* in, int64_t count, float* out, void* stream) {
   if (in == nullptr || out == nullptr || count <= 0) return DRSA_ERR_ARG;
   DRSA_TRY(require_sm100());
@@ -171,8 +179,10 @@ int drsa_rownorm_max(const float* in, int64_t rows, int d, float* out, void* str
 int64_t drsa_step_workspace_bytes(int64_t M, int d, int m, int K, int precision) {
   if (!shape_ok(M, d, m, K)) return DRSA_ERR_ARG;
   if (precision == DRSA_PREC_FP32) return step_fp32_workspace_bytes(M, d, m, K);
-  if (precision == DRSA_PREC_TC_F16X2 || precision == DRSA_PREC_TC_F16) {
-    if (!tc_shape_supported(d, m, K) || (d == 512 && precision == DRSA_PREC_TC_F16X2)) return DRSA_ERR_SHAPE;
+  if (precision == DRSA_PREC_TC_F16X2 || precision == DRSA_PREC_TC_F16 || precision == DRSA_PREC_TC_F16_AC2 ||
+      precision == DRSA_PREC_TC_F32C) {
+    const bool split_u = precision == DRSA_PREC_TC_F16X2 || precision == DRSA_PREC_TC_F32C;
+    if (!tc_shape_supported(d, m, K) || (d == 512 && split_u)) return DRSA_ERR_SHAPE;
     return step_tc_workspace_bytes(M, d, m, K);
   }
   return DRSA_ERR_ARG;
@@ -190,13 +200,22 @@ int drsa_step(const void* A, const void* C, const float* U, const void* Ut_hi, c
     return step_fp32(static_cast<const float*>(A), static_cast<const float*>(C), U, M, d, m, K, sums, workspace,
                      workspace_bytes, s);
   }
-  if (precision == DRSA_PREC_TC_F16X2 || precision == DRSA_PREC_TC_F16) {
-    const bool split = precision == DRSA_PREC_TC_F16X2;
+  if (precision == DRSA_PREC_TC_F16X2 || precision == DRSA_PREC_TC_F16 || precision == DRSA_PREC_TC_F16_AC2 ||
+      precision == DRSA_PREC_TC_F32C) {
+    const bool split = precision == DRSA_PREC_TC_F16X2 || precision == DRSA_PREC_TC_F32C;
+    const bool split_ac = precision == DRSA_PREC_TC_F16_AC2 || precision == DRSA_PREC_TC_F32C;
     if (Ut_hi == nullptr || (split && Ut_lo == nullptr) || !(scaleA > 0.f) || !(scaleC > 0.f) || !(pq_scale > 0.f))
       return DRSA_ERR_ARG;
-    return step_tc(A, C, Ut_hi, Ut_lo, M, d, m, K, scaleA, scaleC, pq_scale, split, sums, workspace, workspace_bytes, s);
+    return step_tc(A, C, Ut_hi, Ut_lo, M, d, m, K, scaleA, scaleC, pq_scale, split, split_ac, sums, workspace,
+                   workspace_bytes, s);
   }
   return DRSA_ERR_ARG;
+}
+
+int drsa_sums_combine(const float* a, const float* b, float beta, float* out, int64_t n, void* stream) {
+  if (a == nullptr || b == nullptr || out == nullptr || n <= 0) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return sums_combine(a, b, beta, out, n, static_cast<cudaStream_t>(stream));
 }
 
 int drsa_split_u(const float* U, int d, int m, void* Ut_hi, void* Ut_lo, void* stream) {

@@ -119,13 +119,24 @@ __device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
 //     epilogue   :        E(0)        E(1)        E(2)   ...               E(i) starts when G1(i) completes
 // so the epilogue of subtile i runs under GEMM1 of subtile i+1 and the tensor pipe never waits for it as long as
 // E(i) is shorter than G1(i+1) + G2(i-1).  H[i & 1] is free for G1(i) because G2(i-2), issued earlier, has read it.
-template <int D, bool kSplitU>
+//
+// kSplitAC (DRSA_PREC_TC_F16_AC2 / DRSA_PREC_TC_F32C): the rows are stored as TWO fp16 planes, A = A_hi + A_lo (22 bits), and
+// every product with them is two MMAs into the same accumulator:
+//     GEMM1:  H   += U_hi^T [A_hi; C_hi]  (+ U_lo^T [A_hi; C_hi])  + U_hi^T [A_lo; C_lo]
+//     GEMM2:  X^T += P^T A_hi + Q^T C_hi + P^T A_lo + Q^T C_lo
+// The lo planes travel through the same stage ring as extra stages (hi pass, then lo pass).  The single fp16 rounding of
+// the rows is a FIXED perturbation of the data set that moves the optimisation trajectory by ~1/sqrt(M) (3e-3 rad after the
+// reference's 2 000 steps at M = 8 192); with the lo planes the rows carry fp32-class precision.
+template <int D, bool kSplitU, bool kSplitAC>
 __global__ void __launch_bounds__(kThreads, 1)
 drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmC,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmC2,
+                    const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmCl,
+                    const __grid_constant__ CUtensorMap tmA2l, const __grid_constant__ CUtensorMap tmC2l,
                     const __grid_constant__ CUtensorMap tmUh, const __grid_constant__ CUtensorMap tmUl,
                     int n_sub, int G, int nRB, int d_k, float inv_scale, float pq_scale, float* __restrict__ part,
                     float* __restrict__ ss_part, int* __restrict__ err_flag, long long* __restrict__ prof) {
+  constexpr int kPlanes = kSplitAC ? 2 : 1;
   using C = Cfg<D, kSplitU>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sU_hi = smem;
@@ -170,32 +181,41 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (kSplitU) tma_load_2d(sU_lo + p * kPanelBytes, &tmUl, u_full, 64 * p, g * kNG);
       }
       tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmC2);
+      if (kSplitAC) { tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmCl); tma_prefetch_desc(&tmA2l); tma_prefetch_desc(&tmC2l); }
       int stage = 0; uint32_t phase = 0;
       // GEMM1 operand: per 64-channel panel the stacked tile [A rows r0..r0+63 ; C rows r0..r0+63] (K-major), two panels per stage
       auto load_g1 = [&](int sub) {
-        for (int hs = 0; hs < C::kPanels / 2; ++hs) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], C::kStageBytes);
-          uint8_t* dst = sStage + stage * C::kStageBytes;
+        for (int pl = 0; pl < kPlanes; ++pl) {
+          const CUtensorMap* mA = pl ? &tmAl : &tmA;
+          const CUtensorMap* mC = pl ? &tmCl : &tmC;
+          for (int hs = 0; hs < C::kPanels / 2; ++hs) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], C::kStageBytes);
+            uint8_t* dst = sStage + stage * C::kStageBytes;
 #pragma unroll
-          for (int pp = 0; pp < 2; ++pp) {
-            tma_load_2d(dst + pp * kPanelBytes, &tmA, &full[stage], 64 * (2 * hs + pp), sub * kSub);
-            tma_load_2d(dst + pp * kPanelBytes + kPanelBytes / 2, &tmC, &full[stage], 64 * (2 * hs + pp), sub * kSub);
+            for (int pp = 0; pp < 2; ++pp) {
+              tma_load_2d(dst + pp * kPanelBytes, mA, &full[stage], 64 * (2 * hs + pp), sub * kSub);
+              tma_load_2d(dst + pp * kPanelBytes + kPanelBytes / 2, mC, &full[stage], 64 * (2 * hs + pp), sub * kSub);
+            }
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
           }
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       };
       // GEMM2 operand: row chunks [32 rows x D ch] of A and of C as D/64 panels of 4 KB each (MN-major, N = D)
       auto load_g2 = [&](int sub) {
         for (int c = 0; c < 2; ++c) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], 2 * C::kNPanels * 4096);
-          uint8_t* dst = sStage + stage * C::kStageBytes;
-          for (int p = 0; p < C::kNPanels; ++p) {
-            tma_load_2d(dst + p * 4096, &tmA2, &full[stage], C::kDN * ih + 64 * p, sub * kSub + 32 * c);
-            tma_load_2d(dst + kPanelBytes + p * 4096, &tmC2, &full[stage], C::kDN * ih + 64 * p, sub * kSub + 32 * c);
+          for (int pl = 0; pl < kPlanes; ++pl) {
+            const CUtensorMap* mA = pl ? &tmA2l : &tmA2;
+            const CUtensorMap* mC = pl ? &tmC2l : &tmC2;
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], 2 * C::kNPanels * 4096);
+            uint8_t* dst = sStage + stage * C::kStageBytes;
+            for (int p = 0; p < C::kNPanels; ++p) {
+              tma_load_2d(dst + p * 4096, mA, &full[stage], C::kDN * ih + 64 * p, sub * kSub + 32 * c);
+              tma_load_2d(dst + kPanelBytes + p * 4096, mC, &full[stage], C::kDN * ih + 64 * p, sub * kSub + 32 * c);
+            }
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
           }
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       };
       int prev = -1;
@@ -220,26 +240,29 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       auto gemm1 = [&](int i) {
         const long long t0 = prof ? clock64() : 0;
         const uint32_t tH = tmem_base + 256 + 128 * (i & 1);
-        for (int hs = 0; hs < C::kPanels / 2; ++hs) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t base = smem_u32(sStage + stage * C::kStageBytes);
 #pragma unroll
-          for (int pp = 0; pp < 2; ++pp) {
-            const int p = 2 * hs + pp;
-            // descriptors: the high word is constant, the low word is (address >> 4) | LBO field; advancing
-            // along K inside the 128-byte swizzle atom adds 32 B (>> 4 = 2) to the low word
-            const uint32_t uh = kdesc_lo(smem_u32(sU_hi + p * kPanelBytes)), ul = kdesc_lo(smem_u32(sU_lo + p * kPanelBytes));
-            const uint32_t dAC = kdesc_lo(base + pp * kPanelBytes);
+        for (int pl = 0; pl < kPlanes; ++pl) {
+          for (int hs = 0; hs < C::kPanels / 2; ++hs) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t base = smem_u32(sStage + stage * C::kStageBytes);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t d_ac = desc64(dAC + 2 * kk);
-              umma_ss_f16(tH, desc64(uh + 2 * kk), d_ac, idesc1, (p | kk) ? 1u : 0u);
-              if (kSplitU) umma_ss_f16(tH, desc64(ul + 2 * kk), d_ac, idesc1, 1u);
+            for (int pp = 0; pp < 2; ++pp) {
+              const int p = 2 * hs + pp;
+              // descriptors: the high word is constant, the low word is (address >> 4) | LBO field; advancing
+              // along K inside the 128-byte swizzle atom adds 32 B (>> 4 = 2) to the low word
+              const uint32_t uh = kdesc_lo(smem_u32(sU_hi + p * kPanelBytes)), ul = kdesc_lo(smem_u32(sU_lo + p * kPanelBytes));
+              const uint32_t dAC = kdesc_lo(base + pp * kPanelBytes);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t d_ac = desc64(dAC + 2 * kk);
+                umma_ss_f16(tH, desc64(uh + 2 * kk), d_ac, idesc1, (pl | p | kk) ? 1u : 0u);
+                if (kSplitU && pl == 0) umma_ss_f16(tH, desc64(ul + 2 * kk), d_ac, idesc1, 1u);   // U_lo x rows_lo is O(2^-22): dropped
+              }
             }
+            umma_commit(&empty[stage]);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&empty[stage]);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&h_full[i & 1]);
         if (prof) pa += clock64() - t0;
@@ -254,20 +277,23 @@ drsa_tc_step_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int c = 0; c < 2; ++c) {
           mbar_wait(&p_full[2 * (i & 1) + c], par);
           if (prof && c == 0) t1 = clock64();
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t base = smem_u32(sStage + stage * C::kStageBytes);
-          const uint32_t dA = mndesc_lo(base), dC = mndesc_lo(base + kPanelBytes);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            // 16 rows of K = two 8-row swizzle atoms = 2048 B (>> 4 = 128); P^T k-step = 8 TMEM columns
-            const uint32_t off = 32 * c + 8 * h;
-            umma_ts_f16(tX, tH + off, desc64(dA + 128 * h), idesc2, first ? 0u : 1u);
-            umma_ts_f16(tX, tH + kSub + off, desc64(dC + 128 * h), idesc2, 1u);
-            first = false;
+          for (int pl = 0; pl < kPlanes; ++pl) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t base = smem_u32(sStage + stage * C::kStageBytes);
+            const uint32_t dA = mndesc_lo(base), dC = mndesc_lo(base + kPanelBytes);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              // 16 rows of K = two 8-row swizzle atoms = 2048 B (>> 4 = 128); P^T k-step = 8 TMEM columns
+              const uint32_t off = 32 * c + 8 * h;
+              umma_ts_f16(tX, tH + off, desc64(dA + 128 * h), idesc2, first ? 0u : 1u);
+              umma_ts_f16(tX, tH + kSub + off, desc64(dC + 128 * h), idesc2, 1u);
+              first = false;
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&empty[stage]);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         if (prof) { pb += t1 - t0; pc += clock64() - t1; }
       };
@@ -1067,6 +1093,33 @@ __global__ void pack_f16_kernel(const float4* __restrict__ in, int64_t n4, float
     out[i] = o;
   }
 }
+// hi = fp16(x * scale), lo = fp16(x * scale - hi): x * scale = hi + lo up to 2^-22 relative (2^-25 absolute where lo is subnormal)
+__global__ void pack_f16_hilo_kernel(const float4* __restrict__ in, int64_t n4, float scale, uint2* __restrict__ out_hi,
+                                     uint2* __restrict__ out_lo) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(in + i);
+    const float x0 = v.x * scale, x1 = v.y * scale, x2 = v.z * scale, x3 = v.w * scale;
+    uint2 h, l;
+    h.x = pack_h2_sat(x0, x1);
+    h.y = pack_h2_sat(x2, x3);
+    const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+    const float2 h23 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+    l.x = pack_h2_sat(x0 - h01.x, x1 - h01.y);
+    l.y = pack_h2_sat(x2 - h23.x, x3 - h23.y);
+    out_hi[i] = h;
+    out_lo[i] = l;
+  }
+}
+__global__ void pack_f16_hilo_tail_kernel(const float* __restrict__ in, int64_t begin, int64_t count, float scale,
+                                          __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  const int64_t i = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < count) {
+    const float x = fminf(fmaxf(in[i] * scale, -65504.f), 65504.f);
+    const __half h = __float2half_rn(x);
+    out_hi[i] = h;
+    out_lo[i] = __float2half_rn(x - __half2float(h));
+  }
+}
 __global__ void pack_f16_tail_kernel(const float* __restrict__ in, int64_t begin, int64_t count, float scale,
                                      __half* __restrict__ out) {
   const int64_t i = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -1154,15 +1207,15 @@ int launch_step32(int grid, cudaStream_t stream, const CUtensorMap& tmA, const C
   return DRSA_OK;
 }
 
-template <int D, bool kSplitU, typename... Args>
+template <int D, bool kSplitU, bool kSplitAC, typename... Args>
 int launch_step(int grid, cudaStream_t stream, Args... args) {
   static bool attr_set = false;      // one process per GPU: a per-process flag is enough
   if (!attr_set) {
-    DRSA_CUDA(cudaFuncSetAttribute(drsa_tc_step_kernel<D, kSplitU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DRSA_CUDA(cudaFuncSetAttribute(drsa_tc_step_kernel<D, kSplitU, kSplitAC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg<D, kSplitU>::kSmemBytes));
     attr_set = true;
   }
-  drsa_tc_step_kernel<D, kSplitU><<<grid, kThreads, Cfg<D, kSplitU>::kSmemBytes, stream>>>(args...);
+  drsa_tc_step_kernel<D, kSplitU, kSplitAC><<<grid, kThreads, Cfg<D, kSplitU>::kSmemBytes, stream>>>(args...);
   DRSA_LAUNCH_CHECK();
   return DRSA_OK;
 }
@@ -1192,14 +1245,16 @@ int pair_max_clusters() {
 }
 
 // split_u = true: U^T = hi + lo, two MMAs per product (DRSA_PREC_TC_F16X2); false: U^T = fp16(U) only (DRSA_PREC_TC_F16)
+// split_ac = true: A16 / C16 are [2][M][d] fp16, the hi plane followed by the lo plane (pack_f16_hilo); two MMAs per product
+// with the rows (DRSA_PREC_TC_F16_AC2 / DRSA_PREC_TC_F32C)
 int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_lo, int64_t M, int d, int m, int K,
-            float scaleA, float scaleC, float pq_scale, bool split_u, float* sums, void* workspace, int64_t workspace_bytes,
-            cudaStream_t stream) {
+            float scaleA, float scaleC, float pq_scale, bool split_u, bool split_ac, float* sums, void* workspace,
+            int64_t workspace_bytes, cudaStream_t stream) {
   if (!tc_shape_supported(d, m, K)) return DRSA_ERR_SHAPE;
   if (!split_u) Ut_lo = Ut_hi;       // never read; keeps the tensor map valid
   if (!aligned16(A16) || !aligned16(C16) || !aligned16(Ut_hi) || !aligned16(Ut_lo)) return DRSA_ERR_ALIGN;
   if (M >= ((int64_t)1 << 31)) return DRSA_ERR_SHAPE;
-  const bool tmem_u = !split_u && d <= 256 && g_tc_variant == 1;
+  const bool tmem_u = !split_u && !split_ac && d <= 256 && g_tc_variant == 1;
   TcPlan p = plan_for(M, d, m, K, tmem_u ? kSub32 : kSub);
   if (workspace_bytes < p.part_bytes + p.ss_bytes + 256) return DRSA_ERR_WORKSPACE;
   char* w = static_cast<char*>(workspace);
@@ -1207,7 +1262,7 @@ int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_
   float* ss_part = reinterpret_cast<float*>(w); w += p.ss_bytes;
   int* err = reinterpret_cast<int*>(w);
 
-  if ((g_tc_variant == 2 || g_tc_variant == 3) && !split_u && d == 256 && p.G % 2 == 0 && pair_max_clusters() > 0) {
+  if ((g_tc_variant == 2 || g_tc_variant == 3) && !split_u && !split_ac && d == 256 && p.G % 2 == 0 && pair_max_clusters() > 0) {
     // CTA pairs: one cluster per (row block, pair of column groups); never more row blocks than the plan sized the
     // workspace for, never more clusters than fit the device at once (a second wave would double the time)
     const int G2 = p.G / 2;
@@ -1246,11 +1301,17 @@ int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_
     DRSA_LAUNCH_CHECK();
     return DRSA_OK;
   }
-  CUtensorMap tmA, tmC, tmA2, tmC2, tmUh, tmUl;
+  CUtensorMap tmA, tmC, tmA2, tmC2, tmAl, tmCl, tmA2l, tmC2l, tmUh, tmUl;
+  const __half* Alo = static_cast<const __half*>(A16) + (split_ac ? M * d : 0);      // without the lo planes the maps alias
+  const __half* Clo = static_cast<const __half*>(C16) + (split_ac ? M * d : 0);      // the hi planes and are never used
   DRSA_TRY(make_tmap_f16_sw128(&tmA, A16, (uint64_t)M, (uint64_t)d, kSub));
   DRSA_TRY(make_tmap_f16_sw128(&tmC, C16, (uint64_t)M, (uint64_t)d, kSub));
   DRSA_TRY(make_tmap_f16_sw128(&tmA2, A16, (uint64_t)M, (uint64_t)d, 32));
   DRSA_TRY(make_tmap_f16_sw128(&tmC2, C16, (uint64_t)M, (uint64_t)d, 32));
+  DRSA_TRY(make_tmap_f16_sw128(&tmAl, Alo, (uint64_t)M, (uint64_t)d, kSub));
+  DRSA_TRY(make_tmap_f16_sw128(&tmCl, Clo, (uint64_t)M, (uint64_t)d, kSub));
+  DRSA_TRY(make_tmap_f16_sw128(&tmA2l, Alo, (uint64_t)M, (uint64_t)d, 32));
+  DRSA_TRY(make_tmap_f16_sw128(&tmC2l, Clo, (uint64_t)M, (uint64_t)d, 32));
   DRSA_TRY(make_tmap_f16_sw128(&tmUh, Ut_hi, (uint64_t)m, (uint64_t)d, kNG));
   DRSA_TRY(make_tmap_f16_sw128(&tmUl, Ut_lo, (uint64_t)m, (uint64_t)d, kNG));
 
@@ -1259,19 +1320,18 @@ int step_tc(const void* A16, const void* C16, const void* Ut_hi, const void* Ut_
   const int grid = p.nRB * p.G * (d > 256 ? d / 256 : 1);
   if (d == 512 && split_u) return DRSA_ERR_SHAPE;      // U^T hi + lo of a column group (256 KB) does not fit in shared memory
   int st;
+#define DRSA_TC_LAUNCH(DD, SU, SAC)                                                                                          \
+  launch_step<DD, SU, SAC>(grid, stream, tmA, tmC, tmA2, tmC2, tmAl, tmCl, tmA2l, tmC2l, tmUh, tmUl, p.num_tiles, p.G, p.nRB, \
+                           d_k, inv_scale, pq_scale, part, ss_part, err, g_tc_prof)
   if (d == 512)
-    st = launch_step<512, false>(grid, stream, tmA, tmC, tmA2, tmC2, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale,
-                                 pq_scale, part, ss_part, err, g_tc_prof);
+    st = split_ac ? DRSA_TC_LAUNCH(512, false, true) : DRSA_TC_LAUNCH(512, false, false);
   else if (d == 256)
-    st = split_u ? launch_step<256, true>(grid, stream, tmA, tmC, tmA2, tmC2, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale,
-                                          pq_scale, part, ss_part, err, g_tc_prof)
-                 : launch_step<256, false>(grid, stream, tmA, tmC, tmA2, tmC2, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale,
-                                           pq_scale, part, ss_part, err, g_tc_prof);
+    st = split_u ? (split_ac ? DRSA_TC_LAUNCH(256, true, true) : DRSA_TC_LAUNCH(256, true, false))
+                 : (split_ac ? DRSA_TC_LAUNCH(256, false, true) : DRSA_TC_LAUNCH(256, false, false));
   else
-    st = split_u ? launch_step<128, true>(grid, stream, tmA, tmC, tmA2, tmC2, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale,
-                                          pq_scale, part, ss_part, err, g_tc_prof)
-                 : launch_step<128, false>(grid, stream, tmA, tmC, tmA2, tmC2, tmUh, tmUl, p.num_tiles, p.G, p.nRB, d_k, inv_scale,
-                                           pq_scale, part, ss_part, err, g_tc_prof);
+    st = split_u ? (split_ac ? DRSA_TC_LAUNCH(128, true, true) : DRSA_TC_LAUNCH(128, true, false))
+                 : (split_ac ? DRSA_TC_LAUNCH(128, false, true) : DRSA_TC_LAUNCH(128, false, false));
+#undef DRSA_TC_LAUNCH
   DRSA_TRY(st);
   dim3 rgrid(m / 16, d / 32);
   // X' = pq_scale * (sA sC)^2 * X
@@ -1292,6 +1352,25 @@ int pack_f16(const float* in, int64_t count, float scale, void* out, cudaStream_
   }
   if (count % 4) {
     pack_f16_tail_kernel<<<1, 32, 0, stream>>>(in, n4 * 4, count, scale, static_cast<__half*>(out));
+    DRSA_LAUNCH_CHECK();
+  }
+  return DRSA_OK;
+}
+
+int pack_f16_hilo(const float* in, int64_t count, float scale, void* out_hi, void* out_lo, cudaStream_t stream) {
+  if (!aligned16(in) || (reinterpret_cast<uintptr_t>(out_hi) & 7u) != 0 || (reinterpret_cast<uintptr_t>(out_lo) & 7u) != 0)
+    return DRSA_ERR_ALIGN;
+  const int64_t n4 = count / 4;
+  if (n4 > 0) {
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pack_f16_hilo_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(in), n4, scale,
+                                                          reinterpret_cast<uint2*>(out_hi), reinterpret_cast<uint2*>(out_lo));
+    DRSA_LAUNCH_CHECK();
+  }
+  if (count % 4) {
+    pack_f16_hilo_tail_kernel<<<1, 32, 0, stream>>>(in, n4 * 4, count, scale, static_cast<__half*>(out_hi),
+                                                    static_cast<__half*>(out_lo));
     DRSA_LAUNCH_CHECK();
   }
   return DRSA_OK;
@@ -1319,8 +1398,16 @@ int tc_kernel_attrs(int d, int split, int* out5) {
     out5[4] = pair_max_clusters();
     return DRSA_OK;
   }
-  const void* fn = d == 512 ? (const void*)drsa_tc_step_kernel<512, false> : d == 256 ? (split ? (const void*)drsa_tc_step_kernel<256, true> : (const void*)drsa_tc_step_kernel<256, false>)
-                            : (split ? (const void*)drsa_tc_step_kernel<128, true> : (const void*)drsa_tc_step_kernel<128, false>);
+  // split: 0 = DRSA_PREC_TC_F16, 1 = _F16X2, 3 = _F16_AC2, 4 = _F32C
+  const bool su = split == 1 || split == 4, sac = split == 3 || split == 4;
+  const void* fn;
+  if (d == 512) fn = sac ? (const void*)drsa_tc_step_kernel<512, false, true> : (const void*)drsa_tc_step_kernel<512, false, false>;
+  else if (d == 256)
+    fn = su ? (sac ? (const void*)drsa_tc_step_kernel<256, true, true> : (const void*)drsa_tc_step_kernel<256, true, false>)
+            : (sac ? (const void*)drsa_tc_step_kernel<256, false, true> : (const void*)drsa_tc_step_kernel<256, false, false>);
+  else
+    fn = su ? (sac ? (const void*)drsa_tc_step_kernel<128, true, true> : (const void*)drsa_tc_step_kernel<128, true, false>)
+            : (sac ? (const void*)drsa_tc_step_kernel<128, false, true> : (const void*)drsa_tc_step_kernel<128, false, false>);
   DRSA_CUDA(cudaFuncGetAttributes(&a, fn));
   out5[0] = a.numRegs; out5[1] = a.maxThreadsPerBlock; out5[2] = (int)a.sharedSizeBytes; out5[3] = (int)a.localSizeBytes;
   out5[4] = a.maxDynamicSharedSizeBytes;

@@ -108,7 +108,19 @@ __global__ void __launch_bounds__(256) subspace_rel_kernel(const float* __restri
   s = warp_sum(s);
   if (lane == 0) out[b * K + k] = s;
 }
+// out[i] = a[i] + beta * b[i] over the d*m + K row sums (deferred correction of the row rounding, see drsa_sums_combine)
+__global__ void __launch_bounds__(256) sums_combine_kernel(const float* __restrict__ a, const float* __restrict__ b, float beta,
+                                                           float* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fmaf(beta, b[i], a[i]);
+}
 }  // namespace
+
+int sums_combine(const float* a, const float* b, float beta, float* out, int64_t n, cudaStream_t stream) {
+  sums_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a, b, beta, out, n);
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
 
 int context_gather(const float* a_map, const float* R_map, int64_t N, int d, int HW, const int64_t* idx, int L,
                    float* act_out, float* ctx_out, double* sumsq, cudaStream_t stream) {

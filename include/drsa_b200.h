@@ -49,11 +49,19 @@ typedef enum drsa_precision {
   DRSA_PREC_FP32 = 0,       /* CUDA-core FFMA, fp32 throughout                        */
   DRSA_PREC_TC_F16X2 = 1,   /* tcgen05 kind::f16, fp32 accumulate in TMEM; A and C are
                                stored once as scaled fp16, U is split hi+lo every step */
-  DRSA_PREC_TC_F16 = 2      /* as above with U rounded to fp16 once per step (one MMA per
+  DRSA_PREC_TC_F16 = 2,     /* as above with U rounded to fp16 once per step (one MMA per
                                product): the sums are exact for fp16(U); drsa_finish_step
                                (u_rounded = 1) adds the first-order term <grad, U - fp16(U)>
                                to the logged objective, so the objective stays second-order
                                accurate in the rounding                  */
+  DRSA_PREC_TC_F16_AC2 = 3, /* as DRSA_PREC_TC_F16 (U rounded once per step, u_rounded = 1)
+                               with the rows stored as TWO fp16 planes A = A_hi + A_lo (22
+                               bits, drsa_pack_f16_hilo): two MMAs per product with the rows */
+  DRSA_PREC_TC_F32C = 4     /* fp32-class operands on the tensor cores: rows hi + lo AND
+                               U hi + lo (3 MMAs per forward product, 2 per gradient product,
+                               the O(2^-22) lo x lo term dropped); d <= 256.  The mode that
+                               follows the reference's fp32 trajectory over its full
+                               2 000-step horizon for any row count        */
 } drsa_precision;
 
 const char* drsa_status_string(int status);
@@ -77,6 +85,11 @@ int drsa_check_device(int device);
  * aligned. */
 int drsa_pack_f16(const float* in, int64_t count, float scale, void* out_f16, void* stream);
 
+/* Data preparation for DRSA_PREC_TC_F16_AC2 / DRSA_PREC_TC_F32C: out_hi[i] = fp16(in[i]*scale),
+ * out_lo[i] = fp16(in[i]*scale - out_hi[i]).  drsa_step expects the two planes of a matrix
+ * back to back: out_lo = out_hi + M*d elements. */
+int drsa_pack_f16_hilo(const float* in, int64_t count, float scale, void* out_hi_f16, void* out_lo_f16, void* stream);
+
 /* max |x| over `count` floats -> *out (one float).  Used to choose the pack scale. */
 int drsa_absmax(const float* in, int64_t count, float* out, void* stream);
 
@@ -98,7 +111,8 @@ int64_t drsa_step_workspace_bytes(int64_t M, int d, int m, int K, int precision)
  * sums are additive over row shards, so under data parallelism the caller all-reduces
  * `sums` (d*m+K floats) between drsa_step and drsa_finish_step.
  *
- *   A, C      [M, d]   fp32 (DRSA_PREC_FP32) or scaled fp16 from drsa_pack_f16 (TC mode)
+ *   A, C      [M, d]   fp32 (DRSA_PREC_FP32) or scaled fp16 from drsa_pack_f16 (TC modes 1, 2), or
+ *             [2, M, d] fp16 hi plane + lo plane from drsa_pack_f16_hilo (TC modes 3, 4)
  *   U         [d, m]   fp32, m = K*d_k <= d               (FP32 mode; may be NULL in TC mode)
  *   Ut_hi/lo  [m, d]   fp16 split of U^T written by drsa_finish_step / drsa_split_u
  *                      (TC modes; may be NULL in FP32 mode; Ut_lo is not read by DRSA_PREC_TC_F16)
@@ -109,6 +123,13 @@ int64_t drsa_step_workspace_bytes(int64_t M, int d, int m, int K, int precision)
 int drsa_step(const void* A, const void* C, const float* U, const void* Ut_hi, const void* Ut_lo,
               int64_t M, int d, int m, int K, int precision, float scaleA, float scaleC,
               float pq_scale, float* sums, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* out[i] = a[i] + beta * b[i] over n floats (out may alias a or b).  Used for the DEFERRED CORRECTION of the row rounding
+ * (SubspaceOptimizer precision 'tc_dc'): every few steps the row sums are evaluated twice at the same U, with single-plane
+ * rows (DRSA_PREC_TC_F16) and with hi + lo rows (DRSA_PREC_TC_F16_AC2); delta = sums_hilo - sums_hi is kept and added to the
+ * cheap single-plane sums of the following steps.  At a fixed point of the iteration the correction is exact, so the
+ * optimisation converges to the optimum of the 22-bit data set at (n + 2)/n of the single-plane cost. */
+int drsa_sums_combine(const float* a, const float* b, float beta, float* out, int64_t n, void* stream);
 
 /* U [d,m] fp32 -> Ut_hi, Ut_lo [m,d] fp16 with U^T = hi + lo (+ O(2^-22)); Ut_lo may be NULL. */
 int drsa_split_u(const float* U, int d, int m, void* Ut_hi, void* Ut_lo, void* stream);
@@ -123,8 +144,12 @@ int64_t drsa_finish_workspace_bytes(int d, int m);
  *     Y = U + sqrt(obj) / (K M q_k^1.5) * X_k      (ascent, unit step)  drsa.py:102
  *     U_out = Y (Y^T Y)^(-1/2)                      (polar retraction)   drsa.py:201-221
  *     Ut_hi/Ut_lo (optional, Ut_lo alone may be NULL) = fp16 split of U_out^T for the next TC step
- *   u_rounded != 0: `sums` came from DRSA_PREC_TC_F16, i.e. were evaluated at fp16(U); the logged objective is
- *     f(fp16 U) + <grad f(fp16 U), U - fp16 U>, which equals f(U) up to second order in the rounding.
+ *   u_rounded != 0: `sums` came from DRSA_PREC_TC_F16 / _F16_AC2, i.e. were evaluated at a rounded matrix U^; the logged
+ *     objective is f(U^) + <grad f(U^), U - U^>, which equals f(U) up to second order in the rounding.
+ *     u_rounded = 1: U^ = fp16(U).  u_rounded = 2: U^ is the matrix stored in Ut_hi (must be passed, it is read even when
+ *     U_out == NULL), and the new Ut_hi is written with ERROR FEEDBACK: hi = fp16(U_out + lo_prev), lo = U_out + lo_prev - hi
+ *     with the residual carried in Ut_lo from step to step (initialise both with drsa_split_u).  The rounding errors of
+ *     successive steps then cancel instead of accumulating along flat directions of the objective.
  * The polar factor is computed on the device by a scaled Newton-Schulz iteration in
  * fp32 (at most `max_iters` sweeps, stops when ||Y^T Y - I||_F < tol*sqrt(m)); the
  * reference uses an fp64 eigendecomposition on the host, both converge to the same

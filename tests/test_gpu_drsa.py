@@ -227,7 +227,10 @@ def _golden(golden_dir, name):
                                              ("d128", "fp32", False), ("d256", "fp32", True), ("rect", "fp32", True),
                                              ("d128", "tc", True), ("d256", "tc", True), ("d256", "tc", False),
                                              ("d128", "tc_split", True), ("d256", "tc_split", False),
-                                             ("d512", "fp32", True), ("d512", "tc", True)])
+                                             ("d512", "fp32", True), ("d512", "tc", True),
+                                             ("d128", "tc_hilo", True), ("d256", "tc_hilo", False), ("d512", "tc_hilo", True),
+                                             ("d128", "tc32", False), ("d256", "tc32", True),
+                                             ("d128", "tc_dc", True), ("d256", "tc_dc", False), ("d512", "tc_dc", True)])
 def test_run_matches_reference_golden(golden_dir, name, prec, graph, tmp_path):
     from cxai.xai.drsa.drsa import SubspaceOptimizer
     g, A, C, U0, K = _golden(golden_dir, name)

@@ -98,3 +98,19 @@ def test_vectors_from_maps_modes():
     assert not np.array_equal(scr.numpy(), fixed.numpy())
     allp = drsa_ref.vectors_from_maps_all(maps)
     np.testing.assert_array_equal(allp[5].numpy(), maps[1, :, 0, 1].numpy())
+
+
+def test_port_matches_reference_at_the_full_horizon(golden_dir):
+    """The oracle port over the reference's own 2 000 steps (drsa.py:76) on BASELINE cfg 1 (M = 16 000, d = 64, K = 4)
+    against the golden trajectory of the unmodified reference (oracle/gen_golden_long.py).  The reference's distance to
+    itself under another thread count is stored in the fixture; the port must be as close."""
+    g = np.load(os.path.join(golden_dir, "drsa_long_cfg1.npz"))
+    M, d, K, steps = int(g["M"]), int(g["d"]), int(g["K"]), int(g["steps"])
+    A, C = drsa_ref.synth_pairs(M, d, int(g["seed"]))
+    U0 = drsa_ref.synth_U0(d, d, int(g["seed"]) + 1)
+    torch.set_num_threads(4)
+    objs, U = drsa_ref.run_autograd(A, C, U0, K, steps)
+    assert np.max(np.abs(objs - g["objs"]) / g["objs"]) < 1e-4
+    ang = drsa_ref.principal_angle(U, g["U_final"], K)
+    assert ang < max(1e-4, 5 * float(g["self_angle"])), ang
+    assert float(g["self_angle"]) < 1e-3 and float(g["self_rel"]) < 1e-4
