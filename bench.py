@@ -1,16 +1,20 @@
 #!/usr/bin/env python
-"""Benchmark of the DRSA/LRP hot path on B200 (contract: see the task statement / DESIGN.md).
+"""Benchmark of the DRSA/LRP hot path on B200 (contract: see the task statement / DESIGN.md section 7).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm
+    python bench.py --gpus N --steps K --warmup W [--workload cfg1|cfg2|cfg3|cfg4|cfg5]   # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W                        # the reference's CPU code
 
-Workload (config.workload = "cfg2"): BASELINE.json configs[1] -- DRSA at the last conv of the
-widened genre CNN: N = 10 000 samples x P = 64 positions -> M = 640 000 (activation, context)
-rows per GPU, d = 256, K = 4 concepts of d_k = 64.  A "step" is one DRSA optimisation step
-(row pass + d*m all-reduce + ascent + polar retraction).  Rows shard across ranks with the
-per-GPU row count fixed (weak scaling); `value` is whole-job throughput in cfg2-sized steps per
-second, i.e. (rows processed per step by all ranks / 640 000) * steps/s, which equals plain
-steps/s at N = 1.
+Workloads = BASELINE.json configs.  A "step" is one DRSA optimisation step (row pass + exchange of d*m+K
+floats + ascent + polar retraction) over ALL rows of the workload.
+  cfg1  toy scale, the reference's CPU-runnable case: M = 16 000 rows (N = 1k x P = 16), d = 64, K = 4 per GPU (weak)
+  cfg2  (default; the configuration the metric is quoted on) genre CNN, last conv: N = 10 000 samples x P = 64 positions
+        -> M = 640 000 rows per GPU, d = 256, K = 4 x 64 (weak scaling: rows per GPU fixed; `value` counts cfg2-sized
+        steps per second of the whole job = (rows of all ranks / 640 000) * steps/s, plain steps/s at N = 1)
+  cfg3  N = 100 000 samples: M = 6.4 M rows in total, sharded over the ranks (strong scaling), d = 256, K = 4
+  cfg4  wide split layer: d = 512, K = 8 x 64, M = 12.8 M rows in total (51.2 M on 8 GPUs), strong scaling
+  cfg5  end to end per class: for 10 classes, 10 000 synthetic log-mel spectrograms -> CNN forward -> LRP to features[33]
+        -> (a, c) pairs -> normalise -> DRSA (K = 4, --e2e-steps steps); value = DRSA steps per second of wall clock
+        through the whole pipeline
 """
 from __future__ import annotations
 
@@ -27,8 +31,27 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 CFG2 = dict(samples=10_000, positions=64, d=256, K=4)
+WORKLOADS = {
+    "cfg1": dict(rows_per_gpu=16_000, d=64, K=4, scaling="weak", unit_rows=16_000),
+    "cfg2": dict(rows_per_gpu=640_000, d=256, K=4, scaling="weak", unit_rows=640_000),
+    "cfg3": dict(rows_total=6_400_000, d=256, K=4, scaling="strong"),
+    "cfg4": dict(rows_total=12_800_000, rows_total_8=51_200_000, d=512, K=8, scaling="strong"),
+}
 METRIC = "DRSA steps/s (cfg2: M=640k rows x d=256, K=4; LRP context vecs/s reported in 'lrp')"
 UNIT = "steps/s"
+OBJ_TOL, ANGLE_TOL = 1e-4, 1e-3        # BASELINE.json north_star
+
+
+def workload_shape(args, world: int):
+    """(rows on this rank, d, K, scaling, value scale = cfg-sized steps per step of the whole job, label)."""
+    if args.rows or args.d or args.K:
+        M, d, K = args.rows or 640_000, args.d or 256, args.K or 4
+        return M, d, K, "weak", float(world), f"custom rows={M} d={d} K={K} (steps/s of THIS shape per GPU x GPUs)"
+    w = WORKLOADS[args.workload]
+    if w["scaling"] == "weak":
+        return w["rows_per_gpu"], w["d"], w["K"], "weak", float(world), args.workload
+    total = w.get("rows_total_8", w["rows_total"]) if world >= 8 else w["rows_total"]
+    return total // world, w["d"], w["K"], "strong", 1.0, args.workload
 
 
 def _peaks():
@@ -74,15 +97,27 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def synth_rows_cuda(M: int, d: int, seed: int, device):
-    """SURVEY 8(d) synthetic pairs, generated on the device: A = relu(randn)*mask, C = randn*(A>0),
-    each normalised like normalize_vectors."""
+def synth_rows_cuda(M: int, d: int, seed: int, device, chunk: int = 1 << 20):
+    """SURVEY 8(d) synthetic pairs, generated on the device in row chunks (cfg 4 is 26 GB per matrix): A = relu(randn)*mask,
+    C = randn*(A>0), each normalised like normalize_vectors (global statistic)."""
     import torch
     g = torch.Generator(device=device).manual_seed(seed)
-    A = torch.relu(torch.randn(M, d, generator=g, device=device)) * (torch.rand(M, d, generator=g, device=device) < 0.7)
-    C = torch.randn(M, d, generator=g, device=device) * (A > 0)
-    nv = lambda v: v / torch.sqrt(torch.mean(v * v)) / d ** 0.25
-    return nv(A).contiguous(), nv(C).contiguous()
+    A = torch.empty(M, d, device=device)
+    C = torch.empty(M, d, device=device)
+    ssA = torch.zeros((), dtype=torch.float64, device=device)
+    ssC = torch.zeros((), dtype=torch.float64, device=device)
+    for r0 in range(0, M, chunk):
+        r1 = min(M, r0 + chunk)
+        a = torch.relu(torch.randn(r1 - r0, d, generator=g, device=device))
+        a *= (torch.rand(r1 - r0, d, generator=g, device=device) < 0.7)
+        c = torch.randn(r1 - r0, d, generator=g, device=device)
+        c *= (a > 0)
+        A[r0:r1], C[r0:r1] = a, c
+        ssA += (a.double() ** 2).sum()
+        ssC += (c.double() ** 2).sum()
+    A *= float(1.0 / (torch.sqrt(ssA / (M * d)) * d ** 0.25))
+    C *= float(1.0 / (torch.sqrt(ssC / (M * d)) * d ** 0.25))
+    return A, C
 
 
 def synth_U0(d: int, seed: int = 5):
@@ -92,12 +127,95 @@ def synth_U0(d: int, seed: int = 5):
     return torch.linalg.qr(torch.randn(d, d, generator=g))[0].contiguous()
 
 
+def principal_angle(U1, U2, K: int) -> float:
+    """Largest principal angle (rad) between matching concept subspaces: asin of the singular values of (I - Q1 Q1^T) Q2 in
+    fp64 on the host (acos of the cosines has a 1e-3 rad noise floor in fp32)."""
+    import torch
+    U1, U2 = U1.detach().double().cpu(), U2.detach().double().cpu()
+    d, m = U1.shape
+    dk, worst = m // K, 0.0
+    eye = torch.eye(d, dtype=torch.float64)
+    for k in range(K):
+        Q1 = torch.linalg.qr(U1[:, k * dk:(k + 1) * dk])[0]
+        Q2 = torch.linalg.qr(U2[:, k * dk:(k + 1) * dk])[0]
+        sv = torch.linalg.svdvals((eye - Q1 @ Q1.T) @ Q2)
+        worst = max(worst, float(torch.asin(sv.clamp(max=1.0)).max()))
+    return worst
+
+
+def launches_in(opt, first_step: int, n: int) -> int:
+    """Kernels of libdrsa_b200.so launched by steps first_step .. first_step+n-1 (counted from the host code in csrc/):
+    row pass = tcgen05 kernel + partial reduce (fp32: sgemm chain), 'tc_dc' adds the combine kernel and, on a correction
+    step, a second (hi + lo) row pass; the finish step is one cooperative kernel."""
+    from cxai.xai.drsa import drsa as D
+    prec = opt.precision
+    if prec == "fp32":
+        row = 1 if (opt._rows.d <= 64 and opt._rows.m <= 64 and opt._rows.K <= 4) else 8 * max(1, -(-opt._rows.M // (1 << 18)))
+        return n * (row + 1)
+    if prec != "tc_dc":
+        return n * 3
+    corr = sum(1 for i in range(first_step, first_step + n) if i % D.DC_EVERY == 0)
+    return corr * 6 + (n - corr) * 4
+
+
+def time_steps(opt, n: int, warm: int = 6):
+    """Device time of n steps (ms per step), CUDA events on the launching stream, after `warm` steps (graph capture)."""
+    import torch
+    opt.reset_log(warm + n + 8)
+    opt.enqueue_steps(warm)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    opt.enqueue_steps(n)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def parity_block(A, C, U0, K, precision, dev, steps, timed_objs, timed_U, budget_s=90.0):
+    """The timed arithmetic mode against the on-device fp32 CUDA-core path (itself pinned to the reference's golden
+    trajectories over 2 000 steps, tests/test_gpu_drsa_long.py) on the SAME rows and start, over the e2e horizon: largest
+    relative objective error over all steps and the final principal angle.  If the fp32 run of the full shape does not fit
+    the time budget, both runs are repeated on a row subset (stated)."""
+    import numpy as np
+    import torch
+    from cxai.xai.drsa.drsa import SubspaceOptimizer
+    M = A.size(0)
+    probe = SubspaceOptimizer(U0, A, C, None, num_concepts=K, device=dev, precision="fp32")
+    probe._rows.split_u(probe._Uw)
+    ms32 = time_steps(probe, 3, warm=2)
+    del probe
+    rows = M
+    if ms32 * 1e-3 * steps > budget_s:
+        rows = max(65536, int(M * budget_s / (ms32 * 1e-3 * steps)) // 65536 * 65536)
+    if rows < M:
+        A, C = A[:rows].contiguous(), C[:rows].contiguous()
+        o = SubspaceOptimizer(U0, A, C, None, num_concepts=K, device=dev, precision=precision)
+        o.run(steps=steps, save=False)
+        timed_objs, timed_U = o.obj_history, o.U.clone()
+        del o
+    t0 = time.perf_counter()
+    ref = SubspaceOptimizer(U0, A, C, None, num_concepts=K, device=dev, precision="fp32")
+    ref.run(steps=steps, save=False)
+    t32 = time.perf_counter() - t0
+    rel = float(np.max(np.abs(timed_objs - ref.obj_history) / np.abs(ref.obj_history)))
+    ang = principal_angle(timed_U, ref.U, K)
+    return {"mode": precision, "rows": rows, "steps": steps,
+            "against": "on-device fp32 CUDA-core path (pinned to the reference's 2000-step golden trajectories in "
+                       "tests/test_gpu_drsa_long.py), same rows and start matrix",
+            "max_rel_objective_err": rel, "principal_angle_rad": ang, "tol": {"objective": OBJ_TOL, "angle_rad": ANGLE_TOL},
+            "ok": bool(rel < OBJ_TOL and ang < ANGLE_TOL), "fp32_path_steps_per_s": steps / t32,
+            **({"note": f"fp32 run of the full {M} rows exceeds the {budget_s:.0f} s budget: both modes run on the first {rows} rows"}
+               if rows < M else {})}
+
+
 # =========================================================================== this repo's arm
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
     from cxai.xai.drsa.drsa import SubspaceOptimizer
+    from cxai.xai.drsa import drsa as D
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -106,14 +224,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    M, d, K = CFG2["samples"] * CFG2["positions"], CFG2["d"], CFG2["K"]
-    if args.rows:
-        M = args.rows
-    if args.d:
-        d = args.d
-    if args.K:
-        K = args.K
-    custom = bool(args.rows or args.d or args.K)
+    if args.workload == "cfg5" and not (args.rows or args.d or args.K):
+        return run_cfg5(args, dev, rank, world)
+    M, d, K, scaling, scale_units, label = workload_shape(args, world)
     m = d
     A, C = synth_rows_cuda(M, d, 20262 + rank, dev)
     U0 = synth_U0(d, seed=5)
@@ -129,10 +242,11 @@ def run_ours(args):
         sampler.start()                             # started early: nvidia-smi start-up must not land in the timed region
     opt = SubspaceOptimizer(U0, A, C, None, num_concepts=K, device=dev, precision=args.precision,
                             use_cuda_graph=not args.no_graph, exchange=args.exchange)
+    precision = opt.precision
     opt._rows.split_u(opt._Uw)
-    opt.reset_log(args.warmup + args.steps + 8)
-    warm = max(args.warmup, 4 if not args.no_graph else 3)      # >= 4 so that the CUDA graph of one step is captured here,
-    opt.enqueue_steps(warm)                                     # not inside the timed region
+    warm = max(args.warmup, 4 if not args.no_graph else 3)      # >= 4 so that the CUDA graph(s) of a step are captured here,
+    opt.reset_log(warm + args.steps + 8)                        # not inside the timed region
+    opt.enqueue_steps(warm)
     barrier()
     if rank == 0:
         t_wait = time.time() + 5.0
@@ -140,6 +254,7 @@ def run_ours(args):
             time.sleep(0.05)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    first_timed = opt._steps_done
     e0.record()
     opt.enqueue_steps(args.steps)                   # EXACTLY K steps
     e1.record()
@@ -149,26 +264,40 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    # ---- dominant kernel alone (row pass = tcgen05 kernel + partial reduce), CUDA events on its stream
+    n_launch = launches_in(opt, first_timed, args.steps)
+    # ---- dominant kernel alone: the single-plane row pass (tcgen05 kernel + partial reduce), CUDA events on its stream
+    is_tc = precision != "fp32"
+    kcode = {"tc_dc": D._L.PREC_TC_F16}.get(precision, opt._rows.prec_code)
+    kout = opt._rows.sums_raw if opt._rows.dc else opt._rows.sums
+    krun = (lambda: opt._rows._row_sums(opt._Uw, kcode, kout)) if is_tc else (lambda: opt._rows.step(opt._Uw))
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3):
-        opt._rows.step(opt._Uw)
+        krun()
     torch.cuda.synchronize()
+    nk = max(args.steps, 20)
     k0.record()
-    for _ in range(args.steps):
-        opt._rows.step(opt._Uw)
+    for _ in range(nk):
+        krun()
     k1.record()
     torch.cuda.synchronize()
-    ms_kernel = k0.elapsed_time(k1) / args.steps
+    ms_kernel = k0.elapsed_time(k1) / nk
+    ms_hilo = None
+    if opt._rows.dc:                                # the hi + lo row pass of a correction step
+        k0.record()
+        for _ in range(10):
+            opt._rows._row_sums(opt._Uw, D._L.PREC_TC_F16_AC2, opt._rows.sums)
+        k1.record()
+        torch.cuda.synchronize()
+        ms_hilo = k0.elapsed_time(k1) / 10
     # ---- the replicated tail of a step alone (ascent + polar retraction)
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     Utmp = opt._Uw.clone()
     f0.record()
-    for _ in range(args.steps):
+    for _ in range(nk):
         opt._rows.finish(Utmp, opt.M_global, None, 0, True, opt.retraction_iters, opt.retraction_tol)
     f1.record()
     torch.cuda.synchronize()
-    ms_finish = f0.elapsed_time(f1) / args.steps
+    ms_finish = f0.elapsed_time(f1) / nk
     status = opt._rows.status.cpu().numpy().tolist()
     per_rank = None
     if world > 1:          # the step is synchronous: the slowest rank's row pass sets the pace (power capping differs per GPU)
@@ -176,13 +305,32 @@ def run_ours(args):
         allk = [torch.zeros_like(tk) for _ in range(world)]
         dist.all_gather(allk, tk)
         per_rank = [round(float(v.item()), 4) for v in allk]
-    lrp = None if args.no_lrp else lrp_throughput(args, dev, rank, world, barrier)
+    exchange = opt.exchange
+    use_graph = bool(opt.use_cuda_graph)
+    del opt, Utmp
+    lrp = None if (args.no_lrp or args.workload in ("cfg3", "cfg4")) else lrp_throughput(args, dev, rank, world, barrier)
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the other arithmetic modes at the same shape (device-timed, 1 GPU)
+    modes = None
+    if world == 1 and not args.no_modes:
+        modes = {}
+        for pm in ("tc", "tc_dc", "tc_hilo", "tc32", "fp32"):
+            try:
+                o = SubspaceOptimizer(U0, A, C, None, num_concepts=K, device=dev, precision=pm)
+            except Exception:                       # noqa: BLE001 -- mode not available for this shape (tc32 at d = 512)
+                continue
+            o._rows.split_u(o._Uw)
+            msm = time_steps(o, 16 if pm == "fp32" else 64)
+            modes[pm] = {"steps_per_s": 1000.0 / msm, "ms_per_step": msm}
+            del o
+        modes["note"] = ("'tc' = rows once in fp16; 'tc_dc' = 'tc' + deferred correction of the row rounding every "
+                         f"{D.DC_EVERY} steps; 'tc_hilo' = rows as hi + lo fp16 planes; 'tc32' = rows and U hi + lo "
+                         "(fp32-class operands); 'fp32' = CUDA cores.  'auto' never picks 'tc'.")
 
     # ---- end to end through the public API with HOST buffers: construct (H2D + pack) + run + D2H
     e2e_steps = args.e2e_steps
     Ah, Ch = A.cpu().pin_memory(), C.cpu().pin_memory()
-    del opt
     torch.cuda.synchronize()
     # one untimed call first (like the warm-up steps above): the stage-1 benchmark left the caching allocator fragmented
     # and the first construction after it pays for cudaFree/cudaMalloc round trips that are not part of the path
@@ -206,46 +354,68 @@ def run_ours(args):
     objs = opt2.obj_history
     h2d = (Ah.numel() + Ch.numel() + U0.numel()) * 4
     d2h = U_host.numel() * 4 + (e2e_steps + 1) * 4
+    U_dev = opt2.U.clone()
+    del opt2, Ah, Ch
+    replicas = None
+    if world > 1:          # every rank ran the same deterministic finish kernel on the same sums: U must be BIT-identical
+        digest = torch.stack([U_dev.view(torch.int32).to(torch.int64).sum(), U_dev.double().abs().sum().view(torch.int64)])
+        alld = [torch.zeros_like(digest) for _ in range(world)]
+        dist.all_gather(alld, digest)
+        replicas = {"ranks": world, "bit_identical": bool(all(torch.equal(v, alld[0]) for v in alld))}
+    parity = None
+    if world == 1 and not args.no_parity and precision != "fp32":
+        parity = parity_block(A, C, U0, K, precision, dev, e2e_steps, objs, U_dev, budget_s=args.parity_budget)
 
     if rank == 0:
         ms_per_step = ms_total / args.steps
-        scale = world if custom else (M * world) / float(CFG2["samples"] * CFG2["positions"])
+        unit_rows = WORKLOADS.get(args.workload, {}).get("unit_rows")
+        scale = scale_units if (scaling == "strong" or unit_rows is None or label.startswith("custom")) else \
+            (M * world) / float(unit_rows)
         value = scale * 1000.0 / ms_per_step
         flops = 8.0 * M * d * m
         achieved = flops / (ms_kernel * 1e-3) / 1e12
-        is_tc = opt2.precision in ("tc", "tc_split")
-        mma_factor = {"tc": 1.0, "tc_split": 1.5}.get(opt2.precision, 1.0)
         elem = 2 if is_tc else 4
+        dtype = {"fp32": "f32", "tc": "f16 operands / f32 accumulate",
+                 "tc_split": "f16 operands (U hi+lo) / f32 accumulate",
+                 "tc_hilo": "f16 hi+lo row planes (22 bit) / f32 accumulate",
+                 "tc_dc": "f16 operands / f32 accumulate + deferred 22-bit correction of the row rounding",
+                 "tc32": "f16 hi+lo operands (22 bit rows and U) / f32 accumulate"}[precision]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"tc": "f16 operands / f32 accumulate", "tc_split": "f16 operands (U split hi+lo) / f32 accumulate"}.get(opt2.precision, "f32"),
-            "data": "synthetic",
-            "config": {"workload": "cfg2" if not custom else f"custom rows={M} d={d} K={K} (steps/s of THIS shape per GPU x GPUs)",
-                       "rows_per_gpu": M, "d": d, "m": m, "K": K, "d_k": m // K, "precision": opt2.precision, "cuda_graph": bool(opt2.use_cuda_graph),
+            "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": {"workload": label, "rows_per_gpu": M, "rows_total": M * world, "d": d, "m": m, "K": K, "d_k": m // K,
+                       "precision": precision, "precision_requested": args.precision, "cuda_graph": use_graph,
                        "exchange": {"none": "single rank", "nccl": "NCCL all-reduce of d*m+K floats per step",
                                     "p2p": "all-reduce fused into the finish kernel over NVLink peer memory (cudaIpc buffers)",
-                                    "p2p_symm": "all-reduce fused into the finish kernel over NVLink peer memory (torch symmetric memory)"}[opt2.exchange],
-                       "l2_policy": f"inputs larger than L2 ({2 * M * d * elem / 1e6:.0f} MB of rows per step vs 126 MB L2)",
+                                    "p2p_symm": "all-reduce fused into the finish kernel over NVLink peer memory (torch symmetric memory)"}[exchange],
+                       "l2_policy": f"inputs larger than L2 ({2 * M * d * elem / 1e6:.0f} MB of rows per step vs 126 MB L2)"
+                       if 2 * M * d * elem > 126e6 else "rows fit in L2 (cfg 1 is the reference's toy scale: latency-bound)",
                        "retraction_sweeps_last_step": status[0], "retraction_not_converged": status[1]},
             "rows_per_s": M * world * 1000.0 / ms_per_step,
-            "gpu_launches": int(args.steps * launches_per_step(opt2)),
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tf_sustained"], "traffic": TRAFFIC_BYTES_PER_LAUNCH if (is_tc and not custom) else None,
-                         "kernel": "drsa_tc_step_kernel (+ tc_reduce_kernel)" if is_tc else "sgemm_kernel chain",
+            "gpu_launches": int(n_launch),
+            "roofline": {"bound": "tensor" if d >= 128 else "hbm", "achieved": achieved, "peak": peaks["tf_burst"],
+                         "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
+                         "frac_of_sustained_peak": achieved / peaks["tf_sustained"],
+                         "traffic": TRAFFIC_BYTES_PER_LAUNCH if (is_tc and args.workload == "cfg2" and not label.startswith("custom")) else None,
+                         "kernel": "drsa_tc_step_kernel, single-plane rows (+ tc_reduce_kernel)" if is_tc else "fp32 row-pass kernels",
                          "kernel_ms": ms_kernel, "algorithmic_flop_per_launch": flops,
                          "algorithmic_bytes_per_launch": 2.0 * M * d * elem,
-                         "executed_mma_flop_per_launch": flops * mma_factor * (1.5 if (is_tc and d > 256) else 1.0),
+                         "executed_mma_flop_per_launch": flops * {"tc_split": 1.25, "tc_hilo": 2.0, "tc32": 2.5}.get(precision, 1.0)
+                         * (1.5 if (is_tc and d > 256) else 1.0),
                          "hbm_frac": (2.0 * M * d * elem / (ms_kernel * 1e-3) / 1e9) / peaks["hbm"],
-                         "peak_source": peaks["source"] + "; sustained bf16 figure (kernel timed in a loop)",
+                         "peak_source": peaks["source"] + f"; burst bf16 figure (kernel timed alone, {nk} back-to-back launches); "
+                                        f"sustained figure {peaks['tf_sustained']} TFLOP/s in frac_of_sustained_peak",
                          "share_of_step": ms_kernel / ms_per_step},
             "step_breakdown_ms": {"row_pass": ms_kernel, "ascent_and_retraction": ms_finish,
+                                  **({"row_pass_hi_lo_on_correction_steps": ms_hilo, "correction_every": D.DC_EVERY} if ms_hilo else {}),
                                   **({"row_pass_per_rank": per_rank} if per_rank else {})},
             "lrp": lrp,
             "e2e": {"value": scale * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_steps,
                     "d2h_bytes_per_step": d2h / e2e_steps, "steps": e2e_steps,
                     "what": "SubspaceOptimizer(U0, A_host_pinned, C_host_pinned).run(steps) + U.cpu(): H2D of all rows, "
                             "fp16 pack, steps, final objective, D2H of U and the objective history, wall clock"},
+            "parity": parity, "modes": modes, "replicas": replicas,
             "clocks": clocks,
             "objective_first_last": [float(objs[0]), float(objs[-1])],
         }
@@ -396,9 +566,19 @@ LRP_CONV_TRAFFIC_BYTES_PER_LAUNCH = 598.4e6
 
 
 def lrp_cpu_baseline(P: int, n: int = 4):
-    """The reference's stage 1 on the host cores: get_intermediate over the oracle's restatement of zennit's rules (general
-    multi-pass Gamma, backward continued to the input as zennit does), fp32, cfg-2 CNN, n samples."""
+    """The reference's stage 1 on the host cores.  With ``oracle/_ref`` present (byte copy of the reference sources made by
+    oracle/make_ref.py) the reference's OWN get_intermediate runs in a subprocess on the mini-zennit restatement
+    (kind = "reference"); otherwise the oracle port (oracle/lrp_ref.py, general multi-pass rules, kind = "port")."""
     import torch
+    if os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "cxai", "xai", "drsa", "preprocessing.py")):
+        try:
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_baseline.py"), "lrp", str(n)],
+                                 capture_output=True, text=True, timeout=600, cwd=ROOT)
+            res = json.loads(out.stdout.strip().splitlines()[-1])
+            if "value" in res:
+                return res
+        except Exception:                           # noqa: BLE001 -- fall through to the port
+            pass
     from oracle import lrp_ref
     from cxai.utils.constants import lrp_name_map_6s
     threads = os.cpu_count() or 1
@@ -420,81 +600,151 @@ def lrp_cpu_baseline(P: int, n: int = 4):
 TRAFFIC_BYTES_PER_LAUNCH = 662.8e6      # 656.3 MB read + ~6.5 MB written (profiles/r01_ncu_full_drsa_tc_step_kernel_v4.csv)
 
 
-def launches_per_step(opt) -> int:
-    """Kernels of libdrsa_b200.so launched per DRSA step (counted from the host code in csrc/)."""
-    row = 2 if opt.precision in ("tc", "tc_split") else 8 * max(1, -(-opt.act_vecs.size(0) // (1 << 18)))
-    return row + 1                      # row pass (+ partial reduce) and the fused cooperative finish kernel
-
-
 # =========================================================================== CPU baseline / reference arm
-def cpu_step_time(M_sample: int, d: int, K: int, budget_s: float, threads: int):
-    """Times the reference's algorithm (torch CPU ops in the reference's order: obj_val, autograd
-    backward, orthogonalize with the fp64 eigh -- oracle/drsa_ref.step_autograd restates drsa.py:84-104)."""
+def reference_stepper(threads: int):
+    """(step function (A, C, U, K) -> U_next, kind, description).  With ``oracle/_ref`` present this is the reference's
+    own code, unmodified: ``SubspaceOptimizer.obj_val`` (drsa.py:123-155) + ``backward`` (:100) + ``orthogonalize``
+    (:201-221) exactly as ``run`` (:84-104) strings them together; otherwise the oracle port of the same lines."""
     import torch
-    from oracle import drsa_ref
     torch.set_num_threads(threads)
-    A, C = drsa_ref.synth_pairs(M_sample, d, 20262, structured=False)
-    U = drsa_ref.synth_U0(d, seed=5)
-    _, _, U = drsa_ref.step_autograd(A, C, U, K)          # warm-up
+    from oracle import make_ref
+    if make_ref.available():
+        ref = make_ref.load_drsa()
+
+        def step(A, C, U, K):
+            U = U.detach().requires_grad_(True)                                   # drsa.py:86-88
+            obj = ref.SubspaceOptimizer.obj_val(A, C, U, ref.objective_fn, K, U.size(1) // K)   # :91-98
+            obj.backward()                                                        # :100
+            with torch.no_grad():
+                return ref.orthogonalize(U + U.grad)                              # :102
+        return step, "reference", "the reference's own drsa.py (byte copy in oracle/_ref): obj_val + backward + orthogonalize"
+    from oracle import drsa_ref
+    return (lambda A, C, U, K: drsa_ref.step_autograd(A, C, U, K)[2]), "port", \
+        "the reference algorithm restated in oracle/drsa_ref.step_autograd (oracle/_ref absent)"
+
+
+def synth_rows_cpu(M: int, d: int, seed: int):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    A = torch.relu(torch.randn(M, d, generator=g)) * (torch.rand(M, d, generator=g) < 0.7)
+    C = torch.randn(M, d, generator=g) * (A > 0)
+    nv = lambda v: v / torch.sqrt(torch.mean(v * v)) / d ** 0.25
+    return nv(A).contiguous(), nv(C).contiguous()
+
+
+def cpu_baseline(M: int, d: int, K: int, budget_s: float = 15.0):
+    """The reference's step on the host cores on a BOUNDED sample of the workload: at most 640 000 rows (cfg 2 in full) and
+    about `budget_s` seconds; larger workloads are scaled linearly in the row count (the step is O(M d^2) + O(d^3))."""
+    import torch
+    threads = os.cpu_count() or 1
+    step, kind, what = reference_stepper(threads)
+    M_sample = min(M, 640_000)
+    A, C = synth_rows_cpu(M_sample, d, 20262)
+    U = synth_U0(d, seed=5)
+    U = step(A, C, U, K)                            # warm-up
     times = []
     t_end = time.perf_counter() + budget_s
     while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 50):
         t0 = time.perf_counter()
-        _, _, U = drsa_ref.step_autograd(A, C, U, K)
+        U = step(A, C, U, K)
         times.append(time.perf_counter() - t0)
-    return sum(times) / len(times), len(times)
-
-
-def cpu_baseline(M: int, d: int, K: int, budget_s: float = 15.0):
-    import torch
-    threads = os.cpu_count() or 1
-    M_sample = min(M, 64_000)
-    t, n = cpu_step_time(M_sample, d, K, budget_s, threads)
-    return {"value": (M_sample / M) / t, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{n} steps of the reference algorithm (oracle/drsa_ref.step_autograd, torch {torch.__version__} CPU, "
-                      f"{threads} threads) on {M_sample} of the {M} rows; steps/s scaled linearly in rows",
+    t = sum(times) / len(times)
+    return {"value": (M_sample / M) / t, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"{len(times)} steps of {what}, torch {torch.__version__} CPU, {threads} threads, on {M_sample} of the {M} rows"
+                      + ("" if M_sample == M else "; steps/s scaled linearly in rows"),
             "sample_ms_per_step": t * 1e3}
 
 
 def run_reference(args):
+    """The reference's CPU implementation of the path on the box's host cores, all threads, on the workload's FULL row count
+    where that is at most cfg 2's (larger workloads: 640 000 rows, scaled linearly, stated); --steps / --warmup honoured."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    M, d, K = CFG2["samples"] * CFG2["positions"], CFG2["d"], CFG2["K"]
-    if args.rows:
-        M = args.rows
-    if args.d:
-        d = args.d
-    if args.K:
-        K = args.K
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == "cfg5" and not (args.rows or args.d or args.K):
+        args.workload = "cfg2"                      # the DRSA stage of one class of cfg 5 is the cfg 2 step
+    M, d, K, scaling, scale_units, label = workload_shape(args, world)
     threads = os.cpu_count() or 1
-    M_sample = min(M, 64_000)
-    from oracle import drsa_ref
-    torch.set_num_threads(threads)
-    A, C = drsa_ref.synth_pairs(M_sample, d, 20262, structured=False)
-    U = drsa_ref.synth_U0(d, seed=5)
-    for _ in range(max(1, min(args.warmup, 3))):
-        _, _, U = drsa_ref.step_autograd(A, C, U, K)
-    steps = min(args.steps, 40)
+    step, kind, what = reference_stepper(threads)
+    M_sample = min(M, 640_000)
+    A, C = synth_rows_cpu(M_sample, d, 20262)
+    U = synth_U0(d, seed=5)
+    for _ in range(max(1, args.warmup)):
+        U = step(A, C, U, K)
     t0 = time.perf_counter()
-    for _ in range(steps):
-        _, _, U = drsa_ref.step_autograd(A, C, U, K)
-    t = (time.perf_counter() - t0) / steps
+    for _ in range(args.steps):
+        U = step(A, C, U, K)
+    t = (time.perf_counter() - t0) / args.steps
     value = (M_sample / M) / t
-    sample = (f"{steps} steps of the reference algorithm (drsa.py:84-104 restated in oracle/drsa_ref.step_autograd; "
-              f"/root/reference is a Python repo that cannot travel to the GPU box) on {M_sample} of {M} rows, torch CPU, "
-              f"{threads} threads; steps/s scaled linearly in rows")
+    if scaling == "weak":
+        value *= 1.0                                # one host, one problem of the per-GPU size: the N = 1 figure
+    sample = (f"{args.steps} steps of {what} on {M_sample} of {M} rows, torch {torch.__version__} CPU, {threads} threads"
+              + ("" if M_sample == M else "; steps/s scaled linearly in rows"))
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
-        "warmup": max(1, min(args.warmup, 3)), "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(1, args.warmup), "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2" if not args.rows else f"custom rows={M}", "rows_per_gpu": M, "d": d, "m": d, "K": K,
-                   "d_k": d // K},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": label, "rows_per_gpu": M, "d": d, "m": d, "K": K, "d_k": d // K},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
+
+
+# =========================================================================== cfg 5: the per-class pipeline end to end
+def run_cfg5(args, dev, rank, world):
+    """10 classes x 10 000 synthetic spectrograms -> forward -> LRP to features[33] with class_idx = c -> pairs ->
+    normalise -> DRSA (K = 4, --e2e-steps steps per class).  --steps / --warmup do not apply (one pass = 10 classes)."""
+    import torch
+    import torch.distributed as dist
+    from cxai.utils.constants import lrp_name_map_6s
+    from cxai.xai.explain.rules import NameMapComposite, SequentialMergeBatchNorm
+    from cxai.xai.drsa.cluster.optsubspaces import all_classes_pipeline, class_pipeline
+    n_class, steps, classes = args.cfg5_samples, args.e2e_steps, 10
+    net = build_cfg2_model(dev)
+    comp = NameMapComposite(lrp_name_map_6s(), canonizers=[SequentialMergeBatchNorm()])
+    n_local = n_class // world
+    g = torch.Generator(device=dev).manual_seed(20265 + rank)
+    batch = lambda: (1.2 * torch.randn(n_local, 1, 128, 256, generator=g, device=dev) - 1.5).clamp(min=-4.0)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        sampler.start()
+    class_pipeline(net, batch()[:64], comp, 33, 0, None, num_concepts=4, steps=8, precision=args.precision)   # warm-up
+    data = {c: batch() for c in range(classes)}                 # this rank's spectrograms of every class, resident
+    sync()
+    t0 = time.perf_counter()
+    out = all_classes_pipeline(net, data, comp, 33, None, num_concepts=4, steps=steps, precision=args.precision)
+    sync()
+    wall = time.perf_counter() - t0
+    tw = torch.tensor([wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    wall = float(tw.item())
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        vecs = classes * n_local * world * 64
+        objs = [(float(out[c][1][0]), float(out[c][1][-1])) for c in range(classes)]
+        print(json.dumps({
+            "metric": METRIC, "value": classes * steps / wall, "unit": UNIT, "n_gpus": world, "steps": classes * steps,
+            "warmup": 8, "ms_per_step": wall * 1e3 / (classes * steps), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f16 hi+lo operands / f32 accumulate (stage 1), DRSA precision 'auto'", "data": "synthetic",
+            "config": {"workload": "cfg5", "classes": classes, "samples_per_class": n_local * world, "positions": 64,
+                       "d": 256, "K": 4, "drsa_steps_per_class": steps, "precision": args.precision,
+                       "l2_policy": "inputs larger than L2 (1.3 GB of spectrograms and 1.3 GB of rows per class)"},
+            "wall_s": wall, "context_vectors": vecs, "vectors_per_s_whole_pipeline": vecs / wall,
+            "gpu_launches": None, "clocks": clocks, "objective_first_last_per_class": objs,
+            "e2e": {"value": classes * steps / wall, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
+                    "what": "spectrograms resident on the device (synthetic); wall clock over all 10 classes incl. the D2H "
+                            "of every objective history"},
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -503,19 +753,25 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="tc", choices=["tc", "tc_split", "fp32", "auto"])
-    ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (default: cfg2 = 640000)")
-    ap.add_argument("--d", type=int, default=0, help="override the split-layer width (default: cfg2 = 256); cfg4 uses 512")
-    ap.add_argument("--K", type=int, default=0, help="override the number of concepts (default: cfg2 = 4); cfg4 uses 8")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "tc", "tc_dc", "tc_hilo", "tc32", "tc_split", "fp32"],
+                    help="arithmetic of the row pass; 'auto' (what a user gets) = 'tc_dc' at cfg 2")
+    ap.add_argument("--rows", type=int, default=0, help="custom shape: rows per GPU")
+    ap.add_argument("--d", type=int, default=0, help="custom shape: split-layer width")
+    ap.add_argument("--K", type=int, default=0, help="custom shape: number of concepts")
     ap.add_argument("--e2e-steps", type=int, default=2000,
-                    help="steps of the end-to-end call (default: the reference's run(steps=2000), drsa.py:76)")
+                    help="steps of the end-to-end call and of the parity check (default: the reference's run(steps=2000), drsa.py:76)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--parity-budget", type=float, default=90.0, help="seconds the fp32 yardstick run of the parity block may take")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lrp", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-modes", action="store_true")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "p2p_symm", "nccl"],
                     help="how the row sums are joined across ranks (see SubspaceOptimizer)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly (used for the ncu captures)")
     ap.add_argument("--lrp-samples", type=int, default=256)
+    ap.add_argument("--cfg5-samples", type=int, default=10_000, help="cfg 5: samples per class (over all ranks)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

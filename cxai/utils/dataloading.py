@@ -36,11 +36,23 @@ def peak_normalizer(wav: torch.Tensor) -> torch.Tensor:
     return wav / wav.abs().amax(dim=-1, keepdim=True).clamp(min=1e-12)
 
 
-def get_slice(wav: torch.Tensor, slice_length: int, startpoint: int, num_chunks: int, sample_rate: int) -> torch.Tensor:
-    """``num_chunks`` consecutive snippets of ``slice_length`` seconds starting at ``startpoint`` seconds."""
-    n = slice_length * sample_rate
-    s0 = int(startpoint * sample_rate)
-    return torch.stack([wav[..., s0 + i * n: s0 + (i + 1) * n].reshape(-1) for i in range(num_chunks)], 0)
+def get_slice(wav: torch.Tensor, slice_length: int = 6, start_point: int = 0, num_chunks: int = 1,
+              sample_rate: int = 16000) -> torch.Tensor:
+    """Snippets of ``slice_length`` seconds from a waveform [channels, samples] (reference utils/sound.py:8-44).
+
+    ``num_chunks > 1``: evenly spaced, OVERLAPPING windows over the first 29 s (the shortest GTZAN clip is ~29.3 s) with
+    ``hop = floor((29 - slice_length) / (num_chunks - 1) * 10) / 10`` seconds, ``start_point`` ignored ->
+    [channels * num_chunks, 1, window].  Otherwise one window starting at ``start_point`` seconds -> [channels, window]."""
+    wav = torch.as_tensor(wav)
+    window_size = int(slice_length * sample_rate)
+    if num_chunks > 1:
+        hop = int(math.floor(((29 - slice_length) / (num_chunks - 1)) * 10) / 10 * sample_rate)
+        out = wav[:, :29 * sample_rate].unfold(1, window_size, hop).reshape(-1, 1, window_size)
+        assert out.shape[0] == num_chunks, "not equal num_chunks"
+        return out
+    start_sample = int(start_point * sample_rate)
+    assert start_point <= wav.size(1) - window_size, f"Start_point has to be in range [{0},{wav.size(1) - window_size}]"
+    return wav[:, start_sample:start_sample + window_size]
 
 
 class Loader:

@@ -211,35 +211,84 @@ class _PeerExchange:
 
     _cache = {}
 
-    def __init__(self, group, world: int, rank: int, nbytes: int, dev: torch.device, how: str):
-        import ctypes as C
-        lib = _L.lib()
+    def __init__(self, world: int, rank: int, nbytes: int, ptrs, keep=None):
         self.world, self.rank, self.nbytes = world, rank, nbytes
         self.desc = _L.PeerExchange()
         self.desc.world, self.desc.rank = world, rank
-        if how == "symm":
-            import torch.distributed._symmetric_memory as symm
-            self._t = symm.empty(nbytes // 4, dtype=torch.float32, device=dev)
-            self._t.zero_()
-            self._hdl = symm.rendezvous(self._t, group if group is not None else torch.distributed.group.WORLD)
-            ptrs = [int(p) for p in self._hdl.buffer_ptrs]
-        else:
-            own = C.c_void_p()
-            handle = C.create_string_buffer(64)
-            _L.check(lib.drsa_ipc_alloc(nbytes, C.byref(own), handle), "drsa_ipc_alloc")
-            handles = [None] * world
-            torch.distributed.all_gather_object(handles, bytes(handle.raw), group=group)
-            ptrs = []
-            for r in range(world):
-                if r == rank:
-                    ptrs.append(own.value)
-                else:
-                    q = C.c_void_p()
-                    _L.check(lib.drsa_ipc_open(handles[r], C.byref(q)), "drsa_ipc_open")
-                    ptrs.append(q.value)
         for r in range(world):
             self.desc.buffers[r] = ptrs[r]
-        torch.cuda.synchronize(dev)
+        self._keep = keep              # symmetric-memory tensor / handle: must outlive the exchange
+
+    @staticmethod
+    def _vote(ok: bool, group, dev) -> bool:
+        """Joint decision: True only if every rank of the group succeeded so far.  Every rank calls this the same number
+        of times, so a rank that failed never leaves the others alone inside a collective."""
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=group)
+        return int(flag.item()) == 1
+
+    @classmethod
+    def _setup(cls, group, world: int, rank: int, nbytes: int, dev: torch.device, how: str):
+        """Collective.  Phases with a vote after each: (1) allocate this rank's buffer, (2) exchange the handles,
+        (3) map the peers' buffers.  A failed vote releases what this rank holds and returns None on EVERY rank."""
+        import ctypes as C
+        import warnings
+        lib = _L.lib()
+        dist = torch.distributed
+        if how == "symm":
+            t = hdl = None
+            try:
+                import torch.distributed._symmetric_memory as symm
+                t = symm.empty(nbytes // 4, dtype=torch.float32, device=dev)
+                t.zero_()
+                err = None
+            except Exception as e:          # noqa: BLE001
+                err = e
+            if not cls._vote(err is None, group, dev):
+                if err is not None:
+                    warnings.warn(f"DRSA: symmetric memory unavailable ({err}); using the NCCL all-reduce")
+                return None
+            try:                             # rendezvous is itself a collective: every rank reaches it (vote above)
+                hdl = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                err = None
+            except Exception as e:          # noqa: BLE001
+                err = e
+            if not cls._vote(err is None, group, dev):
+                return None
+            return cls(world, rank, nbytes, ptrs, keep=(t, hdl))
+        # ---- cudaIpc
+        own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        st = lib.drsa_ipc_alloc(nbytes, C.byref(own), handle)
+        if not cls._vote(st == 0, group, dev):
+            if st == 0:
+                lib.drsa_ipc_free(own)
+            else:
+                warnings.warn(f"DRSA: peer buffer allocation failed ({_L.status_string(st)}); using the NCCL all-reduce")
+            return None
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        ptrs, opened, ok = [], [], True
+        for r in range(world):
+            if r == rank:
+                ptrs.append(own.value)
+                continue
+            q = C.c_void_p()
+            st = lib.drsa_ipc_open(handles[r], C.byref(q))
+            if st != 0:
+                ok = False
+                warnings.warn(f"DRSA: cannot map the buffer of rank {r} ({_L.status_string(st)}); using the NCCL all-reduce")
+                break
+            opened.append(q)
+            ptrs.append(q.value)
+        if not cls._vote(ok, group, dev):
+            for q in opened:                 # close every mapping before the owners free (drsa_b200.h)
+                lib.drsa_ipc_close(q)
+            dist.barrier(group=group)
+            lib.drsa_ipc_free(own)
+            return None
+        return cls(world, rank, nbytes, ptrs)
 
     @classmethod
     def get(cls, group, nbytes: int, dev: torch.device, how: str):
@@ -249,42 +298,15 @@ class _PeerExchange:
         # one exchange per stream: the protocol state inside the buffers assumes stream-ordered calls
         key = (id(group) if group is not None else 0, str(dev), nbytes, how, torch.cuda.current_stream(dev).cuda_stream)
         px = cls._cache.get(key)
-        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        # the cache is filled collectively, so either every rank has the entry or none has
         if px is None:
-            try:
-                px = cls(group, world, rank, nbytes, dev, how)
-            except Exception as e:          # noqa: BLE001 -- any failure means "keep NCCL", decided jointly below
-                import warnings
-                warnings.warn(f"DRSA: peer-memory exchange unavailable ({e}); using the NCCL all-reduce")
-                px = None
-                ok.zero_()
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-            if int(ok.item()) == 0:
+            px = cls._setup(group, world, rank, nbytes, dev, how)
+            if px is None:
                 return None
             cls._cache[key] = px
+            torch.cuda.synchronize(dev)
             dist.barrier(group=group)       # every buffer is zero-filled and mapped before anyone pushes into it
         return px
-
-
-# Long-horizon accuracy of the arithmetic modes (tests/test_gpu_drsa_long.py, scripts/horizon_parity.py,
-# scripts/sim_feedback_gpu.py).  Over the reference's horizon of 2 000 steps (drsa.py:76) two roundings move the final
-# subspaces against the fp32 trajectory (tolerance 1e-3 rad):
-#   * the per-step rounding of U to fp16 (3.8e-4 .. 7e-3 rad, worst where the objective has flat directions) -- removed by
-#     the error feedback of drsa_finish_step (u_rounded = 2): 1e-5 .. 1.4e-4 rad, at no cost;
-#   * storing the rows once in fp16, a FIXED perturbation of the data set: 4.2e-4 rad at M = 640 000 (d = 256) but
-#     1e-3 .. 5.6e-3 rad at M = 8 192 .. 65 536 -- removed by hi + lo planes ('tc_hilo', 2x the MMA work) or, at (n+2)/n of
-#     the single-plane cost, by the deferred correction 'tc_dc' (2.7e-5 .. 5.1e-4 rad at n = 8).
-# 'auto': CUDA-core fp32 below 8 192 rows per rank (the tensor cores do not matter there), 'tc_hilo' for medium problems (the
-# step is latency-bound anyway), 'tc_dc' from 262 144 rows.  'tc' (single plane, no correction) is never chosen
-# automatically: it is the fastest mode and within tolerance at cfg 2, but with less than 2x margin.
-_AUTO_FP32_BELOW = 8192
-_AUTO_DC_FROM = 262_144
-
-
-def _auto_precision(M_global: int, avg_rows: int, d: int, m: int, K: int) -> str:
-    if avg_rows < _AUTO_FP32_BELOW:
-        return "fp32"
-    return "tc_dc" if M_global >= _AUTO_DC_FROM else "tc_hilo"
 
 
 def _pad_plan(d: int, m: int, K: int, rows: int):

@@ -632,6 +632,11 @@ class LRPPlan:
                 if not seen_relu:
                     raise _L.DRSAError(f"{op.name}: Gamma/ZPlus on a layer with signed input is not on this path "
                                        "(use WSquare/Flat/Epsilon for the first layer, as the reference does)")
+                # zennit switches to the W + gamma*W^- branch where the layer's OUTPUT is negative; the collapsed form
+                # assumes the relevance arriving there is zero, which only a ReLU right behind the layer guarantees
+                if not op.relu:
+                    raise _L.DRSAError(f"{op.name}: Gamma/ZPlus needs a ReLU directly behind the layer (BatchNorm / Dropout "
+                                       "in between are fine); the negative-output branch of the rule is not on this path")
             if op.kind == "relu" or (op.kind in ("conv", "dense") and op.relu):
                 seen_relu = True
             elif op.kind in ("conv", "dense"):
@@ -656,7 +661,6 @@ class LRPPlan:
         return True
 
 
-_PLAN_CACHE = {}
 
 # Samples per engine pass.  The reference cuts the batch into minibatches of ``attr_batch_size`` = 64 to bound autograd
 # memory (preprocessing.py:150-167); every kernel here treats samples independently (per-sample scales, eval-mode
@@ -671,15 +675,38 @@ def _engine_chunk(x: torch.Tensor, requested: int) -> int:
     return max(int(requested), min(ENGINE_CHUNK, max(1, (12 << 30) // per_sample)))
 
 
+def _fingerprint(model) -> tuple:
+    """Cheap identity of everything a plan bakes in: storage and in-place version of every parameter, buffer and
+    projection matrix, and the train/eval state.  ``load_state_dict``, an optimiser step or ``model.train()`` change it."""
+    parts = [bool(model.training)]
+    for t in list(model.parameters()) + list(model.buffers()):
+        parts.append((t.data_ptr(), t._version))
+    for mod in model.modules():
+        for name in ("U", "U_inv"):
+            t = mod.__dict__.get(name)
+            if isinstance(t, torch.Tensor):
+                parts.append((t.data_ptr(), t._version, tuple(t.shape)))
+    return tuple(parts)
+
+
 def _plan(model, composite, device) -> LRPPlan:
-    key = (id(model), id(composite), str(device))
-    p = _PLAN_CACHE.get(key)
-    if p is None:
+    """The compiled plan of (model, composite) on ``device``.  It lives ON the model object (and dies with it: ids of freed
+    models / composites can be reused by CPython), holds a strong reference to its composite, and is rebuilt whenever the
+    model's fingerprint changes."""
+    cache = model.__dict__.setdefault("_drsa_b200_plans", {})
+    key = str(device)
+    entry = cache.get(key)
+    fp = _fingerprint(model)
+    if entry is None or entry[1] is not composite or entry[2] != fp:
         p = LRPPlan(model, composite, device)
         p.check_nonneg_inputs()
-        _PLAN_CACHE.clear()
-        _PLAN_CACHE[key] = p
-    return p
+        cache[key] = entry = (p, composite, fp)
+    return entry[0]
+
+
+def invalidate_plans(model) -> None:
+    """Drop the compiled plans of ``model`` (only needed after changes the fingerprint cannot see)."""
+    model.__dict__.pop("_drsa_b200_plans", None)
 
 
 def _prep_input(input_batch: torch.Tensor) -> torch.Tensor:

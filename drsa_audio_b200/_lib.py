@@ -147,6 +147,10 @@ def lib():
     return _lib
 
 
+def status_string(status: int) -> str:
+    return lib().drsa_status_string(int(status)).decode()
+
+
 def check(status: int, what: str = "") -> int:
     """Raise DRSAError for a negative status; returns non-negative values unchanged."""
     if status < 0:

@@ -1,0 +1,44 @@
+"""Host-side pieces of the audio frontend (no GPU): ``get_slice`` against the reference's slicing (utils/sound.py:8-44)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from cxai.utils.dataloading import get_slice, peak_normalizer
+
+
+def _ref_get_slice(wav, slice_length=6, start_point=0, num_chunks=1, sample_rate=16000):
+    """utils/sound.py:31-44 restated (test infrastructure)."""
+    window_size = int(slice_length * sample_rate)
+    if num_chunks > 1:
+        hop = int(math.floor(((29 - slice_length) / (num_chunks - 1)) * 10 ** 1) / 10 ** 1 * sample_rate)
+        out = wav[:, :29 * sample_rate].unfold(1, window_size, hop).reshape(-1, 1, window_size)
+        assert out.shape[0] == num_chunks
+        return out
+    s0 = int(start_point * sample_rate)
+    return wav[:, s0:s0 + window_size]
+
+
+@pytest.mark.parametrize("slice_length,num_chunks", [(3, 10), (6, 3), (6, 5), (3, 2)])
+def test_get_slice_overlapping_chunks_match_reference(slice_length, num_chunks):
+    sr = 1000
+    wav = torch.randn(1, int(29.3 * sr), generator=torch.Generator().manual_seed(0))      # a ~29.3 s clip, like GTZAN
+    got = get_slice(wav, slice_length, 7, num_chunks, sr)                                    # start_point is ignored here
+    want = _ref_get_slice(wav, slice_length, 7, num_chunks, sr)
+    assert got.shape == (num_chunks, 1, slice_length * sr)
+    np.testing.assert_array_equal(got.numpy(), want.numpy())
+    # the windows stay inside the first 29 s and overlap or tile with the rounded-down hop
+    hop = int(math.floor((29 - slice_length) / (num_chunks - 1) * 10) / 10 * sr)
+    np.testing.assert_array_equal(got[1, 0, :5].numpy(), wav[0, hop:hop + 5].numpy())
+
+
+def test_get_slice_single_window_and_range_check():
+    sr = 100
+    wav = torch.arange(2 * 30 * sr, dtype=torch.float32).reshape(2, -1)                    # two channels stay separate
+    got = get_slice(wav, 6, 4, 1, sr)
+    assert got.shape == (2, 6 * sr)
+    np.testing.assert_array_equal(got.numpy(), wav[:, 4 * sr:10 * sr].numpy())
+    with pytest.raises(AssertionError):
+        get_slice(wav, 6, 30 * sr, 1, sr)
+    np.testing.assert_allclose(peak_normalizer(got).abs().amax(dim=-1).numpy(), 1.0)
