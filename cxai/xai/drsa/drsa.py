@@ -65,7 +65,7 @@ def _pow2_scale(absmax: float) -> float:
 
 _PRECISIONS = {"fp32": _L.PREC_FP32, "tc": _L.PREC_TC_F16, "tc_split": _L.PREC_TC_F16X2, "tc_hilo": _L.PREC_TC_F16_AC2,
                "tc32": _L.PREC_TC_F32C, "tc_dc": _L.PREC_TC_F16_AC2}
-DC_EVERY = 8                        # 'tc_dc': steps between two evaluations of the row-rounding correction
+DC_EVERY = 16                       # 'tc_dc': steps between two evaluations of the row-rounding correction
 _PACK_CHUNK_ROWS = 1 << 20          # rows per host->device chunk when the fp32 rows do not fit next to the packed copy
 
 
@@ -309,6 +309,27 @@ class _PeerExchange:
         return px
 
 
+# Long-horizon accuracy of the arithmetic modes (tests/test_gpu_drsa_long.py, scripts/horizon_parity.py,
+# scripts/sim_feedback_gpu.py).  Over the reference's horizon of 2 000 steps (drsa.py:76) two roundings move the final
+# subspaces against the fp32 trajectory (tolerance 1e-3 rad):
+#   * the per-step rounding of U to fp16 (3.8e-4 .. 7e-3 rad, worst where the objective has flat directions) -- removed by
+#     the error feedback of drsa_finish_step (u_rounded = 2): 1e-5 .. 1.4e-4 rad, at no cost;
+#   * storing the rows once in fp16, a FIXED perturbation of the data set: 4.4e-4 rad at M = 640 000 (d = 256) but
+#     1e-3 .. 5.7e-3 rad at M = 8 192 .. 65 536 -- removed by hi + lo planes ('tc_hilo', 2x the MMA work: 2e-5 .. 1.3e-4 rad
+#     measured) or, at (n+2)/n of the single-plane cost, by the deferred correction 'tc_dc' (5e-5 .. 3e-4 rad at n = 8).
+# 'auto': CUDA-core fp32 below 8 192 rows per rank (the tensor cores do not matter there), 'tc_hilo' for medium problems (the
+# step is latency-bound anyway), 'tc_dc' from 262 144 rows.  'tc' (single plane, no correction) is never chosen
+# automatically: it is the fastest mode and within tolerance at cfg 2, but with only a factor of two in hand.
+_AUTO_FP32_BELOW = 8192
+_AUTO_DC_FROM = 262_144
+
+
+def _auto_precision(M_global: int, avg_rows: int, d: int, m: int, K: int) -> str:
+    if avg_rows < _AUTO_FP32_BELOW:
+        return "fp32"
+    return "tc_dc" if M_global >= _AUTO_DC_FROM else "tc_hilo"
+
+
 def _pad_plan(d: int, m: int, K: int, rows: int):
     """Shape (d', m') of an equivalent zero-padded problem that the tensor-core row pass covers, or None.
 
@@ -352,7 +373,7 @@ class SubspaceOptimizer:
             trajectory over the reference's 2 000 steps (see ``_auto_precision``).
         process_group: torch.distributed group over which the rows are sharded; ``activation_vecs``
             / ``context_vecs`` are then this rank's slice.  Defaults to the world group if
-            torch.distributed is initialised.
+            torch.distributed is initialised; ``False`` = this rank alone (no exchange).
         retraction_iters / retraction_tol: bounds of the on-device Newton-Schulz polar iteration (it stops as soon
             as it has converged: 4-5 sweeps in a normal step; the first steps of a tiny problem, where the
             gradient dwarfs U, need 15-25).
@@ -384,8 +405,11 @@ class SubspaceOptimizer:
             # needs one ('fp32') or on access of .act_vecs / .ctx_vecs -- the tensor-core modes keep only the packed planes
             self._act_src, self._ctx_src = activation_vecs.detach(), context_vecs.detach()
             self._act_dev = self._ctx_dev = None
-            self._dist = torch.distributed.is_available() and torch.distributed.is_initialized()
-            self._group = process_group
+            # process_group=False: this rank optimises its rows ALONE although torch.distributed is initialised (independent
+            # problems scheduled across the GPUs, e.g. one class per GPU in the cfg-5 pipeline)
+            self._dist = process_group is not False and torch.distributed.is_available() and \
+                torch.distributed.is_initialized()
+            self._group = process_group if process_group is not False else None
             rows = int(activation_vecs.size(0))
             M_local = torch.tensor([rows], dtype=torch.int64, device=self.device)
             if self._dist:

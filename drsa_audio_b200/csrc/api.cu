@@ -111,6 +111,8 @@ void set_tc_profile(long long* p);
 int tc_kernel_attrs(int d, int split, int* out5);
 void set_tc_variant(int v);
 int64_t subspace_relevances_workspace_bytes(int64_t B, int64_t P, int d, int m);
+int subset_objectives(const float* act, const float* ctx, const float* U, int64_t S, int64_t R, int d, int m, int K,
+                      float* obj, float* sumsq, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 int subspace_relevances(const float* act, const float* ctx, const float* U, int64_t B, int64_t P, int d, int m, int K,
                         float* out, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 int context_gather(const float* a_map, const float* R_map, int64_t N, int d, int HW, const int64_t* idx, int L,
@@ -325,6 +327,16 @@ int drsa_subspace_relevances(const float* act, const float* ctx, const float* U,
   DRSA_TRY(require_sm100());
   return subspace_relevances(act, ctx, U, B, P, d, m, K, out, workspace, workspace_bytes,
                              static_cast<cudaStream_t>(stream));
+}
+
+int drsa_subset_objectives(const float* act, const float* ctx, const float* U, int64_t S, int64_t R, int d, int m, int K,
+                           float* obj, float* sumsq, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (act == nullptr || ctx == nullptr || U == nullptr || obj == nullptr || sumsq == nullptr || workspace == nullptr ||
+      S <= 0 || R <= 0 || !shape_ok(S * R, d, m, K))
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return subset_objectives(act, ctx, U, S, R, d, m, K, obj, sumsq, workspace, workspace_bytes,
+                           static_cast<cudaStream_t>(stream));
 }
 
 int drsa_context_gather(const float* a_map, const float* R_map, int64_t N, int d, int HW, const int64_t* idx, int L,

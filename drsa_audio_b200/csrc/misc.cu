@@ -108,6 +108,34 @@ __global__ void __launch_bounds__(256) subspace_rel_kernel(const float* __restri
   s = warp_sum(s);
   if (lane == 0) out[b * K + k] = s;
 }
+// Prototype search (prototypes.py:98-119): one warp per (subset, concept) sums relu(s_rk)^2 over the subset's rows
+__global__ void __launch_bounds__(256) subset_sumsq_kernel(const float* __restrict__ HA, const float* __restrict__ HC,
+                                                           int64_t S, int64_t R, int m, int K, float* __restrict__ sumsq) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= S * K) return;
+  const int64_t b = wid / K; const int k = (int)(wid % K); const int d_k = m / K;
+  float acc = 0.f;
+  for (int64_t r = 0; r < R; ++r) {
+    const float* ha = HA + (b * R + r) * m + k * d_k;
+    const float* hc = HC + (b * R + r) * m + k * d_k;
+    float s = 0.f;
+    for (int j = lane; j < d_k; j += 32) s = fmaf(ha[j], hc[j], s);
+    s = fmaxf(warp_sum(s), 0.f);                  // ReLU per row (drsa.py:155), then the p = 2 pooling over rows
+    acc = fmaf(s, s, acc);
+  }
+  if (lane == 0) sumsq[b * K + k] = acc;
+}
+// obj[b] = (mean_k sqrt(sqrt(sumsq[b][k] / R)))^2   (drsa.py:224-238)
+__global__ void subset_objective_kernel(const float* __restrict__ sumsq, int64_t S, int64_t R, int K, float* __restrict__ obj) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= S) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc += sqrtf(sqrtf(sumsq[b * K + k] / (float)R));
+  acc /= (float)K;
+  obj[b] = acc * acc;
+}
+
 // out[i] = a[i] + beta * b[i] over the d*m + K row sums (deferred correction of the row rounding, see drsa_sums_combine)
 __global__ void __launch_bounds__(256) sums_combine_kernel(const float* __restrict__ a, const float* __restrict__ b, float beta,
                                                            float* __restrict__ out, int64_t n) {
@@ -176,6 +204,25 @@ int subspace_relevances(const float* act, const float* ctx, const float* U, int6
   g.A = ctx; g.C = HC;          DRSA_TRY(sgemm(g, stream));
   const int64_t warps = B * K;
   subspace_rel_kernel<<<cdiv(warps, 8), 256, 0, stream>>>(HA, HC, B, P, m, K, out);
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+// DRSA objective of S subsets of R consecutive rows each, in one pass (get_prototypes_ts, prototypes.py:98-119, evaluates
+// obj_val once per subset): two projections of ALL rows, one segmented reduction, S objectives.
+int subset_objectives(const float* act, const float* ctx, const float* U, int64_t S, int64_t R, int d, int m, int K,
+                      float* obj, float* sumsq, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  if (workspace_bytes < subspace_relevances_workspace_bytes(S, R, d, m)) return DRSA_ERR_WORKSPACE;
+  if (S * R > 2147483647LL) return DRSA_ERR_SHAPE;
+  float* HA = static_cast<float*>(workspace);
+  float* HC = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up(S * R * m * 4, 256));
+  GemmDesc g{};
+  g.M = (int)(S * R); g.N = m; g.K = d; g.lda = d; g.ldb = m; g.ldc = m; g.alpha = 1.f; g.splits = 1;
+  g.A = act; g.B = U; g.C = HA; DRSA_TRY(sgemm(g, stream));
+  g.A = ctx; g.C = HC;          DRSA_TRY(sgemm(g, stream));
+  subset_sumsq_kernel<<<cdiv(S * K, 8), 256, 0, stream>>>(HA, HC, S, R, m, K, sumsq);
+  DRSA_LAUNCH_CHECK();
+  subset_objective_kernel<<<cdiv(S, 128), 128, 0, stream>>>(sumsq, S, R, K, obj);
   DRSA_LAUNCH_CHECK();
   return DRSA_OK;
 }

@@ -215,6 +215,13 @@ int drsa_subspace_relevances(const float* act, const float* ctx, const float* U,
                              int64_t workspace_bytes, void* stream);
 int64_t drsa_subspace_relevances_workspace_bytes(int64_t B, int64_t P, int d, int m);
 
+/* DRSA objective (drsa.py:123-155, 224-238) of S subsets of R consecutive rows each in ONE pass -- the prototype search of
+ * cxai/xai/drsa/prototypes.py:98-119 evaluates obj_val once per subset of n samples:
+ *   sumsq[s][k] = sum_{r in subset s} relu(sum_{j in k} (a_r U)_j (c_r U)_j)^2,  obj[s] = (mean_k sqrt(sqrt(sumsq[s][k] / R)))^2
+ *   act, ctx [S*R, d] fp32, U [d, m], obj [S], sumsq [S, K]; workspace as drsa_subspace_relevances_workspace_bytes(S, R, d, m). */
+int drsa_subset_objectives(const float* act, const float* ctx, const float* U, int64_t S, int64_t R, int d, int m, int K,
+                           float* obj, float* sumsq, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Stage 1 helpers: context vectors and normalisation
  *   reference: cxai/xai/drsa/preprocessing.py compute_context_vectors :179-193,

@@ -157,6 +157,8 @@ def _heatmaps(model_name, H, W, layer_idx, sample_class, name_map_fn, canon, N, 
     d = [m for m in list(net.features)[:layer_idx] if isinstance(m, torch.nn.Conv2d)][-1].out_channels
     out = dict(model=model_name, seed=0, x_seed=x_seed, N=N, K=K, layer_idx=layer_idx, d=d,
                sample_class=sample_class, wsum=synth.weight_checksum(net))
+    if canon:
+        out["bn_seed"] = 1
     for tag, U in (("perm", synth.signed_permutation(d, 5)), ("orth", synth.random_orthogonal(d, 6))):
         res = {}
         for dt in (torch.float32, torch.float64):

@@ -356,3 +356,17 @@ def test_subspace_relevances_and_context_helpers():
                                    rtol=3e-6, atol=1e-7)
     v_ref = pp.get_vectors_from_maps(amap, idcs, layout="reference")
     np.testing.assert_array_equal(v_ref.numpy(), drsa_ref.vectors_from_maps_ref(amap, idcs).numpy())
+
+
+def test_batched_subset_objectives_match_obj_val_per_subset():
+    """Prototype search (prototypes.py:98-119): the objective of every subset from one batched call equals the reference's
+    obj_val evaluated subset by subset (oracle), also when the call is cut into several chunks."""
+    from cxai.xai.drsa.prototypes import subset_objectives
+    S, R, d, K = 37, 48, 64, 4
+    A, C = drsa_ref.synth_pairs(S * R, d, 71)
+    U = drsa_ref.synth_U0(d, d, 72)
+    want = np.array([float(drsa_ref.obj_val(A[s * R:(s + 1) * R].double(), C[s * R:(s + 1) * R].double(), U.double(), K, d // K))
+                     for s in range(S)])
+    for max_rows in (1 << 21, 5 * R):
+        got = subset_objectives(A.cuda(), C.cuda(), U.cuda(), S, R, K, max_rows=max_rows).cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=2e-5)

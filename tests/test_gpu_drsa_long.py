@@ -21,7 +21,9 @@ def _load(golden_dir, name):
     M, d, K = int(g["M"]), int(g["d"]), int(g["K"])
     A, C = drsa_ref.synth_pairs(M, d, int(g["seed"]), structured=bool(int(g["structured"])))
     chk = np.array([A.double().sum().item(), C.double().sum().item(), (A.double() * C.double()).sum().item()])
-    np.testing.assert_allclose(chk, g["in_checksum"], rtol=1e-12)        # the seeded inputs reproduce on this machine
+    # the seeded inputs reproduce on this machine (the structured rows contain a CPU GEMM whose summation order depends on
+    # the host: agreement to fp32 rounding, 1e-7 relative, is what can be asked for)
+    np.testing.assert_allclose(chk, g["in_checksum"], rtol=1e-6)
     return g, A, C, drsa_ref.synth_U0(d, d, int(g["seed"]) + 1), K
 
 
