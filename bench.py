@@ -154,7 +154,8 @@ def launches_in(opt, first_step: int, n: int) -> int:
         return n * (row + 1)
     if prec != "tc_dc":
         return n * 3
-    corr = sum(1 for i in range(first_step, first_step + n) if i % D.DC_EVERY == 0)
+    every = D.dc_every(opt.M_global)
+    corr = sum(1 for i in range(first_step, first_step + n) if i % every == 0)
     return corr * 6 + (n - corr) * 4
 
 
@@ -325,7 +326,7 @@ def run_ours(args):
             modes[pm] = {"steps_per_s": 1000.0 / msm, "ms_per_step": msm}
             del o
         modes["note"] = ("'tc' = rows once in fp16; 'tc_dc' = 'tc' + deferred correction of the row rounding every "
-                         f"{D.DC_EVERY} steps; 'tc_hilo' = rows as hi + lo fp16 planes; 'tc32' = rows and U hi + lo "
+                         f"{D.dc_every(M * world)} steps; 'tc_hilo' = rows as hi + lo fp16 planes; 'tc32' = rows and U hi + lo "
                          "(fp32-class operands); 'fp32' = CUDA cores.  'auto' never picks 'tc'.")
 
     # ---- end to end through the public API with HOST buffers: construct (H2D + pack) + run + D2H
@@ -408,7 +409,7 @@ def run_ours(args):
                                         f"sustained figure {peaks['tf_sustained']} TFLOP/s in frac_of_sustained_peak",
                          "share_of_step": ms_kernel / ms_per_step},
             "step_breakdown_ms": {"row_pass": ms_kernel, "ascent_and_retraction": ms_finish,
-                                  **({"row_pass_hi_lo_on_correction_steps": ms_hilo, "correction_every": D.DC_EVERY} if ms_hilo else {}),
+                                  **({"row_pass_hi_lo_on_correction_steps": ms_hilo, "correction_every": D.dc_every(M * world)} if ms_hilo else {}),
                                   **({"row_pass_per_rank": per_rank} if per_rank else {})},
             "lrp": lrp,
             "e2e": {"value": scale * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_steps,

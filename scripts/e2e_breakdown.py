@@ -10,6 +10,7 @@ from bench import synth_rows_cuda          # noqa: E402
 from cxai.xai.drsa.drsa import SubspaceOptimizer          # noqa: E402
 from bench import synth_U0          # noqa: E402
 
+PREC = sys.argv[1] if len(sys.argv) > 1 else "tc"
 dev = torch.device("cuda", 0)
 M, d, K = 640_000, 256, 4
 A, C = synth_rows_cuda(M, d, 20262, dev)
@@ -28,7 +29,7 @@ for rep in range(3):
     t0 = t()
     Ad = Ah.to(dev); Cd = Ch.to(dev)
     t1 = t()
-    opt = SubspaceOptimizer(U0, Ad, Cd, None, num_concepts=K, device=dev, precision="tc")
+    opt = SubspaceOptimizer(U0, Ad, Cd, None, num_concepts=K, device=dev, precision=PREC)
     t2 = t()
     opt.run(steps=4, save=False)
     t3 = t()
@@ -40,9 +41,11 @@ for rep in range(3):
           f"first run(4) incl. capture {1e3 * (t3 - t2):.1f} ms  run(500) {1e3 * (t4 - t3):.1f} ms  D2H {1e3 * (t5 - t4):.2f} ms", flush=True)
     del opt, Ad, Cd
     t0 = t()
-    opt = SubspaceOptimizer(U0, Ah, Ch, None, num_concepts=K, device=dev, precision="tc")
+    opt = SubspaceOptimizer(U0, Ah, Ch, None, num_concepts=K, device=dev, precision=PREC)
     t1 = t()
     opt.run(steps=500, save=False)
     t2 = t()
-    print(f"        host rows: construct {1e3 * (t1 - t0):.1f} ms  run(500) {1e3 * (t2 - t1):.1f} ms", flush=True)
+    opt.run(steps=2000, save=False)
+    t3 = t()
+    print(f"        host rows: construct {1e3 * (t1 - t0):.1f} ms  run(500) {1e3 * (t2 - t1):.1f} ms  run(2000) {1e3 * (t3 - t2):.1f} ms", flush=True)
     del opt
