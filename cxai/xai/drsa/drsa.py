@@ -585,12 +585,20 @@ class SubspaceOptimizer:
             torch.cuda.current_stream().wait_stream(side)
             count += 1
             n -= 1
+            # raw capture_begin / capture_end on the side stream: the torch.cuda.graph() context manager runs gc.collect()
+            # and torch.cuda.empty_cache() first, which hands GBs of cached blocks back to the driver (100 ms .. 1 s of
+            # cudaFree / cudaMalloc inside the end-to-end time); a step allocates nothing, so no private pool is needed
             graphs = {}
-            for correct in ((True, False) if self._rows.dc else (True,)):
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    self._step(self._obj_log, -1, True, correct)          # capture does not execute
-                graphs[correct] = graph
+            with torch.cuda.stream(side):
+                for correct in ((True, False) if self._rows.dc else (True,)):
+                    graph = torch.cuda.CUDAGraph()
+                    graph.capture_begin()
+                    try:
+                        self._step(self._obj_log, -1, True, correct)      # capture does not execute
+                    finally:
+                        graph.capture_end()
+                    graphs[correct] = graph
+            torch.cuda.current_stream().wait_stream(side)
             self._graph = graphs
         for _ in range(n):
             self._graph[count % every == 0].replay()
