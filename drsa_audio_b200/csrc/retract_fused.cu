@@ -150,9 +150,13 @@ struct FuseY {
   const __half* Ut_hi; int d; int u_rounded; const float* U; float corr;   // first-order objective correction over the A panel
 };
 
-template <int MODE, bool kFuseY = false>
+// kScaleT (MODE 1 only): the B panel is loaded from the Gram matrix G and turned into the first Newton-Schulz factor
+// T_0 = (1.5 I - 0.5 G / c) / sqrt(c) in shared memory (c = 1: unscaled start), so that neither T_0 nor the scaled start
+// X_0 = Y / sqrt(c) is ever formed in a phase of its own: X_1 = X_0 (1.5 I - 0.5 X_0^T X_0) = Y T_0.
+template <int MODE, bool kFuseY = false, bool kScaleT = false>
 __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, int i0, const float* __restrict__ B,
-                                          int ldb, int j0, int Kdim, float (&acc)[2][2], float* sm, FuseY* fuse = nullptr) {
+                                          int ldb, int j0, int Kdim, float (&acc)[2][2], float* sm, FuseY* fuse = nullptr,
+                                          float inv_c = 1.f, float inv_s = 1.f) {
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int lda_s = MODE == 0 ? LDT : Kdim + 4;
@@ -184,38 +188,69 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
     cp_async_wait_pending(0);
     FuseY& f = *fuse;
     float corr = 0.f;
-    for (int g = 0; g < groups; ++g) {
-      const int k0 = g * Kg;
-      for (int p = 0; p < Kg / 32; ++p) {
-        const int idx = tid + 256 * p;
-        const int k = k0 + (idx >> 3), seg = idx & 7;
+    // segments of this thread: s = 0 .. nseg-1 -> (panel ab, group g, round p); the loads of 8 segments are issued together
+    // (one L2 round trip per batch instead of one per segment)
+    const int per_panel = Kdim / 32;                 // rounds over all groups
+    const int nseg = 2 * per_panel;
+    for (int s0 = 0; s0 < nseg; s0 += 8) {
+      float4 sv[8];
 #pragma unroll
-        for (int ab = 0; ab < 2; ++ab) {
+      for (int u = 0; u < 8; ++u) {
+        const int sidx = s0 + u;
+        if (sidx < nseg) {
+          const int ab = sidx / per_panel, r = sidx % per_panel;
+          const int idx = tid + 256 * r;
+          const int k = idx >> 3, seg = idx & 7;
+          const int c0 = (ab == 0 ? i0 : j0) + 4 * seg;
+          sv[u] = __ldcg(reinterpret_cast<const float4*>(f.sums + (int64_t)k * f.m + c0));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int sidx = s0 + u;
+        if (sidx < nseg) {
+          const int ab = sidx / per_panel, r = sidx % per_panel;
+          const int idx = tid + 256 * r;
+          const int k = idx >> 3, seg = idx & 7;
           const int c0 = (ab == 0 ? i0 : j0) + 4 * seg;
           float* dst = (ab == 0 ? As : Bs) + k * LDT + 4 * seg;
-          const float4 sv = __ldcg(reinterpret_cast<const float4*>(f.sums + (int64_t)k * f.m + c0));
           const float cf = f.coef[c0 / f.d_k];                     // 4 consecutive columns share a concept (d_k % 4 == 0)
-          float4 u = *reinterpret_cast<float4*>(dst);
-          const float4 gr = make_float4(cf * sv.x, cf * sv.y, cf * sv.z, cf * sv.w);
+          float4 uu = *reinterpret_cast<float4*>(dst);
+          const float4 gr = make_float4(cf * sv[u].x, cf * sv[u].y, cf * sv[u].z, cf * sv[u].w);
           if (ab == 0 && f.write_a && f.u_rounded) {
             float uh[4];
             if (f.u_rounded == 2) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) uh[e] = __half2float(f.Ut_hi[(int64_t)(c0 + e) * f.d + k]);
             } else {
-              uh[0] = __half2float(__float2half_rn(u.x)); uh[1] = __half2float(__float2half_rn(u.y));
-              uh[2] = __half2float(__float2half_rn(u.z)); uh[3] = __half2float(__float2half_rn(u.w));
+              uh[0] = __half2float(__float2half_rn(uu.x)); uh[1] = __half2float(__float2half_rn(uu.y));
+              uh[2] = __half2float(__float2half_rn(uu.z)); uh[3] = __half2float(__float2half_rn(uu.w));
             }
-            corr = fmaf(gr.x, u.x - uh[0], corr); corr = fmaf(gr.y, u.y - uh[1], corr);
-            corr = fmaf(gr.z, u.z - uh[2], corr); corr = fmaf(gr.w, u.w - uh[3], corr);
+            corr = fmaf(gr.x, uu.x - uh[0], corr); corr = fmaf(gr.y, uu.y - uh[1], corr);
+            corr = fmaf(gr.z, uu.z - uh[2], corr); corr = fmaf(gr.w, uu.w - uh[3], corr);
           }
-          u.x += gr.x; u.y += gr.y; u.z += gr.z; u.w += gr.w;
-          *reinterpret_cast<float4*>(dst) = u;
-          if (ab == 0 && f.write_a) *reinterpret_cast<float4*>(f.Y_out + (int64_t)k * f.m + c0) = u;
+          uu.x += gr.x; uu.y += gr.y; uu.z += gr.z; uu.w += gr.w;
+          *reinterpret_cast<float4*>(dst) = uu;
+          if (ab == 0 && f.write_a) *reinterpret_cast<float4*>(f.Y_out + (int64_t)k * f.m + c0) = uu;
         }
       }
     }
     f.corr = corr;
+  }
+  if (kScaleT) {
+    cp_async_wait_pending(0);                  // this thread's own segments have landed; the barrier below publishes them
+    for (int r = 0; r < Kdim / 32; ++r) {
+      const int idx = tid + 256 * r;
+      const int k = idx >> 3, seg = idx & 7;
+      float* dst = Bs + k * LDT + 4 * seg;
+      float4 g4 = *reinterpret_cast<float4*>(dst);
+      const int c0 = j0 + 4 * seg;
+      g4.x = ((k == c0 ? 1.5f : 0.f) - 0.5f * g4.x * inv_c) * inv_s;
+      g4.y = ((k == c0 + 1 ? 1.5f : 0.f) - 0.5f * g4.y * inv_c) * inv_s;
+      g4.z = ((k == c0 + 2 ? 1.5f : 0.f) - 0.5f * g4.z * inv_c) * inv_s;
+      g4.w = ((k == c0 + 3 ? 1.5f : 0.f) - 0.5f * g4.w * inv_c) * inv_s;
+      *reinterpret_cast<float4*>(dst) = g4;
+    }
   }
   // Each warp takes 4 consecutive k of every 32 and accumulates a full 32 x 32 partial tile in registers (4 x 8 per
   // lane: 3 LDS.128 per 32 FMA); the eight partials are summed through shared memory at the end.
@@ -431,19 +466,18 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
     hdr[0] = __ldcg(hdr) + 1u;
   }
   auto log_objective = [&]() {
-    if (p.have_sums && blockIdx.x == 0 && tid == 0 && p.obj_log != nullptr) {
-      float extra = 0.f;
-      if (p.u_rounded)
-        for (int b = 0; b < (int)gridDim.x; ++b) extra += __ldcg(p.corr + b);      // fixed order: bit-identical replicas
-      long long idx = p.log_index;
-      if (idx < 0) { idx = p.status[3]; p.status[3] = (int)idx + 1; }
-      p.obj_log[idx] = bc[0] * bc[0] + extra;
+    if (p.have_sums && blockIdx.x == 0 && p.obj_log != nullptr) {      // block-uniform condition
+      const float extra = p.u_rounded ? fixed_total(p.corr, (int)gridDim.x, red) : 0.f;   // fixed order: bit-identical replicas
+      if (tid == 0) {
+        long long idx = p.log_index;
+        if (idx < 0) { idx = p.status[3]; p.status[3] = (int)idx + 1; }
+        p.obj_log[idx] = bc[0] * bc[0] + extra;
+      }
     }
   };
   if (!fuse0) log_objective();
 
   const int tm = m / TS, td = d / TS;
-  float* Tfast = p.X0;      // T = 1.5 I - 0.5 G of the unscaled start, written by the first Gram phase (X0 is free then)
   // ---------------- phase 1: G = Y^T Y, row sums of |G|, ||G - I||_F^2, T for the unscaled start
   {
     float corr = 0.f;
@@ -457,26 +491,28 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
       } else {
         tile_gemm<0>(p.Y, m, ti * TS, p.Y, m, tj * TS, d, acc, panels);
       }
-      float fr = 0.f;
+      float fr = 0.f, sq = 0.f, tr = 0.f;
 #pragma unroll
       for (int a = 0; a < 2; ++a) {
         const int gi = ti * TS + 2 * ty + a;
         float rs = fabsf(acc[a][0]) + fabsf(acc[a][1]);
         const int gj = tj * TS + 2 * tx;
         *reinterpret_cast<float2*>(&p.G[(int64_t)gi * m + gj]) = make_float2(acc[a][0], acc[a][1]);
-        *reinterpret_cast<float2*>(&Tfast[(int64_t)gi * m + gj]) =
-            make_float2((gi == gj ? 1.5f : 0.f) - 0.5f * acc[a][0], (gi == gj + 1 ? 1.5f : 0.f) - 0.5f * acc[a][1]);
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
           const float e = acc[a][b] - (gi == gj + b ? 1.f : 0.f);
           fr = fmaf(e, e, fr);
+          sq = fmaf(acc[a][b], acc[a][b], sq);
+          if (gi == gj + b) tr += acc[a][b];
         }
         // the 16 threads of a half-warp share the row gi
         for (int o = 8; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
         if (tx == 0) p.rowsum[(int64_t)tj * m + gi] = rs;     // every (tj, gi) is written by exactly one tile
       }
       const float tot = block_sum(fr, red);
-      if (tid == 0) p.fro[t] = tot;
+      const float tot_sq = block_sum(sq, red);
+      const float tot_tr = block_sum(tr, red);
+      if (tid == 0) { p.fro[t] = tot; p.fro[tm * tm + t] = tot_sq; p.fro[2 * tm * tm + t] = tot_tr; }
     }
     if (fuse0 && p.u_rounded) {
       const float tot = block_sum(corr, red);
@@ -487,18 +523,17 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
   grid.sync();
   stamp(p, slot);
   if (fuse0) log_objective();
-  // ---------------- start of the iteration
-  // Newton-Schulz converges for ||G||_2 < 3.  After an ascent step from an orthonormal U the Gram matrix is I + E with
-  // E small, and then the iteration starts from Y itself with the T the Gram phase has already written (no phase, no
-  // barrier): ||E||_2 <= ||E||_F < 1/2 guarantees convergence and the first residual is ||E||.  Otherwise (first steps of
-  // a tiny problem, drsa_polar_retract on arbitrary input) X0 = Y / sqrt(c), T_0 = 1.5 I - 0.5 G / c with the safe scaling
-  // c = ||G||_inf in a phase of its own.  The decision is taken from the same partials by every CTA on every rank.
+  // ---------------- start of the iteration (no phase, no barrier of its own)
+  // Newton-Schulz maps a singular value s of the iterate to s (1.5 - 0.5 s^2) and converges to 1 for s in (0, sqrt 3).
+  // After an ascent step from an orthonormal U the Gram matrix is I + E; for ||E||_F < 1 its eigenvalues lie in (0, 2) and
+  // the iteration starts from Y itself (c = 1).  Otherwise (first steps of a tiny problem, drsa_polar_retract on arbitrary
+  // input) X_0 = Y / sqrt(c) with the safe scaling c = ||G||_inf.  Either way the first multiply forms
+  // T_0 = (1.5 I - 0.5 G / c) / sqrt(c) from G in its operand panel (tile_gemm<1, false, true>), and the residual of the
+  // start, ||G / c - I||_F^2 = sum g^2 / c^2 - 2 tr G / c + m, comes from partials the Gram phase left behind.  The decision
+  // is taken from the same partials, summed in the same order, by every CTA on every rank.
   const float fro2 = fixed_total(p.fro, tm * tm, red);
-  const bool fast = fro2 < 0.25f;
-  float* cur = p.Y;
-  float* nxt = p.X1;
-  const float* Tcur = Tfast;
-  if (!fast) {
+  float c = 1.f, res0 = fro2;
+  if (!(fro2 < 1.0f)) {
     float best = 0.f;
     for (int i = tid; i < m; i += blockDim.x) {
       float rs = 0.f;
@@ -515,30 +550,20 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
       bc[1] = v;
     }
     __syncthreads();
-    const float c = bc[1];
-    const float inv_s = rsqrtf(c), inv_c = 1.f / c;
-    for (int64_t i = gtid; i < n; i += gthreads) p.X0[i] = p.Y[i] * inv_s;
-    float r = 0.f;
-    for (int64_t i = gtid; i < (int64_t)m * m; i += gthreads) {
-      const int rr = (int)(i / m), cc = (int)(i % m);
-      const float gv = p.G[i] * inv_c;
-      const float e = gv - (rr == cc ? 1.f : 0.f);
-      r = fmaf(e, e, r);
-      p.G[i] = (rr == cc ? 1.5f : 0.f) - 0.5f * gv;
-    }
-    const float tot = block_sum(r, red);
-    if (tid == 0) p.resid[blockIdx.x] = tot;
-    stamp(p, slot);
-    grid.sync();
-    stamp(p, slot);
-    cur = p.X0; nxt = p.X1; Tcur = p.G;
+    c = bc[1];
+    const float sum_sq = fixed_total(p.fro + tm * tm, tm * tm, red);
+    const float trace = fixed_total(p.fro + 2 * tm * tm, tm * tm, red);
+    res0 = fmaxf(sum_sq / (c * c) - 2.f * trace / c + (float)m, 0.f);
   }
+  const float inv_c0 = 1.f / c, inv_s0 = rsqrtf(c);
+  float* cur = p.Y;
+  float* nxt = p.X1;
 
   // ---------------- Newton-Schulz sweeps
   int it = 0, converged = 0;
   bool wrote_out = false;
   while (true) {
-    const float res = (fast && it == 0) ? fro2 : grid_total(p.resid + (int64_t)it * gridDim.x, red);
+    const float res = it == 0 ? res0 : grid_total(p.resid + (int64_t)it * gridDim.x, red);
     if (res < p.tol2_m) { converged = 1; break; }
     if (it >= p.max_iters) break;
     // In the quadratic regime ||G' - I||_F <= 0.75 ||G - I||_F^2 (eigenvalues g -> -0.75 g^2 + O(g^3)).  If that bound
@@ -549,7 +574,8 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
     for (int t = blockIdx.x; t < td * tm; t += gridDim.x) {
       const int tr = t / tm, tj = t % tm;
       float acc[2][2];
-      tile_gemm<1>(cur, m, tr * TS, Tcur, m, tj * TS, m, acc, panels);
+      if (it == 0) tile_gemm<1, false, true>(cur, m, tr * TS, p.G, m, tj * TS, m, acc, panels, nullptr, inv_c0, inv_s0);
+      else tile_gemm<1>(cur, m, tr * TS, p.G, m, tj * TS, m, acc, panels);
 #pragma unroll
       for (int a = 0; a < 2; ++a) {
         const int gi = tr * TS + 2 * ty + a;
@@ -593,7 +619,7 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
     stamp(p, slot);
     // the buffer that held the previous iterate is free now (the unscaled start leaves Y untouched: X0 takes its place)
     float* freebuf = (cur == p.Y) ? p.X0 : cur;
-    cur = nxt; nxt = freebuf; Tcur = p.G;
+    cur = nxt; nxt = freebuf;
     ++it;
   }
   // ---------------- output (only when the iteration did not end in a multiply that wrote it)
