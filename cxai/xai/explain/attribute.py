@@ -44,6 +44,7 @@ def lrp_output_modifier(class_idx: int = None, num_classes: int = None, one_hot_
             mask[..., class_idx] = 1
             return mask if one_hot_encoded else output * mask
         extract_output_class.rowwise = True         # the seed of a row does not depend on the rest of the batch
+        extract_output_class.key = ("class", int(class_idx), bool(one_hot_encoded))   # identifies the seed (graph replay)
         return extract_output_class
 
     def attribute_all_classes(output):

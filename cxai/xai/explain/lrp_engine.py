@@ -56,6 +56,7 @@ class LRPPlan:
         self.fuse_pool = True       # max-pooling in the epilogue of the convolution before it, where nothing reads the un-pooled map
         self._tc_err = None
         self._tc_ok_cache = {}
+        self._graphs = {}                   # replay_pass: key -> "seen" | (graph, static input, static outputs)
         self.ops: List[_Op] = []
         self.module_to_op = {}
         self.filter_index = None          # index of the Projection op of a ProjectionModel
@@ -643,6 +644,38 @@ class LRPPlan:
                 seen_relu = False
 
 
+    # ------------------------------------------------------------------ CUDA-graph replay of whole engine passes
+    def replay_pass(self, key, xb: torch.Tensor, body):
+        """``body(xb)`` -> tuple of tensors, as ONE CUDA-graph launch from the third call with the same key on.
+
+        An engine pass is ~180 launches (35 layers forward and backward, plus the fill / copy kernels of the tensors it
+        allocates); launched one by one they leave ~0.25 ms of gaps per 256 samples and keep the host busy.  A pass
+        has no host synchronisation and no data-dependent control flow, so it is captured once per (pass kind, input
+        shape, split layer, seed, arithmetic) into a graph whose private memory pool keeps every intermediate at a fixed
+        address; a replay copies the batch into the static input and the results out of the static outputs.  First
+        call with a key: plain launches (one-time initialisations must not happen inside a capture); second call:
+        capture; at most ``GRAPH_CACHE`` graphs are kept (each pins the intermediates of one pass, ~46 MB per sample of
+        128 x 256)."""
+        entry = self._graphs.get(key)
+        if entry is None:
+            self._graphs[key] = "seen"
+            return body(xb)
+        if entry == "seen":
+            while len([v for v in self._graphs.values() if v != "seen"]) >= GRAPH_CACHE:
+                oldest = next(k for k, v in self._graphs.items() if v != "seen")
+                del self._graphs[oldest]
+            static_x = xb.clone()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = body(static_x)
+            entry = (graph, static_x, outs)
+            self._graphs.pop(key, None)
+            self._graphs[key] = entry                  # (re)inserted last: the dict order is the age
+        else:
+            entry[1].copy_(xb)
+        entry[0].replay()
+        return tuple(o.clone() for o in entry[2])      # the static outputs are overwritten by the next replay
+
     def tc_failed(self) -> bool:
         """True (and the tensor-core stack is switched off for this plan) if a tensor-core kernel raised its error
         flag: a value left the fp16 range of the split planes.  The caller reruns on the fp32 CUDA-core kernels."""
@@ -668,6 +701,9 @@ class LRPPlan:
 # the last conv layers and the dense head only fill the 148 SMs from ~256 samples on.  ``attr_batch_size`` is honoured
 # as a lower bound; the upper bound keeps the activation planes of one pass below ~12 GB.
 ENGINE_CHUNK = 256
+USE_GRAPH = True             # replay whole engine passes as CUDA graphs (LRPPlan.replay_pass)
+GRAPH_MIN_SAMPLES = 32       # small passes are latency-bound either way and not worth pinning memory for
+GRAPH_CACHE = 2
 
 
 def _engine_chunk(x: torch.Tensor, requested: int) -> int:
@@ -759,14 +795,23 @@ def lrp_intermediate(model, input_batch, composite, layer, class_idx, attr_batch
                 nxt += 1
             raise _L.DRSAError(f"split at {plan.ops[split].name} (pre-activation) is not on this path; "
                                f"use the ReLU {plan.ops[nxt].name} like the reference (layers 19/26/33)")
+        def one_pass(xb):
+            logits, saved, outs = plan.forward(xb, keep_from=split + 1, out_index=split)
+            seed = fn(logits).contiguous()
+            r = plan.backward(seed, saved, stop_after=split)
+            o = outs[split]
+            return (plan._nhwc_to_nchw(o[1]) if isinstance(o, tuple) else o), r
+        fn_key = getattr(fn, "key", None)
         while True:
             a_maps, r_maps = [], []
             for i in range(0, x.size(0), attr_batch_size):
-                logits, saved, outs = plan.forward(x[i:i + attr_batch_size], keep_from=split + 1, out_index=split)
-                seed = fn(logits).contiguous()
-                r_maps.append(plan.backward(seed, saved, stop_after=split))
-                o = outs[split]
-                a_maps.append(plan._nhwc_to_nchw(o[1]) if isinstance(o, tuple) else o)
+                xb = x[i:i + attr_batch_size]
+                if USE_GRAPH and fn_key is not None and xb.size(0) >= GRAPH_MIN_SAMPLES:
+                    a, r = plan.replay_pass(("intermediate", tuple(xb.shape), split, fn_key, plan.use_tc), xb, one_pass)
+                else:
+                    a, r = one_pass(xb)
+                a_maps.append(a)
+                r_maps.append(r)
             if not plan.tc_failed():
                 break
     return torch.cat(a_maps, 0), torch.cat(r_maps, 0)

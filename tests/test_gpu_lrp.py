@@ -660,3 +660,28 @@ def test_prototypes_and_best_run(tmp_path):
     run, loss, _, path, losses = get_best_run(str(tmp_path))
     finals = {r: float(open(tmp_path / f"run{r}" / "train_stats.csv").read().splitlines()[-1].split(",")[1]) for r in (1, 2, 3)}
     assert run == max(finals, key=finals.get) and abs(loss - finals[run]) < 1e-12 and path.endswith(f"run{run}") and len(losses) == 6
+
+
+def test_graph_replay_of_engine_passes_is_bit_identical(monkeypatch):
+    """From the third call with the same (shape, split layer, seed) an engine pass is one CUDA-graph replay
+    (LRPPlan.replay_pass); inputs are copied into the static buffer, so new data must give new -- and the same -- results."""
+    from cxai.utils.constants import lrp_name_map_6s
+    from cxai.xai.explain.rules import NameMapComposite, SequentialMergeBatchNorm
+    from cxai.xai.explain import lrp_engine
+    from cxai.xai.drsa.preprocessing import get_intermediate
+    net = lrp_ref.genre_model(seed=0, last=64, input_size=(32, 64))
+    comp = NameMapComposite(lrp_name_map_6s(), canonizers=[SequentialMergeBatchNorm()])
+    xs = [lrp_ref.synth_logmel(40, 32, 64, 300 + i).cuda() for i in range(4)]
+    monkeypatch.setattr(lrp_engine, "USE_GRAPH", False)
+    want = [get_intermediate(net, x, comp, net.features[26], 2) for x in xs]
+    monkeypatch.setattr(lrp_engine, "USE_GRAPH", True)
+    got = [get_intermediate(net, x, comp, net.features[26], 2) for x in xs]        # eager, capture + replay, replay, replay
+    plan = lrp_engine._plan(net, comp, xs[0].device)
+    assert any(v != "seen" for v in plan._graphs.values())                          # a graph was captured
+    for (a, r), (aw, rw) in zip(got, want):
+        assert torch.equal(a, aw) and torch.equal(r, rw)
+    # another seed (class) is another graph, not a stale replay
+    a5, r5 = get_intermediate(net, xs[0], comp, net.features[26], 5)
+    monkeypatch.setattr(lrp_engine, "USE_GRAPH", False)
+    a5w, r5w = get_intermediate(net, xs[0], comp, net.features[26], 5)
+    assert torch.equal(r5, r5w) and not torch.equal(r5, got[0][1])
