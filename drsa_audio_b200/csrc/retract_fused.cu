@@ -217,17 +217,9 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
           const float cf = f.coef[c0 / f.d_k];                     // 4 consecutive columns share a concept (d_k % 4 == 0)
           float4 uu = *reinterpret_cast<float4*>(dst);
           const float4 gr = make_float4(cf * sv[u].x, cf * sv[u].y, cf * sv[u].z, cf * sv[u].w);
-          if (ab == 0 && f.write_a && f.u_rounded) {
-            float uh[4];
-            if (f.u_rounded == 2) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) uh[e] = __half2float(f.Ut_hi[(int64_t)(c0 + e) * f.d + k]);
-            } else {
-              uh[0] = __half2float(__float2half_rn(uu.x)); uh[1] = __half2float(__float2half_rn(uu.y));
-              uh[2] = __half2float(__float2half_rn(uu.z)); uh[3] = __half2float(__float2half_rn(uu.w));
-            }
-            corr = fmaf(gr.x, uu.x - uh[0], corr); corr = fmaf(gr.y, uu.y - uh[1], corr);
-            corr = fmaf(gr.z, uu.z - uh[2], corr); corr = fmaf(gr.w, uu.w - uh[3], corr);
+          if (ab == 0 && f.write_a && f.u_rounded) {          // <grad f(U^), U>, see log_objective
+            corr = fmaf(gr.x, uu.x, corr); corr = fmaf(gr.y, uu.y, corr);
+            corr = fmaf(gr.z, uu.z, corr); corr = fmaf(gr.w, uu.w, corr);
           }
           uu.x += gr.x; uu.y += gr.y; uu.z += gr.z; uu.w += gr.w;
           *reinterpret_cast<float4*>(dst) = uu;
@@ -429,9 +421,7 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
           }
           const float u = p.U[i], gr = c * S(i);
           if (p.U_out != nullptr) p.Y[i] = u + gr;
-          if (p.u_rounded == 1) corr = fmaf(gr, u - __half2float(__float2half_rn(u)), corr);
-          else if (p.u_rounded == 2)            // the row pass used the STORED fp16 matrix (error-feedback rounding)
-            corr = fmaf(gr, u - __half2float(p.Ut_hi[(int64_t)(i % m) * d + i / m]), corr);
+          if (p.u_rounded) corr = fmaf(gr, u, corr);          // <grad f(U^), U>, see log_objective
         }
       }
     }
@@ -443,7 +433,7 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
       if (tid == 0 && p.obj_log != nullptr) {
         long long idx = p.log_index;
         if (idx < 0) { idx = p.status[3]; p.status[3] = (int)idx + 1; }
-        p.obj_log[idx] = root * root + (p.u_rounded ? p.corr[0] : 0.f);
+        p.obj_log[idx] = p.u_rounded ? p.corr[0] - root * root : root * root;      // see log_objective
       }
       if (p.world > 1 && tid == 0) {            // single CTA here: close this exchange (see below)
         unsigned* hdr = reinterpret_cast<unsigned*>(p.xbuf[p.rank]);
@@ -465,13 +455,17 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
     hdr[16 + 16 * xpar] = 0u;
     hdr[0] = __ldcg(hdr) + 1u;
   }
+  // Objective of the step.  u_rounded: the sums were evaluated at a rounded matrix U^ (fp16, possibly with error feedback);
+  // the logged value is f(U^) + <grad f(U^), U - U^>, equal to f(U) up to second order in the rounding.  f is homogeneous
+  // of degree 2 in U (s_rk is quadratic in U, the pooling keeps the degree), so <grad f(U^), U^> = 2 f(U^) (Euler) and the
+  // value is <grad f(U^), U> - f(U^): U^ itself, stored transposed for the row pass, never has to be read here.
   auto log_objective = [&]() {
     if (p.have_sums && blockIdx.x == 0 && p.obj_log != nullptr) {      // block-uniform condition
-      const float extra = p.u_rounded ? fixed_total(p.corr, (int)gridDim.x, red) : 0.f;   // fixed order: bit-identical replicas
+      const float gu = p.u_rounded ? fixed_total(p.corr, (int)gridDim.x, red) : 0.f;   // fixed order: bit-identical replicas
       if (tid == 0) {
         long long idx = p.log_index;
         if (idx < 0) { idx = p.status[3]; p.status[3] = (int)idx + 1; }
-        p.obj_log[idx] = bc[0] * bc[0] + extra;
+        p.obj_log[idx] = p.u_rounded ? gu - bc[0] * bc[0] : bc[0] * bc[0];
       }
     }
   };
@@ -524,16 +518,17 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
   stamp(p, slot);
   if (fuse0) log_objective();
   // ---------------- start of the iteration (no phase, no barrier of its own)
-  // Newton-Schulz maps a singular value s of the iterate to s (1.5 - 0.5 s^2) and converges to 1 for s in (0, sqrt 3).
-  // After an ascent step from an orthonormal U the Gram matrix is I + E; for ||E||_F < 1 its eigenvalues lie in (0, 2) and
-  // the iteration starts from Y itself (c = 1).  Otherwise (first steps of a tiny problem, drsa_polar_retract on arbitrary
-  // input) X_0 = Y / sqrt(c) with the safe scaling c = ||G||_inf.  Either way the first multiply forms
-  // T_0 = (1.5 I - 0.5 G / c) / sqrt(c) from G in its operand panel (tile_gemm<1, false, true>), and the residual of the
-  // start, ||G / c - I||_F^2 = sum g^2 / c^2 - 2 tr G / c + m, comes from partials the Gram phase left behind.  The decision
-  // is taken from the same partials, summed in the same order, by every CTA on every rank.
-  const float fro2 = fixed_total(p.fro, tm * tm, red);
-  float c = 1.f, res0 = fro2;
-  if (!(fro2 < 1.0f)) {
+  // Newton-Schulz maps a singular value s of the iterate to s (1.5 - 0.5 s^2) and converges to 1 for s in (0, sqrt 3); the
+  // polar factor does not change when Y is scaled.  The objective is homogeneous of degree 2 in U, so the ascent step has
+  // a large component along U itself (<grad f, U> = 2 f): Y = U + grad f is NOT close to orthonormal in any step of an
+  // optimisation, its singular values sit in a band above 1.  X_0 = Y / sqrt(c) with c = tr(G) / m centres that band on 1
+  // (the mean of the squared singular values becomes 1), which takes one sweep less than the one-sided safe scaling
+  // c = ||G||_inf (used only when ||G||_inf / c >= 2.9, i.e. when the centred start could leave the convergence interval).
+  // The first multiply forms T_0 = (1.5 I - 0.5 G / c) / sqrt(c) from G in its operand panel (tile_gemm<1, false, true>),
+  // and the residual of the start, ||G / c - I||_F^2 = sum g^2 / c^2 - 2 tr G / c + m, comes from partials the Gram phase
+  // left behind.  The decision is taken from the same partials, summed in the same order, by every CTA on every rank.
+  float c, res0;
+  {
     float best = 0.f;
     for (int i = tid; i < m; i += blockDim.x) {
       float rs = 0.f;
@@ -550,9 +545,11 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
       bc[1] = v;
     }
     __syncthreads();
-    c = bc[1];
+    const float ginf = bc[1];
     const float sum_sq = fixed_total(p.fro + tm * tm, tm * tm, red);
     const float trace = fixed_total(p.fro + 2 * tm * tm, tm * tm, red);
+    c = trace / (float)m;
+    if (!(c > 0.f) || !(ginf < 2.9f * c)) c = ginf;          // the centred start needs lambda_max(G) / c < 3
     res0 = fmaxf(sum_sq / (c * c) - 2.f * trace / c + (float)m, 0.f);
   }
   const float inv_c0 = 1.f / c, inv_s0 = rsqrtf(c);
@@ -677,7 +674,6 @@ int finish_fused(const float* sums, int64_t M_global, const float* U, int d, int
   p.prof = g_fused_prof;
   p.status = status; p.have_sums = (Y_in == nullptr) ? 1 : 0;
   p.u_rounded = (u_rounded && Y_in == nullptr) ? u_rounded : 0;
-  if (p.u_rounded == 2 && Ut_hi == nullptr) return DRSA_ERR_ARG;
   p.corr = p.resid + (int64_t)(max_iters + 1) * 1024;       // the row after the last sweep's residual partials
   p.fro = p.resid + (int64_t)(64 + 2) * 1024;                // last row of the 64 + 3 the workspace is sized for
   p.world = 1; p.rank = 0;
