@@ -29,7 +29,7 @@ def _worker(rank, world, port, ret):
     # exchange: NCCL all-reduce between the kernels / fused into the finish kernel over peer memory (CUDA graph replay
     # and direct launches)
     for prec, exch, graph in (("fp32", "nccl", True), ("tc", "nccl", True), ("fp32", "p2p", True), ("tc", "p2p", True),
-                              ("tc", "p2p", False)):
+                              ("tc", "p2p", False), ("tc_dc", "p2p", True), ("tc_hilo", "p2p", True), ("tc_dc", "nccl", False)):
         opt = SubspaceOptimizer(U0, A[lo:hi], C[lo:hi], None, num_concepts=K, device=f"cuda:{rank}", precision=prec,
                                 exchange=exch, use_cuda_graph=graph)
         assert opt.exchange == exch and opt.use_cuda_graph == (graph and exch == "p2p")
@@ -58,7 +58,7 @@ def test_two_rank_row_sharding_matches_reference():
     with mp.Manager() as mgr:
         ret = mgr.dict()
         mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
-        assert len(ret) == 6
+        assert len(ret) == 9
         for key in ret.keys():
             if key == "same_bits":
                 continue
@@ -68,3 +68,55 @@ def test_two_rank_row_sharding_matches_reference():
             assert rel < 1e-4 and ang < 1e-3
             assert rep == 0.0
         assert ret["same_bits"]
+
+
+def _pipeline_worker(rank, world, port, ret):
+    """cfg-5 pipeline with the classes spread over the ranks (plan_class_schedule) against the row-sharded schedule."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from oracle import drsa_ref, synth
+    from cxai.model.create_model import VGGType
+    from cxai.utils.constants import lrp_name_map_6s
+    from cxai.xai.explain.rules import NameMapComposite, SequentialMergeBatchNorm
+    from cxai.xai.drsa.cluster.optsubspaces import all_classes_pipeline
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    net = synth.build_model(VGGType, "archA_small", 0, 1).to(dev)
+    comp = NameMapComposite(lrp_name_map_6s(), canonizers=[SequentialMergeBatchNorm()])
+    classes = 3                                              # one full round (2 classes) + a partial round (1 class on 2 ranks)
+    n = (24, 40)[rank]                                       # uneven sample counts per rank
+    data = {c: synth.synth_logmel(n, 32, 64, 500 + 10 * c + rank).to(dev) for c in range(classes)}
+    res = {}
+    for schedule in ("classes", "shard"):
+        out = all_classes_pipeline(net, data, comp, 26, None, num_concepts=4, steps=30, schedule=schedule, device=dev,
+                                   precision="fp32")
+        res[schedule] = {c: (out[c][0].cpu(), np.asarray(out[c][1])) for c in range(classes)}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, {c: res["classes"][c][0] for c in range(classes)})
+    if rank == 0:
+        ok_rep = all(torch.equal(gathered[0][c], gathered[1][c]) for c in range(classes))       # every rank ends with every U
+        worst_obj = worst_ang = 0.0
+        for c in range(classes):
+            Ua, oa = res["classes"][c]
+            Ub, ob = res["shard"][c]
+            worst_obj = max(worst_obj, float(np.max(np.abs(oa - ob) / np.abs(ob))))
+            worst_ang = max(worst_ang, drsa_ref.principal_angle(Ua, Ub, 4))
+        ret["pipeline"] = (ok_rep, worst_obj, worst_ang, [len(res["classes"][c][1]) for c in range(classes)])
+    dist.destroy_process_group()
+
+
+def test_two_rank_class_schedule_matches_row_sharding():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    port = 29700 + (os.getpid() % 1000)
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_pipeline_worker, args=(2, port, ret), nprocs=2, join=True)
+        ok_rep, worst_obj, worst_ang, lens = ret["pipeline"]
+        print("class schedule vs row sharding:", worst_obj, worst_ang)
+        assert ok_rep and lens == [31, 31, 31]
+        assert worst_obj < 1e-5 and worst_ang < 1e-4          # same rows, same arithmetic, another summation order
