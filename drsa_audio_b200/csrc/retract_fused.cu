@@ -628,6 +628,240 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
   if (p.prof != nullptr && blockIdx.x == 0 && tid == 0) p.prof[15] = slot;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Small problems (d, m <= 64: BASELINE cfg 1, the toy CNN, arch B's first layers): the whole finish step in ONE CTA with
+// every matrix in shared memory -- no cooperative launch, no grid barrier, no L2 round trips between the phases.  Same
+// mathematics, same order of decisions as finish_fused_kernel.  256 threads, a 4 x 4 output tile per thread (d, m
+// multiples of 32 and <= 64, so 16 x 16 threads cover 64 x 64).
+constexpr int SLD = 68;      // row stride (floats) of the shared-memory matrices: float4-aligned rows
+
+__device__ __forceinline__ float block_total256(float v, float* red) {     // identical in every thread, fixed order
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w];
+  return t;
+}
+
+// C[4ti..][4tj..] = sum_k A^T: gram = true  -> sum_k X[k][i] X[k][j]      (X: [rows = Kdim][SLD])
+//                              gram = false -> sum_k X[i][k] T[k][j]      (X: [d][SLD], T: [m][SLD])
+template <bool kGram>
+__device__ __forceinline__ void small_gemm(const float* __restrict__ X, const float* __restrict__ T, int Kdim, int i0, int j0,
+                                           float (&acc)[4][4]) {
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  if (kGram) {
+    for (int k = 0; k < Kdim; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&X[k * SLD + i0]);
+      const float4 bv = *reinterpret_cast<const float4*>(&X[k * SLD + j0]);
+      const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], b4[b], acc[a][b]);
+    }
+  } else {
+    for (int k = 0; k < Kdim; k += 4) {
+      float a4[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const float4 v = *reinterpret_cast<const float4*>(&X[(i0 + a) * SLD + k]);
+        a4[a][0] = v.x; a4[a][1] = v.y; a4[a][2] = v.z; a4[a][3] = v.w;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 bv = *reinterpret_cast<const float4*>(&T[(k + u) * SLD + j0]);
+        const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a][u], b4[b], acc[a][b]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) finish_small_kernel(FusedParams p) {
+  extern __shared__ __align__(16) float sm[];
+  float* Ys = sm;                       // [d][SLD]   Y, then free
+  float* Gs = sm + 64 * SLD;            // [m][SLD]   G / T
+  float* Xa = sm + 2 * 64 * SLD;        // [d][SLD]
+  float* Xb = sm + 3 * 64 * SLD;        // [d][SLD]
+  float* rowpart = sm + 4 * 64 * SLD;   // [16][64] partial row sums of |G|
+  __shared__ float red[8];
+  __shared__ float coef[64];
+  __shared__ float bc[2];
+  const int tid = threadIdx.x, tj = tid & 15, ti = tid >> 4;
+  const int d = p.d, m = p.m;
+  const int n = d * m;
+  int xpar = 0;
+  float gu = 0.f;
+  if (p.have_sums) {
+    const int K = p.K, d_k = m / K;
+    if (p.world > 1) xpar = peer_exchange(p, n + K);        // gridDim.x == 1
+    const float* inbox = p.world > 1 ? p.xbuf[p.rank] + kXHeaderFloats + (int64_t)xpar * p.world * p.xstride : nullptr;
+    auto S = [&](int i) -> float {
+      if (p.world <= 1) return p.sums[i];
+      float v = 0.f;
+      for (int r = 0; r < p.world; ++r) v += (r == p.rank) ? p.sums[i] : __ldcg(inbox + (int64_t)r * p.xstride + i);
+      return v;
+    };
+    if (tid == 0) {
+      float acc = 0.f; int degenerate = 0;
+      for (int k = 0; k < K; ++k) {
+        const float q = sqrtf((float)((double)S(n + k) * p.inv_M));
+        if (q == 0.f) ++degenerate;
+        acc += sqrtf(q);
+      }
+      bc[0] = acc / (float)K;
+      if (p.status != nullptr) p.status[2] = degenerate;
+    }
+    __syncthreads();
+    const float root = bc[0];
+    for (int k = tid; k < K && k < 64; k += blockDim.x) {
+      const float q = sqrtf((float)((double)S(n + k) * p.inv_M));
+      coef[k] = (float)((double)root * p.inv_M / ((double)K * (double)q * sqrt((double)q)));
+    }
+    __syncthreads();
+    if (p.U_out != nullptr || p.u_rounded) {
+      for (int i = tid; i < n; i += blockDim.x) {
+        const int r = i / m, c = i % m;
+        const float u = p.U[i], gr = coef[c / d_k] * S(i);
+        Ys[r * SLD + c] = u + gr;
+        gu = fmaf(gr, u, gu);
+      }
+    }
+    const float gu_tot = p.u_rounded ? block_total256(gu, red) : 0.f;
+    __syncthreads();                        // every thread has read its share of the inbox
+    if (p.world > 1 && tid == 0) {          // single CTA: close this exchange right away (rewind the arrival counter)
+      unsigned* hdr = reinterpret_cast<unsigned*>(p.xbuf[p.rank]);
+      hdr[16 + 16 * xpar] = 0u;
+      hdr[0] = __ldcg(hdr) + 1u;
+    }
+    if (tid == 0 && p.obj_log != nullptr) {
+      long long idx = p.log_index;
+      if (idx < 0) { idx = p.status[3]; p.status[3] = (int)idx + 1; }
+      p.obj_log[idx] = p.u_rounded ? gu_tot - root * root : root * root;      // Euler, see finish_fused_kernel
+    }
+    if (p.U_out == nullptr) return;
+  } else {
+    for (int i = tid; i < n; i += blockDim.x) Ys[(i / m) * SLD + i % m] = p.Y[i];
+  }
+  __syncthreads();
+  const int i0 = 4 * ti, j0 = 4 * tj;
+  const bool in_g = i0 < m && j0 < m;        // this thread owns a tile of the m x m Gram matrix
+  const bool in_x = i0 < d && j0 < m;        // ... of the d x m iterate
+  // ---- Gram of Y, statistics of the start
+  float acc[4][4];
+  float sq = 0.f, tr = 0.f;
+  if (in_g) {
+    small_gemm<true>(Ys, nullptr, d, i0, j0, acc);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      float rs = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const float g = acc[a][b];
+        Gs[(i0 + a) * SLD + j0 + b] = g;
+        rs += fabsf(g);
+        sq = fmaf(g, g, sq);
+        if (i0 + a == j0 + b) tr += g;
+      }
+      rowpart[tj * 64 + i0 + a] = rs;
+    }
+  }
+  const float sum_sq = block_total256(sq, red);
+  const float trace = block_total256(tr, red);
+  float best = 0.f;
+  if (tid < m) {
+    float rs = 0.f;
+    for (int t = 0; t < m / 4; ++t) rs += rowpart[t * 64 + tid];
+    best = rs;
+  }
+  best = warp_max(best);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = best;
+  __syncthreads();
+  float ginf = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) ginf = fmaxf(ginf, red[w]);
+  float c = trace / (float)m;
+  if (!(c > 0.f) || !(ginf < 2.9f * c)) c = ginf;
+  float res = fmaxf(sum_sq / (c * c) - 2.f * trace / c + (float)m, 0.f);
+  {
+    const float inv_c = 1.f / c, inv_s = rsqrtf(c);
+    __syncthreads();
+    if (in_g) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int o = (i0 + a) * SLD + j0 + b;
+          Gs[o] = ((i0 + a == j0 + b ? 1.5f : 0.f) - 0.5f * Gs[o] * inv_c) * inv_s;       // T_0 (own elements only)
+        }
+    }
+    __syncthreads();
+  }
+  // ---- Newton-Schulz sweeps
+  int it = 0, converged = 0;
+  bool wrote_out = false;
+  float* cur = Ys;
+  float* nxt = Xa;
+  while (true) {
+    if (res < p.tol2_m) { converged = 1; break; }
+    if (it >= p.max_iters) break;
+    const bool last = 0.5625f * res * res < 0.25f * p.tol2_m;
+    if (in_x) {
+      small_gemm<false>(cur, Gs, m, i0, j0, acc);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (last) write_outputs(p, i0 + a, j0 + b, acc[a][b]);
+          else nxt[(i0 + a) * SLD + j0 + b] = acc[a][b];
+        }
+    }
+    if (last) { ++it; converged = 1; wrote_out = true; break; }
+    __syncthreads();
+    float r = 0.f;
+    if (in_g) {
+      small_gemm<true>(nxt, nullptr, d, i0, j0, acc);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const float e = acc[a][b] - (i0 + a == j0 + b ? 1.f : 0.f);
+          r = fmaf(e, e, r);
+          acc[a][b] = (i0 + a == j0 + b ? 1.5f : 0.f) - 0.5f * acc[a][b];
+        }
+    }
+    res = block_total256(r, red);            // (barriers inside: every thread is done reading T)
+    if (in_g) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) Gs[(i0 + a) * SLD + j0 + b] = acc[a][b];
+    }
+    __syncthreads();
+    float* freebuf = (cur == Ys) ? Xb : cur;
+    cur = nxt; nxt = freebuf;
+    ++it;
+  }
+  if (tid == 0 && p.status != nullptr) { p.status[0] = it; if (!converged) p.status[1] += 1; }
+  if (!wrote_out) {
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) write_outputs(p, i / m, i % m, cur[(i / m) * SLD + i % m]);
+  }
+}
+
+constexpr int kSmallSmemBytes = (4 * 64 * SLD + 16 * 64) * 4;
+bool finish_small_supported(int d, int m, int K) { return d <= 64 && m <= 64 && d % 32 == 0 && m % 32 == 0 && K >= 1 && K <= 64 && m % K == 0; }
+
 int fused_smem_bytes(int d, int m) {
   const int gram = 2 * d * LDT, mul = 32 * (m + 4) + m * LDT, red = 8 * 32 * 33;      // floats
   const int mx = gram > mul ? (gram > red ? gram : red) : (mul > red ? mul : red);
@@ -687,6 +921,16 @@ int finish_fused(const float* sums, int64_t M_global, const float* U, int d, int
     }
   }
   if (Y_in != nullptr) DRSA_CUDA(cudaMemcpyAsync(p.Y, Y_in, (int64_t)d * m * 4, cudaMemcpyDeviceToDevice, stream));
+  if (finish_small_supported(d, m, K) && g_fused_prof == nullptr) {
+    static bool small_attr = false;
+    if (!small_attr) {
+      DRSA_CUDA(cudaFuncSetAttribute(finish_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
+      small_attr = true;
+    }
+    finish_small_kernel<<<1, 256, kSmallSmemBytes, stream>>>(p);
+    DRSA_LAUNCH_CHECK();
+    return DRSA_OK;
+  }
   int tiles = (d / TS) * (m / TS);
   const int t2 = (m / TS) * (m / TS);
   if (t2 > tiles) tiles = t2;

@@ -38,7 +38,22 @@ def _worker(rank, world, port, ret):
         dist.all_gather(gathered, opt.U)
         out[(prec, exch, graph)] = (opt.obj_history.copy(), opt.U.cpu(), float((gathered[0] - gathered[1]).abs().max()),
                                     opt.M_global)
+    # small split layers (d <= 64: cfg 1, the toy CNN) take the single-CTA finish kernel, which carries the exchange as well
+    As, Cs = drsa_ref.synth_pairs(6000, 64, 79)
+    Us = drsa_ref.synth_U0(64, seed=80)
+    small = {}
+    for exch in ("p2p", "nccl"):
+        o = SubspaceOptimizer(Us, As[3500 * rank:3500 * (rank + 1)], Cs[3500 * rank:3500 * (rank + 1)], None, num_concepts=K,
+                              device=f"cuda:{rank}", precision="fp32", exchange=exch)
+        o.run(steps=steps, save=False)
+        g2 = [torch.zeros_like(o.U) for _ in range(world)]
+        dist.all_gather(g2, o.U)
+        small[exch] = (o.obj_history.copy(), o.U.cpu(), float((g2[0] - g2[1]).abs().max()))
     if rank == 0:
+        objs_s, U_s = drsa_ref.run_autograd(As, Cs, Us, K, steps)
+        for exch, (objs, U, rep) in small.items():
+            assert rep == 0.0 and float(np.max(np.abs(objs - objs_s) / np.abs(objs_s))) < 1e-5, (exch, rep)
+            assert drsa_ref.principal_angle(U, U_s, K) < 1e-4
         objs_ref, U_ref = drsa_ref.run_autograd(A, C, U0, K, steps)
         for key, (objs, U, rep, Mg) in out.items():
             ret["/".join(map(str, key))] = (float(np.max(np.abs(objs - objs_ref) / np.abs(objs_ref))),
