@@ -38,12 +38,8 @@ def class_pipeline(model, input_batch: torch.Tensor, composite, layer_idx: int, 
     number of rows on this rank)."""
     from scipy.stats import ortho_group
     dev = torch.device(device)
-    a_maps, R_maps = pp.get_intermediate(model, input_batch.to(dev), composite, model.features[layer_idx], class_idx)
-    idcs = None
-    if num_locations:
-        idcs = pp.sample_spatial_locations(a_maps.size(0), tuple(a_maps.shape[-2:]), num_locations)
-    act, ctx = pp.gather_context_pairs(a_maps, R_maps, idcs, normalize=True)
-    del a_maps, R_maps
+    act, ctx = pp.extract_context_pairs(model, input_batch, composite, layer_idx, class_idx, num_locations=num_locations,
+                                        normalize=True, device=dev)
     np.random.seed(seed)                        # same start on every rank (drsa.py:263-272)
     d = act.size(-1)
     U = ortho_group.rvs(d)
@@ -160,13 +156,8 @@ def all_classes_pipeline(model, data_by_class: Dict[int, torch.Tensor], composit
     # ---- stage 1 for every class on this rank's samples
     acts, ctxs = {}, {}
     for pos, class_idx in enumerate(classes):
-        a_maps, R_maps = pp.get_intermediate(model, data_by_class[class_idx].to(dev), composite, model.features[layer_idx],
-                                             class_idx)
-        idcs = None
-        if num_locations:
-            idcs = pp.sample_spatial_locations(a_maps.size(0), tuple(a_maps.shape[-2:]), num_locations)
-        acts[pos], ctxs[pos] = pp.gather_context_pairs(a_maps, R_maps, idcs, normalize=True)
-        del a_maps, R_maps
+        acts[pos], ctxs[pos] = pp.extract_context_pairs(model, data_by_class[class_idx], composite, layer_idx, class_idx,
+                                                        num_locations=num_locations, normalize=True, device=dev)
     mine = torch.tensor([acts[p].size(0) for p in range(len(classes))], dtype=torch.int64, device=dev)
     counts = torch.zeros(world, len(classes), dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(counts, mine)

@@ -15,7 +15,7 @@ import torch
 from drsa_audio_b200 import _lib as _L
 
 __all__ = ["preprocess_data", "get_intermediate", "compute_context_vectors", "sample_spatial_locations",
-           "normalize_vectors", "get_vectors_from_maps", "gather_context_pairs"]
+           "normalize_vectors", "get_vectors_from_maps", "gather_context_pairs", "extract_context_pairs"]
 
 
 def _ptr(t):
@@ -121,6 +121,42 @@ def gather_context_pairs(activation_maps: torch.Tensor, relevance_maps: torch.Te
             c = int(count.item())
             _L.check(lib.drsa_normalize(_ptr(act), N * L, d, _ptr(ss[0:]), c, _stream()), "drsa_normalize")
             _L.check(lib.drsa_normalize(_ptr(ctx), N * L, d, _ptr(ss[1:]), c, _stream()), "drsa_normalize")
+    return act, ctx
+
+
+def extract_context_pairs(model, input_batch, composite, layer_idx: int, class_idx: int,
+                          num_locations: Optional[int] = None, one_hot_encoded: bool = False, normalize: bool = True,
+                          process_group=None, device="cuda"):
+    """Stage 1 in one call: spectrograms -> (activation vectors, context vectors) [N*L, d] at ``model.features[layer_idx]``,
+    ready for ``SubspaceOptimizer`` -- ``get_intermediate`` :106 + ``sample_spatial_locations`` :196 (same RNG call order) +
+    ``get_vectors_from_maps`` :234 (corrected row layout) + ``compute_context_vectors`` :179 + ``normalize_vectors`` :219.
+    Where the split layer lies inside the tensor-core stack the rows are written straight from its NHWC planes
+    (``drsa_context_pairs_nhwc``); otherwise the maps are formed and gathered as in the separate functions."""
+    from cxai.xai.explain.lrp_engine import lrp_context_pairs
+    if isinstance(input_batch, np.ndarray):
+        input_batch = torch.tensor(input_batch)
+    input_batch = input_batch.to(device)
+    layer = model.features[layer_idx]
+    idcs = None
+    if num_locations:
+        # the map size is needed before the pass: one sample through the plain route tells it (cheap, and only here)
+        a1, _ = get_intermediate(model, input_batch[:1], composite, layer, class_idx, one_hot_encoded=one_hot_encoded)
+        idcs = sample_spatial_locations(input_batch.size(0), tuple(a1.shape[-2:]), num_locations)
+    res = lrp_context_pairs(model, input_batch, composite, layer, class_idx, idcs, one_hot_encoded=one_hot_encoded)
+    if res is None:
+        a_maps, R_maps = get_intermediate(model, input_batch, composite, layer, class_idx, one_hot_encoded=one_hot_encoded)
+        return gather_context_pairs(a_maps, R_maps, idcs, normalize=normalize, process_group=process_group)
+    act, ctx, ss = res
+    if normalize and act.numel():
+        lib = _L.lib()
+        count = torch.tensor([act.numel()], dtype=torch.int64, device=act.device)
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(ss, group=process_group)
+            torch.distributed.all_reduce(count, group=process_group)
+        c = int(count.item())
+        with torch.cuda.device(act.device):
+            _L.check(lib.drsa_normalize(_ptr(act), act.size(0), act.size(1), _ptr(ss[0:]), c, _stream()), "drsa_normalize")
+            _L.check(lib.drsa_normalize(_ptr(ctx), ctx.size(0), ctx.size(1), _ptr(ss[1:]), c, _stream()), "drsa_normalize")
     return act, ctx
 
 

@@ -436,7 +436,7 @@ class LRPPlan:
 
     # ------------------------------------------------------------------ backward
     def backward(self, Rel: torch.Tensor, saved, stop_after: int = -1, start: Optional[int] = None, nhwc=None,
-                 bound_feat: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 bound_feat: Optional[torch.Tensor] = None, keep_nhwc: bool = False) -> torch.Tensor:
         """Propagates relevance from the logits (or, with ``start``, from the output of op ``start``) down to the OUTPUT
         of op ``stop_after`` (-1: to the input).  Inside the tensor-core conv stack the relevance travels as NHWC fp32
         with padded channels (``nhwc`` = (C, Cp, H, W) when ``Rel`` already is).  ``bound_feat``: activation with the
@@ -560,6 +560,8 @@ class LRPPlan:
             elif op.kind == "flatten":
                 Rel = Rel.reshape(sv[1])
                 feat = sv[2]
+        if keep_nhwc:            # (relevance, (C, Cp, H, W) or None): the caller reads the NHWC fp32 relevance itself
+            return Rel, nhwc
         if nhwc is not None:
             Rel = self._rel_to_nchw(Rel, nhwc)
         return Rel
@@ -657,12 +659,13 @@ class LRPPlan:
         capture; at most ``GRAPH_CACHE`` graphs are kept (each pins the intermediates of one pass, ~46 MB per sample of
         128 x 256)."""
         entry = self._graphs.get(key)
-        if entry is None:
-            self._graphs[key] = "seen"
-            return body(xb)
+        if entry is None or entry == "never":
+            out = body(xb)
+            self._graphs[key] = "seen" if out is not None and entry is None else "never"
+            return out
         if entry == "seen":
-            while len([v for v in self._graphs.values() if v != "seen"]) >= GRAPH_CACHE:
-                oldest = next(k for k, v in self._graphs.items() if v != "seen")
+            while len([v for v in self._graphs.values() if isinstance(v, tuple)]) >= GRAPH_CACHE:
+                oldest = next(k for k, v in self._graphs.items() if isinstance(v, tuple))
                 del self._graphs[oldest]
             static_x = xb.clone()
             graph = torch.cuda.CUDAGraph()
@@ -815,6 +818,66 @@ def lrp_intermediate(model, input_batch, composite, layer, class_idx, attr_batch
             if not plan.tc_failed():
                 break
     return torch.cat(a_maps, 0), torch.cat(r_maps, 0)
+
+
+def lrp_context_pairs(model, input_batch, composite, layer, class_idx, idcs=None, attr_batch_size: int = 64,
+                      one_hot_encoded: bool = False):
+    """Rows for DRSA straight from the engine: (activation vectors, context vectors c = R / (a + 1e-7)) [N*L, d] at the
+    output of ``layer`` and their two sums of squares (float64 [2], un-normalised) -- what ``get_intermediate`` +
+    ``get_vectors_from_maps`` + ``compute_context_vectors`` (preprocessing.py:106-256) produce, without materialising the
+    NCHW maps: inside the tensor-core stack activations and relevance are NHWC, where a row of the result IS a position.
+    ``idcs`` [N, L] selects positions per sample (None: all).  Returns None if the split layer is not inside the NHWC
+    stack (the caller then takes the map route)."""
+    from cxai.xai.explain.attribute import lrp_output_modifier
+    x = _prep_input(input_batch)
+    fn = lrp_output_modifier(class_idx, one_hot_encoded=one_hot_encoded)
+    bs = _engine_chunk(x, attr_batch_size)
+    lib = _L.lib()
+    with torch.cuda.device(x.device):
+        plan = _plan(model, composite, x.device)
+        op = plan.module_to_op.get(layer)
+        if op is None or not plan._tc_stack_ok(x[:1]) or op.index >= plan._stack_end() or plan.ops[op.index].kind != "relu":
+            return None
+        split = op.index
+        idx_all = None if idcs is None else torch.as_tensor(idcs, dtype=torch.int64).to(x.device).contiguous()
+
+        def one_pass(xb, idx=None):
+            logits, saved, outs = plan.forward(xb, keep_from=split + 1, out_index=split)
+            seed = fn(logits).contiguous()
+            Rel, nhwc = plan.backward(seed, saved, stop_after=split, keep_nhwc=True)
+            o = outs[split]
+            if nhwc is None or not isinstance(o, tuple):
+                return None
+            hi, lo, C, Cp, H, W = o[1]
+            B, HW = xb.size(0), H * W
+            L = HW if idx is None else idx.size(1)
+            act = torch.empty(B * L, C, device=xb.device)
+            ctx = torch.empty_like(act)
+            ss = torch.zeros(2, dtype=torch.float64, device=xb.device)
+            _L.check(lib.drsa_context_pairs_nhwc(_ptr(hi), _ptr(lo), _ptr(Rel), B, HW, Cp, C, _ptr(idx), L, _ptr(act), _ptr(ctx),
+                                                 _ptr(ss), _stream()), "drsa_context_pairs_nhwc")
+            return act, ctx, ss
+        while True:
+            acts, ctxs, total = [], [], torch.zeros(2, dtype=torch.float64, device=x.device)
+            ok = True
+            for i in range(0, x.size(0), bs):
+                xb = x[i:i + bs]
+                idx = None if idx_all is None else idx_all[i:i + bs].contiguous()
+                if USE_GRAPH and idx is None and xb.size(0) >= GRAPH_MIN_SAMPLES and plan.use_tc:
+                    res = plan.replay_pass(("pairs", tuple(xb.shape), split, fn.key, plan.use_tc), xb, one_pass)
+                else:
+                    res = one_pass(xb, idx)
+                if res is None:
+                    ok = False
+                    break
+                acts.append(res[0]); ctxs.append(res[1]); total += res[2]
+            if not ok:
+                return None
+            if not plan.tc_failed():
+                break
+            if not plan.use_tc:
+                return None
+    return torch.cat(acts, 0), torch.cat(ctxs, 0), total
 
 
 def _seed_is_rowwise(fn) -> bool:

@@ -61,6 +61,7 @@ SIGNATURES = {
     "drsa_subspace_relevances": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "drsa_subspace_relevances_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32]),
     "drsa_subset_objectives": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "drsa_context_pairs_nhwc": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "drsa_context_gather": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "drsa_context_vectors": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "drsa_sumsq": (_i32, [_vp, _i64, _vp, _vp]),

@@ -120,6 +120,8 @@ int context_gather(const float* a_map, const float* R_map, int64_t N, int d, int
 int context_vectors(const float* a, const float* R, int64_t count, float* out, cudaStream_t stream);
 int sumsq(const float* v, int64_t count, double* out, cudaStream_t stream);
 int normalize(float* v, int64_t rows, int d, const double* sumsq, int64_t count_global, cudaStream_t stream);
+int context_pairs_nhwc(const void* hi, const void* lo, const float* R, int64_t N, int HW, int Cp, int d, const int64_t* idx,
+                       int L, float* act_out, float* ctx_out, double* sumsq, cudaStream_t stream);
 int sums_combine(const float* a, const float* b, float beta, float* out, int64_t n, cudaStream_t stream);
 
 static bool shape_ok(int64_t M, int d, int m, int K) {
@@ -327,6 +329,15 @@ int drsa_subspace_relevances(const float* act, const float* ctx, const float* U,
   DRSA_TRY(require_sm100());
   return subspace_relevances(act, ctx, U, B, P, d, m, K, out, workspace, workspace_bytes,
                              static_cast<cudaStream_t>(stream));
+}
+
+int drsa_context_pairs_nhwc(const void* a_hi, const void* a_lo, const float* R, int64_t N, int HW, int Cp, int d,
+                            const int64_t* idx, int L, float* act_out, float* ctx_out, double* sumsq, void* stream) {
+  if (a_hi == nullptr || a_lo == nullptr || R == nullptr || act_out == nullptr || ctx_out == nullptr || N <= 0 || HW <= 0 ||
+      d <= 0 || Cp < d || L <= 0 || (idx == nullptr && L != HW))
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return context_pairs_nhwc(a_hi, a_lo, R, N, HW, Cp, d, idx, L, act_out, ctx_out, sumsq, static_cast<cudaStream_t>(stream));
 }
 
 int drsa_subset_objectives(const float* act, const float* ctx, const float* U, int64_t S, int64_t R, int d, int m, int K,

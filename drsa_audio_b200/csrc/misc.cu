@@ -2,6 +2,7 @@
 //   * context vectors + gather from NCHW maps + sum of squares  (preprocessing.py:179-193, 234-256)
 //   * normalize_vectors with a global statistic                  (preprocessing.py:219-231)
 //   * per-instance concept relevances                            (explainer.py:206-242)
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace drsa {
@@ -108,6 +109,48 @@ __global__ void __launch_bounds__(256) subspace_rel_kernel(const float* __restri
   s = warp_sum(s);
   if (lane == 0) out[b * K + k] = s;
 }
+// The same fused tail of stage 1 straight from the tensor-core stack's NHWC layout: activations as hi + lo fp16 planes
+// [N, HW, Cp], relevance fp32 [N, HW, Cp].  A row of the output IS a position of the input, so every access is coalesced along
+// the channels and no layout conversion (NHWC -> NCHW -> rows) is needed.  One warp per output row, 8 rows per CTA iteration.
+__global__ void __launch_bounds__(256) context_pairs_nhwc_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
+                                                                 const float* __restrict__ R, int64_t N, int HW, int Cp, int d,
+                                                                 const int64_t* __restrict__ idx, int L,
+                                                                 float* __restrict__ act_out, float* __restrict__ ctx_out,
+                                                                 double* __restrict__ sumsq) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float sa = 0.f, sc = 0.f;
+  const int64_t rows = N * L;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < rows; r += (int64_t)gridDim.x * 8) {
+    const int64_t n = r / L;
+    const int l = (int)(r % L);
+    const int pos = idx != nullptr ? (int)idx[n * L + l] : l;
+    const int64_t src = (n * HW + pos) * Cp;
+    for (int c = 2 * lane; c < d; c += 64) {            // two channels per lane: half2 / float2 accesses (d, Cp even)
+      const float2 h = __half22float2(*reinterpret_cast<const __half2*>(hi + src + c));
+      const float2 w = __half22float2(*reinterpret_cast<const __half2*>(lo + src + c));
+      const float2 rv = *reinterpret_cast<const float2*>(R + src + c);
+      const float a0 = h.x + w.x, a1 = h.y + w.y;
+      const float c0 = rv.x / (a0 + 1e-7f), c1 = rv.y / (a1 + 1e-7f);      // preprocessing.py:193
+      *reinterpret_cast<float2*>(act_out + r * d + c) = make_float2(a0, a1);
+      *reinterpret_cast<float2*>(ctx_out + r * d + c) = make_float2(c0, c1);
+      sa = fmaf(a0, a0, fmaf(a1, a1, sa));
+      sc = fmaf(c0, c0, fmaf(c1, c1, sc));
+    }
+  }
+  if (sumsq != nullptr) {
+    __shared__ double red[2][8];
+    const double da = warp_sum((double)sa), dc = warp_sum((double)sc);
+    if (lane == 0) { red[0][warp] = da; red[1][warp] = dc; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+      atomicAdd(sumsq + threadIdx.x, t);
+    }
+  }
+}
+
 // Prototype search (prototypes.py:98-119): one warp per (subset, concept) sums relu(s_rk)^2 over the subset's rows
 __global__ void __launch_bounds__(256) subset_sumsq_kernel(const float* __restrict__ HA, const float* __restrict__ HC,
                                                            int64_t S, int64_t R, int m, int K, float* __restrict__ sumsq) {
@@ -156,6 +199,17 @@ int context_gather(const float* a_map, const float* R_map, int64_t N, int d, int
   dim3 grid((unsigned)N, cdiv(L, 32), cdiv(d, 32));
   if (grid.y > 65535 || grid.z > 65535) return DRSA_ERR_SHAPE;
   context_gather_kernel<<<grid, 256, 0, stream>>>(a_map, R_map, d, HW, idx, L, act_out, ctx_out, sumsq);
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
+int context_pairs_nhwc(const void* hi, const void* lo, const float* R, int64_t N, int HW, int Cp, int d, const int64_t* idx,
+                       int L, float* act_out, float* ctx_out, double* sumsq, cudaStream_t stream) {
+  if ((d & 1) || (Cp & 1)) return DRSA_ERR_SHAPE;
+  int64_t blocks = (N * L + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  context_pairs_nhwc_kernel<<<(int)blocks, 256, 0, stream>>>(static_cast<const __half*>(hi), static_cast<const __half*>(lo), R, N,
+                                                              HW, Cp, d, idx, L, act_out, ctx_out, sumsq);
   DRSA_LAUNCH_CHECK();
   return DRSA_OK;
 }

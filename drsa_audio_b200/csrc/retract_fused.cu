@@ -147,7 +147,6 @@ struct FuseY {
   const float* sums; const float* coef; int m, d_k;      // coef[k] in shared memory
   float* Y_out;            // global Y (needed by the first multiply); written for the A panel when write_a, never for B
   bool write_a;
-  const __half* Ut_hi; int d; int u_rounded; const float* U; float corr;   // first-order objective correction over the A panel
 };
 
 // kScaleT (MODE 1 only): the B panel is loaded from the Gram matrix G and turned into the first Newton-Schulz factor
@@ -173,6 +172,10 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
         const int k = k0 + (idx >> 3), seg = idx & 7;
         cp_async16(Bs + k * LDT + 4 * seg, B + (int64_t)k * ldb + j0 + 4 * seg);
         if (MODE == 0) cp_async16(As + k * LDT + 4 * seg, A + (int64_t)k * lda + i0 + 4 * seg);
+        if (kFuseY) {      // the matching segments of `sums`, staged behind the two operand panels
+          cp_async16(Bs + (2 * Kdim + k) * LDT + 4 * seg, fuse->sums + (int64_t)k * fuse->m + j0 + 4 * seg);
+          cp_async16(As + (2 * Kdim + k) * LDT + 4 * seg, fuse->sums + (int64_t)k * fuse->m + i0 + 4 * seg);
+        }
       }
       if (MODE == 1) {   // A panel: 32 rows, Kg/4 segments of this group per row
         const int spr = Kg >> 2;
@@ -181,53 +184,6 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
       }
     }
     cp_async_commit();
-  }
-  if (kFuseY) {
-    // every thread transforms the 16-byte segments it loaded itself (its own cp.async groups are complete after the wait;
-    // the barrier below publishes them): seg -> float4 of sums, same (k, column) mapping as the loads above
-    cp_async_wait_pending(0);
-    FuseY& f = *fuse;
-    float corr = 0.f;
-    // segments of this thread: s = 0 .. nseg-1 -> (panel ab, group g, round p); the loads of 8 segments are issued together
-    // (one L2 round trip per batch instead of one per segment)
-    const int per_panel = Kdim / 32;                 // rounds over all groups
-    const int nseg = 2 * per_panel;
-    for (int s0 = 0; s0 < nseg; s0 += 8) {
-      float4 sv[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int sidx = s0 + u;
-        if (sidx < nseg) {
-          const int ab = sidx / per_panel, r = sidx % per_panel;
-          const int idx = tid + 256 * r;
-          const int k = idx >> 3, seg = idx & 7;
-          const int c0 = (ab == 0 ? i0 : j0) + 4 * seg;
-          sv[u] = __ldcg(reinterpret_cast<const float4*>(f.sums + (int64_t)k * f.m + c0));
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int sidx = s0 + u;
-        if (sidx < nseg) {
-          const int ab = sidx / per_panel, r = sidx % per_panel;
-          const int idx = tid + 256 * r;
-          const int k = idx >> 3, seg = idx & 7;
-          const int c0 = (ab == 0 ? i0 : j0) + 4 * seg;
-          float* dst = (ab == 0 ? As : Bs) + k * LDT + 4 * seg;
-          const float cf = f.coef[c0 / f.d_k];                     // 4 consecutive columns share a concept (d_k % 4 == 0)
-          float4 uu = *reinterpret_cast<float4*>(dst);
-          const float4 gr = make_float4(cf * sv[u].x, cf * sv[u].y, cf * sv[u].z, cf * sv[u].w);
-          if (ab == 0 && f.write_a && f.u_rounded) {          // <grad f(U^), U>, see log_objective
-            corr = fmaf(gr.x, uu.x, corr); corr = fmaf(gr.y, uu.y, corr);
-            corr = fmaf(gr.z, uu.z, corr); corr = fmaf(gr.w, uu.w, corr);
-          }
-          uu.x += gr.x; uu.y += gr.y; uu.z += gr.z; uu.w += gr.w;
-          *reinterpret_cast<float4*>(dst) = uu;
-          if (ab == 0 && f.write_a) *reinterpret_cast<float4*>(f.Y_out + (int64_t)k * f.m + c0) = uu;
-        }
-      }
-    }
-    f.corr = corr;
   }
   if (kScaleT) {
     cp_async_wait_pending(0);                  // this thread's own segments have landed; the barrier below publishes them
@@ -255,6 +211,27 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
     for (int c = 0; c < 8; ++c) part[r][c] = 0.f;
   for (int g = 0; g < groups; ++g) {
     cp_async_wait_pending(groups - 1 - g);
+    if (kFuseY) {
+      // Y = U + coef * sums for the segments of group g THIS thread loaded (complete after the wait above; the barrier below
+      // publishes them), while the later groups are still in flight: the load / FMA overlap of the plain Gram phase is kept
+      FuseY& f = *fuse;
+      for (int p = 0; p < Kg / 32; ++p) {
+        const int idx = tid + 256 * p;
+        const int k = g * Kg + (idx >> 3), seg = idx & 7;
+#pragma unroll
+        for (int ab = 0; ab < 2; ++ab) {
+          const int c0 = (ab == 0 ? i0 : j0) + 4 * seg;
+          float* dst = (ab == 0 ? As : Bs) + k * LDT + 4 * seg;
+          const float4 sv = *reinterpret_cast<const float4*>(dst + 2 * Kdim * LDT);      // its staged sums segment
+          const float cf = f.coef[c0 / f.d_k];                     // 4 consecutive columns share a concept (d_k % 4 == 0)
+          float4 uu = *reinterpret_cast<float4*>(dst);
+          const float4 gr = make_float4(cf * sv.x, cf * sv.y, cf * sv.z, cf * sv.w);
+          uu.x += gr.x; uu.y += gr.y; uu.z += gr.z; uu.w += gr.w;
+          *reinterpret_cast<float4*>(dst) = uu;
+          if (ab == 0 && f.write_a) *reinterpret_cast<float4*>(f.Y_out + (int64_t)k * f.m + c0) = uu;
+        }
+      }
+    }
     __syncthreads();
     for (int kb = g * Kg; kb < (g + 1) * Kg; kb += 32) {
       const int k4 = kb + 4 * warp;
@@ -357,6 +334,44 @@ __device__ __forceinline__ void write_outputs(const FusedParams& p, int r, int c
   }
 }
 
+// First-order term of the objective for the tensor-core modes: the row sums were evaluated at the rounded matrix U^ the row
+// pass read (fp16(U), or with error feedback the stored Ut_hi), and f(U) = f(U^) + <grad f(U^), U - U^> + O(|U - U^|^2).
+// U^ is stored TRANSPOSED ([m][d], K-major for the row pass), so the inner product is taken block-wise: a 32 x 32 block
+// of U and of the gradient is staged in shared memory (coalesced along the columns), the matching block of U^ is read
+// coalesced along its own rows, and every CTA takes its share of the blocks.  (Evaluating it as <grad f, U> - f through
+// Euler's identity -- f is homogeneous of degree 2 -- avoids reading U^ but makes the objective inherit the full rounding
+// of the gradient accumulation: 2e-4 .. 1e-3 relative at 2 .. 2.5 M rows per GPU; measured and discarded.)
+template <typename SumsFn>
+__device__ __forceinline__ float objective_correction(const FusedParams& p, const float* coef, SumsFn S, float (*tu)[33],
+                                                       float (*tg)[33]) {
+  const int d = p.d, m = p.m, d_k = m / p.K;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tm = m / 32, td = d / 32;
+  float corr = 0.f;
+  for (int b = blockIdx.x; b < td * tm; b += gridDim.x) {
+    const int k0 = 32 * (b / tm), c0 = 32 * (b % tm);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int kk = ty + 8 * r;
+      const int64_t i = (int64_t)(k0 + kk) * m + c0 + tx;
+      const float u = p.U[i];
+      tu[kk][tx] = u;
+      tg[kk][tx] = coef[(c0 + tx) / d_k] * S(i);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int cc = ty + 8 * r;
+      const float u = tu[tx][cc];
+      const float uh = p.u_rounded == 2 ? __half2float(p.Ut_hi[(int64_t)(c0 + cc) * d + k0 + tx])
+                                        : __half2float(__float2half_rn(u));
+      corr = fmaf(tg[tx][cc], u - uh, corr);
+    }
+    __syncthreads();
+  }
+  return corr;
+}
+
 // Phases of a normal step on one rank (grid barriers in brackets):
 //   Gram of Y = U + coef*X, formed on the fly in the operand panels  [1]  multiply by T = 1.5 I - 0.5 G  [2]  Gram  [3] ...
 //   last multiply, which also writes U_out and the fp16 planes.
@@ -368,6 +383,7 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
   __shared__ float red[8];
   __shared__ float coef[64];
   __shared__ float bc[2];
+  __shared__ float tile_u[32][33], tile_g[32][33];     // objective_correction
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int d = p.d, m = p.m;
   const int64_t n = (int64_t)d * m;
@@ -375,7 +391,8 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
   int slot = 0;
   stamp(p, slot);
   // single rank, full step: the ascent step is fused into the first Gram phase
-  const bool fuse0 = p.have_sums && p.world <= 1 && p.U_out != nullptr && p.K <= 64 && (m / p.K) % 4 == 0;
+  const bool fuse0 = p.have_sums && p.world <= 1 && p.U_out != nullptr && p.K <= 64 && (m / p.K) % 4 == 0 &&
+                     4 * d * LDT * 4 <= 200 * 1024;
 
   // ---------------- phase 0: pooling scalars, (Y = U + coef_k X_k), objective log
   int xpar = 0;
@@ -421,11 +438,11 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
           }
           const float u = p.U[i], gr = c * S(i);
           if (p.U_out != nullptr) p.Y[i] = u + gr;
-          if (p.u_rounded) corr = fmaf(gr, u, corr);          // <grad f(U^), U>, see log_objective
         }
       }
+      if (p.u_rounded && K <= 64) corr = objective_correction(p, coef, S, tile_u, tile_g);
     }
-    if (p.u_rounded && !fuse0) {
+    if (p.u_rounded) {
       const float tot = block_sum(corr, red);
       if (tid == 0) p.corr[blockIdx.x] = tot;
     }
@@ -433,7 +450,7 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
       if (tid == 0 && p.obj_log != nullptr) {
         long long idx = p.log_index;
         if (idx < 0) { idx = p.status[3]; p.status[3] = (int)idx + 1; }
-        p.obj_log[idx] = p.u_rounded ? p.corr[0] - root * root : root * root;      // see log_objective
+        p.obj_log[idx] = root * root + (p.u_rounded ? p.corr[0] : 0.f);
       }
       if (p.world > 1 && tid == 0) {            // single CTA here: close this exchange (see below)
         unsigned* hdr = reinterpret_cast<unsigned*>(p.xbuf[p.rank]);
@@ -455,17 +472,13 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
     hdr[16 + 16 * xpar] = 0u;
     hdr[0] = __ldcg(hdr) + 1u;
   }
-  // Objective of the step.  u_rounded: the sums were evaluated at a rounded matrix U^ (fp16, possibly with error feedback);
-  // the logged value is f(U^) + <grad f(U^), U - U^>, equal to f(U) up to second order in the rounding.  f is homogeneous
-  // of degree 2 in U (s_rk is quadratic in U, the pooling keeps the degree), so <grad f(U^), U^> = 2 f(U^) (Euler) and the
-  // value is <grad f(U^), U> - f(U^): U^ itself, stored transposed for the row pass, never has to be read here.
   auto log_objective = [&]() {
     if (p.have_sums && blockIdx.x == 0 && p.obj_log != nullptr) {      // block-uniform condition
-      const float gu = p.u_rounded ? fixed_total(p.corr, (int)gridDim.x, red) : 0.f;   // fixed order: bit-identical replicas
+      const float extra = p.u_rounded ? fixed_total(p.corr, (int)gridDim.x, red) : 0.f;   // fixed order: bit-identical replicas
       if (tid == 0) {
         long long idx = p.log_index;
         if (idx < 0) { idx = p.status[3]; p.status[3] = (int)idx + 1; }
-        p.obj_log[idx] = p.u_rounded ? gu - bc[0] * bc[0] : bc[0] * bc[0];
+        p.obj_log[idx] = bc[0] * bc[0] + extra;
       }
     }
   };
@@ -474,14 +487,12 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
   const int tm = m / TS, td = d / TS;
   // ---------------- phase 1: G = Y^T Y, row sums of |G|, ||G - I||_F^2, T for the unscaled start
   {
-    float corr = 0.f;
     for (int t = blockIdx.x; t < tm * tm; t += gridDim.x) {
       const int ti = t / tm, tj = t % tm;
       float acc[2][2];
       if (fuse0) {
-        FuseY f{p.sums, coef, m, m / p.K, p.Y, ti == tj, p.Ut_hi, d, p.u_rounded, p.U, 0.f};
+        FuseY f{p.sums, coef, m, m / p.K, p.Y, ti == tj};
         tile_gemm<0, true>(p.U, m, ti * TS, p.U, m, tj * TS, d, acc, panels, &f);
-        corr += f.corr;
       } else {
         tile_gemm<0>(p.Y, m, ti * TS, p.Y, m, tj * TS, d, acc, panels);
       }
@@ -507,10 +518,6 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
       const float tot_sq = block_sum(sq, red);
       const float tot_tr = block_sum(tr, red);
       if (tid == 0) { p.fro[t] = tot; p.fro[tm * tm + t] = tot_sq; p.fro[2 * tm * tm + t] = tot_tr; }
-    }
-    if (fuse0 && p.u_rounded) {
-      const float tot = block_sum(corr, red);
-      if (tid == 0) p.corr[blockIdx.x] = tot;
     }
   }
   stamp(p, slot);
@@ -733,7 +740,8 @@ __global__ void __launch_bounds__(256) finish_small_kernel(FusedParams p) {
         const int r = i / m, c = i % m;
         const float u = p.U[i], gr = coef[c / d_k] * S(i);
         Ys[r * SLD + c] = u + gr;
-        gu = fmaf(gr, u, gu);
+        if (p.u_rounded)         // first-order objective term, see objective_correction
+          gu = fmaf(gr, u - (p.u_rounded == 2 ? __half2float(p.Ut_hi[(int64_t)c * d + r]) : __half2float(__float2half_rn(u))), gu);
       }
     }
     const float gu_tot = p.u_rounded ? block_total256(gu, red) : 0.f;
@@ -746,7 +754,7 @@ __global__ void __launch_bounds__(256) finish_small_kernel(FusedParams p) {
     if (tid == 0 && p.obj_log != nullptr) {
       long long idx = p.log_index;
       if (idx < 0) { idx = p.status[3]; p.status[3] = (int)idx + 1; }
-      p.obj_log[idx] = p.u_rounded ? gu_tot - root * root : root * root;      // Euler, see finish_fused_kernel
+      p.obj_log[idx] = root * root + gu_tot;
     }
     if (p.U_out == nullptr) return;
   } else {
@@ -862,8 +870,11 @@ __global__ void __launch_bounds__(256) finish_small_kernel(FusedParams p) {
 constexpr int kSmallSmemBytes = (4 * 64 * SLD + 16 * 64) * 4;
 bool finish_small_supported(int d, int m, int K) { return d <= 64 && m <= 64 && d % 32 == 0 && m % 32 == 0 && K >= 1 && K <= 64 && m % K == 0; }
 
+// the fused ascent stages the `sums` panels behind the operand panels of the first Gram phase: 4 * d * LDT floats (147 KB at
+// d = 256); where that does not fit (d = 512) the ascent keeps a phase of its own
+bool fuse_ascent_fits(int d) { return 4 * d * LDT * 4 <= 200 * 1024; }
 int fused_smem_bytes(int d, int m) {
-  const int gram = 2 * d * LDT, mul = 32 * (m + 4) + m * LDT, red = 8 * 32 * 33;      // floats
+  const int gram = (fuse_ascent_fits(d) ? 4 : 2) * d * LDT, mul = 32 * (m + 4) + m * LDT, red = 8 * 32 * 33;      // floats
   const int mx = gram > mul ? (gram > red ? gram : red) : (mul > red ? mul : red);
   return mx * 4;
 }
@@ -908,6 +919,7 @@ int finish_fused(const float* sums, int64_t M_global, const float* U, int d, int
   p.prof = g_fused_prof;
   p.status = status; p.have_sums = (Y_in == nullptr) ? 1 : 0;
   p.u_rounded = (u_rounded && Y_in == nullptr) ? u_rounded : 0;
+  if (p.u_rounded == 2 && Ut_hi == nullptr) return DRSA_ERR_ARG;
   p.corr = p.resid + (int64_t)(max_iters + 1) * 1024;       // the row after the last sweep's residual partials
   p.fro = p.resid + (int64_t)(64 + 2) * 1024;                // last row of the 64 + 3 the workspace is sized for
   p.world = 1; p.rank = 0;

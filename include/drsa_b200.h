@@ -237,6 +237,13 @@ int drsa_context_gather(const float* a_map, const float* R_map, int64_t N, int d
                         const int64_t* idx, int L, float* act_out, float* ctx_out, double* sumsq,
                         void* stream);
 
+/* The same from the NHWC layout of the tensor-core conv stack: activations as hi + lo fp16 planes [N, HW, Cp] (a = hi + lo),
+ * relevance fp32 [N, HW, Cp]; rows are positions, so nothing is transposed.  idx [N, L] int64 selects positions (NULL: all,
+ * L == HW).  Replaces get_vectors_from_maps + compute_context_vectors + the reduction of normalize_vectors
+ * (preprocessing.py:179-256) together with the two NHWC -> NCHW conversions get_intermediate would need first. */
+int drsa_context_pairs_nhwc(const void* a_hi, const void* a_lo, const float* R, int64_t N, int HW, int Cp, int d,
+                            const int64_t* idx, int L, float* act_out, float* ctx_out, double* sumsq, void* stream);
+
 /* out = R / (a + 1e-7) element-wise over `count` floats (compute_context_vectors, any layout). */
 int drsa_context_vectors(const float* a, const float* R, int64_t count, float* out, void* stream);
 

@@ -685,3 +685,35 @@ def test_graph_replay_of_engine_passes_is_bit_identical(monkeypatch):
     monkeypatch.setattr(lrp_engine, "USE_GRAPH", False)
     a5w, r5w = get_intermediate(net, xs[0], comp, net.features[26], 5)
     assert torch.equal(r5, r5w) and not torch.equal(r5, got[0][1])
+
+
+@pytest.mark.parametrize("num_locations", [None, 5])
+def test_context_pairs_from_nhwc_match_the_map_route(num_locations):
+    """extract_context_pairs writes the DRSA rows straight from the tensor-core stack's NHWC planes; the result must equal
+    get_intermediate -> sample_spatial_locations -> gather_context_pairs (same RNG call order, same rows), also when the
+    engine pass is replayed as a CUDA graph."""
+    from cxai.utils.constants import lrp_name_map_6s
+    from cxai.xai.explain.rules import NameMapComposite, SequentialMergeBatchNorm
+    from cxai.xai.drsa import preprocessing as pp
+    net = lrp_ref.genre_model(seed=0, last=64, input_size=(32, 64))
+    comp = NameMapComposite(lrp_name_map_6s(), canonizers=[SequentialMergeBatchNorm()])
+    for rep in range(3):                                      # plain launches, capture, replay
+        x = lrp_ref.synth_logmel(40, 32, 64, 400 + rep).cuda()
+        np.random.seed(9)
+        a_maps, R_maps = pp.get_intermediate(net, x, comp, net.features[26], 2)
+        idcs = pp.sample_spatial_locations(40, tuple(a_maps.shape[-2:]), num_locations) if num_locations else None
+        act_w, ctx_w = pp.gather_context_pairs(a_maps, R_maps, idcs, normalize=True)
+        np.random.seed(9)
+        act, ctx = pp.extract_context_pairs(net, x, comp, 26, 2, num_locations=num_locations, normalize=True)
+        assert act.shape == act_w.shape == (40 * (num_locations or a_maps.shape[-1] * a_maps.shape[-2]), 128)
+        np.testing.assert_allclose(act.cpu().numpy(), act_w.cpu().numpy(), rtol=2e-6, atol=1e-9)
+        np.testing.assert_allclose(ctx.cpu().numpy(), ctx_w.cpu().numpy(), rtol=2e-6, atol=1e-9)
+    # a split layer below the tensor-core stack's reach (or the toy model on the fp32 kernels) takes the map route
+    toy = lrp_ref.toy_model(seed=0, last=64)
+    from cxai.utils.constants import LRP_NAME_MAP_TOY
+    xt = lrp_ref.synth_logmel(6, 64, 64, 3).cuda()
+    act, ctx = pp.extract_context_pairs(toy, xt, NameMapComposite(LRP_NAME_MAP_TOY), 13, 0)
+    a_maps, R_maps = pp.get_intermediate(toy, xt, NameMapComposite(LRP_NAME_MAP_TOY), toy.features[13], 0)
+    act_w, ctx_w = pp.gather_context_pairs(a_maps, R_maps, None, normalize=True)
+    np.testing.assert_allclose(act.cpu().numpy(), act_w.cpu().numpy(), rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(ctx.cpu().numpy(), ctx_w.cpu().numpy(), rtol=2e-6, atol=1e-9)
