@@ -736,6 +736,31 @@ __global__ void __launch_bounds__(256) finish_small_kernel(FusedParams p) {
     }
     __syncthreads();
     if (p.U_out != nullptr || p.u_rounded) {
+      // float4 per thread and iteration, the loads of four iterations in flight together (n is a multiple of 1024)
+      if (p.world <= 1 && !p.u_rounded) {
+        const float4* U4 = reinterpret_cast<const float4*>(p.U);
+        const float4* S4 = reinterpret_cast<const float4*>(p.sums);
+        for (int i4 = tid; i4 < n / 4; i4 += 4 * blockDim.x) {
+          float4 uv[4], sv[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (i4 + q * blockDim.x < n / 4) { uv[q] = U4[i4 + q * blockDim.x]; sv[q] = S4[i4 + q * blockDim.x]; }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (i4 + q * blockDim.x < n / 4) {
+              const int i = 4 * (i4 + q * blockDim.x), r = i / m, c = i % m;
+              const float cf = coef[c / d_k];            // d_k % 4 == 0 or the four columns are handled one by one below
+              float* dst = &Ys[r * SLD + c];
+              if (d_k % 4 == 0) {
+                dst[0] = uv[q].x + cf * sv[q].x; dst[1] = uv[q].y + cf * sv[q].y;
+                dst[2] = uv[q].z + cf * sv[q].z; dst[3] = uv[q].w + cf * sv[q].w;
+              } else {
+                dst[0] = uv[q].x + coef[c / d_k] * sv[q].x; dst[1] = uv[q].y + coef[(c + 1) / d_k] * sv[q].y;
+                dst[2] = uv[q].z + coef[(c + 2) / d_k] * sv[q].z; dst[3] = uv[q].w + coef[(c + 3) / d_k] * sv[q].w;
+              }
+            }
+        }
+      } else
       for (int i = tid; i < n; i += blockDim.x) {
         const int r = i / m, c = i % m;
         const float u = p.U[i], gr = coef[c / d_k] * S(i);
