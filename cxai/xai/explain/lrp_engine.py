@@ -647,8 +647,9 @@ class LRPPlan:
 
 
     # ------------------------------------------------------------------ CUDA-graph replay of whole engine passes
-    def replay_pass(self, key, xb: torch.Tensor, body):
-        """``body(xb)`` -> tuple of tensors, as ONE CUDA-graph launch from the third call with the same key on.
+    def replay_pass(self, key, inputs, body):
+        """``body(*inputs)`` -> tuple of tensors, as ONE CUDA-graph launch from the third call with the same key on
+        (``inputs``: a tensor or a tuple of tensors; everything that changes between calls must be in it).
 
         An engine pass is ~180 launches (35 layers forward and backward, plus the fill / copy kernels of the tensors it
         allocates); launched one by one they leave ~0.25 ms of gaps per 256 samples and keep the host busy.  A pass
@@ -658,24 +659,27 @@ class LRPPlan:
         call with a key: plain launches (one-time initialisations must not happen inside a capture); second call:
         capture; at most ``GRAPH_CACHE`` graphs are kept (each pins the intermediates of one pass, ~46 MB per sample of
         128 x 256)."""
+        if isinstance(inputs, torch.Tensor):
+            inputs = (inputs,)
         entry = self._graphs.get(key)
         if entry is None or entry == "never":
-            out = body(xb)
+            out = body(*inputs)
             self._graphs[key] = "seen" if out is not None and entry is None else "never"
             return out
         if entry == "seen":
             while len([v for v in self._graphs.values() if isinstance(v, tuple)]) >= GRAPH_CACHE:
                 oldest = next(k for k, v in self._graphs.items() if isinstance(v, tuple))
                 del self._graphs[oldest]
-            static_x = xb.clone()
+            static_in = tuple(t.clone() for t in inputs)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                outs = body(static_x)
-            entry = (graph, static_x, outs)
+                outs = body(*static_in)
+            entry = (graph, static_in, outs)
             self._graphs.pop(key, None)
             self._graphs[key] = entry                  # (re)inserted last: the dict order is the age
         else:
-            entry[1].copy_(xb)
+            for dst, src in zip(entry[1], inputs):
+                dst.copy_(src)
         entry[0].replay()
         return tuple(o.clone() for o in entry[2])      # the static outputs are overwritten by the next replay
 
@@ -798,19 +802,24 @@ def lrp_intermediate(model, input_batch, composite, layer, class_idx, attr_batch
                 nxt += 1
             raise _L.DRSAError(f"split at {plan.ops[split].name} (pre-activation) is not on this path; "
                                f"use the ReLU {plan.ops[nxt].name} like the reference (layers 19/26/33)")
-        def one_pass(xb):
+        def one_pass(xb, mask=None):
             logits, saved, outs = plan.forward(xb, keep_from=split + 1, out_index=split)
-            seed = fn(logits).contiguous()
+            seed = fn(logits).contiguous() if mask is None else _class_seed(logits, mask, fn_key[2])
             r = plan.backward(seed, saved, stop_after=split)
             o = outs[split]
             return (plan._nhwc_to_nchw(o[1]) if isinstance(o, tuple) else o), r
         fn_key = getattr(fn, "key", None)
+        mask_row = None
         while True:
             a_maps, r_maps = [], []
             for i in range(0, x.size(0), attr_batch_size):
                 xb = x[i:i + attr_batch_size]
                 if USE_GRAPH and fn_key is not None and xb.size(0) >= GRAPH_MIN_SAMPLES:
-                    a, r = plan.replay_pass(("intermediate", tuple(xb.shape), split, fn_key, plan.use_tc), xb, one_pass)
+                    if mask_row is None:
+                        mask_row = torch.zeros(plan.ops[-1].cout, device=x.device)
+                        mask_row[fn_key[1]] = 1.0
+                    a, r = plan.replay_pass(("intermediate", tuple(xb.shape), split, fn_key[2], plan.use_tc),
+                                            (xb, mask_row), one_pass)
                 else:
                     a, r = one_pass(xb)
                 a_maps.append(a)
@@ -818,6 +827,14 @@ def lrp_intermediate(model, input_batch, composite, layer, class_idx, attr_batch
             if not plan.tc_failed():
                 break
     return torch.cat(a_maps, 0), torch.cat(r_maps, 0)
+
+
+def _class_seed(logits: torch.Tensor, mask_row: torch.Tensor, one_hot: bool) -> torch.Tensor:
+    """The seed of ``lrp_output_modifier(class_idx, one_hot_encoded=...)`` (attribute.py:134-144) with the class mask as a
+    TENSOR [n_classes] instead of a Python index, so that one captured pass serves every class (``mask_row`` is a static
+    input of the graph)."""
+    mask = mask_row.to(logits.dtype).expand_as(logits)
+    return (mask if one_hot else logits * mask).contiguous()
 
 
 def lrp_context_pairs(model, input_batch, composite, layer, class_idx, idcs=None, attr_batch_size: int = 64,
@@ -841,9 +858,11 @@ def lrp_context_pairs(model, input_batch, composite, layer, class_idx, idcs=None
         split = op.index
         idx_all = None if idcs is None else torch.as_tensor(idcs, dtype=torch.int64).to(x.device).contiguous()
 
-        def one_pass(xb, idx=None):
+        mask_row = None
+
+        def one_pass(xb, idx=None, mask=None):
             logits, saved, outs = plan.forward(xb, keep_from=split + 1, out_index=split)
-            seed = fn(logits).contiguous()
+            seed = fn(logits).contiguous() if mask is None else _class_seed(logits, mask, one_hot_encoded)
             Rel, nhwc = plan.backward(seed, saved, stop_after=split, keep_nhwc=True)
             o = outs[split]
             if nhwc is None or not isinstance(o, tuple):
@@ -864,7 +883,12 @@ def lrp_context_pairs(model, input_batch, composite, layer, class_idx, idcs=None
                 xb = x[i:i + bs]
                 idx = None if idx_all is None else idx_all[i:i + bs].contiguous()
                 if USE_GRAPH and idx is None and xb.size(0) >= GRAPH_MIN_SAMPLES and plan.use_tc:
-                    res = plan.replay_pass(("pairs", tuple(xb.shape), split, fn.key, plan.use_tc), xb, one_pass)
+                    if mask_row is None:
+                        n_out = plan.ops[-1].cout
+                        mask_row = torch.zeros(n_out, device=x.device)
+                        mask_row[class_idx] = 1.0
+                    res = plan.replay_pass(("pairs", tuple(xb.shape), split, bool(one_hot_encoded), plan.use_tc),
+                                           (xb, mask_row), lambda a, b: one_pass(a, None, b))
                 else:
                     res = one_pass(xb, idx)
                 if res is None:
