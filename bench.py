@@ -731,7 +731,9 @@ def run_cfg5(args, dev, rank, world):
     data = {c: batch() for c in range(classes)}                 # this rank's spectrograms of every class, resident
     sync()
     t0 = time.perf_counter()
-    out = all_classes_pipeline(net, data, comp, 33, None, num_concepts=4, steps=steps, precision=args.precision)
+    timings = {} if args.cfg5_timings else None
+    out = all_classes_pipeline(net, data, comp, 33, None, num_concepts=4, steps=steps, precision=args.precision,
+                               **({"timings": timings} if world > 1 else {}))
     sync()
     wall = time.perf_counter() - t0
     tw = torch.tensor([wall], dtype=torch.float64, device=dev)
@@ -749,7 +751,7 @@ def run_cfg5(args, dev, rank, world):
             "config": {"workload": "cfg5", "classes": classes, "samples_per_class": n_local * world, "positions": 64,
                        "d": 256, "K": 4, "drsa_steps_per_class": steps, "precision": args.precision,
                        "l2_policy": "inputs larger than L2 (1.3 GB of spectrograms and 1.3 GB of rows per class)"},
-            "wall_s": wall, "context_vectors": vecs, "vectors_per_s_whole_pipeline": vecs / wall,
+            "wall_s": wall, "phases_s_rank0": timings, "context_vectors": vecs, "vectors_per_s_whole_pipeline": vecs / wall,
             "gpu_launches": None, "clocks": clocks, "objective_first_last_per_class": objs,
             "e2e": {"value": classes * steps / wall, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
                     "what": "spectrograms resident on the device (synthetic); wall clock over all 10 classes incl. the D2H "
@@ -784,6 +786,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly (used for the ncu captures)")
     ap.add_argument("--lrp-samples", type=int, default=256)
     ap.add_argument("--cfg5-samples", type=int, default=10_000, help="cfg 5: samples per class (over all ranks)")
+    ap.add_argument("--cfg5-timings", action="store_true", help="cfg 5: wall-clock breakdown of rank 0 (adds synchronisations)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

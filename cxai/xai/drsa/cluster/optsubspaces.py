@@ -129,7 +129,8 @@ def _subgroup(ranks: List[int]):
 
 def all_classes_pipeline(model, data_by_class: Dict[int, torch.Tensor], composite, layer_idx: int, model_root: Optional[str],
                          num_concepts: int = 4, steps: int = 2000, runs: int = 1, seed: int = 42,
-                         num_locations: Optional[int] = None, device="cuda", schedule: str = "auto", **optimizer_kwargs):
+                         num_locations: Optional[int] = None, device="cuda", schedule: str = "auto",
+                         timings: Optional[dict] = None, **optimizer_kwargs):
     """BASELINE cfg 5: the per-class pipeline for every class (class index -> this rank's spectrograms of that class).
 
     Single process, or ``schedule='shard'``: class after class, the rows of a class sharded over all ranks (one exchange
@@ -150,14 +151,23 @@ def all_classes_pipeline(model, data_by_class: Dict[int, torch.Tensor], composit
                                             **optimizer_kwargs)
         return out
     from scipy.stats import ortho_group
+    import time
     dev = torch.device(device)
     rank, world = dist.get_rank(), dist.get_world_size()
     classes = list(data_by_class.keys())
+
+    def mark(name, t0):                                   # optional wall-clock breakdown (synchronises: diagnostics only)
+        if timings is not None:
+            torch.cuda.synchronize(dev)
+            timings[name] = timings.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+    t0 = time.perf_counter()
     # ---- stage 1 for every class on this rank's samples
     acts, ctxs = {}, {}
     for pos, class_idx in enumerate(classes):
         acts[pos], ctxs[pos] = pp.extract_context_pairs(model, data_by_class[class_idx], composite, layer_idx, class_idx,
                                                         num_locations=num_locations, normalize=True, device=dev)
+    t0 = mark("stage1_all_classes", t0)
     mine = torch.tensor([acts[p].size(0) for p in range(len(classes))], dtype=torch.int64, device=dev)
     counts = torch.zeros(world, len(classes), dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(counts, mine)
@@ -171,8 +181,10 @@ def all_classes_pipeline(model, data_by_class: Dict[int, torch.Tensor], composit
             if len(ranks) > 1:
                 _subgroup(ranks)
     for round_plan in plan:
+        t0 = time.perf_counter()
         act = redistribute_rows(acts, round_plan, counts, rank, world)
         ctx = redistribute_rows(ctxs, round_plan, counts, rank, world)
+        t0 = mark("redistribute_rows", t0)
         my = next(((c, ranks) for c, ranks in round_plan if rank in ranks), None)
         if my is not None:
             pos, ranks = my
@@ -193,6 +205,8 @@ def all_classes_pipeline(model, data_by_class: Dict[int, torch.Tensor], composit
             results[pos] = (opt.U, torch.as_tensor(opt.obj_history, device=dev), act.size(0))
             del opt
         del act, ctx
+        mark(f"drsa_round_{len(round_plan)}_classes", t0)
+    t0 = time.perf_counter()
     # ---- every rank ends with every class's U and objective history (d*m floats per class from the group's first rank)
     out = {}
     for round_plan in plan:
@@ -212,4 +226,5 @@ def all_classes_pipeline(model, data_by_class: Dict[int, torch.Tensor], composit
             dist.broadcast(hist, src)
             rows = results[pos][2] if pos in results else 0
             out[classes[pos]] = (U, hist.cpu().numpy(), rows)
+    mark("broadcast_results", t0)
     return out
