@@ -727,7 +727,13 @@ def run_cfg5(args, dev, rank, world):
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     if rank == 0:
         sampler.start()
-    class_pipeline(net, batch()[:64], comp, 33, 0, None, num_concepts=4, steps=8, precision=args.precision)   # warm-up
+    # warm-up: the same schedule on 64 samples per class and rank, 8 steps -- plans, engine-pass graphs, the NCCL channels of
+    # the all-to-all and of the sub-groups and their peer-memory exchanges are set up here, not inside the timed region
+    # (the first all-to-all of a process group alone took 8.5 s of the 11.4 s a cold 8-GPU run needed)
+    warm = {c: batch()[:64].contiguous() for c in range(classes)}
+    for _ in range(2):
+        all_classes_pipeline(net, warm, comp, 33, None, num_concepts=4, steps=8, precision=args.precision)
+    del warm
     data = {c: batch() for c in range(classes)}                 # this rank's spectrograms of every class, resident
     sync()
     t0 = time.perf_counter()

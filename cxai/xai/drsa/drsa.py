@@ -70,9 +70,13 @@ _PRECISIONS = {"fp32": _L.PREC_FP32, "tc": _L.PREC_TC_F16, "tc_split": _L.PREC_T
 # rows, where every 8 steps gives 3.1e-4 rad -- small problems correct twice as often.
 DC_EVERY = 16
 DC_EVERY_SMALL = 8
+DC_EVERY_LARGE = 32          # from 524 288 rows: the correction itself shrinks like 1/sqrt(M) (simulation at cfg 2: 4.2e-5 rad at
+                             # n = 8, 4.8e-5 at 16, 5.8e-5 at 32; measured by bench.py's parity block)
 
 
 def dc_every(M_global: int) -> int:
+    if M_global >= 2 * _AUTO_DC_FROM:
+        return DC_EVERY_LARGE
     return DC_EVERY if M_global >= _AUTO_DC_FROM else DC_EVERY_SMALL
 _PACK_CHUNK_ROWS = 1 << 20          # rows per host->device chunk when the fp32 rows do not fit next to the packed copy
 
