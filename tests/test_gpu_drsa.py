@@ -370,3 +370,22 @@ def test_batched_subset_objectives_match_obj_val_per_subset():
     for max_rows in (1 << 21, 5 * R):
         got = subset_objectives(A.cuda(), C.cuda(), U.cuda(), S, R, K, max_rows=max_rows).cpu().numpy()
         np.testing.assert_allclose(got, want, rtol=2e-5)
+
+
+@pytest.mark.parametrize("prec", ["auto", "tc_dc"])
+def test_padded_production_shape_in_the_default_arithmetic(prec):
+    """The reference's production split layer 19 (arch A: d = 100, K = 4 x 25, getdrsadata.py:72-73,119) at a row count where
+    'auto' takes the tensor cores: the problem runs zero-padded to d = 128 with hi + lo row planes ('tc_hilo') or the deferred
+    correction, and must follow the reference algorithm like any native shape."""
+    from cxai.xai.drsa.drsa import SubspaceOptimizer
+    d, K, M, steps = 100, 4, 70000, 40
+    A, C = drsa_ref.synth_pairs(M, d, 930)
+    U0 = drsa_ref.synth_U0(d, seed=931)
+    opt = SubspaceOptimizer(U0, A, C, None, num_concepts=K, device="cuda", precision=prec)
+    assert opt._pad is not None and opt.precision == ("tc_hilo" if prec == "auto" else "tc_dc")
+    opt.run(steps=steps, save=False)
+    objs_ref, U_ref = drsa_ref.run_autograd(A, C, U0, K, steps)
+    rel = float(np.max(np.abs(opt.obj_history - objs_ref) / np.abs(objs_ref)))
+    ang = drsa_ref.principal_angle(opt.U.cpu(), U_ref, K)
+    assert rel < 1e-4 and ang < 1e-3, (rel, ang)
+    assert tuple(opt.U.shape) == (d, d)
