@@ -20,20 +20,26 @@ REF_OUT = os.path.join(HERE, "_ref")
 REFERENCE_ROOT = os.environ.get("DRSA_REFERENCE_ROOT", "/root/reference")
 
 
+# the files of the hot path and what they import (nothing else of the reference is copied)
+FILES = ["cxai/__init__.py", "cxai/model/__init__.py", "cxai/model/create_model.py", "cxai/xai/__init__.py",
+         "cxai/xai/drsa/__init__.py", "cxai/xai/drsa/drsa.py", "cxai/xai/drsa/preprocessing.py",
+         "cxai/xai/explain/__init__.py", "cxai/xai/explain/attribute.py", "cxai/utils/__init__.py",
+         "cxai/utils/constants.py", "cxai/utils/dataloading.py", "cxai/utils/sound.py", "cxai/utils/utilities.py"]
+
+
 def make() -> bool:
     src = os.path.join(REFERENCE_ROOT, "cxai")
     if not os.path.isdir(src):
         return os.path.isfile(os.path.join(REF_OUT, "MANIFEST.json"))
+    shutil.rmtree(os.path.join(REF_OUT, "cxai"), ignore_errors=True)
     manifest = {}
-    for root, _, files in os.walk(src):
-        for f in sorted(files):
-            if not f.endswith(".py"):
-                continue
-            rel = os.path.relpath(os.path.join(root, f), REFERENCE_ROOT)
-            dst = os.path.join(REF_OUT, rel)
-            os.makedirs(os.path.dirname(dst), exist_ok=True)
-            shutil.copyfile(os.path.join(root, f), dst)
-            manifest[rel] = hashlib.sha256(open(dst, "rb").read()).hexdigest()
+    for rel in FILES:
+        if not os.path.isfile(os.path.join(REFERENCE_ROOT, rel)):
+            continue
+        dst = os.path.join(REF_OUT, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(REFERENCE_ROOT, rel), dst)
+        manifest[rel] = hashlib.sha256(open(dst, "rb").read()).hexdigest()
     with open(os.path.join(REF_OUT, "MANIFEST.json"), "w") as fh:
         json.dump({"source": "sharckhai/drsa-audio (verbatim copies, see oracle/make_ref.py)", "files": manifest}, fh, indent=1)
     return True
