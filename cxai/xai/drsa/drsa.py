@@ -435,7 +435,7 @@ class SubspaceOptimizer:
             if precision == "auto" and native_tc:
                 precision = _auto_precision(self.M_global, avg_rows, d, m, num_concepts)
             plan, pad_prec = None, precision
-            if not native_tc and m == d and (precision in ("tc", "tc_split", "tc_hilo", "tc32") or
+            if not native_tc and m == d and (precision in ("tc", "tc_split", "tc_hilo", "tc_dc", "tc32") or
                                              (precision == "auto" and avg_rows >= 65536)):
                 plan = _pad_plan(d, m, num_concepts, avg_rows)
                 if plan is not None and precision == "auto":
