@@ -341,9 +341,11 @@ __device__ __forceinline__ void write_outputs(const FusedParams& p, int r, int c
 // coalesced along its own rows, and every CTA takes its share of the blocks.  (Evaluating it as <grad f, U> - f through
 // Euler's identity -- f is homogeneous of degree 2 -- avoids reading U^ but makes the objective inherit the full rounding
 // of the gradient accumulation: 2e-4 .. 1e-3 relative at 2 .. 2.5 M rows per GPU; measured and discarded.)
+// write_y: the same pass also forms Y = U + grad (the ascent step of drsa.py:102), so that every element of the (possibly
+// peer-reduced) row sums is read exactly once.
 template <typename SumsFn>
 __device__ __forceinline__ float objective_correction(const FusedParams& p, const float* coef, SumsFn S, float (*tu)[33],
-                                                       float (*tg)[33]) {
+                                                       float (*tg)[33], bool write_y) {
   const int d = p.d, m = p.m, d_k = m / p.K;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int tm = m / 32, td = d / 32;
@@ -355,9 +357,12 @@ __device__ __forceinline__ float objective_correction(const FusedParams& p, cons
       const int kk = ty + 8 * r;
       const int64_t i = (int64_t)(k0 + kk) * m + c0 + tx;
       const float u = p.U[i];
+      const float gr = coef[(c0 + tx) / d_k] * S(i);
       tu[kk][tx] = u;
-      tg[kk][tx] = coef[(c0 + tx) / d_k] * S(i);
+      tg[kk][tx] = gr;
+      if (write_y) p.Y[i] = u + gr;
     }
+    if (!p.u_rounded) continue;          // (uniform) only the ascent step was wanted: the tiles are not read
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -427,20 +432,19 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
         if (K <= 64) coef[k] = (float)((double)root * p.inv_M / ((double)K * (double)q * sqrt((double)q)));
       }
       __syncthreads();
-      if (!fuse0) {
-        for (int64_t i = gtid; i < n; i += gthreads) {
+      if (K <= 64) {
+        // ascent step (unless it is fused into the first Gram phase) and first-order objective term in ONE pass over
+        // 32 x 32 blocks: every element of the row sums (a sum over the ranks' inbox slots under data parallelism) is read once
+        const bool want_y = !fuse0 && p.U_out != nullptr;
+        if (want_y || p.u_rounded) corr = objective_correction(p, coef, S, tile_u, tile_g, want_y);
+      } else if (!fuse0) {
+        for (int64_t i = gtid; i < n; i += gthreads) {     // exotic K > 64: factor recomputed per element, no tensor-core modes
           const int k = (int)(i % m) / d_k;
-          float c;
-          if (K <= 64) c = coef[k];
-          else {
-            const float q = sqrtf((float)((double)S(n + k) * p.inv_M));
-            c = (float)((double)root * p.inv_M / ((double)K * (double)q * sqrt((double)q)));
-          }
-          const float u = p.U[i], gr = c * S(i);
-          if (p.U_out != nullptr) p.Y[i] = u + gr;
+          const float q = sqrtf((float)((double)S(n + k) * p.inv_M));
+          const float c = (float)((double)root * p.inv_M / ((double)K * (double)q * sqrt((double)q)));
+          if (p.U_out != nullptr) p.Y[i] = p.U[i] + c * S(i);
         }
       }
-      if (p.u_rounded && K <= 64) corr = objective_correction(p, coef, S, tile_u, tile_g);
     }
     if (p.u_rounded) {
       const float tot = block_sum(corr, red);
