@@ -225,8 +225,10 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
           const float4 sv = *reinterpret_cast<const float4*>(dst + 2 * Kdim * LDT);      // its staged sums segment
           const float cf = f.coef[c0 / f.d_k];                     // 4 consecutive columns share a concept (d_k % 4 == 0)
           float4 uu = *reinterpret_cast<float4*>(dst);
-          const float4 gr = make_float4(cf * sv.x, cf * sv.y, cf * sv.z, cf * sv.w);
-          uu.x += gr.x; uu.y += gr.y; uu.z += gr.z; uu.w += gr.w;
+          // Y = fma(coef, sums, U) everywhere (here, objective_correction, finish_small_kernel): one rounding, so that the
+          // fused and the separate ascent -- i.e. the NCCL and the peer-memory exchange -- give the same bits
+          uu.x = __fmaf_rn(cf, sv.x, uu.x); uu.y = __fmaf_rn(cf, sv.y, uu.y);
+          uu.z = __fmaf_rn(cf, sv.z, uu.z); uu.w = __fmaf_rn(cf, sv.w, uu.w);
           *reinterpret_cast<float4*>(dst) = uu;
           if (ab == 0 && f.write_a) *reinterpret_cast<float4*>(f.Y_out + (int64_t)k * f.m + c0) = uu;
         }
@@ -357,10 +359,10 @@ __device__ __forceinline__ float objective_correction(const FusedParams& p, cons
       const int kk = ty + 8 * r;
       const int64_t i = (int64_t)(k0 + kk) * m + c0 + tx;
       const float u = p.U[i];
-      const float gr = coef[(c0 + tx) / d_k] * S(i);
+      const float cf = coef[(c0 + tx) / d_k], sv = S(i);
       tu[kk][tx] = u;
-      tg[kk][tx] = gr;
-      if (write_y) p.Y[i] = u + gr;
+      tg[kk][tx] = __fmul_rn(cf, sv);
+      if (write_y) p.Y[i] = __fmaf_rn(cf, sv, u);
     }
     if (!p.u_rounded) continue;          // (uniform) only the ascent step was wanted: the tiles are not read
     __syncthreads();
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
           const int k = (int)(i % m) / d_k;
           const float q = sqrtf((float)((double)S(n + k) * p.inv_M));
           const float c = (float)((double)root * p.inv_M / ((double)K * (double)q * sqrt((double)q)));
-          if (p.U_out != nullptr) p.Y[i] = p.U[i] + c * S(i);
+          if (p.U_out != nullptr) p.Y[i] = __fmaf_rn(c, S(i), p.U[i]);
         }
       }
     }
@@ -756,19 +758,20 @@ __global__ void __launch_bounds__(256) finish_small_kernel(FusedParams p) {
               const float cf = coef[c / d_k];            // d_k % 4 == 0 or the four columns are handled one by one below
               float* dst = &Ys[r * SLD + c];
               if (d_k % 4 == 0) {
-                dst[0] = uv[q].x + cf * sv[q].x; dst[1] = uv[q].y + cf * sv[q].y;
-                dst[2] = uv[q].z + cf * sv[q].z; dst[3] = uv[q].w + cf * sv[q].w;
+                dst[0] = __fmaf_rn(cf, sv[q].x, uv[q].x); dst[1] = __fmaf_rn(cf, sv[q].y, uv[q].y);
+                dst[2] = __fmaf_rn(cf, sv[q].z, uv[q].z); dst[3] = __fmaf_rn(cf, sv[q].w, uv[q].w);
               } else {
-                dst[0] = uv[q].x + coef[c / d_k] * sv[q].x; dst[1] = uv[q].y + coef[(c + 1) / d_k] * sv[q].y;
-                dst[2] = uv[q].z + coef[(c + 2) / d_k] * sv[q].z; dst[3] = uv[q].w + coef[(c + 3) / d_k] * sv[q].w;
+                dst[0] = __fmaf_rn(coef[c / d_k], sv[q].x, uv[q].x); dst[1] = __fmaf_rn(coef[(c + 1) / d_k], sv[q].y, uv[q].y);
+                dst[2] = __fmaf_rn(coef[(c + 2) / d_k], sv[q].z, uv[q].z); dst[3] = __fmaf_rn(coef[(c + 3) / d_k], sv[q].w, uv[q].w);
               }
             }
         }
       } else
       for (int i = tid; i < n; i += blockDim.x) {
         const int r = i / m, c = i % m;
-        const float u = p.U[i], gr = coef[c / d_k] * S(i);
-        Ys[r * SLD + c] = u + gr;
+        const float cf = coef[c / d_k], sv = S(i);
+        const float u = p.U[i], gr = __fmul_rn(cf, sv);
+        Ys[r * SLD + c] = __fmaf_rn(cf, sv, u);
         if (p.u_rounded)         // first-order objective term, see objective_correction
           gu = fmaf(gr, u - (p.u_rounded == 2 ? __half2float(p.Ut_hi[(int64_t)c * d + r]) : __half2float(__float2half_rn(u))), gu);
       }
