@@ -390,6 +390,8 @@ class SubspaceOptimizer:
             as it has converged: 4-5 sweeps in a normal step; the first steps of a tiny problem, where the
             gradient dwarfs U, need 15-25).
         use_cuda_graph: capture one step and replay it (single process, or several ranks with the peer exchange).
+        retraction: 'polar' (default: the reference's retraction) or 'qr' (Q of the QR factorisation with positive diagonal,
+            for comparison only: a different trajectory; fp32, single rank).
         exchange: how the ``d*m + K`` row sums are joined across ranks: 'p2p' = inside the finish kernel over
             NVLink peer memory (drsa_finish_step_p2p; buffers shared through cudaIpc), 'p2p_symm' = the same with
             torch symmetric memory, 'nccl' = ``all_reduce`` between the two kernels, 'auto' = 'p2p' when the process
@@ -399,11 +401,21 @@ class SubspaceOptimizer:
     def __init__(self, U: torch.Tensor, activation_vecs: torch.Tensor, context_vecs: torch.Tensor,
                  path_to_model: Optional[str], num_concepts: int = 4, device=_DEFAULT_DEVICE, *,
                  precision: str = "auto", process_group=None, retraction_iters: int = 40,
-                 retraction_tol: float = 1e-6, use_cuda_graph: bool = True, exchange: str = "auto") -> None:
+                 retraction_tol: float = 1e-6, use_cuda_graph: bool = True, exchange: str = "auto",
+                 retraction: str = "polar") -> None:
         assert num_concepts > 0, "num_concepts must be a positive number"
         assert U.size(1) % num_concepts == 0, "num_concepts must be a divisor of the number of columns of U"
         assert activation_vecs.shape == context_vecs.shape and activation_vecs.dim() == 2
         assert activation_vecs.size(1) == U.size(0), "vector dimension must equal the number of rows of U"
+        if retraction not in ("polar", "qr"):
+            raise ValueError("retraction must be 'polar' (the reference's, drsa.py:201-221) or 'qr'")
+        if retraction == "qr":
+            # comparison only (BASELINE north_star (3)): Q of QR(U + grad) with diag(R) > 0 is NOT the reference's
+            # retraction and the trajectories differ; fp32 arithmetic, single rank
+            if precision not in ("auto", "fp32"):
+                raise _L.DRSAError("retraction='qr' runs in fp32 arithmetic only")
+            precision, process_group = "fp32", False
+        self.retraction = retraction
         self.device = _as_device(device)
         self.path_to_model = path_to_model
         self.num_concepts = num_concepts
@@ -535,6 +547,12 @@ class SubspaceOptimizer:
     # ------------------------------------------------------------------ one step
     def _step(self, obj_log: torch.Tensor, log_index: int, update: bool, correct: bool = True) -> None:
         self._rows.step(self._Uw, correct)
+        if self.retraction == "qr":
+            r = self._rows
+            _L.check(r.lib.drsa_finish_step_qr(_ptr(r.sums), self.M_global, _ptr(self._Uw), r.d, r.m, r.K,
+                                               _ptr(self._Uw) if update else None, _ptr(obj_log), log_index, _ptr(r.status),
+                                               _ptr(r.ws_fin), r.ws_fin.numel(), _stream()), "drsa_finish_step_qr")
+            return
         if self._dist and self._px is None:
             torch.distributed.all_reduce(self._rows.sums, group=self._group)   # d*m + K floats over NVLink
         self._rows.finish(self._Uw, self.M_global, obj_log, log_index, update, self.retraction_iters,
@@ -670,8 +688,9 @@ def project_grad(gradient: torch.Tensor, U: torch.Tensor) -> torch.Tensor:
 
 
 @torch.no_grad()
-def orthogonalize(U: torch.Tensor, max_iters: int = 24, tol: float = 1e-6) -> torch.Tensor:
-    """U (U^T U)^(-1/2) -- the reference's retraction (drsa.py:201-221), computed on the device."""
+def orthogonalize(U: torch.Tensor, max_iters: int = 24, tol: float = 1e-6, method: str = "polar") -> torch.Tensor:
+    """U (U^T U)^(-1/2) -- the reference's retraction (drsa.py:201-221), computed on the device.  ``method='qr'`` returns Q of
+    the thin QR factorisation with diag(R) > 0 instead (comparison only: not the reference's retraction)."""
     dev = _as_device(U.device if U.is_cuda else _DEFAULT_DEVICE)
     lib = _L.lib()
     with torch.cuda.device(dev):
@@ -680,6 +699,10 @@ def orthogonalize(U: torch.Tensor, max_iters: int = 24, tol: float = 1e-6) -> to
         out = torch.empty_like(Y)
         ws = torch.empty(int(_L.check(lib.drsa_finish_workspace_bytes(d, m))), dtype=torch.uint8, device=dev)
         status = torch.zeros(4, dtype=torch.int32, device=dev)
+        if method == "qr":
+            _L.check(lib.drsa_qr_retract(_ptr(Y), d, m, _ptr(out), _ptr(status), _ptr(ws), ws.numel(), _stream()),
+                     "drsa_qr_retract")
+            return out.to(U.dtype)
         _L.check(lib.drsa_polar_retract(_ptr(Y), d, m, _ptr(out), max_iters, tol, _ptr(status), _ptr(ws), ws.numel(),
                                         _stream()), "drsa_polar_retract")
     return out.to(U.dtype)

@@ -54,6 +54,8 @@ SIGNATURES = {
     "drsa_rownorm_max": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "drsa_split_u": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "drsa_sums_combine": (_i32, [_vp, _vp, _f32, _vp, _i64, _vp]),
+    "drsa_qr_retract": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "drsa_finish_step_qr": (_i32, [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     "drsa_finish_workspace_bytes": (_i64, [_i32, _i32]),
     "drsa_finish_step": (_i32, [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp,
                                 _i64, _vp]),

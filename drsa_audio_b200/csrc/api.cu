@@ -106,6 +106,10 @@ int64_t exchange_bytes(int d, int m, int K, int world);
 int polar_retract(const float* Y, int d, int m, float* U_out, int max_iters, float tol, int* status, void* workspace,
                   int64_t workspace_bytes, cudaStream_t stream);
 int split_u(const float* U, int d, int m, void* Ut_hi, void* Ut_lo, cudaStream_t stream);
+int finish_step_qr(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out, float* obj_log,
+                   int64_t log_index, int* status, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+int qr_retract(const float* Y, int d, int m, float* U_out, int* status, void* workspace, int64_t workspace_bytes,
+               cudaStream_t stream);
 int selftest_umma(int variant, float* max_err_host);
 void set_tc_profile(long long* p);
 int tc_kernel_attrs(int d, int split, int* out5);
@@ -214,6 +218,24 @@ int drsa_step(const void* A, const void* C, const float* U, const void* Ut_hi, c
                    workspace_bytes, s);
   }
   return DRSA_ERR_ARG;
+}
+
+int drsa_finish_step_qr(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out,
+                        float* obj_log, int64_t log_index, int* status, void* workspace, int64_t workspace_bytes,
+                        void* stream) {
+  if (sums == nullptr || U == nullptr || status == nullptr || workspace == nullptr || M_global <= 0 || d <= 0 || m <= 0 ||
+      m > d || K <= 0 || m % K != 0)
+    return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return finish_step_qr(sums, M_global, U, d, m, K, U_out, obj_log, log_index, status, workspace, workspace_bytes,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int drsa_qr_retract(const float* Y, int d, int m, float* U_out, int* status, void* workspace, int64_t workspace_bytes,
+                    void* stream) {
+  if (Y == nullptr || U_out == nullptr || workspace == nullptr || d <= 0 || m <= 0 || m > d) return DRSA_ERR_ARG;
+  DRSA_TRY(require_sm100());
+  return qr_retract(Y, d, m, U_out, status, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int drsa_sums_combine(const float* a, const float* b, float beta, float* out, int64_t n, void* stream) {

@@ -181,6 +181,76 @@ __global__ void split_u_kernel(const float* __restrict__ U, int d, int m, __half
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// QR retraction (NON-DEFAULT option, BASELINE.json north_star (3)): Q of the thin QR factorisation Y = QR with diag(R) > 0
+// (what a Householder QR with sign fix returns; the factorisation with positive diagonal is unique).  The reference's
+// retraction is the POLAR factor (drsa.py:201-221) and the two differ by 7.6 % per step: trajectories obtained
+// with this option do not follow the reference.  One CTA (a cluster of one), classical Gram-Schmidt with
+// re-orthogonalisation (CGS2, as accurate as Householder for this purpose), Q kept transposed [m][d] so that every
+// column is contiguous: per column two rounds of { h = Q_<j^T v ; v -= Q_<j h }, then v / ||v||.
+__global__ void __launch_bounds__(1024) qr_retract_kernel(const float* __restrict__ Y, int d, int m, float* __restrict__ Qt,
+                                                          float* __restrict__ U_out, __half* __restrict__ Ut_hi,
+                                                          __half* __restrict__ Ut_lo, int* __restrict__ status) {
+  extern __shared__ float sh[];          // v[d] | h[m] | red[32]
+  float* v = sh;
+  float* h = sh + d;
+  float* red = sh + d + m;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  int rank_deficient = 0;
+  for (int j = 0; j < m; ++j) {
+    for (int t = tid; t < d; t += blockDim.x) v[t] = Y[(int64_t)t * m + j];
+    __syncthreads();
+    for (int round = 0; round < 2; ++round) {
+      for (int i = warp; i < j; i += nwarp) {                    // h_i = q_i . v
+        const float* q = Qt + (int64_t)i * d;
+        float s = 0.f;
+        for (int t = lane; t < d; t += 32) s = fmaf(q[t], v[t], s);
+        s = warp_sum(s);
+        if (lane == 0) h[i] = s;
+      }
+      __syncthreads();
+      for (int t = tid; t < d; t += blockDim.x) {                // v -= sum_i h_i q_i   (fixed order: deterministic)
+        float a = v[t];
+        for (int i = 0; i < j; ++i) a = fmaf(-h[i], Qt[(int64_t)i * d + t], a);
+        v[t] = a;
+      }
+      __syncthreads();
+    }
+    float s = 0.f;
+    for (int t = tid; t < d; t += blockDim.x) s = fmaf(v[t], v[t], s);
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    float nrm2 = 0.f;
+    for (int w = 0; w < nwarp; ++w) nrm2 += red[w];
+    if (!(nrm2 > 1e-30f)) rank_deficient = 1;
+    const float inv = nrm2 > 1e-30f ? rsqrtf(nrm2) : 0.f;         // R_jj = ||v|| > 0: the sign fix is built in
+    for (int t = tid; t < d; t += blockDim.x) Qt[(int64_t)j * d + t] = v[t] * inv;
+    __syncthreads();                                               // also publishes Qt[j] (global) to the whole CTA
+  }
+  __threadfence_block();
+  for (int64_t i = tid; i < (int64_t)d * m; i += blockDim.x) {
+    const int r = (int)(i / m), c = (int)(i % m);
+    const float q = Qt[(int64_t)c * d + r];
+    U_out[i] = q;
+    if (Ut_hi != nullptr) {
+      const __half hi = __float2half_rn(q);
+      Ut_hi[(int64_t)c * d + r] = hi;
+      if (Ut_lo != nullptr) Ut_lo[(int64_t)c * d + r] = __float2half_rn(q - __half2float(hi));
+    }
+  }
+  if (tid == 0 && status != nullptr) { status[0] = 0; if (rank_deficient) status[1] += 1; }
+}
+
+int qr_from_Y(const float* Y, int d, int m, float* Qt, float* U_out, void* Ut_hi, void* Ut_lo, int* status,
+              cudaStream_t stream) {
+  const int smem = (d + m + 32) * 4;
+  qr_retract_kernel<<<1, 1024, smem, stream>>>(Y, d, m, Qt, U_out, static_cast<__half*>(Ut_hi), static_cast<__half*>(Ut_lo),
+                                                status);
+  DRSA_LAUNCH_CHECK();
+  return DRSA_OK;
+}
+
 int polar_from_Y(const PolarWs& p, int d, int m, float* U_out, void* Ut_hi, void* Ut_lo, int max_iters,
                  float tol, int* status, cudaStream_t stream) {
   GemmDesc gram{};
@@ -257,6 +327,29 @@ int polar_retract(const float* Y, int d, int m, float* U_out, int max_iters, flo
   PolarWs p = carve(workspace, d, m);
   DRSA_CUDA(cudaMemcpyAsync(p.Y, Y, (int64_t)d * m * 4, cudaMemcpyDeviceToDevice, stream));
   return polar_from_Y(p, d, m, U_out, nullptr, nullptr, max_iters, tol, status, stream);
+}
+
+// The finish step with the QR retraction instead of the polar factor (non-default; fp32 arithmetic, single rank).
+int finish_step_qr(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out, float* obj_log,
+                   int64_t log_index, int* status, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  if (workspace_bytes < polar_ws_bytes(d, m)) return DRSA_ERR_WORKSPACE;
+  if ((d + m + 32) * 4 > 48 * 1024) return DRSA_ERR_SHAPE;
+  PolarWs p = carve(workspace, d, m);
+  const int64_t n = (int64_t)d * m;
+  const int eb = U_out == nullptr ? 1 : (cdiv(n, 256) < 592 ? cdiv(n, 256) : 592);
+  ascent_kernel<<<eb, 256, K * sizeof(float), stream>>>(sums, 1.0 / (double)M_global, U, d, m, K,
+                                                        U_out == nullptr ? nullptr : p.Y, obj_log, log_index, status);
+  DRSA_LAUNCH_CHECK();
+  if (U_out == nullptr) return DRSA_OK;
+  return qr_from_Y(p.Y, d, m, p.X0, U_out, nullptr, nullptr, status, stream);
+}
+
+int qr_retract(const float* Y, int d, int m, float* U_out, int* status, void* workspace, int64_t workspace_bytes,
+               cudaStream_t stream) {
+  if (workspace_bytes < polar_ws_bytes(d, m)) return DRSA_ERR_WORKSPACE;
+  if ((d + m + 32) * 4 > 48 * 1024) return DRSA_ERR_SHAPE;
+  PolarWs p = carve(workspace, d, m);
+  return qr_from_Y(Y, d, m, p.X0, U_out, nullptr, nullptr, status, stream);
 }
 
 int split_u(const float* U, int d, int m, void* Ut_hi, void* Ut_lo, cudaStream_t stream) {

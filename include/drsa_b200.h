@@ -207,6 +207,17 @@ int drsa_ipc_free(void* ptr);
 int drsa_polar_retract(const float* Y, int d, int m, float* U_out, int max_iters, float tol,
                        int* status, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* NON-DEFAULT retraction, BASELINE.json north_star (3): U_out = Q of the thin QR factorisation of Y with diag(R) > 0 (the
+ * result of a Householder QR with sign fix; one CTA, Gram-Schmidt with re-orthogonalisation).  The reference retracts with
+ * the POLAR factor (drsa.py:201-221); QR yields a different U every step and a different optimisation trajectory
+ * (SURVEY F1), so this exists for comparison only.  drsa_finish_step_qr = drsa_finish_step (fp32 sums, single rank,
+ * u_rounded = 0) with this retraction; workspace as drsa_finish_workspace_bytes; status[1] counts rank-deficient inputs. */
+int drsa_qr_retract(const float* Y, int d, int m, float* U_out, int* status, void* workspace, int64_t workspace_bytes,
+                    void* stream);
+int drsa_finish_step_qr(const float* sums, int64_t M_global, const float* U, int d, int m, int K, float* U_out,
+                        float* obj_log, int64_t log_index, int* status, void* workspace, int64_t workspace_bytes,
+                        void* stream);
+
 /* Per-instance concept relevances, no ReLU, summed over positions
  * (cxai/xai/explain/explainer.py:206-242): out[b][k] = sum_p sum_{j in k} (a U)_j (c U)_j
  *   act, ctx [B, P, d] fp32, U [d, m], out [B, K]. */

@@ -54,6 +54,13 @@ def orthogonalize(U: torch.Tensor) -> torch.Tensor:
     return torch.matmul(U, inv)
 
 
+def orthogonalize_qr(Y: torch.Tensor) -> torch.Tensor:
+    """Q of the thin QR factorisation with diag(R) > 0 (Householder QR + sign fix).  NOT the reference's retraction; the
+    yardstick of the non-default ``retraction='qr'`` option only."""
+    Q, R = torch.linalg.qr(Y.double())
+    return (Q * torch.sign(torch.diagonal(R))[None, :]).to(Y.dtype)
+
+
 def step_autograd(act, ctx, U, num_concepts: int):
     """One iteration of drsa.py:84-104: objective, autograd gradient, U <- polar(U + grad)."""
     d_k = U.shape[1] // num_concepts

@@ -389,3 +389,35 @@ def test_padded_production_shape_in_the_default_arithmetic(prec):
     ang = drsa_ref.principal_angle(opt.U.cpu(), U_ref, K)
     assert rel < 1e-4 and ang < 1e-3, (rel, ang)
     assert tuple(opt.U.shape) == (d, d)
+
+
+@pytest.mark.parametrize("d,m", [(64, 64), (128, 128), (256, 256), (256, 128), (512, 512)])
+def test_qr_retraction_option_matches_householder_qr_with_sign_fix(d, m):
+    """Non-default option (BASELINE north_star (3)): Q of the thin QR factorisation with diag(R) > 0."""
+    from cxai.xai.drsa.drsa import orthogonalize
+    g = torch.Generator().manual_seed(7 * d + m)
+    Y = drsa_ref.synth_U0(d, m, 3) + 0.3 * torch.randn(d, m, generator=g) / d ** 0.5
+    got = orthogonalize(Y.cuda(), method="qr").cpu().double()
+    want = drsa_ref.orthogonalize_qr(Y.double())
+    assert float((got - want).abs().max()) < 5e-6
+    assert float((got.T @ got - torch.eye(m, dtype=torch.float64)).abs().max()) < 5e-6
+
+
+def test_qr_retraction_gives_another_trajectory_than_the_reference():
+    """retraction='qr' follows ITS oracle (same steps with a QR retraction) and, as SURVEY F1 states, not the reference."""
+    from cxai.xai.drsa.drsa import SubspaceOptimizer
+    M, d, K, steps = 3000, 64, 4, 8
+    A, C = drsa_ref.synth_pairs(M, d, 61)
+    U0 = drsa_ref.synth_U0(d, d, 62)
+    opt = SubspaceOptimizer(U0, A, C, None, num_concepts=K, device="cuda", retraction="qr")
+    opt.run(steps=steps, save=False)
+    U, objs = U0.double(), []
+    for _ in range(steps):
+        o, g, _ = drsa_ref.step_closed_form(A.double(), C.double(), U, K)
+        objs.append(float(o))
+        U = drsa_ref.orthogonalize_qr(U + g)
+    objs.append(float(drsa_ref.finish_from_sums(*drsa_ref.step_sums(A.double(), C.double(), U, K), M, K)[0]))
+    np.testing.assert_allclose(opt.obj_history, np.asarray(objs), rtol=1e-4)
+    assert float((opt.U.cpu().double() - U).abs().max()) < 1e-4
+    objs_ref, U_ref = drsa_ref.run_autograd(A, C, U0, K, steps)
+    assert np.max(np.abs(opt.obj_history - objs_ref) / objs_ref) > 1e-3          # a different trajectory
