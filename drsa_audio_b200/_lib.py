@@ -103,6 +103,7 @@ SIGNATURES = {
     "drsa_debug_set_tc_profile": (_i32, [_vp]),
     "drsa_debug_tc_kernel_attrs": (_i32, [_i32, _i32, _vp]),
     "drsa_debug_set_tc_variant": (_i32, [_i32]),
+    "lrp_debug_set_conv_variant": (_i32, [_i32]),
 }
 
 MAX_PEERS = 8

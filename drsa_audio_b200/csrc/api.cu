@@ -114,6 +114,7 @@ int selftest_umma(int variant, float* max_err_host);
 void set_tc_profile(long long* p);
 int tc_kernel_attrs(int d, int split, int* out5);
 void set_tc_variant(int v);
+void set_conv_variant(int v);
 int64_t subspace_relevances_workspace_bytes(int64_t B, int64_t P, int d, int m);
 int subset_objectives(const float* act, const float* ctx, const float* U, int64_t S, int64_t R, int d, int m, int K,
                       float* obj, float* sumsq, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
@@ -638,6 +639,7 @@ int logmel_transform_wav(const float* wav, const float* window, const float* dft
 }
 
 int drsa_debug_set_tc_variant(int variant) { set_tc_variant(variant); return DRSA_OK; }
+int lrp_debug_set_conv_variant(int variant) { set_conv_variant(variant); return DRSA_OK; }
 
 int drsa_debug_tc_kernel_attrs(int d, int split, int* out5) {
   if (out5 == nullptr || (d != 128 && d != 256 && d != 512)) return DRSA_ERR_ARG;

@@ -102,6 +102,7 @@ struct ConvGeom {
   int epi;      // 0: y = relu?(acc + b); 1: y = aux_f32 / stabilize(acc + b, eps); 2: y = (aux_hi + aux_lo) * acc
   float eps;
   int pkh, pkw;   // > 0: MaxPool2d(pkh, pkw) fused into the epi == 0 epilogue (y planes and arg-max are the POOLED maps)
+  int drop_xlo;   // experiment (lrp_debug_set_conv_variant): skip the x_lo * w_hi product (activations at 11 bits)
 };
 
 // kHalo (with resident weights, tiles of th = 8 rows x tw = 16 columns of one image): instead of one TMA box per tap
@@ -235,7 +236,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
               for (int kk = 0; kk < 4; ++kk) {
                 const uint64_t dwh = kdesc(w_hi + 32 * kk);
                 umma_ss_f16(tacc, kdesc(a_hi + 32 * kk), dwh, idesc2, (kx | ky | kk) ? 1u : 0u);   // [x_hi*w_hi | x_hi*w_lo]
-                umma_ss_f16(tacc, kdesc(a_lo + 32 * kk), dwh, idesc, 1u);                         // + x_lo*w_hi
+                if (!g.drop_xlo) umma_ss_f16(tacc, kdesc(a_lo + 32 * kk), dwh, idesc, 1u);        // + x_lo*w_hi
               }
             }
             umma_commit(&empty[stage]);
@@ -256,10 +257,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constan
             const uint64_t dwh = kdesc(w_hi + 32 * kk), dwl = kdesc(w_lo + 32 * kk);
             if (merged) {
               umma_ss_f16(tacc, dah, dwh, idesc2, (it | kk) ? 1u : 0u);      // [x_hi*w_hi | x_hi*w_lo]
-              umma_ss_f16(tacc, dal, dwh, idesc, 1u);                        // + x_lo*w_hi
+              if (!g.drop_xlo) umma_ss_f16(tacc, dal, dwh, idesc, 1u);       // + x_lo*w_hi
             } else {
               umma_ss_f16(tacc, dah, dwh, idesc, (it | kk) ? 1u : 0u);
-              umma_ss_f16(tacc, dal, dwh, idesc, 1u);
+              if (!g.drop_xlo) umma_ss_f16(tacc, dal, dwh, idesc, 1u);
               umma_ss_f16(tacc, dah, dwl, idesc, 1u);
             }
           }
@@ -861,6 +862,10 @@ bool conv_tc_pool_supported(int64_t B, int Cin_p, int Cout_p, int H, int W, int 
   return pow2 && kw <= tw && kh <= 32 / tw && kh * kw <= 255 && H % kh == 0 && W % kw == 0;
 }
 
+// Experiment switch (lrp_debug_set_conv_variant): bit e set = the conv launches with epilogue e skip the x_lo * w_hi product.
+int g_conv_variant = 0;
+void set_conv_variant(int v) { g_conv_variant = v; }
+
 int conv_tc_run(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int64_t B,
                 int H, int W, int Cin_p, int Cout_p, int Cout, int relu, int epi, float eps, const float* aux_f32,
                 const void* aux_hi, const void* aux_lo, void* y_hi, void* y_lo, float* y_f32, float* y_nchw,
@@ -873,6 +878,7 @@ int conv_tc_run(const void* x_hi, const void* x_lo, const void* w_hi, const void
   const bool halo = Cout_p == 64 && Cin_p == 64 && W % kHaloTw == 0 && H % kHaloTh == 0;
   if (halo) { g.nb = 1; g.th = kHaloTh; g.tw = kHaloTw; }
   g.pkh = g.pkw = 0;
+  g.drop_xlo = (g_conv_variant & (1 << epi)) ? 1 : 0;      // bit 0: forward, bit 1: ratio, bit 2: input-multiply
   if (pkh > 0 || pkw > 0) {
     if (epi != 0 || y_f32 != nullptr || y_nchw != nullptr || y_hi == nullptr || !conv_tc_pool_supported(B, Cin_p, Cout_p, H, W, pkh, pkw))
       return DRSA_ERR_SHAPE;

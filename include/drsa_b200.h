@@ -445,6 +445,9 @@ int drsa_debug_tc_kernel_attrs(int d, int split_u, int* out5);
 /* Diagnostics: 0 (default) = the shared-memory-operand row-pass kernel, 1 = DRSA_PREC_TC_F16 with d <= 256 runs the
  * experimental kernel that keeps U^T in tensor memory (correct, measured slower; for A/B comparisons). */
 int drsa_debug_set_tc_variant(int variant);
+/* Diagnostics / experiment: bit e of `variant` makes the tensor-core convolutions with epilogue e (0 forward, 1 ratio,
+ * 2 input-multiply) skip the x_lo * w_hi product, i.e. read their activation operand at 11 instead of 22 bits (default 0). */
+int lrp_debug_set_conv_variant(int variant);
 
 #ifdef __cplusplus
 }
