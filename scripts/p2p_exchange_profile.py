@@ -1,5 +1,5 @@
 """Cost of the fused peer exchange: %globaltimer stamps of CTA 0 of the finish kernel with and without it.
-   torchrun --nproc-per-node 2 scripts/p2p_exchange_profile.py"""
+   torchrun --nproc-per-node N scripts/p2p_exchange_profile.py      (N = 2 .. 8)"""
 import os, sys, torch
 import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -34,9 +34,12 @@ for exch in ("p2p", "nccl"):
         torch.cuda.synchronize()
         v = buf.cpu().tolist(); n = v[15]; st = v[16:16 + n]
         first.append((st[1] - st[0]) / 1e3); total.append((st[-1] - st[0]) / 1e3); ev.append((e0.elapsed_time(e1) * 1e3, e1.elapsed_time(e2) * 1e3))
+        deltas = [(b - a) / 1e3 for a, b in zip(st[:-1], st[1:])]
     L.lib().drsa_debug_set_tc_profile(None)
     med = lambda x: sorted(x)[len(x) // 2]
     print(f"rank {rank} {exch}: phase 0 (incl. exchange) median {med(first):.1f} us, finish kernel {med(total):.1f} us, "
           f"row pass {med([a for a, _ in ev]):.1f} us, after row pass (events) {med([b for _, b in ev]):.1f} us", flush=True)
+    if rank == 0:
+        print(f"rank 0 {exch}: phases of the last finish kernel (us): " + " ".join(f"{v:.1f}" for v in deltas), flush=True)
     del opt
 dist.destroy_process_group()
