@@ -609,7 +609,7 @@ def lrp_cpu_baseline(P: int, n: int = 4):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one drsa_tc_step_kernel launch at cfg2 from the committed
 # ncu --set full capture (profiles/); None until a capture exists.
-TRAFFIC_BYTES_PER_LAUNCH = 662.8e6      # 656.3 MB read + ~6.5 MB written (profiles/r01_ncu_full_drsa_tc_step_kernel_v4.csv)
+TRAFFIC_BYTES_PER_LAUNCH = 661.4e6      # 656.3 MB read + ~5.1 MB written (profiles/r02_ncu_full_drsa_tc_step_kernel.csv)
 
 
 # =========================================================================== CPU baseline / reference arm
