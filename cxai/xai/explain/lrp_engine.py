@@ -910,8 +910,22 @@ def _seed_is_rowwise(fn) -> bool:
 
 def _run_relevance(plan, x, fn, batch_size, seed_rows=None):
     out = []
+    fn_key = getattr(fn, "key", None) if seed_rows is None else None
+    mask_row = None
+
+    def one_pass(xb, mask):
+        logits, saved, _ = plan.forward(xb, keep_from=0, out_index=-1)
+        return (plan.backward(_class_seed(logits, mask, fn_key[2]), saved, stop_after=-1),)
     for i in range(0, x.size(0), batch_size):
-        logits, saved, _ = plan.forward(x[i:i + batch_size], keep_from=0, out_index=-1)
+        xb = x[i:i + batch_size]
+        if USE_GRAPH and fn_key is not None and xb.size(0) >= GRAPH_MIN_SAMPLES and plan.filter_index is None:
+            # full-depth pass of a plain model with the standard class seed: replayed as one CUDA graph (replay_pass)
+            if mask_row is None:
+                mask_row = torch.zeros(plan.ops[-1].cout, device=x.device)
+                mask_row[fn_key[1]] = 1.0
+            out.append(plan.replay_pass(("relevance", tuple(xb.shape), fn_key[2], plan.use_tc), (xb, mask_row), one_pass)[0])
+            continue
+        logits, saved, _ = plan.forward(xb, keep_from=0, out_index=-1)
         seed = fn(logits) if seed_rows is None else seed_rows(logits, i)
         out.append(plan.backward(seed.contiguous(), saved, stop_after=-1))
     return torch.cat(out, 0)

@@ -680,7 +680,15 @@ def test_graph_replay_of_engine_passes_is_bit_identical(monkeypatch):
     assert any(v != "seen" for v in plan._graphs.values())                          # a graph was captured
     for (a, r), (aw, rw) in zip(got, want):
         assert torch.equal(a, aw) and torch.equal(r, rw)
-    # another seed (class) is another graph, not a stale replay
+    # full-depth relevance maps (compute_relevances) replay as well
+    from cxai.xai.explain.attribute import compute_relevances
+    monkeypatch.setattr(lrp_engine, "USE_GRAPH", False)
+    Rw = [compute_relevances(net, x, comp, class_idx=c) for x, c in zip(xs, (1, 1, 4, 7))]
+    monkeypatch.setattr(lrp_engine, "USE_GRAPH", True)
+    Rg = [compute_relevances(net, x, comp, class_idx=c) for x, c in zip(xs, (1, 1, 4, 7))]
+    for a, b in zip(Rg, Rw):
+        assert torch.equal(a, b)
+    # another seed (class) is the same graph with another mask, not a stale replay
     a5, r5 = get_intermediate(net, xs[0], comp, net.features[26], 5)
     monkeypatch.setattr(lrp_engine, "USE_GRAPH", False)
     a5w, r5w = get_intermediate(net, xs[0], comp, net.features[26], 5)
