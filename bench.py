@@ -492,7 +492,8 @@ def lrp_throughput(args, dev, rank, world, barrier):
     # full-depth relevance maps (compute_relevances, attribute.py:70-108: the other output of the same pass)
     from cxai.xai.explain.attribute import compute_relevances
     nf = min(n, 128)
-    compute_relevances(net, x[:nf], comp, class_idx=0)
+    for _ in range(3):                          # plain launches, graph capture, replay
+        compute_relevances(net, x[:nf], comp, class_idx=0)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()

@@ -710,7 +710,7 @@ class LRPPlan:
 ENGINE_CHUNK = 256
 USE_GRAPH = True             # replay whole engine passes as CUDA graphs (LRPPlan.replay_pass)
 GRAPH_MIN_SAMPLES = 32       # small passes are latency-bound either way and not worth pinning memory for
-GRAPH_CACHE = 2
+GRAPH_CACHE = 3
 
 
 def _engine_chunk(x: torch.Tensor, requested: int) -> int:
