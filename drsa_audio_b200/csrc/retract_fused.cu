@@ -31,86 +31,117 @@ struct FusedParams {
   float* corr;     // [gridDim.x] per-CTA partials of that inner product
   long long* prof; // debug: %globaltimer stamps of CTA 0 at the phase boundaries (drsa_debug_set_tc_profile), or NULL
   // peer exchange (world > 1): xbuf[r] = rank r's exchange buffer as mapped into this process (NVLink peer memory).
-  // Layout of a buffer: 64 x u32 header ([0] = exchange counter of the owner, [8] / [9] = local CTA counters and
-  // [16] / [32] = arrival counters of the two parities), then floats data[parity][source rank][xstride].
+  // Layout of a buffer: 64 x u32 header ([0] = exchange counter of the owner), then 8-byte words {value, flag}
+  // [parity][source rank][xstride] (peer_push / peer_read).
   int world, rank;
   float* xbuf[DRSA_MAX_PEERS];
   int64_t xstride;
 };
 
 constexpr int kXHeaderFloats = 64;
-__device__ __forceinline__ void red_release_sys_add(unsigned* p, unsigned v) {
-  asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ long long global_ns() {
   long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
 
-// The all-reduce of the row sums, fused into the head of the finish kernel (push model over NVLink peer memory):
-// every CTA stores its grid-stride share of this rank's `sums` into slot [parity][rank] of EVERY peer's buffer and
-// fences; the last CTA to do so bumps every peer's arrival counter; then all CTAs wait until the world - 1 arrivals
-// of the peers have landed in their own buffer.  The reduced value of element i is the sum over ranks in rank order (own
-// share read from `sums`), so every rank adds the same floats in the same order: replicas of U stay bit-identical.
-// Two parities: a peer can run at most one exchange ahead (it needs this rank's arrivals of exchange s + 1 before it
-// can finish it), so slot [s & 1] is never overwritten while it is still being read.  Returns the parity.
-__device__ __forceinline__ int peer_exchange(const FusedParams& p, int64_t total) {
+// The all-reduce of the row sums, fused into the head of the finish kernel (push model over NVLink peer memory), with the
+// FLAG IN THE DATA: every float travels as an 8-byte word {value, flag} with flag = exchange counter + 1, stored into slot
+// [parity][rank] of EVERY peer's buffer (16-byte stores of two words: each 8-byte half is self-consistent, which is all the
+// protocol needs).  A reader polls the word itself until the flag matches, so there is no fence, no arrival counter and no
+// separate signal: the latency of the exchange is one NVLink store.  (The previous version -- 16-byte data stores, one
+// system-scope fence per CTA, one release-add per peer, a polling loop on the counter -- spent 33-40 us in the head of the
+// kernel on 8 GPUs, profiles/r02_p2p_exchange_profile_n8.log.)  The reduced value of element i is the sum over ranks in rank
+// order (own share read from `sums`), so every rank adds the same floats in the same order: replicas of U stay bit-identical.
+// Two parities: a peer can run at most one exchange ahead (it needs this rank's words of exchange s + 1 before it can finish
+// it, and those are pushed only after this rank has read everything of exchange s), so slot [s & 1] is never overwritten
+// while it is still being read; a stale word of exchange s - 2 carries another flag.  Buffer: 64 x u32 header ([0] = exchange
+// counter of the owner), then uint2 words[2 parities][world][xstride].
+struct PeerView {
+  unsigned flag;
+  const uint2* inbox;      // words[parity][0] of this rank's own buffer
+};
+
+__device__ __forceinline__ PeerView peer_push(const FusedParams& p, int64_t total) {
   unsigned* hdr = reinterpret_cast<unsigned*>(p.xbuf[p.rank]);
   const unsigned s = __ldcg(hdr);
+  const unsigned flag = s + 1u;
   const int par = (int)(s & 1u);
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (int64_t)gridDim.x * blockDim.x;
-  const int64_t slot = ((int64_t)par * p.world + p.rank) * p.xstride + kXHeaderFloats;
-  // 16-byte stores (d*m is a multiple of 1024, the slot offsets of 64 floats; the K pooling scalars follow one by one)
-  const int64_t n4 = (total & ~(int64_t)3) >> 2;
-  for (int64_t i = gtid; i < n4; i += gthreads) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(p.sums) + i);
+  const int64_t slot = ((int64_t)par * p.world + p.rank) * p.xstride;
+  const int64_t n2 = total >> 1;
+  for (int64_t i = gtid; i < n2; i += gthreads) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p.sums) + i);
+    const uint4 w = make_uint4(__float_as_uint(v.x), flag, __float_as_uint(v.y), flag);
     for (int r = 0; r < p.world; ++r)
-      if (r != p.rank) reinterpret_cast<float4*>(p.xbuf[r] + slot)[i] = v;
+      if (r != p.rank) reinterpret_cast<uint4*>(reinterpret_cast<uint2*>(p.xbuf[r] + kXHeaderFloats) + slot)[i] = w;
   }
-  for (int64_t i = 4 * n4 + gtid; i < total; i += gthreads) {
-    const float v = p.sums[i];
+  if ((total & 1) && gtid == 0) {
+    const uint2 w = make_uint2(__float_as_uint(p.sums[total - 1]), flag);
     for (int r = 0; r < p.world; ++r)
-      if (r != p.rank) p.xbuf[r][slot + i] = v;
+      if (r != p.rank) (reinterpret_cast<uint2*>(p.xbuf[r] + kXHeaderFloats) + slot)[total - 1] = w;
   }
-  // Publication: the CTA barrier orders every thread's stores before thread 0, which makes them visible system-wide
-  // with ONE fence per CTA (a __threadfence_system() in every thread, the first version, cost ~20 us) and then counts
-  // itself on a local counter; the last CTA of the grid signals every peer once.  (One remote arrival per CTA and peer,
-  // the second version, serialises (world - 1) * gridDim.x atomics on one address of every receiver: fine for two
-  // ranks; at eight the step went from 0.433 to 0.409 ms with this version.)
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    fence_acq_rel_sys();
-    unsigned* done = hdr + 8 + par;
-    if (atomicAdd(done, 1u) == gridDim.x - 1) {
-      *done = 0u;                                     // next used two exchanges later
-      __threadfence();
-      for (int r = 0; r < p.world; ++r)
-        if (r != p.rank) red_release_sys_add(reinterpret_cast<unsigned*>(p.xbuf[r]) + 16 + 16 * par, 1u);
-    }
-    const unsigned expected = (unsigned)(p.world - 1);
-    const long long t0 = global_ns();
-    unsigned polls = 0;
-    while (ld_relaxed_sys(hdr + 16 + 16 * par) < expected) {
-      // a peer that never arrives (crashed rank, mismatched call sequence) must not hang the GPU: trap after 30 s
-      if ((++polls & 0xffffu) == 0 && global_ns() - t0 > 30000000000LL) __trap();
-    }
-    fence_acq_rel_sys();
-  }
-  __syncthreads();
-  return par;
+  PeerView v;
+  v.flag = flag;
+  v.inbox = reinterpret_cast<const uint2*>(p.xbuf[p.rank] + kXHeaderFloats) + (int64_t)par * p.world * p.xstride;
+  return v;
 }
+
+// Slow path of a read: the word had not arrived at the first look; poll it.
+__device__ __noinline__ unsigned peer_poll(const uint2* w, unsigned flag) {
+  unsigned a, f;
+  unsigned polls = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(f) : "l"(w) : "memory");
+    if (f == flag) return a;
+    // a peer that never pushes (crashed rank, mismatched call sequence) must not hang the GPU: trap after 30 s
+    if ((++polls & 0xfffu) == 0) {
+      if (t0 == 0) t0 = global_ns();
+      else if (global_ns() - t0 > 30000000000LL) __trap();
+    }
+  }
+}
+
+// Element i of the row sums reduced over the ranks (own share + the peers' words of THIS exchange), added in rank order.
+// The first look at the peers' words is a plain (non-volatile) asm so that the compiler can put the loads of all peers --
+// and of the neighbouring elements of an unrolled loop -- in flight together; only words that have not arrived yet go
+// through the polling loop.
+struct ReducedSums {
+  const FusedParams& p;
+  PeerView pv;
+  struct Look { unsigned a[DRSA_MAX_PEERS], f[DRSA_MAX_PEERS]; float own; };
+  __device__ __forceinline__ void look(int64_t i, Look& L) const {          // issue the loads of element i
+    L.own = p.sums[i];
+    if (p.world <= 1) return;
+#pragma unroll
+    for (int r = 0; r < DRSA_MAX_PEERS; ++r) {
+      L.a[r] = 0u; L.f[r] = 0u;
+      if (r < p.world && r != p.rank)
+        asm("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(L.a[r]), "=r"(L.f[r]) : "l"(pv.inbox + (int64_t)r * p.xstride + i));
+    }
+  }
+  __device__ __forceinline__ float take(int64_t i, Look& L) const {         // ... and reduce them (polling the late ones)
+    if (p.world <= 1) return L.own;
+    float v = 0.f;
+#pragma unroll
+    for (int r = 0; r < DRSA_MAX_PEERS; ++r) {
+      if (r < p.world) {
+        if (r == p.rank) v += L.own;
+        else {
+          if (L.f[r] != pv.flag) L.a[r] = peer_poll(pv.inbox + (int64_t)r * p.xstride + i, pv.flag);
+          v += __uint_as_float(L.a[r]);
+        }
+      }
+    }
+    return v;
+  }
+  __device__ __forceinline__ float operator()(int64_t i) const {
+    Look L;
+    look(i, L);
+    return take(i, L);
+  }
+};
 
 __device__ __forceinline__ void stamp(const FusedParams& p, int& slot) {
   if (p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && slot < 40) {
@@ -354,12 +385,15 @@ __device__ __forceinline__ float objective_correction(const FusedParams& p, cons
   float corr = 0.f;
   for (int b = blockIdx.x; b < td * tm; b += gridDim.x) {
     const int k0 = 32 * (b / tm), c0 = 32 * (b % tm);
+    typename SumsFn::Look look[4];       // the loads of the four rows in flight together
+#pragma unroll
+    for (int r = 0; r < 4; ++r) S.look((int64_t)(k0 + ty + 8 * r) * m + c0 + tx, look[r]);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int kk = ty + 8 * r;
       const int64_t i = (int64_t)(k0 + kk) * m + c0 + tx;
       const float u = p.U[i];
-      const float cf = coef[(c0 + tx) / d_k], sv = S(i);
+      const float cf = coef[(c0 + tx) / d_k], sv = S.take(i, look[r]);
       tu[kk][tx] = u;
       tg[kk][tx] = __fmul_rn(cf, sv);
       if (write_y) p.Y[i] = __fmaf_rn(cf, sv, u);
@@ -402,17 +436,11 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
                      4 * d * LDT * 4 <= 200 * 1024;
 
   // ---------------- phase 0: pooling scalars, (Y = U + coef_k X_k), objective log
-  int xpar = 0;
   if (p.have_sums) {
     const int K = p.K, d_k = m / K;
-    if (p.world > 1) xpar = peer_exchange(p, n + K);
-    const float* inbox = p.world > 1 ? p.xbuf[p.rank] + kXHeaderFloats + (int64_t)xpar * p.world * p.xstride : nullptr;
-    auto S = [&](int64_t i) -> float {          // element i of the row sums reduced over the ranks, fixed order
-      if (p.world <= 1) return p.sums[i];
-      float v = 0.f;
-      for (int r = 0; r < p.world; ++r) v += (r == p.rank) ? p.sums[i] : __ldcg(inbox + (int64_t)r * p.xstride + i);
-      return v;
-    };
+    PeerView pv{0u, nullptr};
+    if (p.world > 1) pv = peer_push(p, n + K);
+    const ReducedSums S{p, pv};                 // element i of the row sums reduced over the ranks, fixed order
     if (tid == 0) {
       float acc = 0.f; int degenerate = 0;
       for (int k = 0; k < K; ++k) {
@@ -458,9 +486,9 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
         if (idx < 0) { idx = p.status[3]; p.status[3] = (int)idx + 1; }
         p.obj_log[idx] = root * root + (p.u_rounded ? p.corr[0] : 0.f);
       }
-      if (p.world > 1 && tid == 0) {            // single CTA here: close this exchange (see below)
+      __syncthreads();                          // single CTA here: every thread has read its words
+      if (p.world > 1 && tid == 0) {            // close this exchange (see below)
         unsigned* hdr = reinterpret_cast<unsigned*>(p.xbuf[p.rank]);
-        hdr[16 + 16 * xpar] = 0u;
         hdr[0] = __ldcg(hdr) + 1u;
       }
       return;
@@ -472,10 +500,9 @@ __global__ void __launch_bounds__(256) finish_fused_kernel(FusedParams p) {
     stamp(p, slot);
   }
   if (p.have_sums && p.world > 1 && blockIdx.x == 0 && tid == 0) {
-    // every CTA has passed its wait and read its share: rewind this parity's arrival counter and advance the exchange
-    // counter (the peers' next arrivals on this parity come two exchanges later, after this kernel has ended)
+    // (after the grid barrier) every CTA has read the exchange counter and its words: advance the counter; the peers' next
+    // words on this parity come two exchanges later, after this kernel has ended
     unsigned* hdr = reinterpret_cast<unsigned*>(p.xbuf[p.rank]);
-    hdr[16 + 16 * xpar] = 0u;
     hdr[0] = __ldcg(hdr) + 1u;
   }
   auto log_objective = [&]() {
@@ -712,18 +739,12 @@ __global__ void __launch_bounds__(256) finish_small_kernel(FusedParams p) {
   const int tid = threadIdx.x, tj = tid & 15, ti = tid >> 4;
   const int d = p.d, m = p.m;
   const int n = d * m;
-  int xpar = 0;
   float gu = 0.f;
   if (p.have_sums) {
     const int K = p.K, d_k = m / K;
-    if (p.world > 1) xpar = peer_exchange(p, n + K);        // gridDim.x == 1
-    const float* inbox = p.world > 1 ? p.xbuf[p.rank] + kXHeaderFloats + (int64_t)xpar * p.world * p.xstride : nullptr;
-    auto S = [&](int i) -> float {
-      if (p.world <= 1) return p.sums[i];
-      float v = 0.f;
-      for (int r = 0; r < p.world; ++r) v += (r == p.rank) ? p.sums[i] : __ldcg(inbox + (int64_t)r * p.xstride + i);
-      return v;
-    };
+    PeerView pv{0u, nullptr};
+    if (p.world > 1) pv = peer_push(p, n + K);              // gridDim.x == 1
+    const ReducedSums S{p, pv};
     if (tid == 0) {
       float acc = 0.f; int degenerate = 0;
       for (int k = 0; k < K; ++k) {
@@ -767,6 +788,7 @@ __global__ void __launch_bounds__(256) finish_small_kernel(FusedParams p) {
             }
         }
       } else
+#pragma unroll 4
       for (int i = tid; i < n; i += blockDim.x) {
         const int r = i / m, c = i % m;
         const float cf = coef[c / d_k], sv = S(i);
@@ -780,7 +802,6 @@ __global__ void __launch_bounds__(256) finish_small_kernel(FusedParams p) {
     __syncthreads();                        // every thread has read its share of the inbox
     if (p.world > 1 && tid == 0) {          // single CTA: close this exchange right away (rewind the arrival counter)
       unsigned* hdr = reinterpret_cast<unsigned*>(p.xbuf[p.rank]);
-      hdr[16 + 16 * xpar] = 0u;
       hdr[0] = __ldcg(hdr) + 1u;
     }
     if (tid == 0 && p.obj_log != nullptr) {
@@ -926,7 +947,7 @@ int64_t finish_fused_workspace_bytes(int d, int m) { return fused_ws_bytes(d, m,
 // floats per (parity, source rank) slot of an exchange buffer, and the size of one rank's buffer
 int64_t exchange_stride(int d, int m, int K) { return align_up((int64_t)d * m + K, 64); }
 int64_t exchange_bytes(int d, int m, int K, int world) {
-  return (kXHeaderFloats + 2 * (int64_t)world * exchange_stride(d, m, K)) * 4;
+  return kXHeaderFloats * 4 + 2 * (int64_t)world * exchange_stride(d, m, K) * 8;      // 8-byte {value, flag} words
 }
 
 // have_sums = 1: full finish step; have_sums = 0: retract the matrix already stored in Y_in (copied by the caller).

@@ -174,7 +174,8 @@ int drsa_finish_step(const float* sums, int64_t M_global, const float* U, int d,
  *                    host barrier between the fill and the first call.  Symmetric memory from
  *                    torch.distributed._symmetric_memory or buffers shared with drsa_ipc_* both work.
  *
- * Every CTA pushes its share of this rank's sums into all peers' buffers, signals, waits for the peers' shares and adds
+ * Every CTA pushes its share of this rank's sums into all peers' buffers as 8-byte {value, flag} words (the flag is the
+ * exchange number, so the data is its own arrival signal: no fences, no counters), polls the peers' words and adds
  * the shares in rank order, so all ranks obtain bit-identical results.  All ranks must make the same sequence of
  * calls (same shapes, same U_out == NULL pattern).  Asynchronous, capturable in a CUDA graph; a peer that does not
  * arrive within 30 s makes the kernel trap (launch failure) rather than hang.  Shapes: d, m multiples of 32 (the

@@ -52,7 +52,7 @@ def test_workspace_queries_need_no_gpu(lib):
 def test_peer_exchange_and_fused_pool_queries_need_no_gpu(lib):
     """Shape / argument checks of the entry points added for the multi-GPU exchange and the fused conv + pool."""
     n = lib.drsa_exchange_bytes(256, 256, 4, 8)
-    assert n == (64 + 2 * 8 * (256 * 256 + 64)) * 4                     # header + 2 parities x 8 ranks x padded d*m+K floats
+    assert n == 64 * 4 + 2 * 8 * (256 * 256 + 64) * 8                   # header + 2 parities x 8 ranks x padded d*m+K {value, flag} words
     assert lib.drsa_exchange_bytes(256, 256, 4, 1) == -1                # a single rank has nothing to exchange
     assert lib.drsa_exchange_bytes(256, 256, 4, 9) == -2                # more than DRSA_MAX_PEERS
     assert lib.drsa_exchange_bytes(48, 48, 4, 2) == -2                  # not a shape of the fused finish kernel
