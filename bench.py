@@ -211,6 +211,15 @@ def parity_block(A, C, U0, K, precision, dev, steps, timed_objs, timed_U, budget
 
 
 # =========================================================================== this repo's arm
+def workload_config(label, M, world, d, m, K):
+    """The `config` block of the JSON line: the workload only, identical in both arms."""
+    fp16_mb, fp32_mb = 2 * M * d * 2 / 1e6, 2 * M * d * 4 / 1e6
+    return {"workload": label, "rows_per_gpu": M, "rows_total": M * world, "d": d, "m": m, "K": K, "d_k": m // K,
+            "l2_policy": (f"inputs larger than L2 ({fp32_mb:.0f} MB of fp32 rows per GPU, {fp16_mb:.0f} MB as packed fp16 planes, "
+                          f"read once per step, vs 126 MB L2)") if fp16_mb > 126
+            else "rows fit in L2 (cfg 1 is the reference's toy scale: latency-bound)"}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -331,6 +340,17 @@ def run_ours(args):
                          f"{D.dc_every(M * world)} steps; 'tc_hilo' = rows as hi + lo fp16 planes; 'tc32' = rows and U hi + lo "
                          "(fp32-class operands); 'fp32' = CUDA cores.  'auto' never picks 'tc'.")
 
+    # ---- cfg 2 with the reference's own sampling of L = 20 positions per spectrogram (getdrsadata.py:131): M = 200 000 rows
+    sampled = None
+    if world == 1 and args.workload == "cfg2" and label == "cfg2" and not args.no_modes:
+        Ms = M * 20 // 64
+        o = SubspaceOptimizer(U0, A[:Ms], C[:Ms], None, num_concepts=K, device=dev, precision=args.precision)
+        o._rows.split_u(o._Uw)
+        mss = time_steps(o, 64)
+        sampled = {"rows": Ms, "positions_per_sample": 20, "precision": o.precision, "steps_per_s": 1000.0 / mss,
+                   "ms_per_step": mss, "what": "the first 200 000 of the 640 000 rows (rows are i.i.d. in the synthetic workload)"}
+        del o
+
     # ---- end to end through the public API with HOST buffers: construct (H2D + pack) + run + D2H
     e2e_steps = args.e2e_steps
     # host copies of the rows; workloads whose rows exceed 16 GB (cfg 4: 52 GB) use the first rows only -- the host side of
@@ -394,14 +414,14 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-            "config": {"workload": label, "rows_per_gpu": M, "rows_total": M * world, "d": d, "m": m, "K": K, "d_k": m // K,
-                       "precision": precision, "precision_requested": args.precision, "cuda_graph": use_graph,
-                       "exchange": {"none": "single rank", "nccl": "NCCL all-reduce of d*m+K floats per step",
-                                    "p2p": "all-reduce fused into the finish kernel over NVLink peer memory (cudaIpc buffers)",
-                                    "p2p_symm": "all-reduce fused into the finish kernel over NVLink peer memory (torch symmetric memory)"}[exchange],
-                       "l2_policy": f"inputs larger than L2 ({2 * M * d * elem / 1e6:.0f} MB of rows per step vs 126 MB L2)"
-                       if 2 * M * d * elem > 126e6 else "rows fit in L2 (cfg 1 is the reference's toy scale: latency-bound)",
-                       "retraction_sweeps_last_step": status[0], "retraction_not_converged": status[1]},
+            # `config` names the workload and is the same dict in the reference arm; what THIS arm ran with is in `run`
+            "config": workload_config(label, M, world, d, m, K),
+            "run": {"precision": precision, "precision_requested": args.precision, "cuda_graph": use_graph,
+                    "exchange": {"none": "single rank", "nccl": "NCCL all-reduce of d*m+K floats per step",
+                                 "p2p": "all-reduce fused into the finish kernel over NVLink peer memory (cudaIpc buffers)",
+                                 "p2p_symm": "all-reduce fused into the finish kernel over NVLink peer memory (torch symmetric memory)"}[exchange],
+                    "row_bytes_read_per_step": 2 * M * d * elem,
+                    "retraction_sweeps_last_step": status[0], "retraction_not_converged": status[1]},
             "rows_per_s": M * world * 1000.0 / ms_per_step,
             "gpu_launches": int(n_launch),
             "roofline": {"bound": "tensor" if d >= 128 else "hbm", "achieved": achieved, "peak": peaks["tf_burst"],
@@ -427,7 +447,7 @@ def run_ours(args):
                        if e2e_rows < M else {}),
                     "what": "SubspaceOptimizer(U0, A_host_pinned, C_host_pinned).run(steps) + U.cpu(): H2D of all rows, "
                             "fp16 pack, steps, final objective, D2H of U and the objective history, wall clock"},
-            "parity": parity, "modes": modes, "replicas": replicas,
+            "parity": parity, "modes": modes, "cfg2_L20": sampled, "replicas": replicas,
             "clocks": clocks,
             "objective_first_last": [float(objs[0]), float(objs[-1])],
         }
@@ -699,7 +719,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(1, args.warmup), "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": label, "rows_per_gpu": M, "d": d, "m": d, "K": K, "d_k": d // K},
+        "config": workload_config(label, M, world, d, d, K),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
