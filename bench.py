@@ -255,8 +255,19 @@ def run_ours(args):
     precision = opt.precision
     opt._rows.split_u(opt._Uw)
     warm = max(args.warmup, 4 if not args.no_graph else 3)      # >= 4 so that the CUDA graph(s) of a step are captured here,
-    opt.reset_log(warm + args.steps + 8)                        # not inside the timed region
+    opt.reset_log(warm + args.steps + 8 + 64)                   # not inside the timed region (+ alignment steps, below)
     opt.enqueue_steps(warm)
+    # 'tc_dc' re-evaluates its correction (one extra hi + lo row pass) every `every` steps.  The timed window must carry its
+    # share of those steps -- the integer nearest to K / every -- wherever the K steps happen to start: a few more untimed
+    # steps move the window accordingly (K = 20, every = 32: one correction step inside, 0.625 expected).
+    every = D.dc_every(opt.M_global) if opt._rows.dc else 0
+    align, corrections = 0, 0
+    if every:
+        inside = lambda start: sum(1 for i in range(start, start + args.steps) if i % every == 0)      # noqa: E731
+        target = int(round(args.steps / every))
+        align = next(a for a in range(every) if inside(opt._steps_done + a) == target)
+        opt.enqueue_steps(align)
+        corrections = inside(opt._steps_done)
     barrier()
     if rank == 0:
         t_wait = time.time() + 5.0
@@ -421,6 +432,8 @@ def run_ours(args):
                                  "p2p": "all-reduce fused into the finish kernel over NVLink peer memory (cudaIpc buffers)",
                                  "p2p_symm": "all-reduce fused into the finish kernel over NVLink peer memory (torch symmetric memory)"}[exchange],
                     "row_bytes_read_per_step": 2 * M * d * elem,
+                    "correction_every": every or None, "correction_steps_in_timed_region": corrections,
+                    "untimed_alignment_steps_after_warmup": align,
                     "retraction_sweeps_last_step": status[0], "retraction_not_converged": status[1]},
             "rows_per_s": M * world * 1000.0 / ms_per_step,
             "gpu_launches": int(n_launch),
