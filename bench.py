@@ -211,6 +211,18 @@ def parity_block(A, C, U0, K, precision, dev, steps, timed_objs, timed_U, budget
 
 
 # =========================================================================== this repo's arm
+def correction_window(start: int, steps: int, every: int):
+    """(untimed steps to run first, correction steps then inside the window): the smallest shift of a window of `steps`
+    steps starting at step index `start` after which it contains round(steps / every) indices that are multiples of `every`
+    (the steps on which 'tc_dc' re-evaluates its correction).  every = 0: the mode has no such steps."""
+    if every <= 0:
+        return 0, 0
+    inside = lambda s0: sum(1 for i in range(s0, s0 + steps) if i % every == 0)      # noqa: E731
+    target = int(round(steps / every))
+    align = next(a for a in range(every) if inside(start + a) == target)
+    return align, target
+
+
 def workload_config(label, M, world, d, m, K):
     """The `config` block of the JSON line: the workload only, identical in both arms."""
     fp16_mb, fp32_mb = 2 * M * d * 2 / 1e6, 2 * M * d * 4 / 1e6
@@ -261,13 +273,8 @@ def run_ours(args):
     # share of those steps -- the integer nearest to K / every -- wherever the K steps happen to start: a few more untimed
     # steps move the window accordingly (K = 20, every = 32: one correction step inside, 0.625 expected).
     every = D.dc_every(opt.M_global) if opt._rows.dc else 0
-    align, corrections = 0, 0
-    if every:
-        inside = lambda start: sum(1 for i in range(start, start + args.steps) if i % every == 0)      # noqa: E731
-        target = int(round(args.steps / every))
-        align = next(a for a in range(every) if inside(opt._steps_done + a) == target)
-        opt.enqueue_steps(align)
-        corrections = inside(opt._steps_done)
+    align, corrections = correction_window(opt._steps_done, args.steps, every)
+    opt.enqueue_steps(align)
     barrier()
     if rank == 0:
         t_wait = time.time() + 5.0
