@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(256) finish_small_kernel(FusedParams p) {
     }
     const float gu_tot = p.u_rounded ? block_total256(gu, red) : 0.f;
     __syncthreads();                        // every thread has read its share of the inbox
-    if (p.world > 1 && tid == 0) {          // single CTA: close this exchange right away (rewind the arrival counter)
+    if (p.world > 1 && tid == 0) {          // single CTA: close this exchange right away
       unsigned* hdr = reinterpret_cast<unsigned*>(p.xbuf[p.rank]);
       hdr[0] = __ldcg(hdr) + 1u;
     }
