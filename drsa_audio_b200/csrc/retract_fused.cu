@@ -53,6 +53,8 @@ __device__ __forceinline__ long long global_ns() {
 // system-scope fence per CTA, one release-add per peer, a polling loop on the counter -- spent 33-40 us in the head of the
 // kernel on 8 GPUs, profiles/r02_p2p_exchange_profile_n8.log.)  The reduced value of element i is the sum over ranks in rank
 // order (own share read from `sums`), so every rank adds the same floats in the same order: replicas of U stay bit-identical.
+// (The pushes must be single 16- / 8-byte stores -- value and flag of a word may not be torn apart: STG.E.128 / STG.E.64 in
+// the SASS of both finish kernels, checked with cuobjdump; the polls are 8-byte ld.relaxed.sys.v2.)
 // Two parities: a peer can run at most one exchange ahead (it needs this rank's words of exchange s + 1 before it can finish
 // it, and those are pushed only after this rank has read everything of exchange s), so slot [s & 1] is never overwritten
 // while it is still being read; a stale word of exchange s - 2 carries another flag.  Buffer: 64 x u32 header ([0] = exchange
