@@ -45,7 +45,7 @@ from cxai.model.create_model import VGGType as RefVGGType  # noqa: E402
 from cxai.xai.drsa.preprocessing import get_intermediate  # noqa: E402
 from cxai.xai.explain.attribute import compute_relevances  # noqa: E402
 from cxai.xai.explain.explainer import HeatmapGenerator, compute_subspace_relevances  # noqa: E402
-from cxai.utils.constants import LRP_NAME_MAP_TOY  # noqa: E402
+from cxai.utils.constants import LRP_NAME_MAP_GTZAN, LRP_NAME_MAP_TOY  # noqa: E402
 from zennit.rules import Epsilon, Gamma, WSquare  # noqa: E402
 from zennit.composites import NameMapComposite  # noqa: E402
 from zennit.canonizers import SequentialMergeBatchNorm  # noqa: E402
@@ -149,6 +149,25 @@ def case_cfg2_full():
     return out
 
 
+def case_archB():
+    """The 3-second GTZAN model of pixelflipping/cpf.py:410-412 (arch B) at its own resolution with the reference's own rule
+    map for it (constants.py:27-38), split at two of the layers cpf.py:141 uses."""
+    net = synth.build_model(RefVGGType, "archB", seed=0, bn_seed=None)      # flat size 2048: the reference's forward fits
+    x = synth.synth_logmel(3, 128, 128, 20266)
+    comp = lambda: NameMapComposite(LRP_NAME_MAP_GTZAN)
+
+    def run(net, x):
+        o = {"Rin_c6": compute_relevances(net, x.clone(), comp(), class_idx=6)}
+        for layer in (7, 13):
+            a, R = get_intermediate(net, x, comp(), net.features[layer], 6)
+            o[f"a_l{layer}"], o[f"R_l{layer}"] = a, R
+        o["logits"] = net(x).detach()
+        return o
+    out = _both(run, net, x)
+    out.update(model="archB", seed=0, x_seed=20266, N=3, wsum=synth.weight_checksum(net))
+    return out
+
+
 def _heatmaps(model_name, H, W, layer_idx, sample_class, name_map_fn, canon, N, x_seed, K=4):
     """HeatmapGenerator (explainer.py:15-177) for a signed-permutation U (projections exact) and a random orthogonal U."""
     net = synth.build_model(RefVGGType if model_name == "archA" else FlatVGG, model_name, seed=0,
@@ -204,7 +223,7 @@ def case_heat_archA():
     return _heatmaps("archA", 128, 256, 33, "rock", name_map_6s, True, N=2, x_seed=20265)   # N = 1 crashes explainer.py:175
 
 
-CASES = {"toy": case_toy, "archA_small": case_archA_small, "cfg2_full": case_cfg2_full, "heat_toy": case_heat_toy,
+CASES = {"toy": case_toy, "archA_small": case_archA_small, "archB": case_archB, "cfg2_full": case_cfg2_full, "heat_toy": case_heat_toy,
          "heat_archA": case_heat_archA}
 
 if __name__ == "__main__":

@@ -64,6 +64,10 @@ MODEL_CONFIGS = {
     "archA": dict(n_filters=[64, 64, 100, 128, 128], pool_kernels=[(2, 4), (2, 2), (2, 2), (2, 2), (2, 2)],
                   n_dense=100, n_classes=10, dropout=0.3, block_depth=2, dense_depth=2, input_size=(128, 256),
                   conv_bn=True, dense_bn=True),
+    # arch B, the reference's 3-second GTZAN model (pixelflipping/cpf.py:410-412; rules LRP_NAME_MAP_GTZAN, constants.py:27-38):
+    # one conv per block, no BatchNorm, 128 x 128 input, flat size 2048; split layers 1, 4, 7, 10, 13 (cpf.py:141)
+    "archB": dict(n_filters=[32, 32, 64, 64, 128], pool_kernels=[(2, 2)] * 5, n_dense=128, n_classes=10, dropout=0.4,
+                  block_depth=1, dense_depth=2, input_size=(128, 128), conv_bn=False, dense_bn=False),
     # BASELINE cfg 2: arch A with the last block widened to d = 256
     "cfg2": dict(n_filters=[64, 64, 100, 128, 256], pool_kernels=[(2, 4), (2, 2), (2, 2), (2, 2), (2, 2)],
                  n_dense=100, n_classes=10, dropout=0.3, block_depth=2, dense_depth=2, input_size=(128, 256),

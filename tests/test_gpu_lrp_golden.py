@@ -75,6 +75,24 @@ def test_bn_model_against_reference_fixture(golden_dir):
     assert not lrp_engine._plan(net, comp, x.device).tc_failed()
 
 
+def test_arch_b_against_reference_fixture(golden_dir):
+    """The reference's 3-second GTZAN model (cpf.py:410-412: 32/32/64/64/128 filters, one conv per block, no BatchNorm,
+    128 x 128 input, square pools) under LRP_NAME_MAP_GTZAN (constants.py:27-38), split at features[7] and features[13]."""
+    from cxai.utils.constants import LRP_NAME_MAP_GTZAN
+    from cxai.xai.drsa.preprocessing import get_intermediate
+    from cxai.xai.explain.attribute import compute_relevances
+    from cxai.xai.explain.rules import NameMapComposite
+    g, net = _load(golden_dir, "archB")
+    x = synth.synth_logmel(int(g["N"]), 128, 128, int(g["x_seed"])).cuda()
+    comp = NameMapComposite(LRP_NAME_MAP_GTZAN)
+    _check(compute_relevances(net, x, comp, class_idx=6), g, "Rin_c6")
+    for layer, d, hw in ((7, 64, 32), (13, 128, 8)):
+        a, R = get_intermediate(net, x, comp, net.features[layer], 6)
+        assert tuple(a.shape) == (3, d, hw, hw)
+        _check(a, g, f"a_l{layer}")
+        _check(R, g, f"R_l{layer}")
+
+
 def test_cfg2_cnn_full_resolution_against_reference_fixture(golden_dir):
     """BASELINE cfg 2 CNN (128 x 256 log-mel, d = 256 at features[33]) on the tensor-core stack vs the reference's code."""
     from cxai.xai.drsa.preprocessing import get_intermediate

@@ -14,7 +14,7 @@ import torch
 
 from oracle import lrp_ref, synth, drsa_ref
 from cxai.model.create_model import VGGType
-from cxai.utils.constants import LRP_NAME_MAP_TOY, lrp_name_map_6s
+from cxai.utils.constants import LRP_NAME_MAP_GTZAN, LRP_NAME_MAP_TOY, lrp_name_map_6s
 
 TOL = 1e-4
 
@@ -58,6 +58,22 @@ def test_bn_model_matches_reference_fixture(golden_dir):
         a, R = lrp_ref.get_intermediate(net, x, nm, net.features[layer], 3)
         assert _rel(a, g[f"a_l{layer}_f64"]).max() < 1e-6
         assert _rel(R, g[f"R_l{layer}_f64"]).max() < 1e-6
+
+
+def test_arch_b_matches_reference_fixture(golden_dir):
+    """The reference's 3-second GTZAN model (cpf.py:410-412: one conv per block, no BatchNorm, 128 x 128) under its own rule
+    map LRP_NAME_MAP_GTZAN (constants.py:27-38), split at two of the layers cpf.py:141 uses."""
+    g, net = _load(golden_dir, "archB")
+    x = synth.synth_logmel(int(g["N"]), 128, 128, int(g["x_seed"]))
+    o = lrp_ref.lrp_pass(net, x, LRP_NAME_MAP_GTZAN, lrp_ref.output_modifier(6))
+    assert _rel(o["R_input"], g["Rin_c6_f64"]).max() < 1e-6
+    np.testing.assert_allclose(o["logits"].numpy(), g["logits_f64"], rtol=1e-5, atol=1e-7)
+    for layer, d, hw in ((7, 64, 32), (13, 128, 8)):
+        a, R = lrp_ref.get_intermediate(net, x, LRP_NAME_MAP_GTZAN, net.features[layer], 6)
+        assert a.shape == (3, d, hw, hw)
+        assert _rel(a, g[f"a_l{layer}_f64"]).max() < 1e-6
+        assert _rel(R, g[f"R_l{layer}_f64"]).max() < 1e-6
+    assert max(float(g[k].max()) for k in g.files if k.startswith("noise_")) < TOL
 
 
 def test_cfg2_full_resolution_maps_match_reference_fixture(golden_dir):
