@@ -223,8 +223,13 @@ def case_heat_archA():
     return _heatmaps("archA", 128, 256, 33, "rock", name_map_6s, True, N=2, x_seed=20265)   # N = 1 crashes explainer.py:175
 
 
+def case_heat_archB():
+    """Concept heatmaps on arch B at the deepest split layer cpf.py:141 uses (features[13], d = 128)."""
+    return _heatmaps("archB", 128, 128, 13, "rock", lambda: list(LRP_NAME_MAP_GTZAN), False, N=2, x_seed=20267)
+
+
 CASES = {"toy": case_toy, "archA_small": case_archA_small, "archB": case_archB, "cfg2_full": case_cfg2_full, "heat_toy": case_heat_toy,
-         "heat_archA": case_heat_archA}
+         "heat_archA": case_heat_archA, "heat_archB": case_heat_archB}
 
 if __name__ == "__main__":
     torch.set_num_threads(4)

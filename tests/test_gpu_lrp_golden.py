@@ -116,19 +116,19 @@ def test_cfg2_cnn_full_resolution_against_reference_fixture(golden_dir):
     assert _rel(c, Rf / (af + 1e-7)).max() < 5e-4
 
 
-@pytest.mark.parametrize("case", ["heat_toy", "heat_archA"])
+@pytest.mark.parametrize("case", ["heat_toy", "heat_archA", "heat_archB"])
 def test_heatmaps_against_reference_fixture(golden_dir, case):
     """HeatmapGenerator on the CUDA engine vs the reference's HeatmapGenerator (K + 1 clones through its ProjectionModel)."""
-    from cxai.utils.constants import LRP_NAME_MAP_TOY, lrp_name_map_6s
+    from cxai.utils.constants import LRP_NAME_MAP_GTZAN, LRP_NAME_MAP_TOY, lrp_name_map_6s
     from cxai.xai.explain.explainer import HeatmapGenerator, compute_subspace_relevances
     from cxai.xai.explain.rules import SequentialMergeBatchNorm
     from cxai.xai.drsa.preprocessing import get_intermediate
     g, net = _load(golden_dir, case)
     K, layer_idx, d, N = int(g["K"]), int(g["layer_idx"]), int(g["d"]), int(g["N"])
     bn = case == "heat_archA"
-    H, W = (128, 256) if bn else (64, 64)
+    H, W = {"heat_toy": (64, 64), "heat_archA": (128, 256), "heat_archB": (128, 128)}[case]
     x = synth.synth_logmel(N, H, W, int(g["x_seed"]))
-    nm = lrp_name_map_6s() if bn else LRP_NAME_MAP_TOY
+    nm = {"heat_toy": LRP_NAME_MAP_TOY, "heat_archA": lrp_name_map_6s(), "heat_archB": LRP_NAME_MAP_GTZAN}[case]
     for tag, U in (("perm", synth.signed_permutation(d, 5)), ("orth", synth.random_orthogonal(d, 6))):
         gen = HeatmapGenerator(net, U, nm, str(g["sample_class"]), num_concepts=K, layer_idx=layer_idx, device="cuda",
                                canonizers=[SequentialMergeBatchNorm()] if bn else ())

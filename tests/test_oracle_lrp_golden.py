@@ -113,6 +113,29 @@ def test_projection_model_matches_reference_fixture(golden_dir, tag):
                                rtol=2e-4, atol=1e-6 * float(np.abs(g[f"{tag}_Rk"]).max()))
 
 
+@pytest.mark.parametrize("tag", ["perm", "orth"])
+def test_projection_model_arch_b_matches_reference_fixture(golden_dir, tag):
+    """The same on arch B (cpf.py:410-412) split at features[13] (d = 128), rule map LRP_NAME_MAP_GTZAN, class 'rock'."""
+    from cxai.model.modify_model import ProjectionModel
+    from cxai.xai.explain.explainer import get_class_composite
+    g, net = _load(golden_dir, "heat_archB")
+    K, layer_idx, d, N = int(g["K"]), int(g["layer_idx"]), int(g["d"]), int(g["N"])
+    assert (K, layer_idx, d) == (4, 13, 128)
+    x = synth.synth_logmel(N, 128, 128, int(g["x_seed"]))
+    U = synth.signed_permutation(d, 5) if tag == "perm" else synth.random_orthogonal(d, 6)
+    pm = ProjectionModel(net, layer_idx, U.double(), K, case="gtzan")
+    comp = get_class_composite(LRP_NAME_MAP_GTZAN, K)
+    o = lrp_ref.lrp_pass(pm, x.repeat_interleave(K + 1, dim=0), comp.name_map, lrp_ref.output_modifier(6))
+    H = o["R_input"].view(N, K + 1, 128, 128)
+    assert _rel(H[:, 0], g[f"{tag}_standard_heatmaps"][:, 0]).max() < max(1e-6, 3 * float(g[f"noise_{tag}_standard_heatmaps"].max()))
+    mask = g[f"{tag}_mask"]
+    sub = np.take_along_axis(H[:, 1:].numpy(), mask[:, :, None, None], axis=1)
+    tol = 1e-6 if tag == "perm" else 0.05
+    for j in range(K):
+        assert _rel(sub[:, j], g[f"{tag}_subspace_heatmaps"][:, j]).max() < tol
+    assert _rel(H[:, 1:].sum(1), g[f"{tag}_subspace_heatmaps"].sum(1)).max() < 1e-4
+
+
 def test_mini_zennit_gamma_collapses_and_restores_parameters():
     """The restated hooks leave the model untouched after the context and the 5-pass Gamma equals the one-pass form for
     non-negative input (what the CUDA kernels rely on)."""
