@@ -223,13 +223,31 @@ def case_heat_archA():
     return _heatmaps("archA", 128, 256, 33, "rock", name_map_6s, True, N=2, x_seed=20265)   # N = 1 crashes explainer.py:175
 
 
+def case_archB_early():
+    """The other split layers of cpf.py:141 on arch B: features[1], [4] (d = 32) and [10] (d = 64).  The maps of the two early
+    layers are large (32 x 128 x 128 per sample) and are stored at every 4th pixel in both directions."""
+    net = synth.build_model(RefVGGType, "archB", seed=0, bn_seed=None)
+    x = synth.synth_logmel(3, 128, 128, 20266)[:2]          # the first two samples of case_archB
+    comp = lambda: NameMapComposite(LRP_NAME_MAP_GTZAN)
+
+    def run(net, x):
+        o = {}
+        for layer, st in ((1, 4), (4, 4), (10, 1)):
+            a, R = get_intermediate(net, x, comp(), net.features[layer], 6)
+            o[f"a_l{layer}"], o[f"R_l{layer}"] = a[..., ::st, ::st].contiguous(), R[..., ::st, ::st].contiguous()
+        return o
+    out = _both(run, net, x)
+    out.update(model="archB", seed=0, x_seed=20266, N=2, wsum=synth.weight_checksum(net))
+    return out
+
+
 def case_heat_archB():
     """Concept heatmaps on arch B at the deepest split layer cpf.py:141 uses (features[13], d = 128)."""
     return _heatmaps("archB", 128, 128, 13, "rock", lambda: list(LRP_NAME_MAP_GTZAN), False, N=2, x_seed=20267)
 
 
 CASES = {"toy": case_toy, "archA_small": case_archA_small, "archB": case_archB, "cfg2_full": case_cfg2_full, "heat_toy": case_heat_toy,
-         "heat_archA": case_heat_archA, "heat_archB": case_heat_archB}
+         "heat_archA": case_heat_archA, "heat_archB": case_heat_archB, "archB_early": case_archB_early}
 
 if __name__ == "__main__":
     torch.set_num_threads(4)

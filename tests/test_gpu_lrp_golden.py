@@ -93,6 +93,22 @@ def test_arch_b_against_reference_fixture(golden_dir):
         _check(R, g, f"R_l{layer}")
 
 
+def test_arch_b_early_split_layers_against_reference_fixture(golden_dir):
+    """features[1], [4] (d = 32) and [10] (d = 64): the remaining split layers of cpf.py:141 (early maps compared at stride 4,
+    as stored)."""
+    from cxai.utils.constants import LRP_NAME_MAP_GTZAN
+    from cxai.xai.drsa.preprocessing import get_intermediate
+    from cxai.xai.explain.rules import NameMapComposite
+    g, net = _load(golden_dir, "archB_early")
+    x = synth.synth_logmel(3, 128, 128, int(g["x_seed"]))[:int(g["N"])].cuda()
+    comp = NameMapComposite(LRP_NAME_MAP_GTZAN)
+    for layer, st, d, hw in ((1, 4, 32, 128), (4, 4, 32, 64), (10, 1, 64, 16)):
+        a, R = get_intermediate(net, x, comp, net.features[layer], 6)
+        assert tuple(a.shape) == (2, d, hw, hw)
+        _check(a[..., ::st, ::st], g, f"a_l{layer}")
+        _check(R[..., ::st, ::st], g, f"R_l{layer}")
+
+
 def test_cfg2_cnn_full_resolution_against_reference_fixture(golden_dir):
     """BASELINE cfg 2 CNN (128 x 256 log-mel, d = 256 at features[33]) on the tensor-core stack vs the reference's code."""
     from cxai.xai.drsa.preprocessing import get_intermediate

@@ -76,6 +76,17 @@ def test_arch_b_matches_reference_fixture(golden_dir):
     assert max(float(g[k].max()) for k in g.files if k.startswith("noise_")) < TOL
 
 
+def test_arch_b_early_split_layers_match_reference_fixture(golden_dir):
+    """features[1], [4] (d = 32) and [10] (d = 64), the remaining split layers of cpf.py:141 (early maps stored at stride 4)."""
+    g, net = _load(golden_dir, "archB_early")
+    x = synth.synth_logmel(3, 128, 128, int(g["x_seed"]))[:int(g["N"])]
+    for layer, st, d, hw in ((1, 4, 32, 128), (4, 4, 32, 64), (10, 1, 64, 16)):
+        a, R = lrp_ref.get_intermediate(net, x, LRP_NAME_MAP_GTZAN, net.features[layer], 6)
+        assert a.shape == (2, d, hw, hw)
+        assert _rel(a[..., ::st, ::st], g[f"a_l{layer}_f64"]).max() < 1e-6
+        assert _rel(R[..., ::st, ::st], g[f"R_l{layer}_f64"]).max() < 1e-6
+
+
 def test_cfg2_full_resolution_maps_match_reference_fixture(golden_dir):
     g, net = _load(golden_dir, "cfg2_full")
     x = synth.synth_logmel(int(g["N"]), 128, 256, int(g["x_seed"]))[:1]       # one sample keeps the CPU suite short
