@@ -257,6 +257,34 @@ def test_run_matches_reference_golden(golden_dir, name, prec, graph, tmp_path):
     assert float((UtU - torch.eye(UtU.shape[0], device="cuda")).abs().max()) < 5e-6
 
 
+def test_main_matches_reference_result_tree(golden_dir, tmp_path):
+    """drsa.main (drsa.py:241-300) against the result tree the reference's own main wrote for the same seed
+    (oracle/gen_golden_main.py): numpy seed -> ortho_group.rvs -> compounding column permutations -> run{r}/ files."""
+    import pickle
+    from cxai.xai.drsa import drsa
+    g = np.load(os.path.join(golden_dir, "drsa_main.npz"))
+    M, d, K, steps, runs = (int(g[k]) for k in ("M", "d", "K", "steps", "runs"))
+    A, C = drsa_ref.synth_pairs(M, d, int(g["row_seed"]))
+    drsa.main(A, C, str(tmp_path), num_concepts=K, steps=steps, runs=runs, seed=int(g["seed"]), device="cuda")
+    assert sorted(os.listdir(tmp_path)) == [f"run{r}" for r in range(1, runs + 1)]
+    for r in range(1, runs + 1):
+        lines = open(tmp_path / f"run{r}" / "train_stats.csv").read().splitlines()
+        assert lines[0] == str(g["header"]) and len(lines) == steps + 2
+        assert [l.split(",")[0] for l in lines[1:]] == [str(i) for i in range(steps + 1)]        # pandas index column
+        loss = np.asarray([float(l.split(",")[1]) for l in lines[1:]])
+        want = g[f"loss_run{r}"]
+        rel = float(np.max(np.abs(loss - want) / np.abs(want)))
+        with open(tmp_path / f"run{r}" / "projection_matrix.pkl", "rb") as f:
+            U = pickle.load(f)
+        assert isinstance(U, np.ndarray) and U.dtype == np.float32 and U.shape == (d, d)
+        ang = drsa_ref.principal_angle(torch.from_numpy(U), torch.from_numpy(g[f"U_run{r}"]), K)
+        print(f"main run{r}: rel obj {rel:.2e} angle {ang:.2e} max |dU| {np.abs(U - g[f'U_run{r}']).max():.2e}")
+        assert rel < OBJ_TOL and ang < ANGLE_TOL
+        assert np.abs(U - g[f"U_run{r}"]).max() < 1e-4          # same start (same permutation), same trajectory
+    # the three runs start from different column orders: their logs differ
+    assert abs(g["loss_run1"][0] - g["loss_run2"][0]) > 1e-6
+
+
 def test_obj_val_static_and_autograd(golden_dir):
     from cxai.xai.drsa.drsa import SubspaceOptimizer, objective_fn
     g, A, C, U0, K = _golden(golden_dir, "toy64")

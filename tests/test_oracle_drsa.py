@@ -114,3 +114,20 @@ def test_port_matches_reference_at_the_full_horizon(golden_dir):
     ang = drsa_ref.principal_angle(U, g["U_final"], K)
     assert ang < max(1e-4, 5 * float(g["self_angle"])), ang
     assert float(g["self_angle"]) < 1e-3 and float(g["self_rel"]) < 1e-4
+
+
+def test_multi_run_driver_sequence_matches_reference_result_tree(golden_dir):
+    """The start matrices of the reference's main (drsa.py:265-283: numpy seed, ortho_group.rvs(d), one compounding column
+    permutation per run) restated here, pushed through the oracle's trajectory, against the files the reference's own main
+    wrote (oracle/gen_golden_main.py)."""
+    from scipy.stats import ortho_group
+    g = np.load(os.path.join(golden_dir, "drsa_main.npz"))
+    M, d, K, steps, runs = (int(g[k]) for k in ("M", "d", "K", "steps", "runs"))
+    A, C = drsa_ref.synth_pairs(M, d, int(g["row_seed"]))
+    np.random.seed(int(g["seed"]))
+    U = ortho_group.rvs(d)
+    for r in range(1, runs + 1):
+        U = U[:, np.random.permutation(d)]
+        objs, Uf = drsa_ref.run_autograd(A, C, torch.tensor(U, dtype=torch.float32), K, steps)
+        np.testing.assert_allclose(objs, g[f"loss_run{r}"], rtol=2e-6)
+        assert drsa_ref.principal_angle(Uf, torch.from_numpy(g[f"U_run{r}"]), K) < 1e-5
