@@ -43,6 +43,7 @@ import cxai  # noqa: E402
 assert os.path.abspath(cxai.__file__).startswith(os.path.abspath(REFERENCE_ROOT)), cxai.__file__
 from cxai.model.create_model import VGGType as RefVGGType  # noqa: E402
 from cxai.xai.drsa.preprocessing import get_intermediate  # noqa: E402
+from cxai.xai.drsa import preprocessing as ref_pp  # noqa: E402
 from cxai.xai.explain.attribute import compute_relevances  # noqa: E402
 from cxai.xai.explain.explainer import HeatmapGenerator, compute_subspace_relevances  # noqa: E402
 from cxai.utils.constants import LRP_NAME_MAP_GTZAN, LRP_NAME_MAP_TOY  # noqa: E402
@@ -241,13 +242,30 @@ def case_archB_early():
     return out
 
 
+def case_prep():
+    """The small helpers between the LRP pass and the optimiser, the reference's own functions (preprocessing.py:179-256):
+    sample_spatial_locations (global numpy RNG), get_vectors_from_maps (with its row scrambling),
+    compute_context_vectors, normalize_vectors.  Not a `_both` case: outputs are stored as the fp32 run produced them."""
+    g = torch.Generator().manual_seed(20269)
+    B, d, H, W, L = 6, 40, 4, 8, 5
+    amap = torch.relu(torch.randn(B, d, H, W, generator=g))
+    Rmap = torch.randn(B, d, H, W, generator=g) * (amap > 0)
+    np.random.seed(3)
+    idcs = ref_pp.sample_spatial_locations(B, (H, W), L)                 # :196-216
+    va, vr = ref_pp.get_vectors_from_maps(amap, idcs), ref_pp.get_vectors_from_maps(Rmap, idcs)      # :234-256
+    c = ref_pp.compute_context_vectors(va, vr)                           # :179-193
+    call = ref_pp.compute_context_vectors(amap, Rmap)
+    return dict(seed=20269, np_seed=3, B=B, d=d, H=H, W=W, L=L, idcs=idcs, va=va.numpy(), vr=vr.numpy(), c=c.numpy(),
+                c_maps=call.numpy(), na=ref_pp.normalize_vectors(va).numpy(), nc=ref_pp.normalize_vectors(c).numpy())
+
+
 def case_heat_archB():
     """Concept heatmaps on arch B at the deepest split layer cpf.py:141 uses (features[13], d = 128)."""
     return _heatmaps("archB", 128, 128, 13, "rock", lambda: list(LRP_NAME_MAP_GTZAN), False, N=2, x_seed=20267)
 
 
 CASES = {"toy": case_toy, "archA_small": case_archA_small, "archB": case_archB, "cfg2_full": case_cfg2_full, "heat_toy": case_heat_toy,
-         "heat_archA": case_heat_archA, "heat_archB": case_heat_archB, "archB_early": case_archB_early}
+         "heat_archA": case_heat_archA, "heat_archB": case_heat_archB, "archB_early": case_archB_early, "prep": case_prep}
 
 if __name__ == "__main__":
     torch.set_num_threads(4)

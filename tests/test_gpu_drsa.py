@@ -386,6 +386,29 @@ def test_subspace_relevances_and_context_helpers():
     np.testing.assert_array_equal(v_ref.numpy(), drsa_ref.vectors_from_maps_ref(amap, idcs).numpy())
 
 
+def test_preprocessing_kernels_match_reference_fixture(golden_dir):
+    """compute_context_vectors / normalize_vectors (preprocessing.py:179-193, 219-231) on the GPU against the outputs of the
+    reference's own functions (tests/golden/lrp_prep.npz, oracle/gen_golden_lrp.py `prep`)."""
+    from cxai.xai.drsa import preprocessing as pp
+    g = np.load(os.path.join(golden_dir, "lrp_prep.npz"))
+    va, vr, c = (torch.from_numpy(g[k]).cuda() for k in ("va", "vr", "c"))
+    np.testing.assert_array_equal(pp.compute_context_vectors(va, vr).cpu().numpy(), g["c"])         # one IEEE division
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    B, d, H, W = (int(g[k]) for k in ("B", "d", "H", "W"))
+    amap = torch.relu(torch.randn(B, d, H, W, generator=gen))
+    Rmap = torch.randn(B, d, H, W, generator=gen) * (amap > 0)
+    np.testing.assert_array_equal(pp.compute_context_vectors(amap.cuda(), Rmap.cuda()).cpu().numpy(), g["c_maps"])
+    np.testing.assert_allclose(pp.normalize_vectors(va).cpu().numpy(), g["na"], rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(pp.normalize_vectors(c).cpu().numpy(), g["nc"], rtol=2e-6, atol=1e-9)
+    # the fused gather (corrected row layout) holds the same numbers as the reference's pipeline applied to the same rows
+    act, ctx = pp.gather_context_pairs(amap.cuda(), Rmap.cuda(), g["idcs"], normalize=False)
+    L = int(g["L"])
+    rows_a = torch.stack([amap[b].flatten(1)[:, g["idcs"][b, l]] for b in range(B) for l in range(L)])
+    rows_r = torch.stack([Rmap[b].flatten(1)[:, g["idcs"][b, l]] for b in range(B) for l in range(L)])
+    np.testing.assert_array_equal(act.cpu().numpy(), rows_a.numpy())
+    np.testing.assert_allclose(ctx.cpu().numpy(), (rows_r / (rows_a + 1e-7)).numpy(), rtol=1e-6, atol=0)
+
+
 def test_batched_subset_objectives_match_obj_val_per_subset():
     """Prototype search (prototypes.py:98-119): the objective of every subset from one batched call equals the reference's
     obj_val evaluated subset by subset (oracle), also when the call is cut into several chunks."""

@@ -147,6 +147,42 @@ def test_projection_model_arch_b_matches_reference_fixture(golden_dir, tag):
     assert _rel(H[:, 1:].sum(1), g[f"{tag}_subspace_heatmaps"].sum(1)).max() < 1e-4
 
 
+def _prep_inputs(g):
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    B, d, H, W = (int(g[k]) for k in ("B", "d", "H", "W"))
+    amap = torch.relu(torch.randn(B, d, H, W, generator=gen))
+    Rmap = torch.randn(B, d, H, W, generator=gen) * (amap > 0)
+    return amap, Rmap
+
+
+def test_preprocessing_helpers_match_reference_fixture(golden_dir):
+    """sample_spatial_locations / get_vectors_from_maps / compute_context_vectors / normalize_vectors of the reference
+    (preprocessing.py:179-256, run unmodified by oracle/gen_golden_lrp.py `prep`) against the oracle's restatements and against
+    the host-side parts of the product (numpy RNG call order, the reference's scrambled row layout)."""
+    from cxai.xai.drsa import preprocessing as pp
+    g = np.load(os.path.join(golden_dir, "lrp_prep.npz"))
+    amap, Rmap = _prep_inputs(g)
+    B, H, W, L = (int(g[k]) for k in ("B", "H", "W", "L"))
+    np.random.seed(int(g["np_seed"]))
+    idcs = pp.sample_spatial_locations(B, (H, W), L)                         # product, host only
+    np.testing.assert_array_equal(idcs, g["idcs"])
+    assert idcs.dtype == g["idcs"].dtype
+    np.testing.assert_array_equal(pp.get_vectors_from_maps(amap, idcs, layout="reference").numpy(), g["va"])
+    # oracle restatements
+    va, vr = drsa_ref.vectors_from_maps_ref(amap, idcs), drsa_ref.vectors_from_maps_ref(Rmap, idcs)
+    np.testing.assert_array_equal(va.numpy(), g["va"])
+    np.testing.assert_array_equal(vr.numpy(), g["vr"])
+    c = drsa_ref.compute_context_vectors(va, vr)
+    np.testing.assert_array_equal(c.numpy(), g["c"])
+    np.testing.assert_array_equal(drsa_ref.compute_context_vectors(amap, Rmap).numpy(), g["c_maps"])
+    np.testing.assert_allclose(drsa_ref.normalize_vectors(va).numpy(), g["na"], rtol=1e-6)
+    np.testing.assert_allclose(drsa_ref.normalize_vectors(c).numpy(), g["nc"], rtol=1e-6)
+    # the corrected layout holds the same vectors, row (b, l) = position idcs[b, l] of sample b
+    fixed = pp.get_vectors_from_maps(amap, idcs, layout="fixed")
+    want = torch.stack([amap[b].flatten(1)[:, idcs[b, l]] for b in range(B) for l in range(L)])
+    np.testing.assert_array_equal(fixed.numpy(), want.numpy())
+
+
 def test_mini_zennit_gamma_collapses_and_restores_parameters():
     """The restated hooks leave the model untouched after the context and the 5-pass Gamma equals the one-pass form for
     non-negative input (what the CUDA kernels rely on)."""
