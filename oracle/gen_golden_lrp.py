@@ -259,13 +259,41 @@ def case_prep():
                 c_maps=call.numpy(), na=ref_pp.normalize_vectors(va).numpy(), nc=ref_pp.normalize_vectors(c).numpy())
 
 
+def case_hostutils():
+    """Host-side utilities either side of the path, the reference's own functions: get_slice (utils/sound.py:8-44) on a seeded
+    ~29.3 s clip at a reduced sample rate, get_best_run (utils/evaluation.py:107-141) on a result tree written here."""
+    import tempfile
+    from cxai.utils.sound import get_slice
+    for name in ("matplotlib", "matplotlib.pyplot", "seaborn"):       # plotting imports of evaluation.py:5-7, unused here
+        sys.modules.setdefault(name, types.ModuleType(name))
+    from cxai.utils.evaluation import get_best_run
+    sr = 1000
+    wav = torch.randn(1, int(29.3 * sr), generator=torch.Generator().manual_seed(20270))
+    out = dict(sr=sr, wav_seed=20270, wav_len=wav.size(1))
+    combos = [(3, 10), (6, 3), (6, 5), (3, 2)]
+    out["slice_combos"] = np.asarray(combos)
+    for sl, nc in combos:
+        out[f"slices_{sl}_{nc}"] = get_slice(wav, sl, 7, nc, sr).numpy()
+    out["slice_single"] = get_slice(wav, 6, 4, 1, sr).numpy()
+    losses = {1: [0.10, 0.20, 0.31], 2: [0.12, 0.25, 0.42], 3: [0.11, 0.22, 0.40]}
+    with tempfile.TemporaryDirectory() as tmp:
+        for r, ls in losses.items():
+            os.makedirs(os.path.join(tmp, f"run{r}"))
+            with open(os.path.join(tmp, f"run{r}", "train_stats.csv"), "w") as f:       # the layout drsa.py:157-165 writes
+                f.write(",loss\n" + "".join(f"{i},{v}\n" for i, v in enumerate(ls)))
+        run, loss, crel, path, _ = get_best_run(tmp)
+        out.update(best_run=run, best_loss=loss, best_dir=os.path.basename(path), n_concept_relevances=len(crel))
+    out["tree_losses"] = np.asarray([losses[r] for r in (1, 2, 3)])
+    return out
+
+
 def case_heat_archB():
     """Concept heatmaps on arch B at the deepest split layer cpf.py:141 uses (features[13], d = 128)."""
     return _heatmaps("archB", 128, 128, 13, "rock", lambda: list(LRP_NAME_MAP_GTZAN), False, N=2, x_seed=20267)
 
 
 CASES = {"toy": case_toy, "archA_small": case_archA_small, "archB": case_archB, "cfg2_full": case_cfg2_full, "heat_toy": case_heat_toy,
-         "heat_archA": case_heat_archA, "heat_archB": case_heat_archB, "archB_early": case_archB_early, "prep": case_prep}
+         "heat_archA": case_heat_archA, "heat_archB": case_heat_archB, "archB_early": case_archB_early, "prep": case_prep, "hostutils": case_hostutils}
 
 if __name__ == "__main__":
     torch.set_num_threads(4)

@@ -42,3 +42,23 @@ def test_get_slice_single_window_and_range_check():
     with pytest.raises(AssertionError):
         get_slice(wav, 6, 30 * sr, 1, sr)
     np.testing.assert_allclose(peak_normalizer(got).abs().amax(dim=-1).numpy(), 1.0)
+
+
+def test_get_slice_and_best_run_match_reference_fixture(golden_dir, tmp_path):
+    """The same two host utilities against the outputs of the reference's OWN functions (utils/sound.py:8-44,
+    utils/evaluation.py:107-141; oracle/gen_golden_lrp.py `hostutils`)."""
+    import os
+    from cxai.utils.evaluation import get_best_run
+    g = np.load(os.path.join(golden_dir, "lrp_hostutils.npz"))
+    sr = int(g["sr"])
+    wav = torch.randn(1, int(g["wav_len"]), generator=torch.Generator().manual_seed(int(g["wav_seed"])))
+    for sl, nc in g["slice_combos"].tolist():
+        np.testing.assert_array_equal(get_slice(wav, sl, 7, nc, sr).numpy(), g[f"slices_{sl}_{nc}"])
+    np.testing.assert_array_equal(get_slice(wav, 6, 4, 1, sr).numpy(), g["slice_single"])
+    for r, ls in zip((1, 2, 3), g["tree_losses"].tolist()):
+        os.makedirs(tmp_path / f"run{r}")
+        with open(tmp_path / f"run{r}" / "train_stats.csv", "w") as f:
+            f.write(",loss\n" + "".join(f"{i},{v}\n" for i, v in enumerate(ls)))
+    run, loss, crel, path, losses = get_best_run(str(tmp_path))
+    assert run == int(g["best_run"]) and loss == float(g["best_loss"]) and os.path.basename(path) == str(g["best_dir"])
+    assert len(crel) == int(g["n_concept_relevances"]) and len(losses) == 3
